@@ -1,0 +1,313 @@
+"""Synthetic DVL / IMU / stereo trajectory graphs in the shape /root/reference/batch.py builds.
+
+The reference's input is a private rosbag (README.md:52), so the BASELINE.json configs are
+generated here: an AUV on a breathing helix at ~0.5 m/s, keyframes every 0.2 s
+(batch.py:328), IMU at 200 Hz / dt = 0.005 (batch.py:34, :290), with the reference's constants
+(noise sigmas batch.py:95-98, :118; IMU covariances :183-185; gravity :88; calibration :110-115).
+
+Factor insertion order reproduces batch.py:275-305 exactly:
+  [0] PriorFactorPose3(X0)  [1] PriorFactorVector(V0)  then for i >= 1: ImuFactor_i,
+  DvlVelocityFactor_i, GenericStereoFactor3D_{i,0..k_i-1};  loop-closure BetweenFactorPose3 last.
+Everything is built through the bulk construction API (graph.add_*_factors).
+"""
+import numpy as np
+from .graph import NonlinearFactorGraph
+from .values import Values
+from .symbol import symbols
+from .navigation import PreintegrationParams, preintegrate_batch, _exp_and_jr, _hat_b
+from .geometry import Cal3_S2Stereo
+
+# reference constants
+KEYFRAME_DT = 0.2
+IMU_DT = 0.005                                   # batch.py:34, :290
+SAMPLES_PER_KF = 40
+GRAV = 9.81                                      # batch.py:88
+ACC_COV = 8.999999999999999e-08                  # batch.py:183
+GYRO_COV = 1.2184696791468346e-07                # batch.py:184
+INT_COV = 1e-07                                  # batch.py:185
+POSE_PRIOR_SIGMAS = np.array([0.1, 0.1, 0.1, 0.3, 0.3, 0.3])   # batch.py:95
+VEL_PRIOR_SIGMA = 0.1                            # batch.py:96
+DVL_SIGMA = 0.1                                  # batch.py:98
+STEREO_SIGMA = 10.0                              # batch.py:118
+CALIB = (1827.0, 1827.5999755859375, 0.0, 968.9000244140625, 561.4000244140625, 0.063)  # batch.py:110-115
+LOOP_SIGMAS = np.array([0.02, 0.02, 0.02, 0.05, 0.05, 0.05])
+
+
+def reference_imu_params():
+    """preintegration_parameters() of batch.py:178-193."""
+    p = PreintegrationParams.MakeSharedU(GRAV)
+    p.setAccelerometerCovariance(np.eye(3) * ACC_COV)
+    p.setGyroscopeCovariance(np.eye(3) * GYRO_COV)
+    p.setIntegrationCovariance(np.eye(3) * INT_COV)
+    p.setUse2ndOrderCoriolis(False)
+    p.setOmegaCoriolis(np.zeros(3))
+    return p
+
+
+# ------------------------------------------------------------------ small batched helpers
+def _rot_zyx(psi, th, ph):
+    cz, sz, cy, sy, cx, sx = np.cos(psi), np.sin(psi), np.cos(th), np.sin(th), np.cos(ph), np.sin(ph)
+    R = np.empty(psi.shape + (3, 3))
+    R[..., 0, 0] = cz * cy
+    R[..., 0, 1] = cz * sy * sx - sz * cx
+    R[..., 0, 2] = cz * sy * cx + sz * sx
+    R[..., 1, 0] = sz * cy
+    R[..., 1, 1] = sz * sy * sx + cz * cx
+    R[..., 1, 2] = sz * sy * cx - cz * sx
+    R[..., 2, 0] = -sy
+    R[..., 2, 1] = cy * sx
+    R[..., 2, 2] = cy * cx
+    return R
+
+
+def _log_small(R):
+    """SO(3) log for rotations well away from pi (batched)."""
+    vee = 0.5 * np.stack([R[:, 2, 1] - R[:, 1, 2], R[:, 0, 2] - R[:, 2, 0], R[:, 1, 0] - R[:, 0, 1]], -1)
+    s = np.linalg.norm(vee, axis=1)
+    c = 0.5 * (R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2] - 1.0)
+    th = np.arctan2(s, c)
+    k = np.where(s > 1e-12, th / np.where(s > 1e-12, s, 1.0), 1.0 + s * s / 6.0)
+    return vee * k[:, None]
+
+
+def _pose_exp(xi):
+    w, v = xi[:, :3], xi[:, 3:]
+    R, _ = _exp_and_jr(w)
+    th2 = np.sum(w * w, axis=1)
+    big = th2 > np.finfo(float).eps
+    wxv = np.cross(w, v)
+    t = (wxv - np.einsum('nij,nj->ni', R, wxv) + w * np.sum(w * v, 1)[:, None]) / np.where(big, th2, 1.0)[:, None]
+    return R, np.where(big[:, None], t, v)
+
+
+def _trajectory(t):
+    """Analytic attitude R(t) (body z down: camera looks at the sea floor) and world velocity v(t)."""
+    Om = 0.025
+    rad = 20.0 + 5.0 * np.sin(0.003 * t)
+    drad = 5.0 * 0.003 * np.cos(0.003 * t)
+    c, s = np.cos(Om * t), np.sin(Om * t)
+    v = np.stack([drad * c - rad * Om * s, drad * s + rad * Om * c, 0.02 * np.cos(0.02 * t)], -1)
+    psi = Om * t + 0.5 * np.pi + 0.1 * np.sin(0.013 * t)
+    th = 0.05 * np.sin(0.11 * t)
+    ph = 0.05 * np.sin(0.07 * t + 1.0)
+    R = _rot_zyx(psi, th, ph)
+    flip = np.diag([1.0, -1.0, -1.0])            # Rx(pi): body z points down
+    return R @ flip, v
+
+
+def make_trajectory_graph(n_poses, seed=1, n_landmarks=0, obs_per_landmark=10, n_loops=0,
+                          noise_scale=1.0, pixel_noise=None, true_bias=True, drift=True,
+                          loop_min_gap=200, key_offset=0):
+    """C1/C2/C3/C4-style graph. Returns dict(graph, initial, truth, meta).
+
+    noise_scale=0 gives an exactly consistent (zero-residual-at-truth) known-answer problem.
+    """
+    rng = np.random.default_rng(seed)
+    n = int(n_poses)
+    K = SAMPLES_PER_KF
+    ns = (n - 1) * K
+    g = np.array([0.0, 0.0, -GRAV])
+    params = reference_imu_params()
+
+    # ---- truth at 200 Hz (chunked to bound memory)
+    R_kf = np.empty((n, 3, 3))
+    v_kf = np.empty((n, 3))
+    p_kf = np.empty((n, 3))
+    acc = np.empty((n - 1, K, 3))
+    gyr = np.empty((n - 1, K, 3))
+    p_cur = np.array([20.0, 0.0, -5.0])
+    CH = 4096                                     # keyframe intervals per chunk
+    for c0 in range(0, n - 1, CH):
+        c1 = min(n - 1, c0 + CH)
+        m = (c1 - c0) * K
+        ts = (c0 * K + np.arange(m + 1)) * IMU_DT
+        Rs, vs = _trajectory(ts)
+        w = _log_small(np.swapaxes(Rs[:-1], 1, 2) @ Rs[1:]) / IMU_DT
+        a = np.einsum('nji,nj->ni', Rs[:-1], (vs[1:] - vs[:-1]) / IMU_DT - g)
+        acc[c0:c1] = a.reshape(c1 - c0, K, 3)
+        gyr[c0:c1] = w.reshape(c1 - c0, K, 3)
+        steps = 0.5 * (vs[:-1] + vs[1:]) * IMU_DT
+        ps = p_cur + np.concatenate([np.zeros((1, 3)), np.cumsum(steps, axis=0)])
+        R_kf[c0:c1 + 1] = Rs[::K]
+        v_kf[c0:c1 + 1] = vs[::K]
+        p_kf[c0:c1 + 1] = ps[::K]
+        p_cur = ps[-1]
+
+    bias_true = (np.array([0.02, -0.01, 0.015, 0.002, -0.001, 0.0015]) if true_bias else np.zeros(6)) \
+        * (1.0 if noise_scale > 0 else 0.0)
+    sa = np.sqrt(ACC_COV / IMU_DT) * noise_scale
+    sg = np.sqrt(GYRO_COV / IMU_DT) * noise_scale
+    acc_m = acc + bias_true[:3] + sa * rng.standard_normal(acc.shape)
+    gyr_m = gyr + bias_true[3:] + sg * rng.standard_normal(gyr.shape)
+    pim, imu_info, _cov = preintegrate_batch(acc_m, gyr_m, IMU_DT, params)
+
+    # ---- DVL body velocity (batch.py:243)
+    dvl = np.einsum('nji,nj->ni', R_kf, v_kf) + DVL_SIGMA * noise_scale * rng.standard_normal((n, 3))
+
+    # ---- initial poses: truth corrupted by integrated odometry drift
+    Rrel = np.swapaxes(R_kf[:-1], 1, 2) @ R_kf[1:]
+    trel = np.einsum('nji,nj->ni', R_kf[:-1], p_kf[1:] - p_kf[:-1])
+    if drift and noise_scale > 0:
+        xi = rng.standard_normal((n - 1, 6)) * np.array([0.002] * 3 + [0.01] * 3) * noise_scale
+        dR, dt_ = _pose_exp(xi)
+        trel = trel + np.einsum('nij,nj->ni', Rrel, dt_)
+        Rrel = Rrel @ dR
+    R_in = np.empty_like(R_kf)
+    p_in = np.empty_like(p_kf)
+    R_in[0], p_in[0] = R_kf[0], p_kf[0]
+    Rc, pc = R_kf[0].copy(), p_kf[0].copy()
+    for i in range(n - 1):
+        pc = pc + Rc @ trel[i]
+        Rc = Rc @ Rrel[i]
+        if (i & 1023) == 1023:                   # re-orthonormalise now and then
+            u, _, vt = np.linalg.svd(Rc)
+            Rc = u @ vt
+        R_in[i + 1], p_in[i + 1] = Rc, pc
+
+    idx = np.arange(n)
+    xk, vk = symbols('x', idx + key_offset), symbols('v', idx + key_offset)
+    bk = symbols('b', [key_offset])
+    poses_in = np.concatenate([R_in.reshape(n, 9), p_in], axis=1)
+    initial = Values()
+    initial.insert_bulk("bias", bk, np.zeros((1, 6)))                 # batch.py:274
+    initial.insert_bulk("pose", xk, poses_in)                         # batch.py:283, :287
+    initial.insert_bulk("vel", vk, np.zeros((n, 3)))                  # batch.py:279, :284, :288
+
+    # ---- stereo observations
+    fx, fy, _s, u0, v0, b = CALIB
+    n_lm = int(n_landmarks)
+    obs_pose = np.zeros(0, dtype=np.int64)
+    obs_lm = np.zeros(0, dtype=np.int64)
+    lm_true = np.zeros((0, 3))
+    if n_lm > 0:
+        span = int(obs_per_landmark)
+        start = 1 + (np.arange(n_lm) * (n - span)) // n_lm            # first observing pose (>= 1, batch.py:295)
+        mid = start + span // 2
+        depth = rng.uniform(1.0, 5.0, n_lm)
+        q = np.stack([rng.uniform(-0.4, 0.4, n_lm) * depth, rng.uniform(-0.25, 0.25, n_lm) * depth, depth], -1)
+        lm_true = np.einsum('nij,nj->ni', R_kf[mid], q) + p_kf[mid]
+        obs_pose = (start[:, None] + np.arange(span)[None, :]).ravel()
+        obs_lm = np.repeat(np.arange(n_lm), span)
+        order = np.lexsort((obs_lm, obs_pose))                         # per pose, landmark id ascending
+        obs_pose, obs_lm = obs_pose[order], obs_lm[order]
+        qc = np.einsum('nji,nj->ni', R_kf[obs_pose], lm_true[obs_lm] - p_kf[obs_pose])
+        if np.any(qc[:, 2] <= 0.1):
+            raise RuntimeError("synthetic landmark behind camera")
+        px = STEREO_SIGMA if pixel_noise is None else pixel_noise
+        z = np.stack([u0 + fx * qc[:, 0] / qc[:, 2], u0 + fx * (qc[:, 0] - b) / qc[:, 2],
+                      v0 + fy * qc[:, 1] / qc[:, 2]], -1) + px * noise_scale * rng.standard_normal((len(qc), 3))
+        # landmark initial value: back-projection of its FIRST observation from the initial pose (batch.py:297-298)
+        first = np.full(n_lm, -1, dtype=np.int64)
+        first[obs_lm[::-1]] = np.arange(len(obs_lm))[::-1]
+        zf = z[first]
+        disp = np.maximum(zf[:, 0] - zf[:, 1], 2.0)
+        qz = fx * b / disp
+        q0 = np.stack([(zf[:, 0] - u0) * qz / fx, (zf[:, 2] - v0) * qz / fy, qz], -1)
+        pf = obs_pose[first]
+        lm_init = np.einsum('nij,nj->ni', R_in[pf], q0) + p_in[pf]
+        lk = symbols('l', np.arange(n_lm) + key_offset * 0)
+        initial.insert_bulk("lm", lk, lm_init)
+
+    # ---- factor insertion order of batch.py:275-305
+    cnt = np.bincount(obs_pose, minlength=n) if n_lm > 0 else np.zeros(n, dtype=np.int64)
+    base = np.zeros(n, dtype=np.int64)
+    base[1:] = 2 + np.concatenate([[0], np.cumsum(2 + cnt[1:-1])])
+    graph = NonlinearFactorGraph()
+    graph.add_prior_pose_factors(xk[:1], poses_in[:1], 1.0 / POSE_PRIOR_SIGMAS)          # batch.py:281
+    graph.add_prior_vector_factors(vk[:1], np.zeros((1, 3)), np.full(3, 1.0 / VEL_PRIOR_SIGMA))  # batch.py:282
+    graph.add_imu_factors(xk[:-1], vk[:-1], xk[1:], vk[1:], np.repeat(bk, n - 1), pim, imu_info, g)
+    graph.set_insertion_order("imu", base[1:])
+    graph.add_dvl_factors(vk[1:], xk[1:], dvl[1:], np.full(3, 1.0 / DVL_SIGMA))
+    graph.set_insertion_order("dvl", base[1:] + 1)
+    n_f = 2 + 2 * (n - 1)
+    if n_lm > 0:
+        first_of_pose = np.concatenate([[0], np.cumsum(cnt)])[:-1]
+        rank = np.arange(len(obs_pose)) - first_of_pose[obs_pose]
+        graph.add_stereo_factors(xk[obs_pose], lk[obs_lm], z, np.full(3, 1.0 / STEREO_SIGMA), Cal3_S2Stereo(*CALIB))
+        graph.set_insertion_order("stereo", base[obs_pose] + 2 + rank)
+        n_f += len(obs_pose)
+    loops = np.zeros((0, 2), dtype=np.int64)
+    if n_loops > 0:
+        gap = min(loop_min_gap, max(1, n // 3))
+        i = rng.integers(0, n - gap, n_loops)
+        j = i + gap + (rng.random(n_loops) * (n - gap - i)).astype(np.int64)
+        j = np.minimum(j, n - 1)
+        loops = np.stack([i, j], 1)
+        Rm = np.swapaxes(R_kf[i], 1, 2) @ R_kf[j]
+        tm = np.einsum('nji,nj->ni', R_kf[i], p_kf[j] - p_kf[i])
+        xi = rng.standard_normal((n_loops, 6)) * LOOP_SIGMAS * noise_scale
+        dR, dt_ = _pose_exp(xi)
+        tm = tm + np.einsum('nij,nj->ni', Rm, dt_)
+        Rm = Rm @ dR
+        graph.add_between_factors(xk[i], xk[j], np.concatenate([Rm.reshape(-1, 9), tm], 1), 1.0 / LOOP_SIGMAS)
+        n_f += n_loops
+    graph._n = n_f
+
+    truth = dict(poses=np.concatenate([R_kf.reshape(n, 9), p_kf], 1), vels=v_kf, bias=bias_true, lms=lm_true)
+    meta = dict(n_poses=n, n_landmarks=n_lm, n_stereo=int(len(obs_pose)), n_loops=int(n_loops), loops=loops,
+                n_factors=n_f, seed=seed, preintegration="manifold")
+    return dict(graph=graph, initial=initial, truth=truth, meta=meta)
+
+
+def make_pose_graph(n_poses, seed=5, n_loops=None, noise_scale=1.0):
+    """C5-style pose-graph-only problem: 1 prior + odometry (i,i+1) + skip (i,i+2) + loop closures (i,j),
+    j uniform in [0, i-100].  All BetweenFactorPose3, sigma = LOOP_SIGMAS."""
+    rng = np.random.default_rng(seed)
+    n = int(n_poses)
+    t = np.arange(n) * KEYFRAME_DT
+    R_kf, v = _trajectory(t)
+    p_kf = np.array([20.0, 0.0, -5.0]) + np.concatenate([np.zeros((1, 3)), np.cumsum(0.5 * (v[:-1] + v[1:]) * KEYFRAME_DT, 0)])
+    if n_loops is None:
+        n_loops = n // 2 + 2
+
+    def rel(i, j):
+        Rm = np.swapaxes(R_kf[i], 1, 2) @ R_kf[j]
+        tm = np.einsum('nji,nj->ni', R_kf[i], p_kf[j] - p_kf[i])
+        xi = rng.standard_normal((len(i), 6)) * LOOP_SIGMAS * noise_scale
+        dR, dt_ = _pose_exp(xi)
+        return np.concatenate([(Rm @ dR).reshape(-1, 9), tm + np.einsum('nij,nj->ni', Rm, dt_)], 1)
+
+    idx = np.arange(n)
+    xk = symbols('x', idx)
+    i1, j1 = idx[:-1], idx[1:]
+    i2, j2 = idx[:-2], idx[2:]
+    il = rng.integers(100, n, n_loops) if n > 100 else np.zeros(0, dtype=np.int64)
+    jl = (rng.random(len(il)) * (il - 99)).astype(np.int64)
+    odo = rel(i1, j1)
+    # initial = chained noisy odometry
+    R_in = np.empty_like(R_kf)
+    p_in = np.empty_like(p_kf)
+    R_in[0], p_in[0] = R_kf[0], p_kf[0]
+    Rc, pc = R_kf[0].copy(), p_kf[0].copy()
+    for k in range(n - 1):
+        pc = pc + Rc @ odo[k, 9:]
+        Rc = Rc @ odo[k, :9].reshape(3, 3)
+        if (k & 1023) == 1023:
+            u, _, vt = np.linalg.svd(Rc)
+            Rc = u @ vt
+        R_in[k + 1], p_in[k + 1] = Rc, pc
+    poses_in = np.concatenate([R_in.reshape(n, 9), p_in], 1)
+    initial = Values()
+    initial.insert_bulk("pose", xk, poses_in)
+    graph = NonlinearFactorGraph()
+    graph.add_prior_pose_factors(xk[:1], poses_in[:1], 1.0 / POSE_PRIOR_SIGMAS)
+    graph.add_between_factors(xk[i1], xk[j1], odo, 1.0 / LOOP_SIGMAS)
+    graph.add_between_factors(xk[i2], xk[j2], rel(i2, j2), 1.0 / LOOP_SIGMAS)
+    if len(il):
+        graph.add_between_factors(xk[jl], xk[il], rel(jl, il), 1.0 / LOOP_SIGMAS)
+    truth = dict(poses=np.concatenate([R_kf.reshape(n, 9), p_kf], 1))
+    meta = dict(n_poses=n, n_factors=graph.size(), seed=seed)
+    return dict(graph=graph, initial=initial, truth=truth, meta=meta)
+
+
+CONFIGS = {
+    "C1": dict(n_poses=2000, seed=1, n_loops=50),
+    "C2": dict(n_poses=5000, seed=2, n_landmarks=20000),
+    "C3": dict(n_poses=100000, seed=3, n_landmarks=200000),
+}
+
+
+def make_config(name, **over):
+    kw = dict(CONFIGS[name])
+    kw.update(over)
+    return make_trajectory_graph(**kw)
