@@ -1,0 +1,130 @@
+/* vus.h -- C-ABI of the B200-native batch factor-graph optimizer (libvus.so).
+ *
+ * Drop-in boundary for the one hot path of hvak/visual-underwater-slam:
+ *     gtsam.LevenbergMarquardtOptimizer(graph, initial, gtsam.LevenbergMarquardtParams()).optimize()
+ *                                                                   (/root/reference/batch.py:337)
+ * over the graph that /root/reference/batch.py:270-305 builds.  The reference has no FFI of its own
+ * (it calls gtsam through gtsam's pybind11 wrapper); these entry points are what a binding for this
+ * path would bind.  Each one cites the reference / gtsam interface it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every call returns 0 on success or a negative vus_status;
+ *     vus_last_error() returns a message owned by the handle.  No exceptions cross the ABI.
+ *   - all numeric tables are FP64 structure-of-arrays, COMPONENT-MAJOR:  table[c * n + i].
+ *   - `mem` says where a numeric table lives: VUS_MEM_HOST (the library copies host->device) or
+ *     VUS_MEM_DEVICE (a device pointer, e.g. torch.Tensor.data_ptr(); copied device->device).
+ *     Key / index / insertion-order arrays are always host memory.
+ *   - one handle per GPU, one host thread per handle; all kernels run on the stream passed in.
+ */
+#ifndef VUS_H_
+#define VUS_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vus_handle vus_handle;
+
+enum vus_status { VUS_OK = 0, VUS_ERR_INVALID = -1, VUS_ERR_UNSUPPORTED = -2, VUS_ERR_CUDA = -3, VUS_ERR_STATE = -4 };
+enum vus_mem { VUS_MEM_HOST = 0, VUS_MEM_DEVICE = 1 };
+
+/* Variable kinds (gtsam::Values entries, batch.py:274, :283-288, :297-298).
+ *   POSE  12 comps: R row-major (9) then t (3)      X(i)   gtsam::Pose3
+ *   VEL    3 comps                                   V(i)   Vector3
+ *   BIAS   6 comps: accelerometer (3), gyro (3)      B(0)   imuBias::ConstantBias
+ *   LM     3 comps                                   L(id)  Point3                                  */
+enum vus_var_kind { VUS_VAR_POSE = 0, VUS_VAR_VEL = 1, VUS_VAR_BIAS = 2, VUS_VAR_LM = 3 };
+
+/* Factor types.  idx = int32 variable indices [slots][n] into the per-kind tables (ascending-key order).
+ *   type          replaces (reference)                         slots (kind)            meas comps            sqrt_info comps
+ *   PRIOR_POSE    gtsam.PriorFactorPose3   batch.py:281        x                       12 (Pose3)            6  (1/sigma)
+ *   PRIOR_VEL     gtsam.PriorFactorVector  batch.py:282        v                       3                     3
+ *   BETWEEN       gtsam.BetweenFactorPose3 (north_star)        x1, x2                  12 (Pose3)            6
+ *   DVL           gtsam.CustomFactor + velocity_error          v, x   (batch.py:247)   3 (body velocity)     3
+ *                 batch.py:196-233, :241-250
+ *   STEREO        gtsam.GenericStereoFactor3D batch.py:300-305 x, l                    3 (uL, uR, v)         3
+ *   IMU           gtsam.ImuFactor          batch.py:238        xi, vi, xj, vj, b       67 (packed PIM)       45 (upper-tri R, R^T R = Sigma^-1)
+ * Packed PIM: dR 9 | dP 3 | dV 3 | dt 1 | bias_hat 6 | dR/dbg 9 | dP/dba 9 | dP/dbg 9 | dV/dba 9 | dV/dbg 9.
+ * Whitened Jacobian layouts returned by vus_linearize (node order, element (row,col) at J[(row*cols+col)*n+f]):
+ *   PRIOR_POSE 6x6 | PRIOR_VEL 3x3 | BETWEEN 6x12 [H1|H2] | DVL 3x9 [Hx|Hv] | STEREO 3x9 [Hpose|Hlm]
+ *   IMU 9x24 [Hxi Hvi | Hxj Hvj | Hbias]                                                              */
+enum vus_factor_type { VUS_FACTOR_PRIOR_POSE = 0, VUS_FACTOR_PRIOR_VEL = 1, VUS_FACTOR_BETWEEN = 2,
+                       VUS_FACTOR_DVL = 3, VUS_FACTOR_STEREO = 4, VUS_FACTOR_IMU = 5 };
+
+/* gtsam::LevenbergMarquardtParams (defaults = gtsam's, batch.py:337 passes a default-constructed object)
+ * plus the knobs of the iterative linear solver that replaces gtsam's multifrontal Cholesky.          */
+typedef struct vus_lm_params {
+  int32_t max_iterations;        /* 100   */
+  double relative_error_tol;     /* 1e-5  */
+  double absolute_error_tol;     /* 1e-5  */
+  double error_tol;              /* 0     */
+  double lambda_initial;         /* 1e-5  */
+  double lambda_factor;          /* 10    */
+  double lambda_upper_bound;     /* 1e5   */
+  double lambda_lower_bound;     /* 0     */
+  double min_model_fidelity;     /* 1e-3  */
+  int32_t pcg_max_iterations;    /* 500   */
+  double pcg_rel_tol;            /* 1e-12: ||r|| <= tol * ||rhs|| (stops earlier if the residual stagnates) */
+  int32_t max_supernode;         /* 0 = auto (band width from the graph, capped so k*D <= 96) */
+  int32_t verbose;
+} vus_lm_params;
+
+typedef struct vus_lm_result {
+  int32_t iterations;            /* accepted LM steps (gtsam's iterations()) */
+  int32_t inner_iterations;      /* lambda tries */
+  int32_t linearizations;
+  int32_t pcg_iterations;        /* total */
+  int32_t solve_failures;
+  int32_t reserved;
+  double initial_error, final_error, final_lambda;
+  double ms_total, ms_linearize, ms_assemble, ms_schur, ms_factor, ms_pcg, ms_update;
+  int64_t kernel_launches;
+  int64_t factors_linearized;    /* sum over linearizations of #factors */
+} vus_lm_result;
+
+void vus_default_lm_params(vus_lm_params* p);
+
+/* lifetime */
+int vus_create(int device, vus_handle** out);
+void vus_destroy(vus_handle* h);
+const char* vus_last_error(const vus_handle* h);
+
+/* gtsam::Values  (batch.py:81, :274, :283-288, :297-298): keys ascending uint64 Symbol keys. */
+int vus_set_variables(vus_handle* h, int kind, int64_t n, const uint64_t* keys, const double* data, int mem);
+int vus_get_variables(vus_handle* h, int kind, double* out, int mem);
+
+/* gtsam::NonlinearFactorGraph::add / push_back (batch.py:281-282, :291-292, :305), one call per type.
+ * orig_index = NonlinearFactorGraph insertion index of each factor (kept for bit-exact factor indexing). */
+int vus_add_factors(vus_handle* h, int type, int64_t n, const int32_t* var_idx, const double* meas,
+                    const double* sqrt_info, const int64_t* orig_index, int mem);
+int vus_set_calibration(vus_handle* h, const double K[6]);       /* Cal3_S2Stereo fx fy s u0 v0 b (batch.py:115) */
+int vus_set_gravity(vus_handle* h, const double g[3]);           /* PreintegrationParams n_gravity (batch.py:181) */
+int vus_set_lm_params(vus_handle* h, const vus_lm_params* p);
+
+/* symbolic phase: node ordering, supernode band layout, off-band blocks, Schur destination lists */
+int vus_analyze(vus_handle* h);
+/* band description after analyze: D (node dof), k (nodes per supernode), Ns, nrem, ndst */
+int vus_get_layout(vus_handle* h, int64_t out[8]);
+
+/* LevenbergMarquardtOptimizer::optimize()  (batch.py:337). Asynchronous work is issued on `stream`
+ * (a cudaStream_t, may be NULL); the call returns after the convergence decision. Values are updated in place. */
+int vus_optimize(vus_handle* h, void* stream, vus_lm_result* result);
+
+/* NonlinearFactorGraph::error(values) = sum 1/2 ||whitened r||^2 at the current values */
+int vus_error(vus_handle* h, void* stream, double* out);
+/* per-factor 1/2 ||r||^2 in ORIGINAL insertion order (length = total factor count) */
+int vus_factor_errors(vus_handle* h, void* stream, double* out);
+/* NonlinearFactorGraph::linearize for one factor type at the current values: whitened r [m][n], J [m*cols][n] -> host */
+int vus_linearize(vus_handle* h, void* stream, int type, double* r_out, double* J_out);
+/* one damped Gauss-Newton step at the current values WITHOUT applying it:
+ * solves (J^T J + lambda I) delta = -J^T r; delta_pose [nx][6], delta_vel [nv][3], delta_bias [nb][6], delta_lm [nl][3] (host, AoS) */
+int vus_solve_step(vus_handle* h, void* stream, double lambda, double* d_pose, double* d_vel, double* d_bias, double* d_lm,
+                   int32_t* pcg_iterations);
+/* time `reps` launches of kernel 1 (linearize, all factor types) with CUDA events; ms per repetition */
+int vus_time_linearize(vus_handle* h, void* stream, int reps, double* ms_per_rep);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VUS_H_ */

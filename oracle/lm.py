@@ -153,6 +153,11 @@ def retract(vals, delta, lay):
     return out
 
 
+def _splu_sym(A):
+    """SuperLU in symmetric mode (minimum-degree on A+A^T, no pivoting): an exact sparse Cholesky-like solve."""
+    return spla.splu(A.tocsc(), permc_spec='MMD_AT_PLUS_A', diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
+
+
 def solve_damped(J, b, lam, lay, schur=True):
     """Exact solve of (J^T J + lam I) d = J^T b.  schur=True eliminates landmarks first (same system)."""
     H = (J.T @ J).tocsc()
@@ -160,8 +165,7 @@ def solve_damped(J, b, lam, lay, schur=True):
     n = lay.n
     H = H + lam * sp.identity(n, format='csc')
     if not schur or lay.nl == 0:
-        lu = spla.splu(H)
-        return lu.solve(g)
+        return _splu_sym(H).solve(g)
     l0, l1 = lay.ol, lay.ov
     cam = np.concatenate([np.arange(0, l0), np.arange(l1, n)])
     lm = np.arange(l0, l1)
@@ -180,7 +184,7 @@ def solve_damped(J, b, lam, lay, schur=True):
     ECi = (E @ Cinv).tocsc()
     S = (Hc - ECi @ E.T).tocsc()
     gc = g[cam] - ECi @ g[lm]
-    dc = spla.splu(S).solve(gc)
+    dc = _splu_sym(S).solve(gc)
     dl = Cinv @ (g[lm] - E.T @ dc)
     d = np.empty(n)
     d[cam] = dc

@@ -1,0 +1,67 @@
+"""CPU (`-m "not gpu"`) checks of the host logic and of the kernel bodies through a sequential host emulation
+(tests/emu/libvus_emu.so, built from the same csrc/ sources with -DVUS_EMU).  The emulation is test
+infrastructure: the package never loads it.  The parity tests proper are the `-m gpu` ones (test_gpu_parity.py)."""
+import os
+import subprocess
+import numpy as np
+import pytest
+from visual_underwater_slam_b200 import _native
+import parity_common as pc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "visual_underwater_slam_b200", "csrc"), "emu"], check=True)
+    return _native.bind(os.path.join(ROOT, "tests", "emu", "libvus_emu.so"))
+
+
+def test_factor_parity_chain_loops(emu):
+    _, prob = pc.make(80, n_loops=4)
+    pc.check_factor_parity(emu, prob)
+
+
+def test_factor_parity_stereo(emu):
+    _, prob = pc.make(60, n_lm=120)
+    pc.check_factor_parity(emu, prob)
+
+
+def test_solve_chain_is_exact(emu):
+    _, prob = pc.make(70)
+    its = pc.check_solve_parity(emu, prob, 1e-3, 1e-6)
+    assert its <= 2          # band + bias border are factored exactly: PCG is only iterative refinement
+
+
+def test_solve_stereo_schur(emu):
+    _, prob = pc.make(60, n_lm=100)
+    its = pc.check_solve_parity(emu, prob, 1e-2, 1e-6)
+    assert its <= 3
+
+
+def test_solve_loop_closures(emu):
+    _, prob = pc.make(120, n_loops=5, loop_min_gap=30)
+    pc.check_solve_parity(emu, prob, 1.0, 1e-6)
+
+
+def test_lm_parity_chain(emu):
+    _, prob = pc.make(120, n_loops=3, loop_min_gap=40)
+    pc.check_lm_parity(emu, prob)
+
+
+def test_lm_parity_stereo(emu):
+    _, prob = pc.make(60, n_lm=100)
+    pc.check_lm_parity(emu, prob)
+
+
+def test_known_answer_noise_free(emu):
+    """Noise-free graph: the optimum is the ground truth."""
+    from visual_underwater_slam_b200.optimizer import Session
+    d, prob = pc.make(50, n_lm=60, noise_scale=0.0)
+    s = Session(prob, lib=emu)
+    res = s.optimize()
+    v = s.values()
+    assert res["final_error"] < 1e-10
+    assert np.abs(v["poses"] - d["truth"]["poses"]).max() < 1e-6
+    assert np.abs(v["vels"] - d["truth"]["vels"]).max() < 1e-6
+    s.close()

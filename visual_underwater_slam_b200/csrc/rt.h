@@ -1,0 +1,104 @@
+// Minimal runtime layer: device memory, copies and the two launch shapes (see vus_common.h).
+// CUDA build: cudaMalloc / cudaMemcpyAsync / <<<>>> on the caller's stream.
+// VUS_EMU build (tests only): malloc / memcpy / sequential loops.
+#pragma once
+#include "vus_common.h"
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <stdexcept>
+#include <vector>
+
+namespace vus { namespace rt {
+
+#ifdef VUS_EMU
+typedef void* stream_t;
+inline void check_last(const char*) {}
+inline void* dalloc(size_t bytes) { void* p = std::calloc(bytes ? bytes : 1, 1); if (!p) throw std::runtime_error("emu alloc failed"); return p; }
+inline void dfree(void* p) { std::free(p); }
+inline void h2d(void* d, const void* s, size_t n, stream_t) { std::memcpy(d, s, n); }
+inline void d2h(void* d, const void* s, size_t n, stream_t) { std::memcpy(d, s, n); }
+inline void d2d(void* d, const void* s, size_t n, stream_t) { std::memmove(d, s, n); }
+inline void dzero(void* d, size_t n, stream_t) { std::memset(d, 0, n); }
+inline void sync(stream_t) {}
+inline int sm_count() { return 4; }
+
+template <class Body, class Args>
+inline void launch_elem(long n, stream_t, const Args& a) {
+  for (long i = 0; i < n; ++i) Body::run(a, i);
+}
+template <class Body, class Args>
+inline void launch_coop(int grid, int /*block*/, size_t smem_bytes, stream_t, const Args& a) {
+  std::vector<double> smem(smem_bytes / sizeof(double) + 8);
+  for (int b = 0; b < grid; ++b) Body::run(a, b, 0, 1, smem.data());
+}
+#else
+typedef cudaStream_t stream_t;
+inline void check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+inline void check_last(const char* what) { check(cudaGetLastError(), what); }
+inline void* dalloc(size_t bytes) { void* p = nullptr; check(cudaMalloc(&p, bytes ? bytes : 8), "cudaMalloc"); return p; }
+inline void dfree(void* p) { if (p) cudaFree(p); }
+inline void h2d(void* d, const void* s, size_t n, stream_t st) { if (n) check(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st), "h2d"); }
+inline void d2h(void* d, const void* s, size_t n, stream_t st) { if (n) check(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st), "d2h"); }
+inline void d2d(void* d, const void* s, size_t n, stream_t st) { if (n) check(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st), "d2d"); }
+inline void dzero(void* d, size_t n, stream_t st) { if (n) check(cudaMemsetAsync(d, 0, n, st), "memset"); }
+inline void sync(stream_t st) { check(cudaStreamSynchronize(st), "stream sync"); }
+inline int sm_count() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+  return n;
+}
+
+template <class Body, class Args>
+__global__ void __launch_bounds__(256) k_elem(Args a, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) Body::run(a, i);
+}
+template <class Body, class Args>
+__global__ void k_coop(Args a) {
+  extern __shared__ double vus_smem[];
+  Body::run(a, (int)blockIdx.x, (int)threadIdx.x, (int)blockDim.x, vus_smem);
+}
+// grid sized in multiples of the SM count (148 on B200), capped by the work available
+template <class Body, class Args>
+inline void launch_elem(long n, stream_t st, const Args& a) {
+  if (n <= 0) return;
+  const int block = 256;
+  long need = (n + block - 1) / block;
+  long cap = (long)sm_count() * 8;
+  int grid = (int)(need < cap ? need : cap);
+  k_elem<Body, Args><<<grid, block, 0, st>>>(a, n);
+  check_last("launch_elem");
+}
+template <class Body, class Args>
+inline void launch_coop(int grid, int block, size_t smem_bytes, stream_t st, const Args& a) {
+  if (grid <= 0) return;
+  if (smem_bytes > 48 * 1024) {
+    static size_t configured = 0;   // per (Body,Args) instantiation
+    if (smem_bytes > configured) {
+      check(cudaFuncSetAttribute(k_coop<Body, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes), "smem attr");
+      configured = smem_bytes;
+    }
+  }
+  k_coop<Body, Args><<<grid, block, smem_bytes, st>>>(a);
+  check_last("launch_coop");
+}
+#endif
+
+// typed device buffer
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DBuf() {}
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  ~DBuf() { dfree(p); }
+  void alloc(size_t count) { if (count > n || !p) { dfree(p); p = (T*)dalloc(count * sizeof(T)); n = count; } }
+  void upload(const T* h, size_t count, stream_t st) { alloc(count); h2d(p, h, count * sizeof(T), st); }
+  void upload(const std::vector<T>& h, stream_t st) { upload(h.data(), h.size(), st); }
+  void zero(stream_t st) { dzero(p, n * sizeof(T), st); }
+};
+
+}}  // namespace vus::rt

@@ -1,0 +1,960 @@
+// libvus: handle, symbolic analysis, the LM driver and the C-ABI of include/vus.h.
+//
+// Replaces gtsam's LevenbergMarquardtOptimizer::optimize() for the graph of /root/reference/batch.py
+// (call site batch.py:337).  Host code here only sequences kernels and takes the accept/reject
+// decisions from device-computed scalars; all arithmetic on graph data is in kernels.cuh.
+#include "../../include/vus.h"
+#include "kernels.cuh"
+#include "rt.h"
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <map>
+#include <numeric>
+
+using namespace vus;
+using rt::DBuf;
+
+namespace {
+
+long g_launches = 0;
+
+template <class Body, class Args>
+void L_elem(long n, rt::stream_t st, const Args& a) {
+  if (n <= 0) return;
+  ++g_launches;
+  rt::launch_elem<Body, Args>(n, st, a);
+}
+template <class Body, class Args>
+void L_coop(int grid, int block, size_t smem, rt::stream_t st, const Args& a) {
+  if (grid <= 0) return;
+  ++g_launches;
+  rt::launch_coop<Body, Args>(grid, block, smem, st, a);
+}
+
+struct FactorTable {
+  long n = 0;
+  std::vector<int> h_idx;        // [slots][n]
+  std::vector<int64_t> orig;
+  DBuf<int> idx;
+  DBuf<double> meas, sinfo, r, J;
+  DBuf<PairDst> pair;
+  long e_off = 0;                // offset into the concatenated per-factor error buffer
+};
+
+const int kVarDim[4] = {12, 3, 6, 3};
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+struct vus_handle {
+  int device = 0;
+  std::string err;
+  vus_lm_params prm;
+  double K[6] = {1, 1, 0, 0, 0, 1};
+  double grav[3] = {0, 0, -9.81};
+  // variables
+  long nvar[4] = {0, 0, 0, 0};
+  std::vector<uint64_t> keys[4];
+  DBuf<double> val[2][4];
+  int cur = 0;
+  // factors
+  FactorTable ft[VUS_F_NTYPES];
+  long nfactors = 0;
+  bool analyzed = false;
+  // layout
+  int D = 6, k = 1, B = 6, has_bias = 0;
+  long N = 0, Ns = 0, Npad = 0, Lc = 0, L = 0;   // Lc = Npad*D camera dofs, L = Lc + 6*has_bias
+  long nrem = 0, sd_off = 0, su_off = 0, rem_off = 0, hlen = 0;
+  DBuf<double> H0, H;            // SD | SU | REM   (undamped base / damped + Schur)
+  DBuf<int> rem_ptr, rem_col;
+  DBuf<double> g0, gs, F, Hbb0, Hbb, gb;     // gs = [reduced camera gradient ; gb] (length L)
+  // stereo
+  long nobs = 0, nposes_obs = 0, ndst = 0;
+  DBuf<int> pose_ptr, pose_obs, pose_ids, lm_ptr, lm_obs, dst_ptr, term_a, term_b;
+  DBuf<PairDst> dst;
+  DBuf<double> C, gl, Cinv, E, W;
+  // BCR
+  DBuf<double> Dw, U1, U2, Dinv, Gl, Gr, GlT, GrT, Z, SbInv;
+  // PCG
+  DBuf<double> x, r, z, p, Ap, d, xl, scal, partials, bpart, e_all, le_all;
+  DBuf<int> fail;
+  int red_grid = 0;
+  // stats
+  vus_lm_result res;
+};
+
+namespace {
+
+int fail(vus_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+ValuesView view_of(vus_handle* h, int which) {
+  ValuesView V;
+  V.pose = h->val[which][0].p; V.nx = h->nvar[0];
+  V.vel = h->val[which][1].p; V.nv = h->nvar[1];
+  V.bias = h->val[which][2].p; V.nb = h->nvar[2];
+  V.lm = h->val[which][3].p; V.nl = h->nvar[3];
+  return V;
+}
+
+template <bool WJ>
+void launch_lin_type(vus_handle* h, int t, const LinArgs& a, rt::stream_t st) {
+  const long n = h->ft[t].n;
+  switch (t) {
+    case VUS_F_PRIOR_POSE: L_elem<LinBody<VUS_F_PRIOR_POSE, WJ>>(n, st, a); break;
+    case VUS_F_PRIOR_VEL: L_elem<LinBody<VUS_F_PRIOR_VEL, WJ>>(n, st, a); break;
+    case VUS_F_BETWEEN: L_elem<LinBody<VUS_F_BETWEEN, WJ>>(n, st, a); break;
+    case VUS_F_DVL: L_elem<LinBody<VUS_F_DVL, WJ>>(n, st, a); break;
+    case VUS_F_STEREO: L_elem<LinBody<VUS_F_STEREO, WJ>>(n, st, a); break;
+    default: L_elem<LinBody<VUS_F_IMU, WJ>>(n, st, a); break;
+  }
+}
+
+// kernel 1 over every factor type; with_J: also write r and J (linearize), else residual norms only
+void run_factors(vus_handle* h, int which, bool with_J, rt::stream_t st) {
+  for (int t = 0; t < VUS_F_NTYPES; ++t) {
+    FactorTable& T = h->ft[t];
+    if (!T.n) continue;
+    LinArgs a;
+    a.V = view_of(h, which);
+    a.F.n = T.n; a.F.idx = T.idx.p; a.F.meas = T.meas.p; a.F.sinfo = T.sinfo.p;
+    a.O.r = with_J ? T.r.p : nullptr;
+    a.O.J = with_J ? T.J.p : nullptr;
+    a.O.e2 = h->e_all.p + T.e_off;
+    for (int i = 0; i < 6; ++i) a.K[i] = h->K[i];
+    for (int i = 0; i < 3; ++i) a.g[i] = h->grav[i];
+    a.type = t;
+    if (with_J) launch_lin_type<true>(h, t, a, st);
+    else launch_lin_type<false>(h, t, a, st);
+  }
+}
+
+// deterministic sum / dot -> scal[slot] with post-op
+void reduce(vus_handle* h, const double* a, const double* b, long n, int slot, int op, rt::stream_t st) {
+  RedArgs r1; r1.a = a; r1.b = b; r1.n = n; r1.partials = h->partials.p; r1.grid = h->red_grid;
+  L_coop<Red1Body>(h->red_grid, 256, 256 * sizeof(double), st, r1);
+  Red2Args r2; r2.partials = h->partials.p; r2.grid = h->red_grid; r2.scal = h->scal.p; r2.slot = slot; r2.op = op;
+  L_coop<Red2Body>(1, 256, 256 * sizeof(double), st, r2);
+}
+
+double read_scalar(vus_handle* h, int slot, rt::stream_t st) {
+  double v = 0;
+  rt::d2h(&v, h->scal.p + slot, sizeof(double), st);
+  rt::sync(st);
+  return v;
+}
+
+double graph_error(vus_handle* h, int which, rt::stream_t st) {
+  run_factors(h, which, false, st);
+  reduce(h, h->e_all.p, nullptr, h->nfactors, S_TMP, RED_STORE, st);
+  return read_scalar(h, S_TMP, st);
+}
+
+// ------------------------------------------------------------------ symbolic analysis
+struct PairKey { long p, q; };
+
+PairDst band_dst(const vus_handle* h, long p, long q, const std::map<std::pair<long, long>, long>& rem_index) {
+  // destination of block (p,q), p != q allowed to be in any order
+  PairDst d; d.pad = 0;
+  const int D = h->D, k = h->k, B = h->B;
+  const long I = p / k, J = q / k;
+  const int rp = (int)(p % k), rq = (int)(q % k);
+  const long BB = (long)B * B;
+  if (I == J) {
+    d.off = h->sd_off + I * BB + (long)(rp * D) * B + rq * D; d.ld = B; d.transposed = 0;
+    d.moff = h->sd_off + I * BB + (long)(rq * D) * B + rp * D; d.mld = B;
+  } else if (J == I + 1) {
+    d.off = h->su_off + I * BB + (long)(rp * D) * B + rq * D; d.ld = B; d.transposed = 0; d.moff = -1; d.mld = 0;
+  } else if (J == I - 1) {
+    d.off = h->su_off + J * BB + (long)(rq * D) * B + rp * D; d.ld = B; d.transposed = 1; d.moff = -1; d.mld = 0;
+  } else {
+    const long b1 = rem_index.at({p, q}), b2 = rem_index.at({q, p});
+    d.off = h->rem_off + b1 * D * D; d.ld = D; d.transposed = 0;
+    d.moff = h->rem_off + b2 * D * D; d.mld = D;
+  }
+  return d;
+}
+
+int analyze(vus_handle* h, rt::stream_t st) {
+  const long NX = h->nvar[0], NV = h->nvar[1], NB = h->nvar[2], NL = h->nvar[3];
+  if (NX == 0) return fail(h, VUS_ERR_INVALID, "no Pose3 variables");
+  if (NB > 1) return fail(h, VUS_ERR_UNSUPPORTED, "more than one imuBias variable: only the shared B(0) of batch.py:238/:274 is supported");
+  h->D = NV > 0 ? 9 : 6;
+  if (NV > 0) {
+    if (NV != NX) return fail(h, VUS_ERR_UNSUPPORTED, "every pose X(i) needs a velocity V(i) (batch.py:283-288)");
+    const uint64_t mask = (uint64_t(1) << 56) - 1;
+    for (long i = 0; i < NX; ++i)
+      if ((h->keys[0][i] & mask) != (h->keys[1][i] & mask))
+        return fail(h, VUS_ERR_UNSUPPORTED, "velocity and pose symbol indices must match (V(i) with X(i))");
+  }
+  h->has_bias = NB ? 1 : 0;
+  const int D = h->D;
+  h->N = NX;
+  // ---- node pairs from two-node factors and landmark tracks
+  FactorTable& FB = h->ft[VUS_F_BETWEEN];
+  FactorTable& FI = h->ft[VUS_F_IMU];
+  FactorTable& FD = h->ft[VUS_F_DVL];
+  FactorTable& FS = h->ft[VUS_F_STEREO];
+  if (D == 6 && (FI.n || FD.n || h->ft[VUS_F_PRIOR_VEL].n))
+    return fail(h, VUS_ERR_INVALID, "velocity factors without velocity variables");
+  for (long f = 0; f < FI.n; ++f)
+    if (FI.h_idx[f] != FI.h_idx[FI.n + f] || FI.h_idx[2 * FI.n + f] != FI.h_idx[3 * FI.n + f])
+      return fail(h, VUS_ERR_UNSUPPORTED, "ImuFactor must connect (X(i),V(i)) to (X(j),V(j)) (batch.py:238)");
+  for (long f = 0; f < FD.n; ++f)
+    if (FD.h_idx[f] != FD.h_idx[FD.n + f])
+      return fail(h, VUS_ERR_UNSUPPORTED, "DVL factor must connect V(i) and X(i) of the same keyframe (batch.py:247)");
+  // stereo CSR structures
+  h->nobs = FS.n;
+  std::vector<int> lm_ptr(NL + 1, 0), lm_obs(FS.n), pose_cnt(NX, 0);
+  for (long o = 0; o < FS.n; ++o) { lm_ptr[FS.h_idx[FS.n + o] + 1]++; pose_cnt[FS.h_idx[o]]++; }
+  for (long l = 0; l < NL; ++l) lm_ptr[l + 1] += lm_ptr[l];
+  {
+    std::vector<int> fill(lm_ptr.begin(), lm_ptr.end() - 1);
+    for (long o = 0; o < FS.n; ++o) lm_obs[fill[FS.h_idx[FS.n + o]]++] = (int)o;
+  }
+  // sort each landmark's observations by pose (stable in factor order)
+  for (long l = 0; l < NL; ++l)
+    std::stable_sort(lm_obs.begin() + lm_ptr[l], lm_obs.begin() + lm_ptr[l + 1],
+                     [&](int a, int b) { return FS.h_idx[a] < FS.h_idx[b]; });
+  std::vector<int> pose_ids, pose_ptr(1, 0), pose_obs(FS.n);
+  {
+    std::vector<int> slot(NX, -1);
+    for (long i = 0; i < NX; ++i)
+      if (pose_cnt[i]) { slot[i] = (int)pose_ids.size(); pose_ids.push_back((int)i); pose_ptr.push_back(pose_ptr.back() + pose_cnt[i]); }
+    std::vector<int> fill(pose_ptr.begin(), pose_ptr.end() - 1);
+    for (long o = 0; o < FS.n; ++o) pose_obs[fill[slot[FS.h_idx[o]]]++] = (int)o;
+  }
+  h->nposes_obs = (long)pose_ids.size();
+  for (long l = 0; l < NL; ++l)
+    if (lm_ptr[l + 1] == lm_ptr[l]) return fail(h, VUS_ERR_INVALID, "a landmark has no stereo factor (indeterminate system)");
+  // ---- band width k
+  const int kcap = h->prm.max_supernode > 0 ? h->prm.max_supernode : 96 / D;
+  long span = 1;
+  auto consider = [&](long p, long q) { long s = p > q ? p - q : q - p; if (s <= kcap && s > span) span = s; };
+  for (long f = 0; f < FB.n; ++f) consider(FB.h_idx[f], FB.h_idx[FB.n + f]);
+  for (long f = 0; f < FI.n; ++f) consider(FI.h_idx[f], FI.h_idx[2 * FI.n + f]);
+  for (long l = 0; l < NL; ++l) {
+    const int a = lm_obs[lm_ptr[l]], b = lm_obs[lm_ptr[l + 1] - 1];
+    consider(FS.h_idx[a], FS.h_idx[b]);
+  }
+  h->k = (int)std::min<long>(span, kcap);
+  if (h->k < 1) h->k = 1;
+  const int k = h->k;
+  h->B = k * D;
+  h->Ns = (NX + k - 1) / k;
+  h->Npad = h->Ns * k;
+  h->Lc = h->Npad * D;
+  h->L = h->Lc + (h->has_bias ? 6 : 0);
+  const long BB = (long)h->B * h->B;
+  auto inband = [&](long p, long q) { long I = p / k, J = q / k; return (I - J <= 1) && (J - I <= 1); };
+  // ---- off-band remainder blocks
+  std::map<std::pair<long, long>, long> rem_index;
+  auto add_rem = [&](long p, long q) { if (p != q && !inband(p, q)) { rem_index[{p, q}] = 0; rem_index[{q, p}] = 0; } };
+  for (long f = 0; f < FB.n; ++f) add_rem(FB.h_idx[f], FB.h_idx[FB.n + f]);
+  for (long f = 0; f < FI.n; ++f) add_rem(FI.h_idx[f], FI.h_idx[2 * FI.n + f]);
+  for (long l = 0; l < NL; ++l)
+    for (int a = lm_ptr[l]; a < lm_ptr[l + 1]; ++a)
+      for (int b = a + 1; b < lm_ptr[l + 1]; ++b) add_rem(FS.h_idx[lm_obs[a]], FS.h_idx[lm_obs[b]]);
+  std::vector<int> rem_ptr(NX + 1, 0), rem_col;
+  {
+    long id = 0;
+    for (auto& kv : rem_index) { kv.second = id++; rem_ptr[kv.first.first + 1]++; rem_col.push_back((int)kv.first.second); }
+    for (long i = 0; i < NX; ++i) rem_ptr[i + 1] += rem_ptr[i];
+    h->nrem = id;
+  }
+  h->sd_off = 0;
+  h->su_off = h->Ns * BB;
+  h->rem_off = h->su_off + (h->Ns > 1 ? (h->Ns - 1) * BB : 0);
+  h->hlen = h->rem_off + h->nrem * D * D;
+  // ---- per-factor pair destinations
+  auto build_pairs = [&](FactorTable& T, int slot_p, int slot_q) {
+    std::vector<PairDst> v(T.n);
+    for (long f = 0; f < T.n; ++f) {
+      const long p = T.h_idx[slot_p * T.n + f], q = T.h_idx[slot_q * T.n + f];
+      if (p == q) { h->err = "a two-pose factor connects a pose with itself"; return false; }
+      v[f] = band_dst(h, p, q, rem_index);
+    }
+    T.pair.upload(v, st);
+    return true;
+  };
+  if (FB.n && !build_pairs(FB, 0, 1)) return VUS_ERR_INVALID;
+  if (FI.n && !build_pairs(FI, 0, 2)) return VUS_ERR_INVALID;
+  // ---- Schur destination lists: unique (i<=j) pose pairs per landmark track
+  {
+    struct Term { long i, j; int a, b; };
+    std::vector<Term> terms;
+    terms.reserve((size_t)FS.n * 6);
+    for (long l = 0; l < NL; ++l)
+      for (int a = lm_ptr[l]; a < lm_ptr[l + 1]; ++a)
+        for (int b = a; b < lm_ptr[l + 1]; ++b) {
+          const int oa = lm_obs[a], ob = lm_obs[b];
+          const long i = FS.h_idx[oa], j = FS.h_idx[ob];   // i <= j (sorted by pose)
+          terms.push_back({i, j, oa, ob});
+          if (i == j && oa != ob) terms.push_back({i, j, ob, oa});
+        }
+    std::stable_sort(terms.begin(), terms.end(), [](const Term& x, const Term& y) { return x.i != y.i ? x.i < y.i : x.j < y.j; });
+    std::vector<PairDst> dst;
+    std::vector<int> dst_ptr(1, 0), ta(terms.size()), tb(terms.size());
+    for (size_t t = 0; t < terms.size(); ++t) {
+      if (t == 0 || terms[t].i != terms[t - 1].i || terms[t].j != terms[t - 1].j) {
+        if (t) dst_ptr.push_back((int)t);
+        PairDst d;
+        if (terms[t].i == terms[t].j) {
+          d.off = h->sd_off + diag_off(terms[t].i, 0, 0, D, k, h->B); d.ld = h->B; d.transposed = 0; d.moff = -1; d.mld = 0; d.pad = 0;
+        } else {
+          d = band_dst(h, terms[t].i, terms[t].j, rem_index);
+        }
+        dst.push_back(d);
+      }
+      ta[t] = terms[t].a; tb[t] = terms[t].b;
+    }
+    if (!terms.empty()) dst_ptr.push_back((int)terms.size());
+    h->ndst = (long)dst.size();
+    h->dst.upload(dst, st); h->dst_ptr.upload(dst_ptr, st); h->term_a.upload(ta, st); h->term_b.upload(tb, st);
+  }
+  // ---- uploads / allocations
+  h->rem_ptr.upload(rem_ptr, st); h->rem_col.upload(rem_col, st);
+  h->pose_ptr.upload(pose_ptr, st); h->pose_obs.upload(pose_obs, st); h->pose_ids.upload(pose_ids, st);
+  h->lm_ptr.upload(lm_ptr, st); h->lm_obs.upload(lm_obs, st);
+  h->H0.alloc(h->hlen); h->H.alloc(h->hlen);
+  h->g0.alloc(h->Lc); h->gs.alloc(h->L);
+  h->F.alloc(h->Lc * 6); h->Hbb0.alloc(36); h->Hbb.alloc(36); h->gb.alloc(6);
+  h->C.alloc(9 * NL); h->gl.alloc(3 * NL); h->Cinv.alloc(9 * NL); h->E.alloc(18 * FS.n); h->W.alloc(18 * FS.n);
+  h->Dw.alloc(h->Ns * BB); h->U1.alloc(h->Ns * BB); h->U2.alloc(h->Ns * BB);
+  h->Dinv.alloc(h->Ns * BB); h->Gl.alloc(h->Ns * BB); h->Gr.alloc(h->Ns * BB); h->GlT.alloc(h->Ns * BB); h->GrT.alloc(h->Ns * BB);
+  h->Z.alloc(6 * h->Lc); h->SbInv.alloc(36);
+  h->x.alloc(h->L); h->d.alloc(h->L); h->r.alloc(h->L); h->z.alloc(h->L); h->p.alloc(h->L); h->Ap.alloc(h->L);
+  h->xl.alloc(3 * NL);
+  h->scal.alloc(S_COUNT); h->scal.zero(st);
+  h->red_grid = std::min<long>(std::max<long>(1, (std::max(h->L, h->nfactors) + 4095) / 4096), 2L * rt::sm_count());
+  h->partials.alloc(h->red_grid);
+  h->bpart.alloc((size_t)h->red_grid * 36);
+  h->fail.alloc(1); h->fail.zero(st);
+  long eoff = 0;
+  for (int t = 0; t < VUS_F_NTYPES; ++t) {
+    FactorTable& T = h->ft[t];
+    T.e_off = eoff; eoff += T.n;
+    T.r.alloc((size_t)kFactorM[t] * T.n);
+    T.J.alloc((size_t)kFactorM[t] * kFactorCols[t] * T.n);
+  }
+  h->e_all.alloc(eoff); h->le_all.alloc(eoff);
+  for (int kind = 0; kind < 4; ++kind) h->val[1 - h->cur][kind].alloc((size_t)kVarDim[kind] * h->nvar[kind]);
+  rt::sync(st);
+  h->analyzed = true;
+  return VUS_OK;
+}
+
+// ------------------------------------------------------------------ kernel 2 driver: base (undamped) system
+template <int T>
+void launch_asm(vus_handle* h, rt::stream_t st) {
+  FactorTable& F = h->ft[T];
+  if (!F.n) return;
+  AsmArgs a;
+  a.type = T; a.n = F.n; a.idx = F.idx.p; a.J = F.J.p; a.r = F.r.p;
+  a.D = h->D; a.k = h->k; a.B = h->B;
+  a.Hval = h->H0.p; a.g = h->g0.p; a.F = h->F.p; a.Hbb = h->Hbb0.p; a.gb = h->gb.p; a.pair = F.pair.p;
+  const long items = (long)(kFactorCols[T] * kFactorCols[T] + kFactorCols[T]) * F.n;
+  L_elem<AsmBody<T>>(items, st, a);
+}
+
+void assemble_base(vus_handle* h, rt::stream_t st) {
+  h->H0.zero(st); h->g0.zero(st); h->F.zero(st); h->Hbb0.zero(st); h->gb.zero(st);
+  launch_asm<VUS_F_PRIOR_POSE>(h, st);
+  launch_asm<VUS_F_PRIOR_VEL>(h, st);
+  launch_asm<VUS_F_BETWEEN>(h, st);
+  launch_asm<VUS_F_DVL>(h, st);
+  launch_asm<VUS_F_IMU>(h, st);
+  FactorTable& S = h->ft[VUS_F_STEREO];
+  if (S.n) {
+    StereoAsmArgs a;
+    a.n = S.n; a.idx = S.idx.p; a.J = S.J.p; a.r = S.r.p; a.D = h->D; a.k = h->k; a.B = h->B;
+    a.SD = h->H0.p + h->sd_off; a.g = h->g0.p; a.C = h->C.p; a.gl = h->gl.p; a.E = h->E.p; a.nl = h->nvar[3];
+    a.pose_ptr = h->pose_ptr.p; a.pose_obs = h->pose_obs.p; a.pose_ids = h->pose_ids.p; a.nposes_obs = h->nposes_obs;
+    a.lm_ptr = h->lm_ptr.p; a.lm_obs = h->lm_obs.p;
+    L_elem<StereoPoseBody>(h->nposes_obs * 42, st, a);
+    L_elem<StereoLmBody>(h->nvar[3] * 12, st, a);
+    L_elem<StereoEBody>(S.n * 18, st, a);
+  }
+}
+
+SchurArgs schur_args(vus_handle* h, double lambda) {
+  FactorTable& S = h->ft[VUS_F_STEREO];
+  SchurArgs a;
+  a.n = S.n; a.nl = h->nvar[3]; a.idx = S.idx.p; a.C = h->C.p; a.gl = h->gl.p; a.Cinv = h->Cinv.p; a.E = h->E.p; a.W = h->W.p;
+  a.lambda = lambda; a.D = h->D; a.k = h->k; a.B = h->B; a.Hval = h->H.p; a.gs = h->gs.p; a.g = h->g0.p;
+  a.pose_ptr = h->pose_ptr.p; a.pose_obs = h->pose_obs.p; a.pose_ids = h->pose_ids.p; a.nposes_obs = h->nposes_obs;
+  a.lm_ptr = h->lm_ptr.p; a.lm_obs = h->lm_obs.p;
+  a.ndst = h->ndst; a.dst = h->dst.p; a.dst_ptr = h->dst_ptr.p; a.term_a = h->term_a.p; a.term_b = h->term_b.p;
+  a.fail = h->fail.p; a.xc = h->x.p; a.xl = h->xl.p;
+  return a;
+}
+
+// damped + Schur-reduced system for this lambda
+void form_system(vus_handle* h, double lambda, rt::stream_t st) {
+  rt::d2d(h->H.p, h->H0.p, h->hlen * sizeof(double), st);
+  rt::d2d(h->Hbb.p, h->Hbb0.p, 36 * sizeof(double), st);
+  rt::d2d(h->gs.p, h->g0.p, h->Lc * sizeof(double), st);
+  if (h->has_bias) rt::d2d(h->gs.p + h->Lc, h->gb.p, 6 * sizeof(double), st);
+  DampArgs d; d.SD = h->H.p + h->sd_off; d.Hbb = h->Hbb.p; d.ndof = h->Lc; d.nreal = h->N * h->D; d.B = h->B; d.lambda = lambda;
+  L_elem<DampBody>(h->Lc + (h->has_bias ? 6 : 0), st, d);
+  if (h->nobs) {
+    SchurArgs a = schur_args(h, lambda);
+    L_elem<LmInvertBody>(a.nl, st, a);
+    L_elem<StereoWBody>(a.n * 18, st, a);
+    L_elem<SchurGradBody>(h->nposes_obs * 6, st, a);
+    L_elem<SchurBlockBody>(h->ndst * 36, st, a);
+  }
+}
+
+// ------------------------------------------------------------------ kernel 3 drivers
+size_t bcr_smem(int B) { return ((size_t)2 * B * B + 2 * B + 8) * sizeof(double); }
+
+BcrArgs bcr_args(vus_handle* h) {
+  BcrArgs a;
+  a.Ns = h->Ns; a.B = h->B; a.s = 1; a.Dw = h->Dw.p; a.Ucur = nullptr; a.Unext = nullptr;
+  a.Dinv = h->Dinv.p; a.Gl = h->Gl.p; a.Gr = h->Gr.p; a.GlT = h->GlT.p; a.GrT = h->GrT.p; a.fail = h->fail.p;
+  a.X = nullptr; a.xstride = 0; a.nrhs = 1;
+  return a;
+}
+
+void bcr_factor(vus_handle* h, rt::stream_t st) {
+  const long BB = (long)h->B * h->B;
+  rt::d2d(h->Dw.p, h->H.p + h->sd_off, h->Ns * BB * sizeof(double), st);
+  BcrArgs a = bcr_args(h);
+  const double* ucur = h->H.p + h->su_off;
+  double* bufs[2] = {h->U1.p, h->U2.p};
+  int w = 0;
+  for (long s = 1; s < h->Ns; s <<= 1) {
+    const long nact = (h->Ns + s - 1) / s;
+    const int nel = (int)(nact / 2), nsv = (int)((nact + 1) / 2);
+    a.s = s; a.Ucur = ucur; a.Unext = bufs[w];
+    L_coop<BcrElimBody>(nel, 256, bcr_smem(h->B), st, a);
+    L_coop<BcrUpdateBody>(nsv, 256, bcr_smem(h->B), st, a);
+    ucur = bufs[w]; w ^= 1;
+  }
+  L_coop<BcrRootBody>(1, 256, bcr_smem(h->B), st, a);
+}
+
+// in-place solve of the band system for nrhs vectors X[v*xstride + ...]
+void bcr_solve(vus_handle* h, double* X, long xstride, int nrhs, rt::stream_t st) {
+  BcrArgs a = bcr_args(h);
+  a.X = X; a.xstride = xstride; a.nrhs = nrhs;
+  const size_t smem = (size_t)2 * nrhs * h->B * sizeof(double);
+  std::vector<long> levels;
+  for (long s = 1; s < h->Ns; s <<= 1) levels.push_back(s);
+  for (long s : levels) {
+    const long nact = (h->Ns + s - 1) / s;
+    a.s = s;
+    L_coop<BcrFwdBody>((int)((nact + 1) / 2), 128, smem, st, a);
+  }
+  L_coop<BcrRootSolveBody>(1, 128, smem, st, a);
+  for (auto it = levels.rbegin(); it != levels.rend(); ++it) {
+    const long s = *it;
+    const long nact = (h->Ns + s - 1) / s;
+    a.s = s;
+    L_coop<BcrBwdBody>((int)(nact / 2), 128, smem, st, a);
+  }
+}
+
+void border_dot(vus_handle* h, const double* Y, long ystride, int nv, rt::stream_t st) {
+  BorderDotArgs a; a.F = h->F.p; a.Y = Y; a.len = h->Lc; a.ystride = ystride; a.nv = nv; a.partials = h->bpart.p; a.grid = h->red_grid;
+  L_coop<BorderDot1Body>(h->red_grid, 256, 256 * sizeof(double), st, a);
+}
+
+// preconditioner set-up for the current damped system: BCR of the band, Z = M^-1 F, Sb^-1
+void precond_setup(vus_handle* h, rt::stream_t st) {
+  bcr_factor(h, st);
+  if (h->has_bias) {
+    BorderColsArgs c; c.F = h->F.p; c.Z = h->Z.p; c.len = h->Lc; c.zstride = h->Lc;
+    L_elem<BorderColsBody>(h->Lc * 6, st, c);
+    bcr_solve(h, h->Z.p, h->Lc, 6, st);
+    border_dot(h, h->Z.p, h->Lc, 6, st);
+    BorderSchurArgs s; s.Hbb = h->Hbb.p; s.partials = h->bpart.p; s.grid = h->red_grid; s.nv = 6; s.SbInv = h->SbInv.p; s.fail = h->fail.p;
+    L_elem<BorderSchurBody>(1, st, s);
+  }
+}
+
+// z = P^-1 r  (z and r are full vectors of length L)
+void precond_apply(vus_handle* h, double* z, const double* r, rt::stream_t st) {
+  rt::d2d(z, r, h->L * sizeof(double), st);
+  bcr_solve(h, z, h->Lc, 1, st);
+  if (h->has_bias) {
+    border_dot(h, z, h->Lc, 1, st);
+    BorderSolveArgs b; b.SbInv = h->SbInv.p; b.rb = r + h->Lc; b.partials = h->bpart.p; b.grid = h->red_grid; b.xb = z + h->Lc;
+    L_elem<BorderSolveBody>(1, st, b);
+    VecArgs v; v.y = z; v.x = z; v.z = nullptr; v.scal = nullptr; v.slot = 0; v.n = h->Lc; v.Z = h->Z.p; v.xb = z + h->Lc; v.zstride = h->Lc;
+    L_elem<SubZxbBody>(h->Lc, st, v);
+  }
+}
+
+// y = A x
+void apply_A(vus_handle* h, double* y, const double* x, rt::stream_t st) {
+  MatvecArgs a;
+  a.SD = h->H.p + h->sd_off; a.SU = h->H.p + h->su_off; a.Ns = h->Ns; a.B = h->B; a.x = x; a.y = y;
+  a.rem_ptr = h->nrem ? h->rem_ptr.p : nullptr; a.rem_col = h->rem_col.p; a.rem_val = h->H.p + h->rem_off; a.nnodes = h->N; a.D = h->D;
+  a.F = h->F.p; a.Hbb = h->Hbb.p; a.xb = x + h->Lc; a.yb = y + h->Lc; a.has_bias = h->has_bias;
+  const size_t smem = ((size_t)h->B * h->B + 2 * h->B) * sizeof(double);
+  L_coop<BandMatvecBody>((int)h->Ns, 128, smem, st, a);
+  if (h->nrem || h->has_bias) L_elem<RemBorderMatvecBody>(h->N * h->D, st, a);
+  if (h->has_bias) {
+    border_dot(h, x, h->Lc, 1, st);
+    BorderRowArgs b; b.Hbb = h->Hbb.p; b.xb = x + h->Lc; b.partials = h->bpart.p; b.grid = h->red_grid; b.yb = y + h->Lc;
+    L_elem<BorderRowBody>(1, st, b);
+  }
+}
+
+void axpy(vus_handle* h, double* y, const double* x, int slot, rt::stream_t st) {
+  VecArgs v; v.y = y; v.x = x; v.z = nullptr; v.scal = h->scal.p; v.slot = slot; v.n = h->L; v.Z = nullptr; v.xb = nullptr; v.zstride = 0;
+  L_elem<AxpyBody>(h->L, st, v);
+}
+void xpby(vus_handle* h, double* y, const double* x, int slot, rt::stream_t st) {
+  VecArgs v; v.y = y; v.x = x; v.z = nullptr; v.scal = h->scal.p; v.slot = slot; v.n = h->L; v.Z = nullptr; v.xb = nullptr; v.zstride = 0;
+  L_elem<XpbyBody>(h->L, st, v);
+}
+
+// y = x - y   (used for the true residual r = rhs - A x)
+struct RsubBody {
+  static VUS_DEV void run(const VecArgs& A, long i) { A.y[i] = A.x[i] - A.y[i]; }
+};
+struct AddBody {
+  static VUS_DEV void run(const VecArgs& A, long i) { A.y[i] += A.x[i]; }
+};
+
+// PCG on the reduced system with residual replacement: the inner recursion solves A d = r for a correction,
+// the outer loop recomputes the TRUE residual r = rhs - A x (the recursive residual drifts on these badly scaled
+// systems: IMU information ~1e10 next to lambda ~1e-5).  Returns inner iterations; solution in h->x.
+int pcg(vus_handle* h, rt::stream_t st, bool* converged) {
+  const long L = h->L;
+  VecArgs v; v.z = nullptr; v.scal = h->scal.p; v.slot = 0; v.n = L; v.Z = nullptr; v.xb = nullptr; v.zstride = 0;
+  h->x.zero(st);
+  rt::d2d(h->r.p, h->gs.p, L * sizeof(double), st);
+  reduce(h, h->r.p, h->r.p, L, S_RR, RED_STORE, st);
+  const double rr0 = read_scalar(h, S_RR, st);
+  *converged = true;
+  if (!(rr0 > 0.0)) return 0;
+  const double tol2 = h->prm.pcg_rel_tol * h->prm.pcg_rel_tol * rr0;
+  *converged = false;
+  int it = 0;
+  double rr_outer = rr0;
+  for (int outer = 0; outer < 6 && !*converged; ++outer) {
+    // ---- inner PCG: A d = r, d = 0
+    h->d.zero(st);
+    precond_apply(h, h->z.p, h->r.p, st);
+    rt::d2d(h->p.p, h->z.p, L * sizeof(double), st);
+    reduce(h, h->r.p, h->z.p, L, S_RZ, RED_RZ0, st);
+    int since_best = 0;
+    double best = rr_outer;
+    bool bad = false;
+    while (it < h->prm.pcg_max_iterations) {
+      apply_A(h, h->Ap.p, h->p.p, st);
+      reduce(h, h->p.p, h->Ap.p, L, S_PAP, RED_PAP, st);
+      axpy(h, h->d.p, h->p.p, S_ALPHA, st);
+      axpy(h, h->r.p, h->Ap.p, S_NEG_ALPHA, st);
+      ++it;
+      reduce(h, h->r.p, h->r.p, L, S_RR, RED_STORE, st);
+      const double rr = read_scalar(h, S_RR, st);
+      if (h->prm.verbose > 1) std::fprintf(stderr, "    pcg %d.%d rel_res %.3e\n", outer, it, std::sqrt(rr / rr0));
+      if (!(rr == rr)) { bad = true; break; }
+      if (rr <= tol2) break;
+      if (rr < best) { best = rr; since_best = 0; }
+      else if (++since_best >= 40) break;              // CG residuals are not monotone: only a long stall ends the recursion
+      precond_apply(h, h->z.p, h->r.p, st);
+      reduce(h, h->r.p, h->z.p, L, S_RZ, RED_RZ, st);
+      xpby(h, h->p.p, h->z.p, S_BETA, st);
+    }
+    if (bad) break;
+    // ---- x += d ; true residual
+    v.y = h->x.p; v.x = h->d.p;
+    L_elem<AddBody>(L, st, v);
+    apply_A(h, h->r.p, h->x.p, st);
+    v.y = h->r.p; v.x = h->gs.p;
+    L_elem<RsubBody>(L, st, v);
+    reduce(h, h->r.p, h->r.p, L, S_RR, RED_STORE, st);
+    const double rr_true = read_scalar(h, S_RR, st);
+    if (h->prm.verbose > 1) std::fprintf(stderr, "    pcg outer %d true rel_res %.3e\n", outer, std::sqrt(rr_true / rr0));
+    if (rr_true <= tol2) { *converged = true; break; }
+    if (!(rr_true < 0.25 * rr_outer) || it >= h->prm.pcg_max_iterations) break;   // no further progress possible
+    rr_outer = rr_true;
+  }
+  return it;
+}
+
+int read_fail(vus_handle* h, rt::stream_t st) {
+  int f = 0;
+  rt::d2h(&f, h->fail.p, sizeof(int), st);
+  rt::sync(st);
+  if (f) h->fail.zero(st);
+  return f;
+}
+
+// solve the damped system at the current linearization; delta in h->x (camera+bias) and h->xl
+bool solve_damped(vus_handle* h, double lambda, rt::stream_t st, int* iters, bool timing) {
+  double t0 = timing ? now_ms() : 0;
+  form_system(h, lambda, st);
+  if (timing) { rt::sync(st); double t1 = now_ms(); h->res.ms_schur += t1 - t0; t0 = t1; }
+  precond_setup(h, st);
+  if (timing) { rt::sync(st); double t1 = now_ms(); h->res.ms_factor += t1 - t0; t0 = t1; }
+  if (read_fail(h, st)) { *iters = 0; return false; }
+  bool conv = false;
+  *iters = pcg(h, st, &conv);
+  if (h->nobs) {
+    SchurArgs a = schur_args(h, lambda);
+    L_elem<LmBacksubBody>(a.nl, st, a);
+  }
+  if (timing) { rt::sync(st); double t1 = now_ms(); h->res.ms_pcg += t1 - t0; t0 = t1; }
+  return true;
+}
+
+template <int T>
+void launch_linerr(vus_handle* h, rt::stream_t st) {
+  FactorTable& F = h->ft[T];
+  if (!F.n) return;
+  LinErrArgs a;
+  a.F.n = F.n; a.F.idx = F.idx.p; a.F.meas = nullptr; a.F.sinfo = nullptr;
+  a.r = F.r.p; a.J = F.J.p;
+  a.X.xc = h->x.p; a.X.xb = h->x.p + h->Lc; a.X.xl = h->xl.p; a.X.nl = h->nvar[3]; a.X.D = h->D;
+  a.out = h->le_all.p + F.e_off; a.type = T;
+  L_elem<LinErrBody<T>>(F.n, st, a);
+}
+double linear_error(vus_handle* h, rt::stream_t st) {
+  launch_linerr<VUS_F_PRIOR_POSE>(h, st); launch_linerr<VUS_F_PRIOR_VEL>(h, st); launch_linerr<VUS_F_BETWEEN>(h, st);
+  launch_linerr<VUS_F_DVL>(h, st); launch_linerr<VUS_F_STEREO>(h, st); launch_linerr<VUS_F_IMU>(h, st);
+  reduce(h, h->le_all.p, nullptr, h->nfactors, S_TMP, RED_STORE, st);
+  return read_scalar(h, S_TMP, st);
+}
+
+void retract(vus_handle* h, rt::stream_t st) {
+  RetractArgs a;
+  const int c = h->cur, t = 1 - h->cur;
+  a.pose = h->val[c][0].p; a.pose_out = h->val[t][0].p; a.nx = h->nvar[0];
+  a.vel = h->val[c][1].p; a.vel_out = h->val[t][1].p; a.nv = h->nvar[1];
+  a.bias = h->val[c][2].p; a.bias_out = h->val[t][2].p; a.nb = h->nvar[2];
+  a.lm = h->val[c][3].p; a.lm_out = h->val[t][3].p; a.nl = h->nvar[3];
+  a.xc = h->x.p; a.xb = h->x.p + h->Lc; a.xl = h->xl.p; a.D = h->D;
+  L_elem<RetractBody>(a.nx + a.nv + a.nl + a.nb, st, a);
+}
+
+// ------------------------------------------------------------------ kernel 4 driver: the LM loop
+int optimize(vus_handle* h, rt::stream_t st) {
+  vus_lm_result& R = h->res;
+  R = vus_lm_result();
+  const vus_lm_params& P = h->prm;
+  const long launches0 = g_launches;
+  const double t_begin = now_ms();
+  double lambda = P.lambda_initial;
+  double err = graph_error(h, h->cur, st);
+  R.initial_error = err;
+  int iterations = 0;
+  if (!(err <= P.error_tol) && P.max_iterations > 0 && std::isfinite(err)) {
+    while (true) {
+      const double cur_err = err;
+      double t0 = now_ms();
+      run_factors(h, h->cur, true, st);
+      rt::sync(st);
+      double t1 = now_ms();
+      R.ms_linearize += t1 - t0;
+      assemble_base(h, st);
+      rt::sync(st);
+      R.ms_assemble += now_ms() - t1;
+      R.linearizations++;
+      R.factors_linearized += h->nfactors;
+      while (true) {                                   // tryLambda
+        int its = 0;
+        const bool solved = solve_damped(h, lambda, st, &its, true);
+        R.pcg_iterations += its;
+        R.inner_iterations++;
+        if (!solved) R.solve_failures++;
+        bool success = false, stop = false;
+        double new_err = INFINITY;
+        double t2 = now_ms();
+        if (solved) {
+          const double old_lin = err;
+          const double new_lin = linear_error(h, st);
+          const double lin_change = old_lin - new_lin;
+          if (lin_change >= 0) {
+            retract(h, st);
+            new_err = graph_error(h, 1 - h->cur, st);
+            const double cost_change = err - new_err;
+            if (lin_change > VUS_EPS * old_lin) {
+              const double fidelity = cost_change / lin_change;
+              success = fidelity > P.min_model_fidelity;
+            }
+            if (std::fabs(cost_change) < P.relative_error_tol * err) stop = true;
+          }
+        }
+        R.ms_update += now_ms() - t2;
+        if (P.verbose) std::fprintf(stderr, "  try lam=%.3e solved=%d pcg=%d new_err=%.9e success=%d\n", lambda, (int)solved, its, new_err, (int)success);
+        if (success) {
+          h->cur = 1 - h->cur;
+          err = new_err;
+          lambda = std::max(P.lambda_lower_bound, lambda / P.lambda_factor);
+          iterations++;
+          break;
+        } else if (!stop) {
+          lambda *= P.lambda_factor;
+          if (lambda >= P.lambda_upper_bound) break;
+        } else {
+          break;
+        }
+      }
+      if (P.verbose) std::fprintf(stderr, "iter %d err=%.12e lam=%.3e\n", iterations, err, lambda);
+      if (iterations >= P.max_iterations || !std::isfinite(cur_err)) break;
+      if (err <= P.error_tol) break;
+      const double absdec = cur_err - err, reldec = absdec / cur_err;
+      if ((P.relative_error_tol != 0.0 && reldec <= P.relative_error_tol) || absdec <= P.absolute_error_tol) break;
+    }
+  }
+  rt::sync(st);
+  R.iterations = iterations;
+  R.final_error = err;
+  R.final_lambda = lambda;
+  R.ms_total = now_ms() - t_begin;
+  R.kernel_launches = g_launches - launches0;
+  return VUS_OK;
+}
+
+}  // namespace
+
+// =====================================================================================
+// C-ABI
+// =====================================================================================
+#define VUS_TRY(h) try {
+#define VUS_CATCH(h)                                                         \
+  } catch (const std::exception& e) { return fail(h, VUS_ERR_CUDA, e.what()); } \
+  catch (...) { return fail(h, VUS_ERR_CUDA, "unknown error"); }
+
+extern "C" {
+
+void vus_default_lm_params(vus_lm_params* p) {
+  p->max_iterations = 100; p->relative_error_tol = 1e-5; p->absolute_error_tol = 1e-5; p->error_tol = 0.0;
+  p->lambda_initial = 1e-5; p->lambda_factor = 10.0; p->lambda_upper_bound = 1e5; p->lambda_lower_bound = 0.0;
+  p->min_model_fidelity = 1e-3; p->pcg_max_iterations = 500; p->pcg_rel_tol = 1e-12; p->max_supernode = 0; p->verbose = 0;
+}
+
+int vus_create(int device, vus_handle** out) {
+  if (!out) return VUS_ERR_INVALID;
+  *out = nullptr;
+#ifndef VUS_EMU
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return VUS_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return VUS_ERR_CUDA;
+#endif
+  vus_handle* h = new vus_handle();
+  h->device = device;
+  vus_default_lm_params(&h->prm);
+  *out = h;
+  return VUS_OK;
+}
+
+void vus_destroy(vus_handle* h) { delete h; }
+
+const char* vus_last_error(const vus_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int vus_set_variables(vus_handle* h, int kind, int64_t n, const uint64_t* keys, const double* data, int mem) {
+  if (!h || kind < 0 || kind >= 4 || n < 0) return fail(h, VUS_ERR_INVALID, "vus_set_variables: bad arguments");
+  VUS_TRY(h)
+  for (int64_t i = 1; i < n; ++i)
+    if (keys[i] <= keys[i - 1]) return fail(h, VUS_ERR_INVALID, "vus_set_variables: keys must be strictly ascending");
+  h->keys[kind].assign(keys, keys + n);
+  h->nvar[kind] = n;
+  DBuf<double>& b = h->val[h->cur][kind];
+  b.alloc((size_t)kVarDim[kind] * n);
+  if (mem == VUS_MEM_HOST) rt::h2d(b.p, data, (size_t)kVarDim[kind] * n * sizeof(double), 0);
+  else rt::d2d(b.p, data, (size_t)kVarDim[kind] * n * sizeof(double), 0);
+  rt::sync(0);
+  h->analyzed = false;
+  return VUS_OK;
+  VUS_CATCH(h)
+}
+
+int vus_get_variables(vus_handle* h, int kind, double* out, int mem) {
+  if (!h || kind < 0 || kind >= 4) return fail(h, VUS_ERR_INVALID, "vus_get_variables: bad arguments");
+  VUS_TRY(h)
+  const size_t bytes = (size_t)kVarDim[kind] * h->nvar[kind] * sizeof(double);
+  if (mem == VUS_MEM_HOST) rt::d2h(out, h->val[h->cur][kind].p, bytes, 0);
+  else rt::d2d(out, h->val[h->cur][kind].p, bytes, 0);
+  rt::sync(0);
+  return VUS_OK;
+  VUS_CATCH(h)
+}
+
+int vus_add_factors(vus_handle* h, int type, int64_t n, const int32_t* var_idx, const double* meas, const double* sqrt_info,
+                    const int64_t* orig_index, int mem) {
+  if (!h || type < 0 || type >= VUS_F_NTYPES || n < 0) return fail(h, VUS_ERR_INVALID, "vus_add_factors: bad arguments");
+  VUS_TRY(h)
+  FactorTable& T = h->ft[type];
+  if (T.n) return fail(h, VUS_ERR_STATE, "vus_add_factors: this factor type was already added (one call per type)");
+  T.n = n;
+  T.h_idx.assign(var_idx, var_idx + (size_t)kFactorSlots[type] * n);
+  T.orig.assign(orig_index, orig_index + n);
+  T.idx.upload(T.h_idx, 0);
+  T.meas.alloc((size_t)kFactorMeas[type] * n);
+  T.sinfo.alloc((size_t)kFactorInfo[type] * n);
+  if (mem == VUS_MEM_HOST) {
+    rt::h2d(T.meas.p, meas, (size_t)kFactorMeas[type] * n * sizeof(double), 0);
+    rt::h2d(T.sinfo.p, sqrt_info, (size_t)kFactorInfo[type] * n * sizeof(double), 0);
+  } else {
+    rt::d2d(T.meas.p, meas, (size_t)kFactorMeas[type] * n * sizeof(double), 0);
+    rt::d2d(T.sinfo.p, sqrt_info, (size_t)kFactorInfo[type] * n * sizeof(double), 0);
+  }
+  rt::sync(0);
+  h->nfactors += n;
+  h->analyzed = false;
+  return VUS_OK;
+  VUS_CATCH(h)
+}
+
+int vus_set_calibration(vus_handle* h, const double K[6]) {
+  if (!h || !K) return VUS_ERR_INVALID;
+  for (int i = 0; i < 6; ++i) h->K[i] = K[i];
+  return VUS_OK;
+}
+int vus_set_gravity(vus_handle* h, const double g[3]) {
+  if (!h || !g) return VUS_ERR_INVALID;
+  for (int i = 0; i < 3; ++i) h->grav[i] = g[i];
+  return VUS_OK;
+}
+int vus_set_lm_params(vus_handle* h, const vus_lm_params* p) {
+  if (!h || !p) return VUS_ERR_INVALID;
+  h->prm = *p;
+  return VUS_OK;
+}
+
+int vus_analyze(vus_handle* h) {
+  if (!h) return VUS_ERR_INVALID;
+  VUS_TRY(h)
+  // validate indices
+  const int slot_kind[VUS_F_NTYPES][5] = {{0}, {1}, {0, 0}, {1, 0}, {0, 3}, {0, 1, 0, 1, 2}};
+  for (int t = 0; t < VUS_F_NTYPES; ++t) {
+    FactorTable& T = h->ft[t];
+    for (int s = 0; s < kFactorSlots[t]; ++s)
+      for (long f = 0; f < T.n; ++f) {
+        const int v = T.h_idx[s * T.n + f];
+        if (v < 0 || v >= h->nvar[slot_kind[t][s]]) return fail(h, VUS_ERR_INVALID, "vus_analyze: factor references a variable index out of range");
+      }
+  }
+  return analyze(h, 0);
+  VUS_CATCH(h)
+}
+
+int vus_get_layout(vus_handle* h, int64_t out[8]) {
+  if (!h || !h->analyzed) return fail(h, VUS_ERR_STATE, "vus_get_layout: call vus_analyze first");
+  out[0] = h->D; out[1] = h->k; out[2] = h->Ns; out[3] = h->nrem; out[4] = h->ndst; out[5] = h->B; out[6] = h->L; out[7] = h->nfactors;
+  return VUS_OK;
+}
+
+int vus_optimize(vus_handle* h, void* stream, vus_lm_result* result) {
+  if (!h) return VUS_ERR_INVALID;
+  if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_optimize: call vus_analyze first");
+  VUS_TRY(h)
+  const int rc = optimize(h, (rt::stream_t)stream);
+  if (result) *result = h->res;
+  return rc;
+  VUS_CATCH(h)
+}
+
+int vus_error(vus_handle* h, void* stream, double* out) {
+  if (!h || !out) return VUS_ERR_INVALID;
+  if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_error: call vus_analyze first");
+  VUS_TRY(h)
+  *out = graph_error(h, h->cur, (rt::stream_t)stream);
+  return VUS_OK;
+  VUS_CATCH(h)
+}
+
+int vus_factor_errors(vus_handle* h, void* stream, double* out) {
+  if (!h || !out) return VUS_ERR_INVALID;
+  if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_factor_errors: call vus_analyze first");
+  VUS_TRY(h)
+  rt::stream_t st = (rt::stream_t)stream;
+  run_factors(h, h->cur, false, st);
+  std::vector<double> tmp(h->nfactors);
+  rt::d2h(tmp.data(), h->e_all.p, h->nfactors * sizeof(double), st);
+  rt::sync(st);
+  for (int t = 0; t < VUS_F_NTYPES; ++t) {
+    FactorTable& T = h->ft[t];
+    for (long f = 0; f < T.n; ++f) {
+      if (T.orig[f] < 0 || T.orig[f] >= h->nfactors) return fail(h, VUS_ERR_INVALID, "orig_index out of range");
+      out[T.orig[f]] = tmp[T.e_off + f];
+    }
+  }
+  return VUS_OK;
+  VUS_CATCH(h)
+}
+
+int vus_linearize(vus_handle* h, void* stream, int type, double* r_out, double* J_out) {
+  if (!h || type < 0 || type >= VUS_F_NTYPES) return VUS_ERR_INVALID;
+  if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_linearize: call vus_analyze first");
+  VUS_TRY(h)
+  rt::stream_t st = (rt::stream_t)stream;
+  run_factors(h, h->cur, true, st);
+  FactorTable& T = h->ft[type];
+  if (r_out) rt::d2h(r_out, T.r.p, (size_t)kFactorM[type] * T.n * sizeof(double), st);
+  if (J_out) rt::d2h(J_out, T.J.p, (size_t)kFactorM[type] * kFactorCols[type] * T.n * sizeof(double), st);
+  rt::sync(st);
+  return VUS_OK;
+  VUS_CATCH(h)
+}
+
+int vus_solve_step(vus_handle* h, void* stream, double lambda, double* d_pose, double* d_vel, double* d_bias, double* d_lm,
+                   int32_t* pcg_iterations) {
+  if (!h) return VUS_ERR_INVALID;
+  if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_solve_step: call vus_analyze first");
+  VUS_TRY(h)
+  rt::stream_t st = (rt::stream_t)stream;
+  run_factors(h, h->cur, true, st);
+  assemble_base(h, st);
+  int its = 0;
+  const bool ok = solve_damped(h, lambda, st, &its, false);
+  if (pcg_iterations) *pcg_iterations = its;
+  if (!ok) return fail(h, VUS_ERR_STATE, "vus_solve_step: damped system is not positive definite");
+  std::vector<double> x(h->L), xl(3 * h->nvar[3]);
+  rt::d2h(x.data(), h->x.p, h->L * sizeof(double), st);
+  rt::d2h(xl.data(), h->xl.p, xl.size() * sizeof(double), st);
+  rt::sync(st);
+  const int D = h->D;
+  for (long i = 0; i < h->nvar[0]; ++i)
+    for (int c = 0; c < 6; ++c) if (d_pose) d_pose[i * 6 + c] = x[i * D + c];
+  for (long i = 0; i < h->nvar[1]; ++i)
+    for (int c = 0; c < 3; ++c) if (d_vel) d_vel[i * 3 + c] = x[i * D + 6 + c];
+  if (h->has_bias && d_bias) for (int c = 0; c < 6; ++c) d_bias[c] = x[h->Lc + c];
+  for (long l = 0; l < h->nvar[3]; ++l)
+    for (int c = 0; c < 3; ++c) if (d_lm) d_lm[l * 3 + c] = xl[c * h->nvar[3] + l];
+  return VUS_OK;
+  VUS_CATCH(h)
+}
+
+int vus_time_linearize(vus_handle* h, void* stream, int reps, double* ms_per_rep) {
+  if (!h || !ms_per_rep || reps <= 0) return VUS_ERR_INVALID;
+  if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_time_linearize: call vus_analyze first");
+  VUS_TRY(h)
+  rt::stream_t st = (rt::stream_t)stream;
+  run_factors(h, h->cur, true, st);
+  rt::sync(st);
+#ifndef VUS_EMU
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < reps; ++i) run_factors(h, h->cur, true, st);
+  cudaEventRecord(e1, st);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_per_rep = ms / reps;
+#else
+  const double t0 = now_ms();
+  for (int i = 0; i < reps; ++i) run_factors(h, h->cur, true, st);
+  *ms_per_rep = (now_ms() - t0) / reps;
+#endif
+  return VUS_OK;
+  VUS_CATCH(h)
+}
+
+}  // extern "C"

@@ -1,2 +1,292 @@
-class LevenbergMarquardtParams: pass
-class LevenbergMarquardtOptimizer: pass
+"""gtsam.LevenbergMarquardtParams / gtsam.LevenbergMarquardtOptimizer facade (batch.py:337) and the
+marshaller that hands the packed problem tables to the C-ABI (include/vus.h).
+
+    results = LevenbergMarquardtOptimizer(graph, initial, LevenbergMarquardtParams()).optimize()
+
+Host side only transposes the tables to component-major structure-of-arrays, passes pointers and
+reads results back; PyTorch tensors are accepted as device-buffer carriers (`Session(..., device_tensors=True)`).
+"""
+import ctypes as C
+import numpy as np
+from . import _native
+from ._native import LmParams, LmResult
+from .values import Values
+
+FACTOR_TYPES = ("prior_pose", "prior_vel", "between", "dvl", "stereo", "imu")
+_SLOTS = {"prior_pose": ("x",), "prior_vel": ("v",), "between": ("x1", "x2"), "dvl": ("v", "x"),
+          "stereo": ("x", "l"), "imu": ("xi", "vi", "xj", "vj", "b")}
+_ROWS = {"prior_pose": 6, "prior_vel": 3, "between": 6, "dvl": 3, "stereo": 3, "imu": 9}
+_COLS = {"prior_pose": 6, "prior_vel": 3, "between": 12, "dvl": 9, "stereo": 9, "imu": 24}
+_KINDS = (("pose", "pose_keys", "poses", 12), ("vel", "vel_keys", "vels", 3), ("bias", "bias_keys", "biases", 6),
+          ("lm", "lm_keys", "lms", 3))
+
+
+def _set(name):
+    def f(self, v):
+        setattr(self, name, v)
+    return f
+
+
+def _get(name):
+    def f(self):
+        return getattr(self, name)
+    return f
+
+
+class LevenbergMarquardtParams:
+    """gtsam::LevenbergMarquardtParams with gtsam's setter/getter names and defaults."""
+
+    def __init__(self):
+        self.maxIterations = 100
+        self.relativeErrorTol = 1e-5
+        self.absoluteErrorTol = 1e-5
+        self.errorTol = 0.0
+        self.lambdaInitial = 1e-5
+        self.lambdaFactor = 10.0
+        self.lambdaUpperBound = 1e5
+        self.lambdaLowerBound = 0.0
+        self.minModelFidelity = 1e-3
+        self.diagonalDamping = False
+        self.useFixedLambdaFactor = True
+        self.verbosityLM = "SILENT"
+        # solver knobs of this implementation (gtsam: linearSolverType / ordering)
+        self.pcgMaxIterations = 500
+        self.pcgRelTol = 1e-12
+        self.maxSupernode = 0
+
+    setMaxIterations, getMaxIterations = _set("maxIterations"), _get("maxIterations")
+    setRelativeErrorTol, getRelativeErrorTol = _set("relativeErrorTol"), _get("relativeErrorTol")
+    setAbsoluteErrorTol, getAbsoluteErrorTol = _set("absoluteErrorTol"), _get("absoluteErrorTol")
+    setErrorTol, getErrorTol = _set("errorTol"), _get("errorTol")
+    setlambdaInitial, getlambdaInitial = _set("lambdaInitial"), _get("lambdaInitial")
+    setlambdaFactor, getlambdaFactor = _set("lambdaFactor"), _get("lambdaFactor")
+    setlambdaUpperBound, getlambdaUpperBound = _set("lambdaUpperBound"), _get("lambdaUpperBound")
+    setlambdaLowerBound, getlambdaLowerBound = _set("lambdaLowerBound"), _get("lambdaLowerBound")
+
+    def setDiagonalDamping(self, flag):
+        if flag:
+            raise NotImplementedError("diagonalDamping=True is not on the reference path (batch.py:337 uses defaults)")
+
+    def setUseFixedLambdaFactor(self, flag):
+        if not flag:
+            raise NotImplementedError("useFixedLambdaFactor=False is not on the reference path")
+
+    def setVerbosityLM(self, v):
+        self.verbosityLM = v
+
+    def to_c(self):
+        p = LmParams()
+        p.max_iterations = int(self.maxIterations)
+        p.relative_error_tol = float(self.relativeErrorTol)
+        p.absolute_error_tol = float(self.absoluteErrorTol)
+        p.error_tol = float(self.errorTol)
+        p.lambda_initial = float(self.lambdaInitial)
+        p.lambda_factor = float(self.lambdaFactor)
+        p.lambda_upper_bound = float(self.lambdaUpperBound)
+        p.lambda_lower_bound = float(self.lambdaLowerBound)
+        p.min_model_fidelity = float(self.minModelFidelity)
+        p.pcg_max_iterations = int(self.pcgMaxIterations)
+        p.pcg_rel_tol = float(self.pcgRelTol)
+        p.max_supernode = int(self.maxSupernode)
+        p.verbose = {"SILENT": 0, "SUMMARY": 1, "TERMINATION": 1, "LAMBDA": 1, "TRYLAMBDA": 1, "TRYCONFIG": 2,
+                     "DAMPED": 2, "TRYDELTA": 2}.get(str(self.verbosityLM).upper(), 0)
+        return p
+
+
+def _soa(a, dtype=np.float64):
+    """[n, d] host table -> contiguous component-major [d, n]."""
+    return np.ascontiguousarray(np.asarray(a, dtype=dtype).T)
+
+
+class Session:
+    """One vus_handle: uploads a packed problem (graph.to_problem), analyses it, exposes the C-ABI calls."""
+
+    def __init__(self, prob, params=None, lib=None, device=0, device_tensors=False):
+        self.lib = lib if lib is not None else _native.load()
+        self.prob = prob
+        self._h = C.c_void_p()
+        rc = self.lib.vus_create(int(device), C.byref(self._h))
+        if rc != 0:
+            raise RuntimeError(f"vus_create failed ({rc}): no usable CUDA device {device}; this path has no CPU fallback")
+        self._keep = []
+        self.n = {}
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        try:
+            self._upload(prob, device_tensors)
+            self.set_params(params or LevenbergMarquardtParams())
+            self._check(self.lib.vus_analyze(self._h))
+        except Exception:
+            self.close()
+            raise
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.lib.vus_last_error(self._h).decode() or f"libvus error {rc}")
+
+    def close(self):
+        if self._h:
+            self.lib.vus_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _table(self, arr, device_tensors):
+        """-> (pointer, mem flag); keeps the carrier alive."""
+        self.h2d_bytes += arr.nbytes
+        if device_tensors:
+            import torch
+            t = torch.from_numpy(arr).cuda()
+            self._keep.append(t)
+            return C.c_void_p(t.data_ptr()), 1
+        self._keep.append(arr)
+        return arr.ctypes.data_as(C.c_void_p), 0
+
+    def _upload(self, prob, device_tensors):
+        lib = self.lib
+        for kind, (name, kname, dname, dim) in enumerate(_KINDS):
+            keys = np.ascontiguousarray(prob[kname], dtype=np.uint64)
+            data = _soa(np.asarray(prob[dname]).reshape(len(keys), dim))
+            self.n[name] = len(keys)
+            ptr, mem = self._table(data, device_tensors)
+            self._check(lib.vus_set_variables(self._h, kind, len(keys), keys.ctypes.data_as(_native.c_u64_p), ptr, mem))
+        K = np.ascontiguousarray(prob["calib"], dtype=np.float64)
+        g = np.ascontiguousarray(prob["gravity"], dtype=np.float64)
+        self._check(lib.vus_set_calibration(self._h, K.ctypes.data_as(_native.c_double_p)))
+        self._check(lib.vus_set_gravity(self._h, g.ctypes.data_as(_native.c_double_p)))
+        self.nf = {}
+        for t, name in enumerate(FACTOR_TYPES):
+            f = prob[name]
+            n = len(f["orig"])
+            self.nf[name] = n
+            if n == 0:
+                continue
+            idx = np.ascontiguousarray(np.stack([f[s] for s in _SLOTS[name]], 0), dtype=np.int32)
+            meas = _soa(f["meas"])
+            info = _soa(f["sqrt_info"])
+            orig = np.ascontiguousarray(f["orig"], dtype=np.int64)
+            pm, mem = self._table(meas, device_tensors)
+            pi, _ = self._table(info, device_tensors)
+            self.h2d_bytes += idx.nbytes
+            self._check(lib.vus_add_factors(self._h, t, n, idx.ctypes.data_as(_native.c_i32_p), pm, pi,
+                                            orig.ctypes.data_as(_native.c_i64_p), mem))
+        self.n_factors = sum(self.nf.values())
+
+    def set_params(self, params):
+        p = params.to_c() if hasattr(params, "to_c") else params
+        self._check(self.lib.vus_set_lm_params(self._h, C.byref(p)))
+
+    # ------------------------------------------------------------------ C-ABI calls
+    def layout(self):
+        out = (C.c_int64 * 8)()
+        self._check(self.lib.vus_get_layout(self._h, out))
+        return dict(D=out[0], k=out[1], Ns=out[2], nrem=out[3], ndst=out[4], B=out[5], L=out[6], n_factors=out[7])
+
+    def error(self, stream=None):
+        v = C.c_double()
+        self._check(self.lib.vus_error(self._h, stream, C.byref(v)))
+        return v.value
+
+    def factor_errors(self, stream=None):
+        out = np.zeros(self.n_factors)
+        self._check(self.lib.vus_factor_errors(self._h, stream, out.ctypes.data_as(_native.c_double_p)))
+        return out
+
+    def linearize(self, name, stream=None):
+        """-> (r [n,m], J [n,m,cols]) whitened, node-ordered columns (include/vus.h)."""
+        n, m, c = self.nf[name], _ROWS[name], _COLS[name]
+        r = np.zeros((m, n))
+        J = np.zeros((m * c, n))
+        self._check(self.lib.vus_linearize(self._h, stream, FACTOR_TYPES.index(name), r.ctypes.data_as(_native.c_double_p),
+                                           J.ctypes.data_as(_native.c_double_p)))
+        return r.T.copy(), J.reshape(m, c, n).transpose(2, 0, 1).copy()
+
+    def solve_step(self, lam, stream=None):
+        dp = np.zeros((self.n["pose"], 6))
+        dv = np.zeros((self.n["vel"], 3))
+        db = np.zeros((max(self.n["bias"], 1), 6))
+        dl = np.zeros((self.n["lm"], 3))
+        its = C.c_int32()
+        P = _native.c_double_p
+        self._check(self.lib.vus_solve_step(self._h, stream, float(lam), dp.ctypes.data_as(P), dv.ctypes.data_as(P),
+                                            db.ctypes.data_as(P), dl.ctypes.data_as(P), C.byref(its)))
+        return dict(pose=dp, vel=dv, bias=db[:self.n["bias"]], lm=dl, pcg_iterations=its.value)
+
+    def optimize(self, stream=None):
+        res = LmResult()
+        self._check(self.lib.vus_optimize(self._h, stream, C.byref(res)))
+        return res.as_dict()
+
+    def time_linearize(self, reps=10, stream=None):
+        v = C.c_double()
+        self._check(self.lib.vus_time_linearize(self._h, stream, int(reps), C.byref(v)))
+        return v.value
+
+    def values(self):
+        """Current values as host tables {name: [n, dim]}."""
+        out = {}
+        self.d2h_bytes = 0
+        for kind, (name, kname, dname, dim) in enumerate(_KINDS):
+            buf = np.zeros((dim, self.n[name]))
+            self._check(self.lib.vus_get_variables(self._h, kind, buf.ctypes.data_as(C.c_void_p), 0))
+            out[dname] = buf.T.copy()
+            self.d2h_bytes += buf.nbytes
+        return out
+
+
+def _values_from(prob, tables):
+    return Values.from_tables({"pose": (prob["pose_keys"], tables["poses"]), "vel": (prob["vel_keys"], tables["vels"]),
+                               "bias": (prob["bias_keys"], tables["biases"]), "lm": (prob["lm_keys"], tables["lms"])})
+
+
+def graph_error(graph, values, lib=None):
+    s = Session(graph.to_problem(values), lib=lib)
+    try:
+        return s.error()
+    finally:
+        s.close()
+
+
+class LevenbergMarquardtOptimizer:
+    """gtsam.LevenbergMarquardtOptimizer(graph, initialValues, params) (batch.py:337)."""
+
+    def __init__(self, graph, initialValues, params=None, lib=None):
+        self._graph = graph
+        self._params = params or LevenbergMarquardtParams()
+        self._prob = graph.to_problem(initialValues)
+        self._session = Session(self._prob, self._params, lib=lib)
+        self._result = None
+        self._values = initialValues
+        self._error = None
+
+    def optimize(self):
+        self._result = self._session.optimize()
+        self._values = _values_from(self._prob, self._session.values())
+        self._error = self._result["final_error"]
+        return self._values
+
+    def optimizeSafely(self):
+        return self.optimize()
+
+    def values(self):
+        return self._values
+
+    def error(self):
+        if self._error is None:
+            self._error = self._session.error()
+        return self._error
+
+    def iterations(self):
+        return 0 if self._result is None else self._result["iterations"]
+
+    def lambda_(self):
+        return self._params.lambdaInitial if self._result is None else self._result["final_lambda"]
+
+    def stats(self):
+        """Per-phase timings, PCG iterations, kernel launches of the last optimize()."""
+        return dict(self._result or {})

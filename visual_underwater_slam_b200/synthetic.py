@@ -214,7 +214,8 @@ def make_trajectory_graph(n_poses, seed=1, n_landmarks=0, obs_per_landmark=10, n
     base[1:] = 2 + np.concatenate([[0], np.cumsum(2 + cnt[1:-1])])
     graph = NonlinearFactorGraph()
     graph.add_prior_pose_factors(xk[:1], poses_in[:1], 1.0 / POSE_PRIOR_SIGMAS)          # batch.py:281
-    graph.add_prior_vector_factors(vk[:1], np.zeros((1, 3)), np.full(3, 1.0 / VEL_PRIOR_SIGMA))  # batch.py:282
+    v0_prior = np.zeros((1, 3)) if noise_scale > 0 else v_kf[:1]      # batch.py:279/:282 uses 0; the noise-free
+    graph.add_prior_vector_factors(vk[:1], v0_prior, np.full(3, 1.0 / VEL_PRIOR_SIGMA))  # known-answer case uses truth
     graph.add_imu_factors(xk[:-1], vk[:-1], xk[1:], vk[1:], np.repeat(bk, n - 1), pim, imu_info, g)
     graph.set_insertion_order("imu", base[1:])
     graph.add_dvl_factors(vk[1:], xk[1:], dvl[1:], np.full(3, 1.0 / DVL_SIGMA))
