@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- LM time-to-converge / factors-per-second of the B200 batch factor-graph optimizer.
+
+One "step" = one full `optimize()` (LM to convergence, gtsam defaults) of the BASELINE.json workload
+"100k-pose underwater trajectory graph with IMU preintegration and 2M stereo factors" (config C3; synthetic,
+generator in visual_underwater_slam_b200/synthetic.py).  At N > 1 every rank solves its own independent
+trajectory graph of the same size (the path shards by trajectory with no data-path collective): weak scaling.
+
+  value        Sum over ranks of (factors x LM linearizations) / time-to-converge, inputs resident in HBM
+  e2e          same metric through the public C-ABI session with HOST tables: host->device copy of every table,
+               symbolic analysis, optimize(), device->host read of all optimised values inside the timed region
+  roofline     dominant kernel class, algorithmic bytes / CUDA-event device time vs MEASURED_PEAKS.json
+  cpu_baseline the CPU oracle (numpy/scipy restatement of gtsam LM, NOT gtsam) on a bounded sample
+
+`--impl reference` times that CPU oracle arm alone (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES = {"prior_pose": 576, "prior_vel": 168, "between": 968, "dvl": 392, "stereo": 392, "imu": 3004}
+METRIC = "lm_factors_per_s"
+UNIT = "factors/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--poses", type=int, default=100000)
+    ap.add_argument("--landmarks", type=int, default=200000)
+    ap.add_argument("--loops", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=3)
+    ap.add_argument("--drift-scale", type=float, default=0.1, help="initial odometry drift: per-step sigma = scale x (0.002 rad, 0.01 m)")
+    ap.add_argument("--cpu-poses", type=int, default=2500, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="do not time individual kernels with CUDA events")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"C3-style synthetic DVL/IMU/stereo trajectory graph: {a.poses} poses, {a.landmarks} landmarks x 10 obs, "
+            f"{a.loops} loop closures, seed {a.seed}(+rank), manifold preintegration, stereo pixel noise 1 px, "
+            f"initial drift scale {a.drift_scale}")
+
+
+def make_problem(a, rank):
+    from visual_underwater_slam_b200 import synthetic
+    d = synthetic.make_trajectory_graph(a.poses, seed=a.seed + rank, n_landmarks=a.landmarks, n_loops=a.loops, pixel_noise=1.0,
+                                        drift_scale=a.drift_scale)
+    return d, d["graph"].to_problem(d["initial"])
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_oracle_run(a, steps=1, warmup=0):
+    """CPU restatement of gtsam LM (oracle/, NOT gtsam) on a bounded sample of the same generator."""
+    from visual_underwater_slam_b200 import synthetic
+    from oracle import lm
+    n = a.cpu_poses
+    ratio = a.landmarks / max(a.poses, 1)
+    d = synthetic.make_trajectory_graph(n, seed=a.seed, n_landmarks=int(round(ratio * n)), n_loops=0, pixel_noise=1.0,
+                                        drift_scale=a.drift_scale)
+    prob = d["graph"].to_problem(d["initial"])
+    times, info = [], None
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, info = lm.lm_optimize(prob)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    lin = info["iterations"] + (1 if len(info["trace"]["tries"]) > info["iterations"] else 0)
+    lin = max(lin, len(info["trace"]["errors"]) - 1)
+    nf = d["meta"]["n_factors"]
+    t = float(np.mean(times))
+    sample = (f"{n}-pose / {int(round(ratio * n))}-landmark graph from the same generator ({nf} factors), full LM to "
+              f"convergence: {info['iterations']} iterations in {t:.2f} s (CPU restatement of gtsam LM, not gtsam)")
+    return dict(value=nf * lin / t, unit=UNIT, cores=1, kind="port", sample=sample, seconds=t, iterations=info["iterations"],
+                final_error=info["error"]), t
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(smax)), reasons=sorted(reasons), samples=len(sm))
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def roofline(res, lay, nf, ms_class, launches):
+    """Algorithmic bytes per launch-group / CUDA-event device time for each HBM-bound kernel class; returns the
+    dominant one in the contract's format plus the full table."""
+    B, Ns, L = lay["B"], lay["Ns"], lay["L"]
+    BB8 = B * B * 8
+    lin = res["linearizations"]
+    tries = res["inner_iterations"]
+    table = {}
+    lin_bytes = sum(ALG_BYTES[k] * nf[k] for k in nf)
+    table["linearize"] = lin_bytes * lin
+    table["error"] = sum((ALG_BYTES[k] - {"prior_pose": 336, "prior_vel": 96, "between": 624, "dvl": 240, "stereo": 240, "imu": 1800}[k]
+                          + 8) * nf[k] for k in nf) * (tries + 1)
+    # BCR solve: one application streams Dinv, Gl, Gr (backward) + GlT, GrT (forward) once, plus the vector
+    # per optimize: (6-rhs border set-up + 1) per try + one per PCG iteration + ...; count applications from launches
+    levels = max(1, int(np.ceil(np.log2(max(Ns, 2)))))
+    per_apply_launches = 2 * levels + 1
+    applies = launches["bcr_solve"] / per_apply_launches if per_apply_launches else 0
+    table["bcr_solve"] = applies * (5 * Ns * BB8 + 4 * L * 8)
+    # BCR factor: reads SD + SU, writes Dinv, Gl, Gr, GlT, GrT (+ level couplings ~ 1x)
+    table["bcr_factor"] = tries * (8 * Ns * BB8)
+    # operator: SD + 2 SU per application + vectors
+    mv_launch = launches["matvec"]
+    table["matvec"] = (mv_launch / 3.0) * (3 * Ns * BB8 + 2 * L * 8)
+    # damp + Schur: copy of the base system (read + write) + E, W streams per try
+    table["schur"] = tries * (2 * (2 * Ns * BB8) + nf.get("stereo", 0) * (18 * 8 * 3))
+    out = {}
+    for k, b in table.items():
+        ms = ms_class.get(k, 0.0)
+        if ms > 0:
+            out[k] = dict(ms=ms, launches=launches.get(k, 0), alg_bytes=b, gbs=b / ms / 1e6)
+    return out
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        cb, t = cpu_oracle_run(a, steps=max(1, a.steps), warmup=min(a.warmup, 1))
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(a), "reference_arm": cb["sample"]},
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this path has no CPU fallback); use --impl reference for the CPU oracle arm")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from visual_underwater_slam_b200.optimizer import Session, LevenbergMarquardtParams
+
+    d, prob = make_problem(a, rank)
+    nf = {k: len(prob[k]["orig"]) for k in ("prior_pose", "prior_vel", "between", "dvl", "stereo", "imu")}
+    n_factors = sum(nf.values())
+    params = LevenbergMarquardtParams()
+    params.profileKernels = not a.no_profile
+
+    t0 = time.perf_counter()
+    sess = Session(prob, params, device=local_rank)
+    setup_s = time.perf_counter() - t0
+    lay = sess.layout()
+    sess.save_values()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    res = None
+    for _ in range(a.warmup):
+        sess.restore_values()
+        res = sess.optimize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    ms_class = {}
+    launches_class = {}
+    launches = 0
+    for _ in range(a.steps):
+        sess.restore_values()
+        res = sess.optimize()
+        launches += res["kernel_launches"]
+        for k, v in res["ms_class"].items():
+            ms_class[k] = ms_class.get(k, 0.0) + v
+        for k, v in res["launches_class"].items():
+            launches_class[k] = launches_class.get(k, 0) + v
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    work = torch.tensor([float(res["factors_linearized"]) * a.steps], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    ms = float(tmax.item())
+    value = float(work.item()) / (ms * 1e-3)
+
+    # ---- end-to-end through the C-ABI with HOST tables (pinned), copies + analysis + read-back in the timed region
+    e2e = None
+    if not a.no_e2e:
+        pinned = dict(prob)
+
+        def pin(x):
+            return torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()
+        for k in ("poses", "vels", "biases", "lms"):
+            pinned[k] = pin(prob[k])
+        for k in nf:
+            f = dict(prob[k])
+            f["meas"] = pin(f["meas"])
+            f["sqrt_info"] = pin(f["sqrt_info"])
+            pinned[k] = f
+        p2 = LevenbergMarquardtParams()
+        times = []
+        for i in range(2):
+            barrier()
+            t0 = time.perf_counter()
+            s2 = Session(pinned, p2, device=local_rank)
+            r2 = s2.optimize()
+            out = s2.values()
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+            h2d, d2h = s2.h2d_bytes, s2.d2h_bytes
+            s2.close()
+        te = torch.tensor([times[-1]], dtype=torch.float64, device="cuda")
+        we = torch.tensor([float(r2["factors_linearized"])], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(we, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(we.item()) / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "seconds": float(te.item()), "includes": "H2D of all tables from pinned host memory, symbolic analysis, LM to convergence, D2H of all values"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    rf_table = roofline(res, lay, nf, ms_class, launches_class) if ms_class and any(ms_class.values()) else {}
+    rf = None
+    if rf_table:
+        # dominant HBM-bound kernel class by device time (bcr_factor is FP64-FMA bound: reported in the table, not as the roofline line)
+        cands = {k: v for k, v in rf_table.items() if k != "bcr_factor"}
+        top = max(cands, key=lambda k: cands[k]["ms"])
+        ach = cands[top]["gbs"]
+        rf = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+              "peak_source": peak_src, "device_ms": cands[top]["ms"], "launches": cands[top]["launches"]}
+    cpu = None
+    if not a.no_cpu_baseline:
+        cpu, _ = cpu_oracle_run(a)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(a), "n_factors_per_gpu": n_factors, "factor_mix": nf, "layout": lay,
+                   "l2_policy": "inputs larger than L2 (factor tables + Jacobians + band system > 1 GB per solve)",
+                   "preintegration": "manifold", "lm_params": "gtsam defaults (batch.py:337)"},
+        "time_to_converge_ms": ms / a.steps, "lm_iterations": res["iterations"], "lm_tries": res["inner_iterations"],
+        "pcg_iterations": res["pcg_iterations"], "final_error": res["final_error"], "setup_s_upload_plus_analyze": setup_s,
+        "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": rf, "cpu_baseline": cpu,
+        "phase_ms_last_step": {k: res[k] for k in ("ms_linearize", "ms_assemble", "ms_schur", "ms_factor", "ms_pcg", "ms_update")},
+        "kernel_class_device_ms": {k: v for k, v in ms_class.items() if v}, "kernel_class_table": rf_table,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -68,6 +68,7 @@ typedef struct vus_lm_params {
   double pcg_rel_tol;            /* 1e-12: ||r|| <= tol * ||rhs|| (stops earlier if the residual stagnates) */
   int32_t max_supernode;         /* 0 = auto (band width from the graph, capped so k*D <= 96) */
   int32_t verbose;
+  int32_t profile_kernels;       /* 1: time every kernel launch with CUDA events, per kernel class (ms_class) */
 } vus_lm_params;
 
 typedef struct vus_lm_result {
@@ -81,6 +82,11 @@ typedef struct vus_lm_result {
   double ms_total, ms_linearize, ms_assemble, ms_schur, ms_factor, ms_pcg, ms_update;
   int64_t kernel_launches;
   int64_t factors_linearized;    /* sum over linearizations of #factors */
+  /* device time per kernel class (CUDA events on the launching stream; only with profile_kernels=1):
+   * 0 linearize | 1 error | 2 linearised error | 3 assemble | 4 stereo assemble | 5 damp+Schur | 6 BCR factor |
+   * 7 BCR solve | 8 matvec | 9 border | 10 vector/reduce | 11 retract */
+  double ms_class[16];
+  int64_t launches_class[16];
 } vus_lm_result;
 
 void vus_default_lm_params(vus_lm_params* p);
@@ -93,6 +99,9 @@ const char* vus_last_error(const vus_handle* h);
 /* gtsam::Values  (batch.py:81, :274, :283-288, :297-298): keys ascending uint64 Symbol keys. */
 int vus_set_variables(vus_handle* h, int kind, int64_t n, const uint64_t* keys, const double* data, int mem);
 int vus_get_variables(vus_handle* h, int kind, double* out, int mem);
+/* keep / restore a device-side copy of the current values (re-running optimize() from the same initial estimate) */
+int vus_save_values(vus_handle* h);
+int vus_restore_values(vus_handle* h);
 
 /* gtsam::NonlinearFactorGraph::add / push_back (batch.py:281-282, :291-292, :305), one call per type.
  * orig_index = NonlinearFactorGraph insertion index of each factor (kept for bit-exact factor indexing). */

@@ -12,12 +12,16 @@ c_i64_p = C.POINTER(C.c_int64)
 c_u64_p = C.POINTER(C.c_uint64)
 
 
+KERNEL_CLASSES = ("linearize", "error", "linerr", "assemble", "stereo_assemble", "schur", "bcr_factor", "bcr_solve",
+                  "matvec", "border", "vector", "retract")
+
+
 class LmParams(C.Structure):
     _fields_ = [("max_iterations", C.c_int32), ("relative_error_tol", C.c_double), ("absolute_error_tol", C.c_double),
                 ("error_tol", C.c_double), ("lambda_initial", C.c_double), ("lambda_factor", C.c_double),
                 ("lambda_upper_bound", C.c_double), ("lambda_lower_bound", C.c_double), ("min_model_fidelity", C.c_double),
                 ("pcg_max_iterations", C.c_int32), ("pcg_rel_tol", C.c_double), ("max_supernode", C.c_int32),
-                ("verbose", C.c_int32)]
+                ("verbose", C.c_int32), ("profile_kernels", C.c_int32)]
 
 
 class LmResult(C.Structure):
@@ -26,10 +30,14 @@ class LmResult(C.Structure):
                 ("initial_error", C.c_double), ("final_error", C.c_double), ("final_lambda", C.c_double),
                 ("ms_total", C.c_double), ("ms_linearize", C.c_double), ("ms_assemble", C.c_double),
                 ("ms_schur", C.c_double), ("ms_factor", C.c_double), ("ms_pcg", C.c_double), ("ms_update", C.c_double),
-                ("kernel_launches", C.c_int64), ("factors_linearized", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("factors_linearized", C.c_int64),
+                ("ms_class", C.c_double * 16), ("launches_class", C.c_int64 * 16)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n not in ("reserved", "ms_class", "launches_class")}
+        d["ms_class"] = dict(zip(KERNEL_CLASSES, list(self.ms_class)))
+        d["launches_class"] = dict(zip(KERNEL_CLASSES, list(self.launches_class)))
+        return d
 
 
 EXPORTS = {
@@ -39,6 +47,8 @@ EXPORTS = {
     "vus_last_error": (C.c_char_p, [C.c_void_p]),
     "vus_set_variables": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_u64_p, C.c_void_p, C.c_int]),
     "vus_get_variables": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "vus_save_values": (C.c_int, [C.c_void_p]),
+    "vus_restore_values": (C.c_int, [C.c_void_p]),
     "vus_add_factors": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_i32_p, C.c_void_p, C.c_void_p, c_i64_p, C.c_int]),
     "vus_set_calibration": (C.c_int, [C.c_void_p, c_double_p]),
     "vus_set_gravity": (C.c_int, [C.c_void_p, c_double_p]),

@@ -37,6 +37,10 @@ struct LinOut {
   double* r;   // [m][n] whitened residual (may be null)
   double* J;   // [m*ncols][n] whitened Jacobian (may be null)
   double* e2;  // [n] 0.5*||r||^2 (may be null)
+  // stereo only (fused assembly products, may be null):
+  double* sE;  // [18][n]  E_o = Jp^T Jl (6x3 row-major), component-major
+  double* sPp; // [n][28]  per-observation pose products: 21 unique Jp^T Jp (a<=b) | 6 Jp^T r | pad
+  double* sPl; // [n][12]  per-observation landmark products: 6 unique Jl^T Jl | 3 Jl^T r | pad
 };
 
 VUS_HD void load_pose(const double* P, long n, long i, double* R, double* t) {
@@ -218,6 +222,14 @@ VUS_HD void f_stereo(const ValuesView& V, const FactorView& F, const LinOut& O, 
     if (WJ) {
 #pragma unroll
       for (int c = 0; c < 27; ++c) O.J[c * n + f] = 0.0;
+      if (O.sE) {
+#pragma unroll
+        for (int c = 0; c < 18; ++c) O.sE[c * n + f] = 0.0;
+#pragma unroll
+        for (int c = 0; c < 28; ++c) O.sPp[f * 28 + c] = 0.0;
+#pragma unroll
+        for (int c = 0; c < 12; ++c) O.sPl[f * 12 + c] = 0.0;
+      }
     }
     return;
   }
@@ -237,15 +249,45 @@ VUS_HD void f_stereo(const ValuesView& V, const FactorView& F, const LinOut& O, 
     const double Hp[18] = {uL * v1, -fx - dx * uL, v2, -d * fx, 0.0, d * uL,
                            uR * v1, -fx - dx * uR, v2, -d * fx, 0.0, d * uR,
                            fy + vv * v1, -dx * vv, -q[0] * d * fy, 0.0, -d * fy, d * vv};
+    double Jp[18], Jl[9];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int c = 0; c < 6; ++c) O.J[(r * 9 + c) * n + f] = s[r] * Hp[6 * r + c];
+      for (int c = 0; c < 6; ++c) { Jp[6 * r + c] = s[r] * Hp[6 * r + c]; O.J[(r * 9 + c) * n + f] = Jp[6 * r + c]; }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {                       // column k of H_lm
-      O.J[(0 * 9 + 6 + k) * n + f] = s[0] * d * (fx * R[3 * k] - R[3 * k + 2] * uL);
-      O.J[(1 * 9 + 6 + k) * n + f] = s[1] * d * (fx * R[3 * k] - R[3 * k + 2] * uR);
-      O.J[(2 * 9 + 6 + k) * n + f] = s[2] * d * (fy * R[3 * k + 1] - R[3 * k + 2] * vv);
+      Jl[k] = s[0] * d * (fx * R[3 * k] - R[3 * k + 2] * uL);
+      Jl[3 + k] = s[1] * d * (fx * R[3 * k] - R[3 * k + 2] * uR);
+      Jl[6 + k] = s[2] * d * (fy * R[3 * k + 1] - R[3 * k + 2] * vv);
+      O.J[(0 * 9 + 6 + k) * n + f] = Jl[k];
+      O.J[(1 * 9 + 6 + k) * n + f] = Jl[3 + k];
+      O.J[(2 * 9 + 6 + k) * n + f] = Jl[6 + k];
+    }
+    if (O.sE) {                                         // fused assembly products (kernel 2 inputs never re-read J)
+      const double rs[3] = {s[0] * e[0], s[1] * e[1], s[2] * e[2]};
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          O.sE[(a * 3 + c) * n + f] = Jp[a] * Jl[c] + Jp[6 + a] * Jl[3 + c] + Jp[12 + a] * Jl[6 + c];
+      double* Pp = O.sPp + f * 28;
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 6; ++b) Pp[q++] = Jp[a] * Jp[b] + Jp[6 + a] * Jp[6 + b] + Jp[12 + a] * Jp[12 + b];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) Pp[21 + a] = Jp[a] * rs[0] + Jp[6 + a] * rs[1] + Jp[12 + a] * rs[2];
+      Pp[27] = 0.0;
+      double* Pl = O.sPl + f * 12;
+      q = 0;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = a; b < 3; ++b) Pl[q++] = Jl[a] * Jl[b] + Jl[3 + a] * Jl[3 + b] + Jl[6 + a] * Jl[6 + b];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) Pl[6 + a] = Jl[a] * rs[0] + Jl[3 + a] * rs[1] + Jl[6 + a] * rs[2];
+      Pl[9] = Pl[10] = Pl[11] = 0.0;
     }
   }
 }

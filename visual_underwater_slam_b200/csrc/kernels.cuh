@@ -224,8 +224,8 @@ struct AsmBody {
       for (int r = 0; r < M; ++r) s += A.J[(r * C + a) * n + f] * A.r[r * n + f];
       int ga, la;
       grp(a, ga, la);
-      if (ga == 2) atomic_add(&A.gb[la], -s);
-      else atomic_add(&A.g[(ga == 0 ? p : q) * D + la], -s);
+      if (ga == 2) return;                           // bias gradient: ImuBiasBody (block reduction, no atomics)
+      atomic_add(&A.g[(ga == 0 ? p : q) * D + la], -s);
       return;
     }
     const int a = e / C, b = e % C;
@@ -233,12 +233,13 @@ struct AsmBody {
     grp(a, ga, la);
     grp(b, gb, lb);
     if (ga > gb) return;                           // (q,p), (bias,p), (bias,q): written by the mirrored item
+    if (ga == 2 && gb == 2) return;                // bias-bias block: ImuBiasBody
     double h = 0.0;
 #pragma unroll
     for (int r = 0; r < M; ++r) h += A.J[(r * C + a) * n + f] * A.J[(r * C + b) * n + f];
     if (ga == gb) {
-      if (ga == 2) atomic_add(&A.Hbb[la * 6 + lb], h);
-      else atomic_add(&A.Hval[diag_off(ga == 0 ? p : q, la, lb, D, A.k, A.B)], h);
+      if (ga == 2) return;                           // bias-bias block: ImuBiasBody
+      atomic_add(&A.Hval[diag_off(ga == 0 ? p : q, la, lb, D, A.k, A.B)], h);
     } else if (gb == 2) {                          // (node, bias) border
       atomic_add(&A.F[((ga == 0 ? p : q) * D + la) * 6 + lb], h);
     } else {                                       // (p, q) coupling
@@ -247,6 +248,45 @@ struct AsmBody {
       else atomic_add(&A.Hval[d.off + (long)la * d.ld + lb], h);
       if (d.moff >= 0) atomic_add(&A.Hval[d.moff + (long)lb * d.mld + la], h);
     }
+  }
+};
+
+// shared-bias block: Hbb = sum_f Jb^T Jb (36) and gb = -sum_f Jb^T r (6) over ALL imu factors -- every factor hits the
+// same 42 addresses, so this is a two-stage block reduction instead of atomics.  partials [grid][42]
+struct ImuBiasArgs { long n; const double* J; const double* r; double* partials; int grid; double* Hbb; double* gb; };
+struct ImuBias1Body {
+  static VUS_DEV void run(const ImuBiasArgs& A, int bid, int tid, int nthr, double* sm) {
+    const long chunk = (A.n + A.grid - 1) / A.grid;
+    const long f0 = (long)bid * chunk;
+    long f1 = f0 + chunk;
+    if (f1 > A.n) f1 = A.n;
+    for (int e = 0; e < 42; ++e) {
+      double acc = 0.0;
+      if (e < 36) {
+        const int a = 18 + e / 6, b = 18 + e % 6;
+        for (long f = f0 + tid; f < f1; f += nthr)
+          for (int r = 0; r < 9; ++r) acc += A.J[(r * 24 + a) * A.n + f] * A.J[(r * 24 + b) * A.n + f];
+      } else {
+        const int a = 18 + e - 36;
+        for (long f = f0 + tid; f < f1; f += nthr)
+          for (int r = 0; r < 9; ++r) acc -= A.J[(r * 24 + a) * A.n + f] * A.r[r * A.n + f];
+      }
+      sm[tid] = acc;
+      VUS_SYNC();
+      for (int s = nthr >> 1; s > 0; s >>= 1) {
+        for (int t = tid; t < s; t += nthr) sm[t] += sm[t + s];
+        VUS_SYNC();
+      }
+      if (tid == 0) A.partials[(long)bid * 42 + e] = sm[0];
+      VUS_SYNC();
+    }
+  }
+};
+struct ImuBias2Body {
+  static VUS_DEV void run(const ImuBiasArgs& A, long e) {
+    double s = 0.0;
+    for (int b = 0; b < A.grid; ++b) s += A.partials[(long)b * 42 + e];
+    if (e < 36) A.Hbb[e] = s; else A.gb[e - 36] = s;
   }
 };
 
@@ -259,73 +299,49 @@ struct StereoAsmArgs {
   double* SD; double* g;       // camera diag blocks / gradient
   double* C; double* gl;       // [9][nl], [3][nl]
   double* E;                   // [18][n]   E_o = Jp^T Jl (6x3 row-major)
+  const double* Pp; const double* Pl;    // per-observation products written by the stereo linearize kernel
   long nl;
   const int* pose_ptr; const int* pose_obs; const int* pose_ids; long nposes_obs;   // CSR pose -> obs
   const int* lm_ptr; const int* lm_obs;                                              // CSR landmark -> obs
 };
-// per (pose-with-observations, e): e < 36 -> B_ii entry, e >= 36 -> gradient
+// per (pose-with-observations, e<28): sums the per-observation products the stereo linearize kernel wrote
+// (P_pose[o][e], contiguous in e -> coalesced) over the pose's observations.  e<21: unique B_ii entry (a<=b), 21..26: gradient
 struct StereoPoseBody {
   static VUS_DEV void run(const StereoAsmArgs& A, long w) {
-    const long pi = w % A.nposes_obs;
-    const int e = (int)(w / A.nposes_obs);
+    const long pi = w / 28;
+    const int e = (int)(w - pi * 28);
+    if (e >= 27) return;
     const long node = A.pose_ids[pi];
-    const long n = A.n;
     double s = 0.0;
-    if (e < 36) {
-      const int a = e / 6, b = e % 6;
-      for (int t = A.pose_ptr[pi]; t < A.pose_ptr[pi + 1]; ++t) {
-        const long o = A.pose_obs[t];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) s += A.J[(r * 9 + a) * n + o] * A.J[(r * 9 + b) * n + o];
-      }
+    for (int t = A.pose_ptr[pi]; t < A.pose_ptr[pi + 1]; ++t) s += A.Pp[(long)A.pose_obs[t] * 28 + e];
+    if (e < 21) {
+      int a = 0, rem = e;
+      while (rem >= 6 - a) { rem -= 6 - a; ++a; }
+      const int b = a + rem;
       A.SD[diag_off(node, a, b, A.D, A.k, A.B)] += s;
+      if (a != b) A.SD[diag_off(node, b, a, A.D, A.k, A.B)] += s;
     } else {
-      const int a = e - 36;
-      for (int t = A.pose_ptr[pi]; t < A.pose_ptr[pi + 1]; ++t) {
-        const long o = A.pose_obs[t];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) s += A.J[(r * 9 + a) * n + o] * A.r[r * n + o];
-      }
-      A.g[node * A.D + a] -= s;
+      A.g[node * A.D + (e - 21)] -= s;
     }
   }
 };
-// per (landmark, e): e < 9 -> C entry, e >= 9 -> g_l
+// per (landmark, e<12): e<6 unique C entry (a<=b), 6..8: g_l
 struct StereoLmBody {
   static VUS_DEV void run(const StereoAsmArgs& A, long w) {
-    const long l = w % A.nl;
-    const int e = (int)(w / A.nl);
-    const long n = A.n;
+    const long l = w / 12;
+    const int e = (int)(w - l * 12);
+    if (e >= 9) return;
     double s = 0.0;
-    if (e < 9) {
-      const int a = e / 3, b = e % 3;
-      for (int t = A.lm_ptr[l]; t < A.lm_ptr[l + 1]; ++t) {
-        const long o = A.lm_obs[t];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) s += A.J[(r * 9 + 6 + a) * n + o] * A.J[(r * 9 + 6 + b) * n + o];
-      }
-      A.C[e * A.nl + l] = s;
+    for (int t = A.lm_ptr[l]; t < A.lm_ptr[l + 1]; ++t) s += A.Pl[(long)A.lm_obs[t] * 12 + e];
+    if (e < 6) {
+      int a = 0, rem = e;
+      while (rem >= 3 - a) { rem -= 3 - a; ++a; }
+      const int b = a + rem;
+      A.C[(a * 3 + b) * A.nl + l] = s;
+      if (a != b) A.C[(b * 3 + a) * A.nl + l] = s;
     } else {
-      const int a = e - 9;
-      for (int t = A.lm_ptr[l]; t < A.lm_ptr[l + 1]; ++t) {
-        const long o = A.lm_obs[t];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) s += A.J[(r * 9 + 6 + a) * n + o] * A.r[r * n + o];
-      }
-      A.gl[a * A.nl + l] = -s;
+      A.gl[(e - 6) * A.nl + l] = -s;
     }
-  }
-};
-// per (obs, e<18): E_o[a][c]
-struct StereoEBody {
-  static VUS_DEV void run(const StereoAsmArgs& A, long w) {
-    const long o = w % A.n;
-    const int e = (int)(w / A.n);
-    const int a = e / 3, c = e % 3;
-    double s = 0.0;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) s += A.J[(r * 9 + a) * A.n + o] * A.J[(r * 9 + 6 + c) * A.n + o];
-    A.E[e * A.n + o] = s;
   }
 };
 
@@ -393,21 +409,32 @@ struct SchurGradBody {   // per (pose-with-obs, a<6): gs -= sum_o W_o g_l
     A.gs[node * A.D + a] -= s;
   }
 };
-struct SchurBlockBody {  // per (destination, e<36): S_(i,j)[r][s] -= sum_terms W_a[r][:] . E_b[s][:]
-  static VUS_DEV void run(const SchurArgs& A, long w) {
-    const long d = w % A.ndst;
-    const int e = (int)(w / A.ndst);
-    const int r = e / 6, s = e % 6;
-    double acc = 0.0;
+struct SchurBlockBody {  // per destination (i<=j): S_(i,j) -= sum_terms W_a E_b^T   (6x6, all 36 outputs in registers)
+  static VUS_DEV void run(const SchurArgs& A, long d) {
+    double acc[36];
+#pragma unroll
+    for (int e = 0; e < 36; ++e) acc[e] = 0.0;
     for (int t = A.dst_ptr[d]; t < A.dst_ptr[d + 1]; ++t) {
       const long oa = A.term_a[t], ob = A.term_b[t];
+      double w[18], eb[18];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) acc += A.W[(r * 3 + c) * A.n + oa] * A.E[(s * 3 + c) * A.n + ob];
+      for (int e = 0; e < 18; ++e) { w[e] = A.W[e * A.n + oa]; eb[e] = A.E[e * A.n + ob]; }
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int s = 0; s < 6; ++s)
+          acc[r * 6 + s] += w[r * 3] * eb[s * 3] + w[r * 3 + 1] * eb[s * 3 + 1] + w[r * 3 + 2] * eb[s * 3 + 2];
     }
     const PairDst D = A.dst[d];
-    if (D.transposed) A.Hval[D.off + (long)s * D.ld + r] -= acc;
-    else A.Hval[D.off + (long)r * D.ld + s] -= acc;
-    if (D.moff >= 0) A.Hval[D.moff + (long)s * D.mld + r] -= acc;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int s = 0; s < 6; ++s) {
+        const double v = acc[r * 6 + s];
+        if (D.transposed) A.Hval[D.off + (long)s * D.ld + r] -= v;
+        else A.Hval[D.off + (long)r * D.ld + s] -= v;
+        if (D.moff >= 0) A.Hval[D.moff + (long)s * D.mld + r] -= v;
+      }
   }
 };
 struct LmBacksubBody {   // per landmark: xl = Cinv (gl - sum_o E_o^T xc[pose_o])
@@ -548,50 +575,131 @@ struct BorderDot1Body {
 // =====================================================================================
 // Kernel 3b: block cyclic reduction of the supernode block-tridiagonal band
 // =====================================================================================
-// CTA-level dense helpers on BxB row-major blocks (B <= 96), operands staged whole in shared memory.
-// In-place Gauss-Jordan inverse of an SPD block held in shared memory (no pivoting).
-VUS_DEV void cta_spd_inverse(double* M, double* rowp, double* colp, int B, int tid, int nthr, int* fail) {
+// CTA-level dense helpers on BxB blocks (B <= 96), operands staged whole in shared memory.
+//   "A" operands: row stride B, bcr_rows_a(B) rows allocated (rows >= B are never initialised: they only feed
+//                 register-tile lanes whose results are discarded);
+//   "B" operands: row stride bcr_ldb(B) (multiple of 4 -> 16/32-byte aligned vector loads), B rows.
+VUS_HD int bcr_ldb(int B) { return (B + 3) & ~3; }
+VUS_HD int bcr_rows_a(int B) { return (B + 7) & ~7; }
+VUS_HD long bcr_smem_doubles(int B) { return (long)bcr_rows_a(B) * B + (long)B * bcr_ldb(B) + 4 * B + 8; }
+
+// In-place Gauss-Jordan inverse of an SPD block held in shared memory with row stride ld (no pivoting).
+#ifdef VUS_EMU
+// host emulation: plain sweep over the block in memory
+VUS_DEV void cta_spd_inverse(double* M, int ld, double* rowp, double* colp, int B, int tid, int nthr, int* fail) {
   for (int p = 0; p < B; ++p) {
-    for (int i = tid; i < B; i += nthr) { colp[i] = M[(long)i * B + p]; rowp[i] = M[(long)p * B + i]; }
+    for (int i = tid; i < B; i += nthr) { colp[i] = M[(long)i * ld + p]; rowp[i] = M[(long)p * ld + i]; }
     VUS_SYNC();
     const double piv = rowp[p];
     if (tid == 0 && !(piv > 0.0)) *fail = 1;
     const double d = 1.0 / piv;
-    for (int e = tid; e < B * B; e += nthr) {
-      const int i = e / B, j = e % B;
-      double v;
-      if (i == p) v = (j == p) ? d : rowp[j] * d;
-      else if (j == p) v = -colp[i] * d;
-      else v = M[e] - colp[i] * rowp[j] * d;
-      M[e] = v;
+    for (int i = tid; i < B; i += nthr) {
+      double* row = M + (long)i * ld;
+      if (i == p) { for (int j = 0; j < B; ++j) row[j] = (j == p) ? d : rowp[j] * d; }
+      else { const double ci = colp[i] * d; for (int j = 0; j < B; ++j) row[j] = (j == p) ? -ci : row[j] - ci * rowp[j]; }
     }
     VUS_SYNC();
   }
 }
-// C(global) = beta*C + alpha * sA * sB with sA, sB in shared memory (row-major BxB), 4x4 register tiles.
-// If CT != null also writes the transpose of the result (only valid with beta == 0).
-VUS_DEV void cta_gemm_ss(double* C, double* CT, const double* sA, const double* sB, int B, double alpha, double beta, int tid, int nthr) {
-  const int T = (B + 3) / 4;
-  for (int tile = tid; tile < T * T; tile += nthr) {
-    const int i0 = (tile / T) * 4, j0 = (tile % T) * 4;
-    double acc[4][4];
+#else
+// sm_100a: the block lives in REGISTERS for all B sweeps (thread (tx,ty) of a 256-thread CTA owns rows ty+8a, columns
+// tx+32b, a<12, b<3); only the pivot row / column travel through shared memory, double-buffered -> one barrier per sweep.
+VUS_DEV void cta_spd_inverse(double* M, int ld, double* rowp, double* colp, int B, int tid, int nthr, int* fail) {
+  const int tx = tid & 31, ty = tid >> 5;                  // requires nthr == 256 and rowp/colp of 2*B doubles each
+  double m[12][3];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 12; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int i = ty + 8 * a, j = tx + 32 * b;
+      m[a][b] = (i < B && j < B) ? M[(long)i * ld + j] : 0.0;
+    }
+  for (int p = 0; p < B; ++p) {
+    double* rp = rowp + (p & 1) * B;
+    double* cp = colp + (p & 1) * B;
+    const int pa = p >> 3, pb = p >> 5;
+    if (ty == (p & 7)) {
+#pragma unroll
+      for (int a = 0; a < 12; ++a)
+        if (a == pa) {
+#pragma unroll
+          for (int b = 0; b < 3; ++b) { const int j = tx + 32 * b; if (j < B) rp[j] = m[a][b]; }
+        }
+    }
+    if (tx == (p & 31)) {
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        if (b == pb) {
+#pragma unroll
+          for (int a = 0; a < 12; ++a) { const int i = ty + 8 * a; if (i < B) cp[i] = m[a][b]; }
+        }
+    }
+    __syncthreads();
+    const double piv = rp[p];
+    if (tid == 0 && !(piv > 0.0)) *fail = 1;
+    const double d = 1.0 / piv;
+    double r[3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) { const int j = tx + 32 * b; r[b] = (j < B) ? rp[j] : 0.0; }
+#pragma unroll
+    for (int a = 0; a < 12; ++a) {
+      const int i = ty + 8 * a;
+      if (i < B) {
+        const double ci = cp[i] * d;
+        if (i == p) {
+#pragma unroll
+          for (int b = 0; b < 3; ++b) m[a][b] = (tx + 32 * b == p) ? d : r[b] * d;
+        } else {
+#pragma unroll
+          for (int b = 0; b < 3; ++b) m[a][b] = (tx + 32 * b == p) ? -ci : m[a][b] - ci * r[b];
+        }
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < 12; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int i = ty + 8 * a, j = tx + 32 * b;
+      if (i < B && j < B) M[(long)i * ld + j] = m[a][b];
+    }
+  __syncthreads();
+}
+#endif
+// C(global, row stride B) = beta*C + alpha * sA * sB, 8x4 register tiles, FP64 FMA pipe bound.
+// If CT != null also writes the transpose of the result.
+VUS_DEV void cta_gemm_ss(double* C, double* CT, const double* sA, const double* sB, int B, double alpha, double beta, int tid, int nthr) {
+  const int ldb = bcr_ldb(B);
+  const int TI = (B + 7) / 8, TJ = (B + 3) / 4;
+  for (int tile = tid; tile < TI * TJ; tile += nthr) {
+    const int i0 = (tile / TJ) * 8, j0 = (tile % TJ) * 4;
+    double acc[8][4];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    const double* pa = sA + (long)i0 * B;
+    const double* pb = sB + j0;
+#pragma unroll 3
     for (int k = 0; k < B; ++k) {
-      double av[4], bv[4];
+      double bv[4];
+#ifdef VUS_EMU
+      for (int b = 0; b < 4; ++b) bv[b] = pb[(long)k * ldb + b];
+#else
+      const double2 b01 = *reinterpret_cast<const double2*>(pb + (long)k * ldb);
+      const double2 b23 = *reinterpret_cast<const double2*>(pb + (long)k * ldb + 2);
+      bv[0] = b01.x; bv[1] = b01.y; bv[2] = b23.x; bv[3] = b23.y;
+#endif
 #pragma unroll
-      for (int a = 0; a < 4; ++a) av[a] = (i0 + a < B) ? sA[(long)(i0 + a) * B + k] : 0.0;
+      for (int a = 0; a < 8; ++a) {
+        const double av = pa[(long)a * B + k];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) bv[b] = (j0 + b < B) ? sB[(long)k * B + j0 + b] : 0.0;
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] += av[a] * bv[b];
+        for (int b = 0; b < 4; ++b) acc[a][b] += av * bv[b];
+      }
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 8; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const int i = i0 + a, j = j0 + b;
@@ -604,10 +712,11 @@ VUS_DEV void cta_gemm_ss(double* C, double* CT, const double* sA, const double* 
       }
   }
 }
-VUS_DEV void cta_load(double* s, const double* g, int B, bool transpose, int tid, int nthr) {
+// stage a global BxB row-major block into shared memory with row stride ld, optionally transposed
+VUS_DEV void cta_load(double* s, int ld, const double* g, int B, bool transpose, int tid, int nthr) {
   const int BB = B * B;
-  if (!transpose) for (int e = tid; e < BB; e += nthr) s[e] = g[e];
-  else for (int e = tid; e < BB; e += nthr) { const int i = e / B, j = e % B; s[(long)j * B + i] = g[e]; }
+  if (!transpose) for (int e = tid; e < BB; e += nthr) { const int i = e / B, j = e - i * B; s[(long)i * ld + j] = g[e]; }
+  else for (int e = tid; e < BB; e += nthr) { const int i = e / B, j = e - i * B; s[(long)j * ld + i] = g[e]; }
 }
 
 struct BcrArgs {
@@ -622,53 +731,53 @@ struct BcrArgs {
 // per eliminated node j = s*(2m+1): Dinv_j, Gl_j = U[j-s] Dinv_j, Gr_j = U[j]^T Dinv_j  (+ transposed copies)
 struct BcrElimBody {
   static VUS_DEV void run(const BcrArgs& A, int m, int tid, int nthr, double* sm) {
-    const int B = A.B;
+    const int B = A.B, ldb = bcr_ldb(B);
     const long BB = (long)B * B;
     const long j = A.s * (2L * m + 1);
-    double* sX = sm;              // Dinv
-    double* sY = sm + BB;         // operand
-    double* rowp = sY + BB;
-    double* colp = rowp + B;
-    cta_load(sX, A.Dw + j * BB, B, false, tid, nthr);
+    double* sA = sm;                                   // "A" operand (row stride B)
+    double* sX = sm + (long)bcr_rows_a(B) * B;         // Dinv as "B" operand (row stride ldb)
+    double* rowp = sX + (long)B * ldb;
+    double* colp = rowp + 2 * B;
+    cta_load(sX, ldb, A.Dw + j * BB, B, false, tid, nthr);
     VUS_SYNC();
-    cta_spd_inverse(sX, rowp, colp, B, tid, nthr, A.fail);
-    for (long e = tid; e < BB; e += nthr) A.Dinv[j * BB + e] = sX[e];
-    cta_load(sY, A.Ucur + (j - A.s) * BB, B, false, tid, nthr);
+    cta_spd_inverse(sX, ldb, rowp, colp, B, tid, nthr, A.fail);
+    for (long e = tid; e < BB; e += nthr) { const int i = (int)(e / B), c = (int)(e - (long)i * B); A.Dinv[j * BB + e] = sX[(long)i * ldb + c]; }
+    cta_load(sA, B, A.Ucur + (j - A.s) * BB, B, false, tid, nthr);
     VUS_SYNC();
-    cta_gemm_ss(A.Gl + j * BB, A.GlT + j * BB, sY, sX, B, 1.0, 0.0, tid, nthr);
+    cta_gemm_ss(A.Gl + j * BB, A.GlT + j * BB, sA, sX, B, 1.0, 0.0, tid, nthr);
     VUS_SYNC();
     if (j + A.s < A.Ns) {
-      cta_load(sY, A.Ucur + j * BB, B, true, tid, nthr);
+      cta_load(sA, B, A.Ucur + j * BB, B, true, tid, nthr);
       VUS_SYNC();
-      cta_gemm_ss(A.Gr + j * BB, A.GrT + j * BB, sY, sX, B, 1.0, 0.0, tid, nthr);
+      cta_gemm_ss(A.Gr + j * BB, A.GrT + j * BB, sA, sX, B, 1.0, 0.0, tid, nthr);
     }
   }
 };
 // per surviving node c = 2*m*s: Dw_c -= Gr_{c-s} U_{c-s} + Gl_{c+s} U_c^T ; Unext_c = -Gl_{c+s} U_{c+s}
 struct BcrUpdateBody {
   static VUS_DEV void run(const BcrArgs& A, int m, int tid, int nthr, double* sm) {
-    const int B = A.B;
+    const int B = A.B, ldb = bcr_ldb(B);
     const long BB = (long)B * B;
     const long c = 2L * m * A.s;
     double* sA = sm;
-    double* sB = sm + BB;
+    double* sB = sm + (long)bcr_rows_a(B) * B;
     if (c - A.s >= 0) {
       const long j = c - A.s;
-      cta_load(sA, A.Gr + j * BB, B, false, tid, nthr);
-      cta_load(sB, A.Ucur + j * BB, B, false, tid, nthr);
+      cta_load(sA, B, A.Gr + j * BB, B, false, tid, nthr);
+      cta_load(sB, ldb, A.Ucur + j * BB, B, false, tid, nthr);
       VUS_SYNC();
       cta_gemm_ss(A.Dw + c * BB, nullptr, sA, sB, B, -1.0, 1.0, tid, nthr);
       VUS_SYNC();
     }
     if (c + A.s < A.Ns) {
       const long j = c + A.s;
-      cta_load(sA, A.Gl + j * BB, B, false, tid, nthr);
-      cta_load(sB, A.Ucur + c * BB, B, true, tid, nthr);
+      cta_load(sA, B, A.Gl + j * BB, B, false, tid, nthr);
+      cta_load(sB, ldb, A.Ucur + c * BB, B, true, tid, nthr);
       VUS_SYNC();
       cta_gemm_ss(A.Dw + c * BB, nullptr, sA, sB, B, -1.0, 1.0, tid, nthr);
       VUS_SYNC();
       if (j + A.s < A.Ns) {
-        cta_load(sB, A.Ucur + j * BB, B, false, tid, nthr);
+        cta_load(sB, ldb, A.Ucur + j * BB, B, false, tid, nthr);
         VUS_SYNC();
         cta_gemm_ss(A.Unext + c * BB, nullptr, sA, sB, B, -1.0, 0.0, tid, nthr);
       }
@@ -678,15 +787,15 @@ struct BcrUpdateBody {
 // root: Dinv_0 = inv(Dw_0)
 struct BcrRootBody {
   static VUS_DEV void run(const BcrArgs& A, int, int tid, int nthr, double* sm) {
-    const int B = A.B;
+    const int B = A.B, ldb = bcr_ldb(B);
     const long BB = (long)B * B;
-    double* sX = sm;
-    double* rowp = sm + BB;
-    double* colp = rowp + B;
-    cta_load(sX, A.Dw, B, false, tid, nthr);
+    double* sX = sm + (long)bcr_rows_a(B) * B;
+    double* rowp = sX + (long)B * ldb;
+    double* colp = rowp + 2 * B;
+    cta_load(sX, ldb, A.Dw, B, false, tid, nthr);
     VUS_SYNC();
-    cta_spd_inverse(sX, rowp, colp, B, tid, nthr, A.fail);
-    for (long e = tid; e < BB; e += nthr) A.Dinv[e] = sX[e];
+    cta_spd_inverse(sX, ldb, rowp, colp, B, tid, nthr, A.fail);
+    for (long e = tid; e < BB; e += nthr) { const int i = (int)(e / B), c = (int)(e - (long)i * B); A.Dinv[e] = sX[(long)i * ldb + c]; }
   }
 };
 // forward sweep, per surviving node c: b_c -= Gr_{c-s} b_{c-s} + Gl_{c+s} b_{c+s}   (reads the transposed copies: coalesced)

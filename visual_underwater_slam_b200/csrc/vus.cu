@@ -19,17 +19,54 @@ namespace {
 
 long g_launches = 0;
 
+// kernel classes for the per-class device timing (vus_lm_result.ms_class / launches_class)
+enum { KC_LINEARIZE = 0, KC_ERROR, KC_LINERR, KC_ASSEMBLE, KC_STEREO_ASM, KC_SCHUR, KC_BCR_FACTOR, KC_BCR_SOLVE,
+       KC_MATVEC, KC_BORDER, KC_VECTOR, KC_RETRACT, KC_COUNT };
+int g_class = KC_VECTOR;
+struct ClassGuard { int prev; explicit ClassGuard(int c) : prev(g_class) { g_class = c; } ~ClassGuard() { g_class = prev; } };
+
+struct Profiler {
+  bool on = false;
+  double ms[16] = {0};
+  long count[16] = {0};
+#ifndef VUS_EMU
+  std::vector<cudaEvent_t> pool;
+  std::vector<int> cls;
+  size_t used = 0;
+  void begin(rt::stream_t st) {
+    if (used + 2 > pool.size()) { pool.resize(pool.size() + 2); cudaEventCreate(&pool[pool.size() - 2]); cudaEventCreate(&pool[pool.size() - 1]); }
+    cudaEventRecord(pool[used], st);
+  }
+  void end(rt::stream_t st) { cudaEventRecord(pool[used + 1], st); cls.push_back(g_class); used += 2; }
+  void collect() {
+    if (!used) return;
+    cudaEventSynchronize(pool[used - 1]);
+    for (size_t i = 0; i < used; i += 2) { float t = 0; cudaEventElapsedTime(&t, pool[i], pool[i + 1]); ms[cls[i / 2]] += t; count[cls[i / 2]]++; }
+    used = 0; cls.clear();
+  }
+#else
+  void begin(rt::stream_t) {}
+  void end(rt::stream_t) { count[g_class]++; }
+  void collect() {}
+#endif
+  void reset() { collect(); for (int i = 0; i < 16; ++i) { ms[i] = 0; count[i] = 0; } }
+} g_prof;
+
 template <class Body, class Args>
 void L_elem(long n, rt::stream_t st, const Args& a) {
   if (n <= 0) return;
   ++g_launches;
+  if (g_prof.on) g_prof.begin(st);
   rt::launch_elem<Body, Args>(n, st, a);
+  if (g_prof.on) g_prof.end(st);
 }
 template <class Body, class Args>
 void L_coop(int grid, int block, size_t smem, rt::stream_t st, const Args& a) {
   if (grid <= 0) return;
   ++g_launches;
+  if (g_prof.on) g_prof.begin(st);
   rt::launch_coop<Body, Args>(grid, block, smem, st, a);
+  if (g_prof.on) g_prof.end(st);
 }
 
 struct FactorTable {
@@ -60,6 +97,8 @@ struct vus_handle {
   long nvar[4] = {0, 0, 0, 0};
   std::vector<uint64_t> keys[4];
   DBuf<double> val[2][4];
+  DBuf<double> saved[4];
+  bool has_saved = false;
   int cur = 0;
   // factors
   FactorTable ft[VUS_F_NTYPES];
@@ -76,7 +115,7 @@ struct vus_handle {
   long nobs = 0, nposes_obs = 0, ndst = 0;
   DBuf<int> pose_ptr, pose_obs, pose_ids, lm_ptr, lm_obs, dst_ptr, term_a, term_b;
   DBuf<PairDst> dst;
-  DBuf<double> C, gl, Cinv, E, W;
+  DBuf<double> C, gl, Cinv, E, W, Pp, Pl;
   // BCR
   DBuf<double> Dw, U1, U2, Dinv, Gl, Gr, GlT, GrT, Z, SbInv;
   // PCG
@@ -118,6 +157,7 @@ void launch_lin_type(vus_handle* h, int t, const LinArgs& a, rt::stream_t st) {
 
 // kernel 1 over every factor type; with_J: also write r and J (linearize), else residual norms only
 void run_factors(vus_handle* h, int which, bool with_J, rt::stream_t st) {
+  ClassGuard kc_guard(with_J ? KC_LINEARIZE : KC_ERROR);
   for (int t = 0; t < VUS_F_NTYPES; ++t) {
     FactorTable& T = h->ft[t];
     if (!T.n) continue;
@@ -127,6 +167,8 @@ void run_factors(vus_handle* h, int which, bool with_J, rt::stream_t st) {
     a.O.r = with_J ? T.r.p : nullptr;
     a.O.J = with_J ? T.J.p : nullptr;
     a.O.e2 = h->e_all.p + T.e_off;
+    const bool fused = with_J && t == VUS_F_STEREO && which == h->cur;
+    a.O.sE = fused ? h->E.p : nullptr; a.O.sPp = fused ? h->Pp.p : nullptr; a.O.sPl = fused ? h->Pl.p : nullptr;
     for (int i = 0; i < 6; ++i) a.K[i] = h->K[i];
     for (int i = 0; i < 3; ++i) a.g[i] = h->grav[i];
     a.type = t;
@@ -325,7 +367,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
   h->H0.alloc(h->hlen); h->H.alloc(h->hlen);
   h->g0.alloc(h->Lc); h->gs.alloc(h->L);
   h->F.alloc(h->Lc * 6); h->Hbb0.alloc(36); h->Hbb.alloc(36); h->gb.alloc(6);
-  h->C.alloc(9 * NL); h->gl.alloc(3 * NL); h->Cinv.alloc(9 * NL); h->E.alloc(18 * FS.n); h->W.alloc(18 * FS.n);
+  h->C.alloc(9 * NL); h->gl.alloc(3 * NL); h->Cinv.alloc(9 * NL); h->E.alloc(18 * FS.n); h->W.alloc(18 * FS.n); h->Pp.alloc(28 * FS.n); h->Pl.alloc(12 * FS.n);
   h->Dw.alloc(h->Ns * BB); h->U1.alloc(h->Ns * BB); h->U2.alloc(h->Ns * BB);
   h->Dinv.alloc(h->Ns * BB); h->Gl.alloc(h->Ns * BB); h->Gr.alloc(h->Ns * BB); h->GlT.alloc(h->Ns * BB); h->GrT.alloc(h->Ns * BB);
   h->Z.alloc(6 * h->Lc); h->SbInv.alloc(36);
@@ -334,7 +376,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
   h->scal.alloc(S_COUNT); h->scal.zero(st);
   h->red_grid = std::min<long>(std::max<long>(1, (std::max(h->L, h->nfactors) + 4095) / 4096), 2L * rt::sm_count());
   h->partials.alloc(h->red_grid);
-  h->bpart.alloc((size_t)h->red_grid * 36);
+  h->bpart.alloc((size_t)h->red_grid * 42);
   h->fail.alloc(1); h->fail.zero(st);
   long eoff = 0;
   for (int t = 0; t < VUS_F_NTYPES; ++t) {
@@ -364,22 +406,30 @@ void launch_asm(vus_handle* h, rt::stream_t st) {
 }
 
 void assemble_base(vus_handle* h, rt::stream_t st) {
+  ClassGuard kc_guard(KC_ASSEMBLE);
   h->H0.zero(st); h->g0.zero(st); h->F.zero(st); h->Hbb0.zero(st); h->gb.zero(st);
   launch_asm<VUS_F_PRIOR_POSE>(h, st);
   launch_asm<VUS_F_PRIOR_VEL>(h, st);
   launch_asm<VUS_F_BETWEEN>(h, st);
   launch_asm<VUS_F_DVL>(h, st);
   launch_asm<VUS_F_IMU>(h, st);
+  if (h->ft[VUS_F_IMU].n) {
+    FactorTable& I = h->ft[VUS_F_IMU];
+    ImuBiasArgs b; b.n = I.n; b.J = I.J.p; b.r = I.r.p; b.partials = h->bpart.p; b.grid = h->red_grid; b.Hbb = h->Hbb0.p; b.gb = h->gb.p;
+    L_coop<ImuBias1Body>(h->red_grid, 256, 256 * sizeof(double), st, b);
+    L_elem<ImuBias2Body>(42, st, b);
+  }
   FactorTable& S = h->ft[VUS_F_STEREO];
   if (S.n) {
+    ClassGuard kc_stereo(KC_STEREO_ASM);
     StereoAsmArgs a;
     a.n = S.n; a.idx = S.idx.p; a.J = S.J.p; a.r = S.r.p; a.D = h->D; a.k = h->k; a.B = h->B;
     a.SD = h->H0.p + h->sd_off; a.g = h->g0.p; a.C = h->C.p; a.gl = h->gl.p; a.E = h->E.p; a.nl = h->nvar[3];
     a.pose_ptr = h->pose_ptr.p; a.pose_obs = h->pose_obs.p; a.pose_ids = h->pose_ids.p; a.nposes_obs = h->nposes_obs;
     a.lm_ptr = h->lm_ptr.p; a.lm_obs = h->lm_obs.p;
-    L_elem<StereoPoseBody>(h->nposes_obs * 42, st, a);
+    a.Pp = h->Pp.p; a.Pl = h->Pl.p;
+    L_elem<StereoPoseBody>(h->nposes_obs * 28, st, a);
     L_elem<StereoLmBody>(h->nvar[3] * 12, st, a);
-    L_elem<StereoEBody>(S.n * 18, st, a);
   }
 }
 
@@ -397,6 +447,7 @@ SchurArgs schur_args(vus_handle* h, double lambda) {
 
 // damped + Schur-reduced system for this lambda
 void form_system(vus_handle* h, double lambda, rt::stream_t st) {
+  ClassGuard kc_guard(KC_SCHUR);
   rt::d2d(h->H.p, h->H0.p, h->hlen * sizeof(double), st);
   rt::d2d(h->Hbb.p, h->Hbb0.p, 36 * sizeof(double), st);
   rt::d2d(h->gs.p, h->g0.p, h->Lc * sizeof(double), st);
@@ -408,12 +459,12 @@ void form_system(vus_handle* h, double lambda, rt::stream_t st) {
     L_elem<LmInvertBody>(a.nl, st, a);
     L_elem<StereoWBody>(a.n * 18, st, a);
     L_elem<SchurGradBody>(h->nposes_obs * 6, st, a);
-    L_elem<SchurBlockBody>(h->ndst * 36, st, a);
+    L_elem<SchurBlockBody>(h->ndst, st, a);
   }
 }
 
 // ------------------------------------------------------------------ kernel 3 drivers
-size_t bcr_smem(int B) { return ((size_t)2 * B * B + 2 * B + 8) * sizeof(double); }
+size_t bcr_smem(int B) { return (size_t)bcr_smem_doubles(B) * sizeof(double); }
 
 BcrArgs bcr_args(vus_handle* h) {
   BcrArgs a;
@@ -424,6 +475,7 @@ BcrArgs bcr_args(vus_handle* h) {
 }
 
 void bcr_factor(vus_handle* h, rt::stream_t st) {
+  ClassGuard kc_guard(KC_BCR_FACTOR);
   const long BB = (long)h->B * h->B;
   rt::d2d(h->Dw.p, h->H.p + h->sd_off, h->Ns * BB * sizeof(double), st);
   BcrArgs a = bcr_args(h);
@@ -443,6 +495,7 @@ void bcr_factor(vus_handle* h, rt::stream_t st) {
 
 // in-place solve of the band system for nrhs vectors X[v*xstride + ...]
 void bcr_solve(vus_handle* h, double* X, long xstride, int nrhs, rt::stream_t st) {
+  ClassGuard kc_guard(KC_BCR_SOLVE);
   BcrArgs a = bcr_args(h);
   a.X = X; a.xstride = xstride; a.nrhs = nrhs;
   const size_t smem = (size_t)2 * nrhs * h->B * sizeof(double);
@@ -463,6 +516,7 @@ void bcr_solve(vus_handle* h, double* X, long xstride, int nrhs, rt::stream_t st
 }
 
 void border_dot(vus_handle* h, const double* Y, long ystride, int nv, rt::stream_t st) {
+  ClassGuard kc_guard(KC_BORDER);
   BorderDotArgs a; a.F = h->F.p; a.Y = Y; a.len = h->Lc; a.ystride = ystride; a.nv = nv; a.partials = h->bpart.p; a.grid = h->red_grid;
   L_coop<BorderDot1Body>(h->red_grid, 256, 256 * sizeof(double), st, a);
 }
@@ -495,6 +549,7 @@ void precond_apply(vus_handle* h, double* z, const double* r, rt::stream_t st) {
 
 // y = A x
 void apply_A(vus_handle* h, double* y, const double* x, rt::stream_t st) {
+  ClassGuard kc_guard(KC_MATVEC);
   MatvecArgs a;
   a.SD = h->H.p + h->sd_off; a.SU = h->H.p + h->su_off; a.Ns = h->Ns; a.B = h->B; a.x = x; a.y = y;
   a.rem_ptr = h->nrem ? h->rem_ptr.p : nullptr; a.rem_col = h->rem_col.p; a.rem_val = h->H.p + h->rem_off; a.nnodes = h->N; a.D = h->D;
@@ -623,6 +678,7 @@ void launch_linerr(vus_handle* h, rt::stream_t st) {
   L_elem<LinErrBody<T>>(F.n, st, a);
 }
 double linear_error(vus_handle* h, rt::stream_t st) {
+  ClassGuard kc_guard(KC_LINERR);
   launch_linerr<VUS_F_PRIOR_POSE>(h, st); launch_linerr<VUS_F_PRIOR_VEL>(h, st); launch_linerr<VUS_F_BETWEEN>(h, st);
   launch_linerr<VUS_F_DVL>(h, st); launch_linerr<VUS_F_STEREO>(h, st); launch_linerr<VUS_F_IMU>(h, st);
   reduce(h, h->le_all.p, nullptr, h->nfactors, S_TMP, RED_STORE, st);
@@ -630,6 +686,7 @@ double linear_error(vus_handle* h, rt::stream_t st) {
 }
 
 void retract(vus_handle* h, rt::stream_t st) {
+  ClassGuard kc_guard(KC_RETRACT);
   RetractArgs a;
   const int c = h->cur, t = 1 - h->cur;
   a.pose = h->val[c][0].p; a.pose_out = h->val[t][0].p; a.nx = h->nvar[0];
@@ -646,6 +703,8 @@ int optimize(vus_handle* h, rt::stream_t st) {
   R = vus_lm_result();
   const vus_lm_params& P = h->prm;
   const long launches0 = g_launches;
+  g_prof.reset();
+  g_prof.on = P.profile_kernels != 0;
   const double t_begin = now_ms();
   double lambda = P.lambda_initial;
   double err = graph_error(h, h->cur, st);
@@ -716,6 +775,9 @@ int optimize(vus_handle* h, rt::stream_t st) {
   R.final_lambda = lambda;
   R.ms_total = now_ms() - t_begin;
   R.kernel_launches = g_launches - launches0;
+  g_prof.collect();
+  g_prof.on = false;
+  for (int i = 0; i < 16; ++i) { R.ms_class[i] = g_prof.ms[i]; R.launches_class[i] = g_prof.count[i]; }
   return VUS_OK;
 }
 
@@ -734,7 +796,7 @@ extern "C" {
 void vus_default_lm_params(vus_lm_params* p) {
   p->max_iterations = 100; p->relative_error_tol = 1e-5; p->absolute_error_tol = 1e-5; p->error_tol = 0.0;
   p->lambda_initial = 1e-5; p->lambda_factor = 10.0; p->lambda_upper_bound = 1e5; p->lambda_lower_bound = 0.0;
-  p->min_model_fidelity = 1e-3; p->pcg_max_iterations = 500; p->pcg_rel_tol = 1e-12; p->max_supernode = 0; p->verbose = 0;
+  p->min_model_fidelity = 1e-3; p->pcg_max_iterations = 500; p->pcg_rel_tol = 1e-12; p->max_supernode = 0; p->verbose = 0; p->profile_kernels = 0;
 }
 
 int vus_create(int device, vus_handle** out) {
@@ -779,6 +841,31 @@ int vus_get_variables(vus_handle* h, int kind, double* out, int mem) {
   const size_t bytes = (size_t)kVarDim[kind] * h->nvar[kind] * sizeof(double);
   if (mem == VUS_MEM_HOST) rt::d2h(out, h->val[h->cur][kind].p, bytes, 0);
   else rt::d2d(out, h->val[h->cur][kind].p, bytes, 0);
+  rt::sync(0);
+  return VUS_OK;
+  VUS_CATCH(h)
+}
+
+int vus_save_values(vus_handle* h) {
+  if (!h) return VUS_ERR_INVALID;
+  VUS_TRY(h)
+  for (int kind = 0; kind < 4; ++kind) {
+    const size_t n = (size_t)kVarDim[kind] * h->nvar[kind];
+    h->saved[kind].alloc(n);
+    rt::d2d(h->saved[kind].p, h->val[h->cur][kind].p, n * sizeof(double), 0);
+  }
+  rt::sync(0);
+  h->has_saved = true;
+  return VUS_OK;
+  VUS_CATCH(h)
+}
+
+int vus_restore_values(vus_handle* h) {
+  if (!h) return VUS_ERR_INVALID;
+  if (!h->has_saved) return fail(h, VUS_ERR_STATE, "vus_restore_values: nothing saved");
+  VUS_TRY(h)
+  for (int kind = 0; kind < 4; ++kind)
+    rt::d2d(h->val[h->cur][kind].p, h->saved[kind].p, (size_t)kVarDim[kind] * h->nvar[kind] * sizeof(double), 0);
   rt::sync(0);
   return VUS_OK;
   VUS_CATCH(h)

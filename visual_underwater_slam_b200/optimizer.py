@@ -53,6 +53,7 @@ class LevenbergMarquardtParams:
         self.pcgMaxIterations = 500
         self.pcgRelTol = 1e-12
         self.maxSupernode = 0
+        self.profileKernels = False
 
     setMaxIterations, getMaxIterations = _set("maxIterations"), _get("maxIterations")
     setRelativeErrorTol, getRelativeErrorTol = _set("relativeErrorTol"), _get("relativeErrorTol")
@@ -88,6 +89,7 @@ class LevenbergMarquardtParams:
         p.pcg_max_iterations = int(self.pcgMaxIterations)
         p.pcg_rel_tol = float(self.pcgRelTol)
         p.max_supernode = int(self.maxSupernode)
+        p.profile_kernels = int(bool(self.profileKernels))
         p.verbose = {"SILENT": 0, "SUMMARY": 1, "TERMINATION": 1, "LAMBDA": 1, "TRYLAMBDA": 1, "TRYCONFIG": 2,
                      "DAMPED": 2, "TRYDELTA": 2}.get(str(self.verbosityLM).upper(), 0)
         return p
@@ -221,6 +223,12 @@ class Session:
         res = LmResult()
         self._check(self.lib.vus_optimize(self._h, stream, C.byref(res)))
         return res.as_dict()
+
+    def save_values(self):
+        self._check(self.lib.vus_save_values(self._h))
+
+    def restore_values(self):
+        self._check(self.lib.vus_restore_values(self._h))
 
     def time_linearize(self, reps=10, stream=None):
         v = C.c_double()

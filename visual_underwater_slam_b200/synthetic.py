@@ -97,7 +97,7 @@ def _trajectory(t):
 
 def make_trajectory_graph(n_poses, seed=1, n_landmarks=0, obs_per_landmark=10, n_loops=0,
                           noise_scale=1.0, pixel_noise=None, true_bias=True, drift=True,
-                          loop_min_gap=200, key_offset=0):
+                          loop_min_gap=200, key_offset=0, drift_scale=1.0):
     """C1/C2/C3/C4-style graph. Returns dict(graph, initial, truth, meta).
 
     noise_scale=0 gives an exactly consistent (zero-residual-at-truth) known-answer problem.
@@ -148,7 +148,7 @@ def make_trajectory_graph(n_poses, seed=1, n_landmarks=0, obs_per_landmark=10, n
     Rrel = np.swapaxes(R_kf[:-1], 1, 2) @ R_kf[1:]
     trel = np.einsum('nji,nj->ni', R_kf[:-1], p_kf[1:] - p_kf[:-1])
     if drift and noise_scale > 0:
-        xi = rng.standard_normal((n - 1, 6)) * np.array([0.002] * 3 + [0.01] * 3) * noise_scale
+        xi = rng.standard_normal((n - 1, 6)) * np.array([0.002] * 3 + [0.01] * 3) * noise_scale * drift_scale
         dR, dt_ = _pose_exp(xi)
         trel = trel + np.einsum('nij,nj->ni', Rrel, dt_)
         Rrel = Rrel @ dR
@@ -303,8 +303,8 @@ def make_pose_graph(n_poses, seed=5, n_loops=None, noise_scale=1.0):
 
 CONFIGS = {
     "C1": dict(n_poses=2000, seed=1, n_loops=50),
-    "C2": dict(n_poses=5000, seed=2, n_landmarks=20000),
-    "C3": dict(n_poses=100000, seed=3, n_landmarks=200000),
+    "C2": dict(n_poses=5000, seed=2, n_landmarks=20000, pixel_noise=1.0, drift_scale=0.1),
+    "C3": dict(n_poses=100000, seed=3, n_landmarks=200000, pixel_noise=1.0, drift_scale=0.1),
 }
 
 
