@@ -130,6 +130,10 @@ int vus_linearize(vus_handle* h, void* stream, int type, double* r_out, double* 
  * solves (J^T J + lambda I) delta = -J^T r; delta_pose [nx][6], delta_vel [nv][3], delta_bias [nb][6], delta_lm [nl][3] (host, AoS) */
 int vus_solve_step(vus_handle* h, void* stream, double lambda, double* d_pose, double* d_vel, double* d_bias, double* d_lm,
                    int32_t* pcg_iterations);
+/* test hook for the band solver (kernel 3b): linearize + assemble + damp/Schur at the current values, copy out the
+ * block-tridiagonal band (SD [Ns][B][B], SU [Ns-1][B][B], host, may be NULL), factor it by block cyclic reduction and
+ * solve nrhs right-hand sides in place (x_inout [nrhs][Ns*B], host).  Returns 1 if a pivot was not positive. */
+int vus_debug_band_solve(vus_handle* h, void* stream, double lambda, double* SD_out, double* SU_out, double* x_inout, int nrhs);
 /* time `reps` launches of kernel 1 (linearize, all factor types) with CUDA events; ms per repetition */
 int vus_time_linearize(vus_handle* h, void* stream, int reps, double* ms_per_rep);
 

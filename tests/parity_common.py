@@ -87,3 +87,29 @@ def check_lm_parity(lib, prob, params=None):
         return res, info
     finally:
         s.close()
+
+
+def check_band_solve(lib, prob, lam, nrhs=3, tol=1e-5, params=None):
+    """Kernel 3b alone: block cyclic reduction of the damped block-tridiagonal band vs a dense LAPACK solve of the
+    same band (read back from the device)."""
+    s = Session(prob, params, lib=lib)
+    try:
+        lay = s.layout()
+        Ns, B = lay["Ns"], lay["B"]
+        rhs = np.random.default_rng(0).standard_normal((nrhs, Ns * B))
+        SD, SU, x, failed = s.debug_band_solve(lam, rhs)
+        assert not failed
+        n = Ns * B
+        A = np.zeros((n, n))
+        for I in range(Ns):
+            A[I * B:(I + 1) * B, I * B:(I + 1) * B] = SD[I]
+            if I + 1 < Ns:
+                A[I * B:(I + 1) * B, (I + 1) * B:(I + 2) * B] = SU[I]
+                A[(I + 1) * B:(I + 2) * B, I * B:(I + 1) * B] = SU[I].T
+        assert np.abs(A - A.T).max() <= 1e-12 * np.abs(A).max()
+        xr = np.linalg.solve(A, rhs.T).T
+        err = np.linalg.norm(x - xr) / np.linalg.norm(xr)
+        assert err <= tol, err
+        return err
+    finally:
+        s.close()

@@ -27,6 +27,13 @@ def test_factor_parity_stereo(emu):
     pc.check_factor_parity(emu, prob)
 
 
+def test_band_solve(emu):
+    _, prob = pc.make(40)
+    pc.check_band_solve(emu, prob, 1e-3, nrhs=6)
+    _, prob = pc.make(30, n_lm=60)
+    pc.check_band_solve(emu, prob, 1e-3, nrhs=2)
+
+
 def test_solve_chain_is_exact(emu):
     _, prob = pc.make(70)
     its = pc.check_solve_parity(emu, prob, 1e-3, 1e-6)

@@ -38,6 +38,26 @@ def test_factor_parity_cheirality(lib):
     pc.check_factor_parity(lib, prob)
 
 
+def test_band_solve_small_blocks(lib):
+    """B = 9 (one pose per supernode), many reduction levels"""
+    _, prob = pc.make(150)
+    pc.check_band_solve(lib, prob, 1e-3, nrhs=6)
+
+
+def test_band_solve_supernodes(lib):
+    """B = 81 (nine poses per supernode: stereo tracks of 10 consecutive poses), DMMA tiles with padding"""
+    _, prob = pc.make(100, n_lm=300)
+    pc.check_band_solve(lib, prob, 1e-3, nrhs=1)
+    pc.check_band_solve(lib, prob, 1e-5, nrhs=6)
+
+
+def test_solve_short_chain_weak_bias(lib):
+    """20-100 poses: the shared bias is barely observable, its Schur complement cancels to ~1e-8 of its terms"""
+    for n in (20, 100):
+        _, prob = pc.make(n)
+        assert pc.check_solve_parity(lib, prob, 1e-3, 1e-5) <= 3
+
+
 def test_solve_chain_is_exact(lib):
     _, prob = pc.make(500)
     assert pc.check_solve_parity(lib, prob, 1e-3, 1e-6) <= 2

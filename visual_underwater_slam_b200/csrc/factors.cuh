@@ -38,7 +38,7 @@ struct LinOut {
   double* J;   // [m*ncols][n] whitened Jacobian (may be null)
   double* e2;  // [n] 0.5*||r||^2 (may be null)
   // stereo only (fused assembly products, may be null):
-  double* sE;  // [18][n]  E_o = Jp^T Jl (6x3 row-major), component-major
+  double* sE;  // [n][18]  E_o = Jp^T Jl (6x3 row-major), one 144-byte record per observation
   double* sPp; // [n][28]  per-observation pose products: 21 unique Jp^T Jp (a<=b) | 6 Jp^T r | pad
   double* sPl; // [n][12]  per-observation landmark products: 6 unique Jl^T Jl | 3 Jl^T r | pad
 };
@@ -224,7 +224,7 @@ VUS_HD void f_stereo(const ValuesView& V, const FactorView& F, const LinOut& O, 
       for (int c = 0; c < 27; ++c) O.J[c * n + f] = 0.0;
       if (O.sE) {
 #pragma unroll
-        for (int c = 0; c < 18; ++c) O.sE[c * n + f] = 0.0;
+        for (int c = 0; c < 18; ++c) O.sE[f * 18 + c] = 0.0;
 #pragma unroll
         for (int c = 0; c < 28; ++c) O.sPp[f * 28 + c] = 0.0;
 #pragma unroll
@@ -269,7 +269,7 @@ VUS_HD void f_stereo(const ValuesView& V, const FactorView& F, const LinOut& O, 
       for (int a = 0; a < 6; ++a)
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-          O.sE[(a * 3 + c) * n + f] = Jp[a] * Jl[c] + Jp[6 + a] * Jl[3 + c] + Jp[12 + a] * Jl[6 + c];
+          O.sE[f * 18 + a * 3 + c] = Jp[a] * Jl[c] + Jp[6 + a] * Jl[3 + c] + Jp[12 + a] * Jl[6 + c];
       double* Pp = O.sPp + f * 28;
       int q = 0;
 #pragma unroll

@@ -298,7 +298,7 @@ struct StereoAsmArgs {
   int D, k, B;
   double* SD; double* g;       // camera diag blocks / gradient
   double* C; double* gl;       // [9][nl], [3][nl]
-  double* E;                   // [18][n]   E_o = Jp^T Jl (6x3 row-major)
+  double* E;                   // [n][18]   E_o = Jp^T Jl (6x3 row-major)
   const double* Pp; const double* Pl;    // per-observation products written by the stereo linearize kernel
   long nl;
   const int* pose_ptr; const int* pose_obs; const int* pose_ids; long nposes_obs;   // CSR pose -> obs
@@ -348,18 +348,17 @@ struct StereoLmBody {
 // ------------------------------------------------------------------ per-lambda landmark Schur complement
 struct SchurArgs {
   long n; long nl;
-  const int* idx;                    // [2][n]
-  const double* C; const double* gl; // undamped landmark blocks
+  const int* idx;                    // [2][n] pose, landmark
+  const double* C; const double* gl; // undamped landmark blocks [9][nl], [3][nl]
   double* Cinv;                      // [9][nl]  (C + lambda I)^-1
-  const double* E; double* W;        // [18][n]  W_o = E_o Cinv
+  const double* E;                   // [n][18]  E_o = Jp^T Jl (6x3 row-major)
   double lambda;
   int D, k, B;
-  double* Hval;                      // damped system being formed
-  double* gs; const double* g;       // reduced gradient
+  double* SD; double* SU; double* REM;   // damped system being formed (Schur complement subtracted in place)
+  const int* rem_ptr; const int* rem_col;
+  double* gs;                        // reduced gradient (in/out)
   const int* pose_ptr; const int* pose_obs; const int* pose_ids; long nposes_obs;
   const int* lm_ptr; const int* lm_obs;
-  // destination lists
-  long ndst; const PairDst* dst; const int* dst_ptr; const int* term_a; const int* term_b;
   int* fail;
   // back-substitution
   const double* xc; double* xl;
@@ -382,59 +381,80 @@ struct LmInvertBody {    // per landmark
     for (int e = 0; e < 9; ++e) A.Cinv[e * A.nl + l] = inv[e];
   }
 };
-struct StereoWBody {     // per (obs, e<18): W_o[a][c] = sum_d E_o[a][d] Cinv[d][c]
-  static VUS_DEV void run(const SchurArgs& A, long w) {
-    const long o = w % A.n;
-    const int e = (int)(w / A.n);
-    const int a = e / 3, c = e % 3;
-    const long l = A.idx[A.n + o];
-    double s = 0.0;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) s += A.E[(a * 3 + d) * A.n + o] * A.Cinv[(d * 3 + c) * A.nl + l];
-    A.W[e * A.n + o] = s;
+// position of column `col` in the sorted remainder row of `node`, -1 if absent
+VUS_DEV int rem_find(const int* rem_ptr, const int* rem_col, long node, int col) {
+  int lo = rem_ptr[node], hi = rem_ptr[node + 1] - 1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    const int c = rem_col[mid];
+    if (c == col) return mid;
+    if (c < col) lo = mid + 1; else hi = mid - 1;
   }
-};
-struct SchurGradBody {   // per (pose-with-obs, a<6): gs -= sum_o W_o g_l
-  static VUS_DEV void run(const SchurArgs& A, long w) {
-    const long pi = w % A.nposes_obs;
-    const int a = (int)(w / A.nposes_obs);
-    const long node = A.pose_ids[pi];
-    double s = 0.0;
-    for (int t = A.pose_ptr[pi]; t < A.pose_ptr[pi + 1]; ++t) {
-      const long o = A.pose_obs[t];
-      const long l = A.idx[A.n + o];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) s += A.W[(a * 3 + c) * A.n + o] * A.gl[c * A.nl + l];
-    }
-    A.gs[node * A.D + a] -= s;
-  }
-};
-struct SchurBlockBody {  // per destination (i<=j): S_(i,j) -= sum_terms W_a E_b^T   (6x6, all 36 outputs in registers)
-  static VUS_DEV void run(const SchurArgs& A, long d) {
-    double acc[36];
-#pragma unroll
-    for (int e = 0; e < 36; ++e) acc[e] = 0.0;
-    for (int t = A.dst_ptr[d]; t < A.dst_ptr[d + 1]; ++t) {
-      const long oa = A.term_a[t], ob = A.term_b[t];
-      double w[18], eb[18];
-#pragma unroll
-      for (int e = 0; e < 18; ++e) { w[e] = A.W[e * A.n + oa]; eb[e] = A.E[e * A.n + ob]; }
-#pragma unroll
-      for (int r = 0; r < 6; ++r)
-#pragma unroll
-        for (int s = 0; s < 6; ++s)
-          acc[r * 6 + s] += w[r * 3] * eb[s * 3] + w[r * 3 + 1] * eb[s * 3 + 1] + w[r * 3 + 2] * eb[s * 3 + 2];
-    }
-    const PairDst D = A.dst[d];
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-      for (int s = 0; s < 6; ++s) {
-        const double v = acc[r * 6 + s];
-        if (D.transposed) A.Hval[D.off + (long)s * D.ld + r] -= v;
-        else A.Hval[D.off + (long)r * D.ld + s] -= v;
-        if (D.moff >= 0) A.Hval[D.moff + (long)s * D.mld + r] -= v;
+  return -1;
+}
+// One CTA per pose i that has observations.  Thread rs = (r,s) owns element (r,s) of every 6x6 block S(i,j), j >= i:
+//   S(i,j) -= sum over landmarks l seen from both i and j of (E_o Cinv_l) E_o'^T ,   gs_i -= sum_o (E_o Cinv_l) gl_l
+// walking pose i's observations and, per landmark, its (pose-sorted) observation list.  In-band blocks (same or next
+// supernode, j - i < 2k) accumulate in shared memory and are written once; off-band blocks go straight to REM.
+// Each block (i,j) and its mirror are written by this CTA only: no atomics, deterministic summation order.
+struct SchurPoseBody {
+  static VUS_DEV void run(const SchurArgs& A, int pi, int tid, int nthr, double* sm) {
+    const long i = A.pose_ids[pi];
+    const int D = A.D, k = A.k, B = A.B;
+    const long BB = (long)B * B;
+    const int ndj = 2 * k;
+    double* acc = sm;                 // [ndj][36]
+    double* touched = sm + ndj * 36;  // [ndj]
+    for (int e = tid; e < ndj * 37; e += nthr) sm[e] = 0.0;
+    VUS_SYNC();
+    const long I = i / k;
+    const int ri = (int)(i - I * k);
+    for (int rs = tid; rs < 36; rs += nthr) {
+      const int r = rs / 6, s = rs - r * 6;
+      double gacc = 0.0;
+      for (int t = A.pose_ptr[pi]; t < A.pose_ptr[pi + 1]; ++t) {
+        const long o = A.pose_obs[t];
+        const long l = A.idx[A.n + o];
+        const double e0 = A.E[o * 18 + r * 3], e1 = A.E[o * 18 + r * 3 + 1], e2 = A.E[o * 18 + r * 3 + 2];
+        const double w0 = e0 * A.Cinv[l] + e1 * A.Cinv[3 * A.nl + l] + e2 * A.Cinv[6 * A.nl + l];
+        const double w1 = e0 * A.Cinv[A.nl + l] + e1 * A.Cinv[4 * A.nl + l] + e2 * A.Cinv[7 * A.nl + l];
+        const double w2 = e0 * A.Cinv[2 * A.nl + l] + e1 * A.Cinv[5 * A.nl + l] + e2 * A.Cinv[8 * A.nl + l];
+        if (s == 0) gacc += w0 * A.gl[l] + w1 * A.gl[A.nl + l] + w2 * A.gl[2 * A.nl + l];
+        for (int q = A.lm_ptr[l]; q < A.lm_ptr[l + 1]; ++q) {
+          const long o2 = A.lm_obs[q];
+          const long j = A.idx[o2];
+          if (j < i) continue;
+          const double v = w0 * A.E[o2 * 18 + s * 3] + w1 * A.E[o2 * 18 + s * 3 + 1] + w2 * A.E[o2 * 18 + s * 3 + 2];
+          const long J = j / k;
+          if (J <= I + 1) {
+            const int dj = (int)(j - i);
+            acc[dj * 36 + rs] += v;
+            if (rs == 0) touched[dj] = 1.0;
+          } else {                                   // off-band co-observation: remainder blocks (i,j) and (j,i)
+            const int t1 = rem_find(A.rem_ptr, A.rem_col, i, (int)j), t2 = rem_find(A.rem_ptr, A.rem_col, j, (int)i);
+            A.REM[(long)t1 * D * D + r * D + s] -= v;
+            A.REM[(long)t2 * D * D + s * D + r] -= v;
+          }
+        }
       }
+      if (s == 0) A.gs[i * D + r] -= gacc;
+    }
+    VUS_SYNC();
+    for (int e = tid; e < ndj * 36; e += nthr) {
+      const int dj = e / 36, rs = e - dj * 36;
+      if (touched[dj] == 0.0) continue;
+      const int r = rs / 6, s = rs - r * 6;
+      const long j = i + dj;
+      const long J = j / k;
+      const int rj = (int)(j - J * k);
+      const double v = acc[e];
+      if (J == I) {
+        A.SD[I * BB + (long)(ri * D + r) * B + rj * D + s] -= v;
+        if (dj) A.SD[I * BB + (long)(rj * D + s) * B + ri * D + r] -= v;
+      } else {
+        A.SU[I * BB + (long)(ri * D + r) * B + rj * D + s] -= v;
+      }
+    }
   }
 };
 struct LmBacksubBody {   // per landmark: xl = Cinv (gl - sum_o E_o^T xc[pose_o])
@@ -447,7 +467,7 @@ struct LmBacksubBody {   // per landmark: xl = Cinv (gl - sum_o E_o^T xc[pose_o]
       for (int a = 0; a < 6; ++a) {
         const double x = A.xc[node * A.D + a];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) t[c] -= A.E[(a * 3 + c) * A.n + o] * x;
+        for (int c = 0; c < 3; ++c) t[c] -= A.E[o * 18 + a * 3 + c] * x;
       }
     }
 #pragma unroll
@@ -476,55 +496,59 @@ struct DampBody {
 // =====================================================================================
 struct MatvecArgs {
   const double* SD; const double* SU; long Ns; int B;
-  const double* x; double* y;        // camera parts, length Ns*B
+  const double* x; double* y;        // camera parts, length Ns*B (per vector)
+  int nv; long xstride, ystride;     // nv vectors: x[v*xstride + i], y[v*ystride + i]
   // remainder
   const int* rem_ptr; const int* rem_col; const double* rem_val; long nnodes; int D;
   // border
   const double* F; const double* Hbb; const double* xb; double* yb; int has_bias;
 };
-// one CTA per supernode: y_I = SD_I x_I + SU_I x_{I+1} + SU_{I-1}^T x_{I-1}.  Blocks are staged in
-// shared memory with coalesced loads, then each thread owns one output row.
+// one CTA per supernode: y_I = SD_I x_I + SU_I x_{I+1} + SU_{I-1}^T x_{I-1} for nv vectors.  Blocks are staged in
+// shared memory with coalesced loads, then each thread owns one (vector, row) output.
 struct BandMatvecBody {
   static VUS_DEV void run(const MatvecArgs& A, int I, int tid, int nthr, double* sm) {
-    const int B = A.B;
+    const int B = A.B, nv = A.nv;
     const long BB = (long)B * B;
     double* M = sm;             // [B*B]
-    double* xs = sm + BB;       // [B]
-    double* acc = xs + B;       // [B]
-    for (int i = tid; i < B; i += nthr) acc[i] = 0.0;
+    double* xs = sm + BB;       // [nv][B]
+    double* acc = xs + nv * B;  // [nv][B]
+    for (int i = tid; i < nv * B; i += nthr) acc[i] = 0.0;
     // diagonal block (symmetric)
     for (long i = tid; i < BB; i += nthr) M[i] = A.SD[I * BB + i];
-    for (int i = tid; i < B; i += nthr) xs[i] = A.x[(long)I * B + i];
+    for (int i = tid; i < nv * B; i += nthr) xs[i] = A.x[(long)(i / B) * A.xstride + (long)I * B + (i % B)];
     VUS_SYNC();
-    for (int r = tid; r < B; r += nthr) {
+    for (int e = tid; e < nv * B; e += nthr) {
+      const int v = e / B, r = e - v * B;
       double s = 0.0;
-      for (int c = 0; c < B; ++c) s += M[(long)c * B + r] * xs[c];     // column r of a symmetric block
-      acc[r] += s;
+      for (int c = 0; c < B; ++c) s += M[(long)c * B + r] * xs[v * B + c];     // column r of a symmetric block
+      acc[e] += s;
     }
     VUS_SYNC();
     if (I + 1 < A.Ns) {
       for (long i = tid; i < BB; i += nthr) M[i] = A.SU[I * BB + i];
-      for (int i = tid; i < B; i += nthr) xs[i] = A.x[(long)(I + 1) * B + i];
+      for (int i = tid; i < nv * B; i += nthr) xs[i] = A.x[(long)(i / B) * A.xstride + (long)(I + 1) * B + (i % B)];
       VUS_SYNC();
-      for (int r = tid; r < B; r += nthr) {
+      for (int e = tid; e < nv * B; e += nthr) {
+        const int v = e / B, r = e - v * B;
         double s = 0.0;
-        for (int c = 0; c < B; ++c) s += M[(long)r * B + c] * xs[c];
-        acc[r] += s;
+        for (int c = 0; c < B; ++c) s += M[(long)r * B + c] * xs[v * B + c];
+        acc[e] += s;
       }
       VUS_SYNC();
     }
     if (I > 0) {
       for (long i = tid; i < BB; i += nthr) M[i] = A.SU[(I - 1) * BB + i];
-      for (int i = tid; i < B; i += nthr) xs[i] = A.x[(long)(I - 1) * B + i];
+      for (int i = tid; i < nv * B; i += nthr) xs[i] = A.x[(long)(i / B) * A.xstride + (long)(I - 1) * B + (i % B)];
       VUS_SYNC();
-      for (int r = tid; r < B; r += nthr) {
+      for (int e = tid; e < nv * B; e += nthr) {
+        const int v = e / B, r = e - v * B;
         double s = 0.0;
-        for (int c = 0; c < B; ++c) s += M[(long)c * B + r] * xs[c];
-        acc[r] += s;
+        for (int c = 0; c < B; ++c) s += M[(long)c * B + r] * xs[v * B + c];
+        acc[e] += s;
       }
       VUS_SYNC();
     }
-    for (int r = tid; r < B; r += nthr) A.y[(long)I * B + r] = acc[r];
+    for (int e = tid; e < nv * B; e += nthr) A.y[(long)(e / B) * A.ystride + (long)I * B + (e % B)] = acc[e];
   }
 };
 // per (node, row): remainder blocks + border column
@@ -572,305 +596,7 @@ struct BorderDot1Body {
   }
 };
 
-// =====================================================================================
-// Kernel 3b: block cyclic reduction of the supernode block-tridiagonal band
-// =====================================================================================
-// CTA-level dense helpers on BxB blocks (B <= 96), operands staged whole in shared memory.
-//   "A" operands: row stride B, bcr_rows_a(B) rows allocated (rows >= B are never initialised: they only feed
-//                 register-tile lanes whose results are discarded);
-//   "B" operands: row stride bcr_ldb(B) (multiple of 4 -> 16/32-byte aligned vector loads), B rows.
-VUS_HD int bcr_ldb(int B) { return (B + 3) & ~3; }
-VUS_HD int bcr_rows_a(int B) { return (B + 7) & ~7; }
-VUS_HD long bcr_smem_doubles(int B) { return (long)bcr_rows_a(B) * B + (long)B * bcr_ldb(B) + 4 * B + 8; }
-
-// In-place Gauss-Jordan inverse of an SPD block held in shared memory with row stride ld (no pivoting).
-#ifdef VUS_EMU
-// host emulation: plain sweep over the block in memory
-VUS_DEV void cta_spd_inverse(double* M, int ld, double* rowp, double* colp, int B, int tid, int nthr, int* fail) {
-  for (int p = 0; p < B; ++p) {
-    for (int i = tid; i < B; i += nthr) { colp[i] = M[(long)i * ld + p]; rowp[i] = M[(long)p * ld + i]; }
-    VUS_SYNC();
-    const double piv = rowp[p];
-    if (tid == 0 && !(piv > 0.0)) *fail = 1;
-    const double d = 1.0 / piv;
-    for (int i = tid; i < B; i += nthr) {
-      double* row = M + (long)i * ld;
-      if (i == p) { for (int j = 0; j < B; ++j) row[j] = (j == p) ? d : rowp[j] * d; }
-      else { const double ci = colp[i] * d; for (int j = 0; j < B; ++j) row[j] = (j == p) ? -ci : row[j] - ci * rowp[j]; }
-    }
-    VUS_SYNC();
-  }
-}
-#else
-// sm_100a: the block lives in REGISTERS for all B sweeps (thread (tx,ty) of a 256-thread CTA owns rows ty+8a, columns
-// tx+32b, a<12, b<3); only the pivot row / column travel through shared memory, double-buffered -> one barrier per sweep.
-VUS_DEV void cta_spd_inverse(double* M, int ld, double* rowp, double* colp, int B, int tid, int nthr, int* fail) {
-  const int tx = tid & 31, ty = tid >> 5;                  // requires nthr == 256 and rowp/colp of 2*B doubles each
-  double m[12][3];
-#pragma unroll
-  for (int a = 0; a < 12; ++a)
-#pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      const int i = ty + 8 * a, j = tx + 32 * b;
-      m[a][b] = (i < B && j < B) ? M[(long)i * ld + j] : 0.0;
-    }
-  for (int p = 0; p < B; ++p) {
-    double* rp = rowp + (p & 1) * B;
-    double* cp = colp + (p & 1) * B;
-    const int pa = p >> 3, pb = p >> 5;
-    if (ty == (p & 7)) {
-#pragma unroll
-      for (int a = 0; a < 12; ++a)
-        if (a == pa) {
-#pragma unroll
-          for (int b = 0; b < 3; ++b) { const int j = tx + 32 * b; if (j < B) rp[j] = m[a][b]; }
-        }
-    }
-    if (tx == (p & 31)) {
-#pragma unroll
-      for (int b = 0; b < 3; ++b)
-        if (b == pb) {
-#pragma unroll
-          for (int a = 0; a < 12; ++a) { const int i = ty + 8 * a; if (i < B) cp[i] = m[a][b]; }
-        }
-    }
-    __syncthreads();
-    const double piv = rp[p];
-    if (tid == 0 && !(piv > 0.0)) *fail = 1;
-    const double d = 1.0 / piv;
-    double r[3];
-#pragma unroll
-    for (int b = 0; b < 3; ++b) { const int j = tx + 32 * b; r[b] = (j < B) ? rp[j] : 0.0; }
-#pragma unroll
-    for (int a = 0; a < 12; ++a) {
-      const int i = ty + 8 * a;
-      if (i < B) {
-        const double ci = cp[i] * d;
-        if (i == p) {
-#pragma unroll
-          for (int b = 0; b < 3; ++b) m[a][b] = (tx + 32 * b == p) ? d : r[b] * d;
-        } else {
-#pragma unroll
-          for (int b = 0; b < 3; ++b) m[a][b] = (tx + 32 * b == p) ? -ci : m[a][b] - ci * r[b];
-        }
-      }
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int a = 0; a < 12; ++a)
-#pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      const int i = ty + 8 * a, j = tx + 32 * b;
-      if (i < B && j < B) M[(long)i * ld + j] = m[a][b];
-    }
-  __syncthreads();
-}
-#endif
-// C(global, row stride B) = beta*C + alpha * sA * sB, 8x4 register tiles, FP64 FMA pipe bound.
-// If CT != null also writes the transpose of the result.
-VUS_DEV void cta_gemm_ss(double* C, double* CT, const double* sA, const double* sB, int B, double alpha, double beta, int tid, int nthr) {
-  const int ldb = bcr_ldb(B);
-  const int TI = (B + 7) / 8, TJ = (B + 3) / 4;
-  for (int tile = tid; tile < TI * TJ; tile += nthr) {
-    const int i0 = (tile / TJ) * 8, j0 = (tile % TJ) * 4;
-    double acc[8][4];
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-    const double* pa = sA + (long)i0 * B;
-    const double* pb = sB + j0;
-#pragma unroll 3
-    for (int k = 0; k < B; ++k) {
-      double bv[4];
-#ifdef VUS_EMU
-      for (int b = 0; b < 4; ++b) bv[b] = pb[(long)k * ldb + b];
-#else
-      const double2 b01 = *reinterpret_cast<const double2*>(pb + (long)k * ldb);
-      const double2 b23 = *reinterpret_cast<const double2*>(pb + (long)k * ldb + 2);
-      bv[0] = b01.x; bv[1] = b01.y; bv[2] = b23.x; bv[3] = b23.y;
-#endif
-#pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        const double av = pa[(long)a * B + k];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] += av * bv[b];
-      }
-    }
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int i = i0 + a, j = j0 + b;
-        if (i < B && j < B) {
-          const long o = (long)i * B + j;
-          const double v = alpha * acc[a][b] + (beta != 0.0 ? beta * C[o] : 0.0);
-          C[o] = v;
-          if (CT) CT[(long)j * B + i] = v;
-        }
-      }
-  }
-}
-// stage a global BxB row-major block into shared memory with row stride ld, optionally transposed
-VUS_DEV void cta_load(double* s, int ld, const double* g, int B, bool transpose, int tid, int nthr) {
-  const int BB = B * B;
-  if (!transpose) for (int e = tid; e < BB; e += nthr) { const int i = e / B, j = e - i * B; s[(long)i * ld + j] = g[e]; }
-  else for (int e = tid; e < BB; e += nthr) { const int i = e / B, j = e - i * B; s[(long)j * ld + i] = g[e]; }
-}
-
-struct BcrArgs {
-  long Ns; int B; long s;          // level stride
-  double* Dw;                      // working diagonal blocks [Ns]
-  const double* Ucur; double* Unext;   // couplings at this level / next level, indexed by node id
-  double* Dinv; double* Gl; double* Gr; double* GlT; double* GrT;   // per eliminated node
-  int* fail;
-  // solve
-  double* X; long xstride; int nrhs;
-};
-// per eliminated node j = s*(2m+1): Dinv_j, Gl_j = U[j-s] Dinv_j, Gr_j = U[j]^T Dinv_j  (+ transposed copies)
-struct BcrElimBody {
-  static VUS_DEV void run(const BcrArgs& A, int m, int tid, int nthr, double* sm) {
-    const int B = A.B, ldb = bcr_ldb(B);
-    const long BB = (long)B * B;
-    const long j = A.s * (2L * m + 1);
-    double* sA = sm;                                   // "A" operand (row stride B)
-    double* sX = sm + (long)bcr_rows_a(B) * B;         // Dinv as "B" operand (row stride ldb)
-    double* rowp = sX + (long)B * ldb;
-    double* colp = rowp + 2 * B;
-    cta_load(sX, ldb, A.Dw + j * BB, B, false, tid, nthr);
-    VUS_SYNC();
-    cta_spd_inverse(sX, ldb, rowp, colp, B, tid, nthr, A.fail);
-    for (long e = tid; e < BB; e += nthr) { const int i = (int)(e / B), c = (int)(e - (long)i * B); A.Dinv[j * BB + e] = sX[(long)i * ldb + c]; }
-    cta_load(sA, B, A.Ucur + (j - A.s) * BB, B, false, tid, nthr);
-    VUS_SYNC();
-    cta_gemm_ss(A.Gl + j * BB, A.GlT + j * BB, sA, sX, B, 1.0, 0.0, tid, nthr);
-    VUS_SYNC();
-    if (j + A.s < A.Ns) {
-      cta_load(sA, B, A.Ucur + j * BB, B, true, tid, nthr);
-      VUS_SYNC();
-      cta_gemm_ss(A.Gr + j * BB, A.GrT + j * BB, sA, sX, B, 1.0, 0.0, tid, nthr);
-    }
-  }
-};
-// per surviving node c = 2*m*s: Dw_c -= Gr_{c-s} U_{c-s} + Gl_{c+s} U_c^T ; Unext_c = -Gl_{c+s} U_{c+s}
-struct BcrUpdateBody {
-  static VUS_DEV void run(const BcrArgs& A, int m, int tid, int nthr, double* sm) {
-    const int B = A.B, ldb = bcr_ldb(B);
-    const long BB = (long)B * B;
-    const long c = 2L * m * A.s;
-    double* sA = sm;
-    double* sB = sm + (long)bcr_rows_a(B) * B;
-    if (c - A.s >= 0) {
-      const long j = c - A.s;
-      cta_load(sA, B, A.Gr + j * BB, B, false, tid, nthr);
-      cta_load(sB, ldb, A.Ucur + j * BB, B, false, tid, nthr);
-      VUS_SYNC();
-      cta_gemm_ss(A.Dw + c * BB, nullptr, sA, sB, B, -1.0, 1.0, tid, nthr);
-      VUS_SYNC();
-    }
-    if (c + A.s < A.Ns) {
-      const long j = c + A.s;
-      cta_load(sA, B, A.Gl + j * BB, B, false, tid, nthr);
-      cta_load(sB, ldb, A.Ucur + c * BB, B, true, tid, nthr);
-      VUS_SYNC();
-      cta_gemm_ss(A.Dw + c * BB, nullptr, sA, sB, B, -1.0, 1.0, tid, nthr);
-      VUS_SYNC();
-      if (j + A.s < A.Ns) {
-        cta_load(sB, ldb, A.Ucur + j * BB, B, false, tid, nthr);
-        VUS_SYNC();
-        cta_gemm_ss(A.Unext + c * BB, nullptr, sA, sB, B, -1.0, 0.0, tid, nthr);
-      }
-    }
-  }
-};
-// root: Dinv_0 = inv(Dw_0)
-struct BcrRootBody {
-  static VUS_DEV void run(const BcrArgs& A, int, int tid, int nthr, double* sm) {
-    const int B = A.B, ldb = bcr_ldb(B);
-    const long BB = (long)B * B;
-    double* sX = sm + (long)bcr_rows_a(B) * B;
-    double* rowp = sX + (long)B * ldb;
-    double* colp = rowp + 2 * B;
-    cta_load(sX, ldb, A.Dw, B, false, tid, nthr);
-    VUS_SYNC();
-    cta_spd_inverse(sX, ldb, rowp, colp, B, tid, nthr, A.fail);
-    for (long e = tid; e < BB; e += nthr) { const int i = (int)(e / B), c = (int)(e - (long)i * B); A.Dinv[e] = sX[(long)i * ldb + c]; }
-  }
-};
-// forward sweep, per surviving node c: b_c -= Gr_{c-s} b_{c-s} + Gl_{c+s} b_{c+s}   (reads the transposed copies: coalesced)
-struct BcrFwdBody {
-  static VUS_DEV void run(const BcrArgs& A, int m, int tid, int nthr, double* sm) {
-    const int B = A.B;
-    const long BB = (long)B * B;
-    const long c = 2L * m * A.s;
-    double* xs = sm;   // [nrhs][B] neighbour rhs
-    for (int side = 0; side < 2; ++side) {
-      const long j = side == 0 ? c - A.s : c + A.s;
-      if (j < 0 || j >= A.Ns) continue;
-      const double* GT = (side == 0 ? A.GrT : A.GlT) + j * BB;
-      for (int e = tid; e < A.nrhs * B; e += nthr) xs[e] = A.X[(long)(e / B) * A.xstride + j * B + (e % B)];
-      VUS_SYNC();
-      for (int e = tid; e < A.nrhs * B; e += nthr) {
-        const int v = e / B, r = e % B;
-        double s = 0.0;
-        for (int k = 0; k < B; ++k) s += GT[(long)k * B + r] * xs[v * B + k];
-        A.X[(long)v * A.xstride + c * B + r] -= s;
-      }
-      VUS_SYNC();
-    }
-  }
-};
-// backward sweep, per eliminated node j: x_j = Dinv_j b_j - Gl_j^T x_{j-s} - Gr_j^T x_{j+s}
-struct BcrBwdBody {
-  static VUS_DEV void run(const BcrArgs& A, int m, int tid, int nthr, double* sm) {
-    const int B = A.B;
-    const long BB = (long)B * B;
-    const long j = A.s * (2L * m + 1);
-    double* xs = sm;                 // [nrhs][B]
-    double* out = sm + A.nrhs * B;   // [nrhs][B]
-    for (int e = tid; e < A.nrhs * B; e += nthr) xs[e] = A.X[(long)(e / B) * A.xstride + j * B + (e % B)];
-    VUS_SYNC();
-    for (int e = tid; e < A.nrhs * B; e += nthr) {
-      const int v = e / B, r = e % B;
-      double s = 0.0;
-      const double* Di = A.Dinv + j * BB;
-      for (int k = 0; k < B; ++k) s += Di[(long)k * B + r] * xs[v * B + k];     // symmetric
-      out[e] = s;
-    }
-    VUS_SYNC();
-    for (int side = 0; side < 2; ++side) {
-      const long nb = side == 0 ? j - A.s : j + A.s;
-      if (nb < 0 || nb >= A.Ns) continue;
-      const double* G = (side == 0 ? A.Gl : A.Gr) + j * BB;
-      for (int e = tid; e < A.nrhs * B; e += nthr) xs[e] = A.X[(long)(e / B) * A.xstride + nb * B + (e % B)];
-      VUS_SYNC();
-      for (int e = tid; e < A.nrhs * B; e += nthr) {
-        const int v = e / B, r = e % B;
-        double s = 0.0;
-        for (int k = 0; k < B; ++k) s += G[(long)k * B + r] * xs[v * B + k];    // (G^T x)[r]
-        out[e] -= s;
-      }
-      VUS_SYNC();
-    }
-    for (int e = tid; e < A.nrhs * B; e += nthr) A.X[(long)(e / B) * A.xstride + j * B + (e % B)] = out[e];
-  }
-};
-// root solve: x_0 = Dinv_0 b_0
-struct BcrRootSolveBody {
-  static VUS_DEV void run(const BcrArgs& A, int, int tid, int nthr, double* sm) {
-    const int B = A.B;
-    double* xs = sm;
-    for (int e = tid; e < A.nrhs * B; e += nthr) xs[e] = A.X[(long)(e / B) * A.xstride + (e % B)];
-    VUS_SYNC();
-    for (int e = tid; e < A.nrhs * B; e += nthr) {
-      const int v = e / B, r = e % B;
-      double s = 0.0;
-      for (int k = 0; k < B; ++k) s += A.Dinv[(long)k * B + r] * xs[v * B + k];
-      A.X[(long)v * A.xstride + r] = s;
-    }
-  }
-};
+// Kernel 3b (block cyclic reduction of the band) lives in bcr.cuh
 
 // =====================================================================================
 // small dense bias-border algebra (one thread)
@@ -954,14 +680,26 @@ struct SubZxbBody {     // y[i] = x[i] - sum_c Z_c[i] xb[c]
     A.y[i] = s;
   }
 };
+// R_c[i] = F[i][c] - Y_c[i]  (residual of the border columns, for one step of iterative refinement of Z = M^-1 F)
+struct BorderResidBody {
+  static VUS_DEV void run(const struct BorderColsArgs& A, long w);
+};
 // Z_c[i] = F[i][c]  (border columns as right-hand sides)
-struct BorderColsArgs { const double* F; double* Z; long len; long zstride; };
+struct BorderColsArgs { const double* F; double* Z; long len; long zstride; double* R; };
 struct BorderColsBody {
   static VUS_DEV void run(const BorderColsArgs& A, long w) {
     const long i = w % A.len;
     const int c = (int)(w / A.len);
     A.Z[(long)c * A.zstride + i] = A.F[i * 6 + c];
   }
+};
+VUS_DEV void BorderResidBody::run(const BorderColsArgs& A, long w) {
+  const long i = w % A.len;
+  const int c = (int)(w / A.len);
+  A.R[(long)c * A.zstride + i] = A.F[i * 6 + c] - A.R[(long)c * A.zstride + i];
+}
+struct AddVecBody {     // y[i] += x[i]
+  static VUS_DEV void run(const VecArgs& A, long i) { A.y[i] += A.x[i]; }
 };
 
 // =====================================================================================
@@ -1009,3 +747,5 @@ struct RetractBody {    // work items: nx poses, then nv velocities, then nl lan
 };
 
 }  // namespace vus
+
+#include "bcr.cuh"

@@ -55,8 +55,10 @@ template <class Body, class Args>
 __global__ void __launch_bounds__(256) k_elem(Args a, long n) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) Body::run(a, i);
 }
+// per-body launch bounds (specialise for register-heavy cooperative bodies that must keep 2 CTAs per SM)
+template <class Body> struct CoopBounds { static constexpr int kMaxThreads = 1024, kMinBlocks = 1; };
 template <class Body, class Args>
-__global__ void k_coop(Args a) {
+__global__ void __launch_bounds__(CoopBounds<Body>::kMaxThreads, CoopBounds<Body>::kMinBlocks) k_coop(Args a) {
   extern __shared__ double vus_smem[];
   Body::run(a, (int)blockIdx.x, (int)threadIdx.x, (int)blockDim.x, vus_smem);
 }

@@ -4,8 +4,8 @@
 // (call site batch.py:337).  Host code here only sequences kernels and takes the accept/reject
 // decisions from device-computed scalars; all arithmetic on graph data is in kernels.cuh.
 #include "../../include/vus.h"
-#include "kernels.cuh"
 #include "rt.h"
+#include "kernels.cuh"
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -112,12 +112,11 @@ struct vus_handle {
   DBuf<int> rem_ptr, rem_col;
   DBuf<double> g0, gs, F, Hbb0, Hbb, gb;     // gs = [reduced camera gradient ; gb] (length L)
   // stereo
-  long nobs = 0, nposes_obs = 0, ndst = 0;
-  DBuf<int> pose_ptr, pose_obs, pose_ids, lm_ptr, lm_obs, dst_ptr, term_a, term_b;
-  DBuf<PairDst> dst;
-  DBuf<double> C, gl, Cinv, E, W, Pp, Pl;
+  long nobs = 0, nposes_obs = 0;
+  DBuf<int> pose_ptr, pose_obs, pose_ids, lm_ptr, lm_obs;
+  DBuf<double> C, gl, Cinv, E, Pp, Pl;
   // BCR
-  DBuf<double> Dw, U1, U2, Dinv, Gl, Gr, GlT, GrT, Z, SbInv;
+  DBuf<double> Dw, U1, U2, Dinv, Gl, Gr, Z, Zr, SbInv;
   // PCG
   DBuf<double> x, r, z, p, Ap, d, xl, scal, partials, bpart, e_all, le_all;
   DBuf<int> fail;
@@ -300,9 +299,12 @@ int analyze(vus_handle* h, rt::stream_t st) {
   auto add_rem = [&](long p, long q) { if (p != q && !inband(p, q)) { rem_index[{p, q}] = 0; rem_index[{q, p}] = 0; } };
   for (long f = 0; f < FB.n; ++f) add_rem(FB.h_idx[f], FB.h_idx[FB.n + f]);
   for (long f = 0; f < FI.n; ++f) add_rem(FI.h_idx[f], FI.h_idx[2 * FI.n + f]);
-  for (long l = 0; l < NL; ++l)
+  for (long l = 0; l < NL; ++l) {
+    const long pf = FS.h_idx[lm_obs[lm_ptr[l]]], pl = FS.h_idx[lm_obs[lm_ptr[l + 1] - 1]];   // observations are pose-sorted
+    if (pl / k - pf / k <= 1) continue;                 // whole track inside the band
     for (int a = lm_ptr[l]; a < lm_ptr[l + 1]; ++a)
       for (int b = a + 1; b < lm_ptr[l + 1]; ++b) add_rem(FS.h_idx[lm_obs[a]], FS.h_idx[lm_obs[b]]);
+  }
   std::vector<int> rem_ptr(NX + 1, 0), rem_col;
   {
     long id = 0;
@@ -327,39 +329,6 @@ int analyze(vus_handle* h, rt::stream_t st) {
   };
   if (FB.n && !build_pairs(FB, 0, 1)) return VUS_ERR_INVALID;
   if (FI.n && !build_pairs(FI, 0, 2)) return VUS_ERR_INVALID;
-  // ---- Schur destination lists: unique (i<=j) pose pairs per landmark track
-  {
-    struct Term { long i, j; int a, b; };
-    std::vector<Term> terms;
-    terms.reserve((size_t)FS.n * 6);
-    for (long l = 0; l < NL; ++l)
-      for (int a = lm_ptr[l]; a < lm_ptr[l + 1]; ++a)
-        for (int b = a; b < lm_ptr[l + 1]; ++b) {
-          const int oa = lm_obs[a], ob = lm_obs[b];
-          const long i = FS.h_idx[oa], j = FS.h_idx[ob];   // i <= j (sorted by pose)
-          terms.push_back({i, j, oa, ob});
-          if (i == j && oa != ob) terms.push_back({i, j, ob, oa});
-        }
-    std::stable_sort(terms.begin(), terms.end(), [](const Term& x, const Term& y) { return x.i != y.i ? x.i < y.i : x.j < y.j; });
-    std::vector<PairDst> dst;
-    std::vector<int> dst_ptr(1, 0), ta(terms.size()), tb(terms.size());
-    for (size_t t = 0; t < terms.size(); ++t) {
-      if (t == 0 || terms[t].i != terms[t - 1].i || terms[t].j != terms[t - 1].j) {
-        if (t) dst_ptr.push_back((int)t);
-        PairDst d;
-        if (terms[t].i == terms[t].j) {
-          d.off = h->sd_off + diag_off(terms[t].i, 0, 0, D, k, h->B); d.ld = h->B; d.transposed = 0; d.moff = -1; d.mld = 0; d.pad = 0;
-        } else {
-          d = band_dst(h, terms[t].i, terms[t].j, rem_index);
-        }
-        dst.push_back(d);
-      }
-      ta[t] = terms[t].a; tb[t] = terms[t].b;
-    }
-    if (!terms.empty()) dst_ptr.push_back((int)terms.size());
-    h->ndst = (long)dst.size();
-    h->dst.upload(dst, st); h->dst_ptr.upload(dst_ptr, st); h->term_a.upload(ta, st); h->term_b.upload(tb, st);
-  }
   // ---- uploads / allocations
   h->rem_ptr.upload(rem_ptr, st); h->rem_col.upload(rem_col, st);
   h->pose_ptr.upload(pose_ptr, st); h->pose_obs.upload(pose_obs, st); h->pose_ids.upload(pose_ids, st);
@@ -367,10 +336,10 @@ int analyze(vus_handle* h, rt::stream_t st) {
   h->H0.alloc(h->hlen); h->H.alloc(h->hlen);
   h->g0.alloc(h->Lc); h->gs.alloc(h->L);
   h->F.alloc(h->Lc * 6); h->Hbb0.alloc(36); h->Hbb.alloc(36); h->gb.alloc(6);
-  h->C.alloc(9 * NL); h->gl.alloc(3 * NL); h->Cinv.alloc(9 * NL); h->E.alloc(18 * FS.n); h->W.alloc(18 * FS.n); h->Pp.alloc(28 * FS.n); h->Pl.alloc(12 * FS.n);
+  h->C.alloc(9 * NL); h->gl.alloc(3 * NL); h->Cinv.alloc(9 * NL); h->E.alloc(18 * FS.n); h->Pp.alloc(28 * FS.n); h->Pl.alloc(12 * FS.n);
   h->Dw.alloc(h->Ns * BB); h->U1.alloc(h->Ns * BB); h->U2.alloc(h->Ns * BB);
-  h->Dinv.alloc(h->Ns * BB); h->Gl.alloc(h->Ns * BB); h->Gr.alloc(h->Ns * BB); h->GlT.alloc(h->Ns * BB); h->GrT.alloc(h->Ns * BB);
-  h->Z.alloc(6 * h->Lc); h->SbInv.alloc(36);
+  h->Dinv.alloc(h->Ns * BB); h->Gl.alloc(h->Ns * BB); h->Gr.alloc(h->Ns * BB);
+  h->Z.alloc(6 * h->Lc); h->Zr.alloc(6 * h->Lc); h->SbInv.alloc(36);
   h->x.alloc(h->L); h->d.alloc(h->L); h->r.alloc(h->L); h->z.alloc(h->L); h->p.alloc(h->L); h->Ap.alloc(h->L);
   h->xl.alloc(3 * NL);
   h->scal.alloc(S_COUNT); h->scal.zero(st);
@@ -436,11 +405,12 @@ void assemble_base(vus_handle* h, rt::stream_t st) {
 SchurArgs schur_args(vus_handle* h, double lambda) {
   FactorTable& S = h->ft[VUS_F_STEREO];
   SchurArgs a;
-  a.n = S.n; a.nl = h->nvar[3]; a.idx = S.idx.p; a.C = h->C.p; a.gl = h->gl.p; a.Cinv = h->Cinv.p; a.E = h->E.p; a.W = h->W.p;
-  a.lambda = lambda; a.D = h->D; a.k = h->k; a.B = h->B; a.Hval = h->H.p; a.gs = h->gs.p; a.g = h->g0.p;
+  a.n = S.n; a.nl = h->nvar[3]; a.idx = S.idx.p; a.C = h->C.p; a.gl = h->gl.p; a.Cinv = h->Cinv.p; a.E = h->E.p;
+  a.lambda = lambda; a.D = h->D; a.k = h->k; a.B = h->B;
+  a.SD = h->H.p + h->sd_off; a.SU = h->H.p + h->su_off; a.REM = h->H.p + h->rem_off;
+  a.rem_ptr = h->rem_ptr.p; a.rem_col = h->rem_col.p; a.gs = h->gs.p;
   a.pose_ptr = h->pose_ptr.p; a.pose_obs = h->pose_obs.p; a.pose_ids = h->pose_ids.p; a.nposes_obs = h->nposes_obs;
   a.lm_ptr = h->lm_ptr.p; a.lm_obs = h->lm_obs.p;
-  a.ndst = h->ndst; a.dst = h->dst.p; a.dst_ptr = h->dst_ptr.p; a.term_a = h->term_a.p; a.term_b = h->term_b.p;
   a.fail = h->fail.p; a.xc = h->x.p; a.xl = h->xl.p;
   return a;
 }
@@ -457,9 +427,7 @@ void form_system(vus_handle* h, double lambda, rt::stream_t st) {
   if (h->nobs) {
     SchurArgs a = schur_args(h, lambda);
     L_elem<LmInvertBody>(a.nl, st, a);
-    L_elem<StereoWBody>(a.n * 18, st, a);
-    L_elem<SchurGradBody>(h->nposes_obs * 6, st, a);
-    L_elem<SchurBlockBody>(h->ndst, st, a);
+    L_coop<SchurPoseBody>((int)h->nposes_obs, 64, (size_t)2 * h->k * 37 * sizeof(double), st, a);
   }
 }
 
@@ -469,7 +437,7 @@ size_t bcr_smem(int B) { return (size_t)bcr_smem_doubles(B) * sizeof(double); }
 BcrArgs bcr_args(vus_handle* h) {
   BcrArgs a;
   a.Ns = h->Ns; a.B = h->B; a.s = 1; a.Dw = h->Dw.p; a.Ucur = nullptr; a.Unext = nullptr;
-  a.Dinv = h->Dinv.p; a.Gl = h->Gl.p; a.Gr = h->Gr.p; a.GlT = h->GlT.p; a.GrT = h->GrT.p; a.fail = h->fail.p;
+  a.Dinv = h->Dinv.p; a.Gl = h->Gl.p; a.Gr = h->Gr.p; a.fail = h->fail.p;
   a.X = nullptr; a.xstride = 0; a.nrhs = 1;
   return a;
 }
@@ -498,20 +466,21 @@ void bcr_solve(vus_handle* h, double* X, long xstride, int nrhs, rt::stream_t st
   ClassGuard kc_guard(KC_BCR_SOLVE);
   BcrArgs a = bcr_args(h);
   a.X = X; a.xstride = xstride; a.nrhs = nrhs;
-  const size_t smem = (size_t)2 * nrhs * h->B * sizeof(double);
+  const int nthr = 256;
+  const size_t smem = (size_t)bcr_solve_smem_doubles(h->B, nrhs, nthr) * sizeof(double);
   std::vector<long> levels;
   for (long s = 1; s < h->Ns; s <<= 1) levels.push_back(s);
   for (long s : levels) {
     const long nact = (h->Ns + s - 1) / s;
     a.s = s;
-    L_coop<BcrFwdBody>((int)((nact + 1) / 2), 128, smem, st, a);
+    L_coop<BcrFwdBody>((int)((nact + 1) / 2), nthr, smem, st, a);
   }
-  L_coop<BcrRootSolveBody>(1, 128, smem, st, a);
+  L_coop<BcrRootSolveBody>(1, nthr, smem, st, a);
   for (auto it = levels.rbegin(); it != levels.rend(); ++it) {
     const long s = *it;
     const long nact = (h->Ns + s - 1) / s;
     a.s = s;
-    L_coop<BcrBwdBody>((int)(nact / 2), 128, smem, st, a);
+    L_coop<BcrBwdBody>((int)(nact / 2), nthr, smem, st, a);
   }
 }
 
@@ -521,13 +490,32 @@ void border_dot(vus_handle* h, const double* Y, long ystride, int nv, rt::stream
   L_coop<BorderDot1Body>(h->red_grid, 256, 256 * sizeof(double), st, a);
 }
 
+// Y = band(SD, SU) X for nv vectors (no remainder, no border)
+void apply_band(vus_handle* h, double* Y, long ystride, const double* X, long xstride, int nv, rt::stream_t st) {
+  ClassGuard kc_guard(KC_MATVEC);
+  MatvecArgs a;
+  a.SD = h->H.p + h->sd_off; a.SU = h->H.p + h->su_off; a.Ns = h->Ns; a.B = h->B; a.x = X; a.y = Y;
+  a.nv = nv; a.xstride = xstride; a.ystride = ystride;
+  a.rem_ptr = nullptr; a.rem_col = nullptr; a.rem_val = nullptr; a.nnodes = h->N; a.D = h->D;
+  a.F = nullptr; a.Hbb = nullptr; a.xb = nullptr; a.yb = nullptr; a.has_bias = 0;
+  const size_t smem = ((size_t)h->B * h->B + 2 * nv * h->B) * sizeof(double);
+  L_coop<BandMatvecBody>((int)h->Ns, 128, smem, st, a);
+}
+
 // preconditioner set-up for the current damped system: BCR of the band, Z = M^-1 F, Sb^-1
 void precond_setup(vus_handle* h, rt::stream_t st) {
   bcr_factor(h, st);
   if (h->has_bias) {
-    BorderColsArgs c; c.F = h->F.p; c.Z = h->Z.p; c.len = h->Lc; c.zstride = h->Lc;
+    BorderColsArgs c; c.F = h->F.p; c.Z = h->Z.p; c.len = h->Lc; c.zstride = h->Lc; c.R = h->Zr.p;
     L_elem<BorderColsBody>(h->Lc * 6, st, c);
     bcr_solve(h, h->Z.p, h->Lc, 6, st);
+    // one step of iterative refinement, Z += M^-1 (F - M Z): the bias Schur complement Hbb - F^T Z cancels to ~1e-8
+    // of its terms on short trajectories (the bias is barely observable), far below the raw accuracy of the band solve
+    apply_band(h, h->Zr.p, h->Lc, h->Z.p, h->Lc, 6, st);
+    L_elem<BorderResidBody>(h->Lc * 6, st, c);
+    bcr_solve(h, h->Zr.p, h->Lc, 6, st);
+    { VecArgs v; v.y = h->Z.p; v.x = h->Zr.p; v.z = nullptr; v.scal = nullptr; v.slot = 0; v.n = 6 * h->Lc; v.Z = nullptr; v.xb = nullptr; v.zstride = 0;
+      ClassGuard kc_v(KC_VECTOR); L_elem<AddVecBody>(6 * h->Lc, st, v); }
     border_dot(h, h->Z.p, h->Lc, 6, st);
     BorderSchurArgs s; s.Hbb = h->Hbb.p; s.partials = h->bpart.p; s.grid = h->red_grid; s.nv = 6; s.SbInv = h->SbInv.p; s.fail = h->fail.p;
     L_elem<BorderSchurBody>(1, st, s);
@@ -552,6 +540,7 @@ void apply_A(vus_handle* h, double* y, const double* x, rt::stream_t st) {
   ClassGuard kc_guard(KC_MATVEC);
   MatvecArgs a;
   a.SD = h->H.p + h->sd_off; a.SU = h->H.p + h->su_off; a.Ns = h->Ns; a.B = h->B; a.x = x; a.y = y;
+  a.nv = 1; a.xstride = 0; a.ystride = 0;
   a.rem_ptr = h->nrem ? h->rem_ptr.p : nullptr; a.rem_col = h->rem_col.p; a.rem_val = h->H.p + h->rem_off; a.nnodes = h->N; a.D = h->D;
   a.F = h->F.p; a.Hbb = h->Hbb.p; a.xb = x + h->Lc; a.yb = y + h->Lc; a.has_bias = h->has_bias;
   const size_t smem = ((size_t)h->B * h->B + 2 * h->B) * sizeof(double);
@@ -932,7 +921,7 @@ int vus_analyze(vus_handle* h) {
 
 int vus_get_layout(vus_handle* h, int64_t out[8]) {
   if (!h || !h->analyzed) return fail(h, VUS_ERR_STATE, "vus_get_layout: call vus_analyze first");
-  out[0] = h->D; out[1] = h->k; out[2] = h->Ns; out[3] = h->nrem; out[4] = h->ndst; out[5] = h->B; out[6] = h->L; out[7] = h->nfactors;
+  out[0] = h->D; out[1] = h->k; out[2] = h->Ns; out[3] = h->nrem; out[4] = h->nobs; out[5] = h->B; out[6] = h->L; out[7] = h->nfactors;
   return VUS_OK;
 }
 
@@ -1014,6 +1003,31 @@ int vus_solve_step(vus_handle* h, void* stream, double lambda, double* d_pose, d
   for (long l = 0; l < h->nvar[3]; ++l)
     for (int c = 0; c < 3; ++c) if (d_lm) d_lm[l * 3 + c] = xl[c * h->nvar[3] + l];
   return VUS_OK;
+  VUS_CATCH(h)
+}
+
+int vus_debug_band_solve(vus_handle* h, void* stream, double lambda, double* SD_out, double* SU_out, double* x_inout, int nrhs) {
+  if (!h) return VUS_ERR_INVALID;
+  if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_debug_band_solve: call vus_analyze first");
+  VUS_TRY(h)
+  rt::stream_t st = (rt::stream_t)stream;
+  const long BB = (long)h->B * h->B;
+  run_factors(h, h->cur, true, st);
+  assemble_base(h, st);
+  form_system(h, lambda, st);
+  if (SD_out) rt::d2h(SD_out, h->H.p + h->sd_off, h->Ns * BB * sizeof(double), st);
+  if (SU_out && h->Ns > 1) rt::d2h(SU_out, h->H.p + h->su_off, (h->Ns - 1) * BB * sizeof(double), st);
+  bcr_factor(h, st);
+  if (x_inout && nrhs > 0) {
+    DBuf<double> X;
+    X.alloc((size_t)nrhs * h->Lc);
+    rt::h2d(X.p, x_inout, (size_t)nrhs * h->Lc * sizeof(double), st);
+    bcr_solve(h, X.p, h->Lc, nrhs, st);
+    rt::d2h(x_inout, X.p, (size_t)nrhs * h->Lc * sizeof(double), st);
+    rt::sync(st);
+  }
+  rt::sync(st);
+  return read_fail(h, st) ? 1 : VUS_OK;
   VUS_CATCH(h)
 }
 

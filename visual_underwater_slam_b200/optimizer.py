@@ -219,6 +219,20 @@ class Session:
                                             db.ctypes.data_as(P), dl.ctypes.data_as(P), C.byref(its)))
         return dict(pose=dp, vel=dv, bias=db[:self.n["bias"]], lm=dl, pcg_iterations=its.value)
 
+    def debug_band_solve(self, lam, rhs, stream=None):
+        """Test hook: -> (SD [Ns,B,B], SU [Ns-1,B,B], x [nrhs, Ns*B], pivot_failed) for the damped band at the current values."""
+        lay = self.layout()
+        Ns, B = lay["Ns"], lay["B"]
+        SD = np.zeros((Ns, B, B))
+        SU = np.zeros((max(Ns - 1, 1), B, B))
+        x = np.array(rhs, dtype=np.float64).reshape(-1, Ns * B).copy()
+        P = _native.c_double_p
+        rc = self.lib.vus_debug_band_solve(self._h, stream, float(lam), SD.ctypes.data_as(P), SU.ctypes.data_as(P),
+                                           x.ctypes.data_as(P), x.shape[0])
+        if rc < 0:
+            self._check(rc)
+        return SD, SU[:Ns - 1], x, bool(rc)
+
     def optimize(self, stream=None):
         res = LmResult()
         self._check(self.lib.vus_optimize(self._h, stream, C.byref(res)))
