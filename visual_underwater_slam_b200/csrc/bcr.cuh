@@ -74,8 +74,8 @@ VUS_DEV void acc_zero(Acc& c) {
 #pragma unroll
     for (int b = 0; b < 6; ++b) c[a][b][0] = c[a][b][1] = 0.0;
 }
-// acc += op(A) op(B); sA / sB operand buffers [KP][LD] (zero padded); TA: A^T is stored, TB: B^T is stored
-template <bool TA, bool TB>
+// acc += op(A) op(B)  (NEG: acc -= op(A) op(B)); sA / sB operand buffers [KP][LD] (zero padded); TA: A^T is stored, TB: B^T is stored
+template <bool TA, bool TB, bool NEG>
 VUS_DEV void mma_gemm(Acc& c, const double* sA, const double* sB, const Tiles& G) {
   if (G.na == 0 || G.nb == 0) return;
   int ia[3], jb[6];
@@ -89,7 +89,7 @@ VUS_DEV void mma_gemm(Acc& c, const double* sA, const double* sB, const Tiles& G
     const int kk = k0 + G.t;
     double af[3], bf[6];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) af[a] = TA ? sA[kk * LD + ia[a]] : sA[ia[a] * LD + kk];
+    for (int a = 0; a < 3; ++a) { const double v = TA ? sA[kk * LD + ia[a]] : sA[ia[a] * LD + kk]; af[a] = NEG ? -v : v; }
 #pragma unroll
     for (int b = 0; b < 6; ++b) bf[b] = TB ? sB[jb[b] * LD + kk] : sB[kk * LD + jb[b]];
 #pragma unroll
@@ -99,11 +99,22 @@ VUS_DEV void mma_gemm(Acc& c, const double* sA, const double* sB, const Tiles& G
         if (a < G.na && b < G.nb) dmma884(c[a][b][0], c[a][b][1], af[a], bf[b]);
   }
 }
-// global row-major B x B block -> operand buffer [KP][LD], zero padded (warp per row, lanes across columns: coalesced)
+// global row-major B x B block -> operand buffer [KP][LD], zero padded.  Warp per row, lanes across columns (coalesced);
+// every element is an asynchronous 8-byte global->shared copy (LDGSTS), so all of a thread's copies are in flight at once.
+// Follow with stage_wait() and a barrier.
 VUS_DEV void stage_block(double* s, const double* g, const Tiles& G) {
   for (int r = G.warp; r < G.KP; r += 8)
-    for (int c = G.lane; c < G.LD; c += 32) s[r * G.LD + c] = (r < G.B && c < G.B) ? g[(long)r * G.B + c] : 0.0;
+    for (int c = G.lane; c < G.LD; c += 32) {
+      double* dst = s + r * G.LD + c;
+      if (r < G.B && c < G.B) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(g + (long)r * G.B + c) : "memory");
+      } else {
+        *dst = 0.0;
+      }
+    }
 }
+VUS_DEV void stage_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
 // accumulator tiles -> global row-major block; dst = alpha * acc (+ dst if ADD); optional second destination
 template <bool ADD>
 VUS_DEV void acc_store_global(double* dst, const Acc& c, double alpha, const Tiles& G) {
@@ -266,17 +277,21 @@ struct BcrElimBody {
     acc_store_global<false>(A.Dinv + j * BB, c, 1.0, G);
     acc_store_smem(buf1, c, G);
     stage_block(buf0, A.Ucur + (j - A.s) * BB, G);
+    stage_wait();
     __syncthreads();
     acc_zero(c);
-    mma_gemm<false, false>(c, buf0, buf1, G);
-    acc_store_global<false>(A.Gl + j * BB, c, 1.0, G);
+    mma_gemm<false, false, false>(c, buf0, buf1, G);
     if (j + A.s < A.Ns) {
       __syncthreads();
-      stage_block(buf0, A.Ucur + j * BB, G);
+      stage_block(buf0, A.Ucur + j * BB, G);           // in flight while Gl is written out
+      acc_store_global<false>(A.Gl + j * BB, c, 1.0, G);
+      stage_wait();
       __syncthreads();
       acc_zero(c);
-      mma_gemm<true, false>(c, buf0, buf1, G);
+      mma_gemm<true, false, false>(c, buf0, buf1, G);
       acc_store_global<false>(A.Gr + j * BB, c, 1.0, G);
+    } else {
+      acc_store_global<false>(A.Gl + j * BB, c, 1.0, G);
     }
   }
 };
@@ -288,34 +303,39 @@ struct BcrUpdateBody {
     const long c = 2L * m * A.s;
     double* buf0 = sm;
     double* buf1 = sm + bcr_buf_doubles(A.B);
+    const bool lo = c - A.s >= 0, hi = c + A.s < A.Ns;
+    if (lo) {
+      stage_block(buf0, A.Gr + (c - A.s) * BB, G);
+      stage_block(buf1, A.Ucur + (c - A.s) * BB, G);
+    }
     Acc acc;
-    acc_zero(acc);
-    if (c - A.s >= 0) {
-      const long j = c - A.s;
-      stage_block(buf0, A.Gr + j * BB, G);
-      stage_block(buf1, A.Ucur + j * BB, G);
+    acc_load_global(acc, A.Dw + c * BB, G);            // D_c rides in the accumulators; the products are subtracted
+    if (lo) {
+      stage_wait();
       __syncthreads();
-      mma_gemm<false, false>(acc, buf0, buf1, G);
+      mma_gemm<false, false, true>(acc, buf0, buf1, G);
       __syncthreads();
     }
-    if (c + A.s < A.Ns) {
+    if (hi) {
       const long j = c + A.s;
       stage_block(buf0, A.Gl + j * BB, G);
       stage_block(buf1, A.Ucur + c * BB, G);
+      stage_wait();
       __syncthreads();
-      mma_gemm<false, true>(acc, buf0, buf1, G);
-      acc_store_global<true>(A.Dw + c * BB, acc, -1.0, G);
+      mma_gemm<false, true, true>(acc, buf0, buf1, G);
       if (j + A.s < A.Ns) {
         __syncthreads();
-        stage_block(buf1, A.Ucur + j * BB, G);
+        stage_block(buf1, A.Ucur + j * BB, G);          // in flight while D_c is written out
+        acc_store_global<false>(A.Dw + c * BB, acc, 1.0, G);
+        stage_wait();
         __syncthreads();
         acc_zero(acc);
-        mma_gemm<false, false>(acc, buf0, buf1, G);
-        acc_store_global<false>(A.Unext + c * BB, acc, -1.0, G);
+        mma_gemm<false, false, true>(acc, buf0, buf1, G);
+        acc_store_global<false>(A.Unext + c * BB, acc, 1.0, G);
+        return;
       }
-    } else {
-      acc_store_global<true>(A.Dw + c * BB, acc, -1.0, G);
     }
+    acc_store_global<false>(A.Dw + c * BB, acc, 1.0, G);
   }
 };
 // root: Dinv_0 = inv(Dw_0)
