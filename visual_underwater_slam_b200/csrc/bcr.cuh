@@ -412,109 +412,144 @@ struct BcrRootBody {
 };
 #endif
 
-// =====================================================================================  triangular-free solve sweeps
-// Shared-memory layout of the solve kernels: xs [3][nrhs][B] staged vectors, part [ngrp][nrhs][B] partial sums.
-VUS_HD long bcr_solve_smem_doubles(int B, int nrhs, int nthr) {
-  int ngrp = nthr / B; if (ngrp < 1) ngrp = 1;
-  return (long)(3 + ngrp) * nrhs * B;
-}
-// out[v][r] = sum_k M[r][k] x[v][k]   (row-major block times staged vectors; one warp per row, shuffle reduction)
-VUS_DEV void cta_rowdot_sub(double* X, long xstride, long node, const double* M, const double* xs, int B, int nrhs, int tid, int nthr) {
+// =====================================================================================  streaming block x panel kernels
+// The solve sweeps and the band operator are HBM-bound: every B x B block is read once per application and multiplied
+// by a thin panel of nv <= 6 vectors.  sm_100a: the block is copied global -> shared with asynchronous 8-byte copies
+// (all of a thread's copies in flight at once, no registers held), the panel is a [KP][12] shared tile, and the product
+// runs as m8n8k4 DMMAs (N padded to 8), so the transposed and the non-transposed products read the block the same
+// coalesced way and the kernel issues ~10x fewer instructions than a shuffle-reduced dot product per (row, vector).
+// One operand buffer + one panel per CTA (64.5 KB) -> three CTAs per SM overlap copy and compute.
+// Launch with 256 threads; nv <= 6.
+#define VUS_MAXV 6
+#define VUS_LDX 12
+VUS_HD long blk_smem_doubles(int B, int nv, int) {
 #ifdef VUS_EMU
-  for (int e = tid; e < nrhs * B; e += nthr) {
-    const int v = e / B, r = e - v * B;
-    double s = 0.0;
-    for (int k = 0; k < B; ++k) s += M[(long)r * B + k] * xs[v * B + k];
-    X[(long)v * xstride + node * B + r] -= s;
-  }
+  return (long)4 * nv * B;
 #else
-  const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
-  for (int r = warp; r < B; r += nw) {
-    const double* row = M + (long)r * B;
-    const double m0 = lane < B ? row[lane] : 0.0;
-    const double m1 = lane + 32 < B ? row[lane + 32] : 0.0;
-    const double m2 = lane + 64 < B ? row[lane + 64] : 0.0;
-    for (int v = 0; v < nrhs; ++v) {
-      const double* x = xs + v * B;
-      double s = lane < B ? m0 * x[lane] : 0.0;
-      if (lane + 32 < B) s += m1 * x[lane + 32];
-      if (lane + 64 < B) s += m2 * x[lane + 64];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) X[(long)v * xstride + node * B + r] -= s;
-    }
-  }
+  return bcr_buf_doubles(B) + (long)bcr_kp(B) * VUS_LDX + 8;
 #endif
 }
+
+#ifndef VUS_EMU
+struct Panel {          // accumulators of one warp: row tiles warp, warp + 8; columns = vectors 2t, 2t+1
+  double c[2][2];
+  VUS_DEV void zero() { c[0][0] = c[0][1] = c[1][0] = c[1][1] = 0.0; }
+};
+// stage panel x[v][k] (global, vector stride xstride) as sX[k][v], zero padded to [KP][8]
+VUS_DEV void stage_panel(double* sX, const double* x, long xstride, bool present, const Tiles& G, int nv, int tid) {
+  for (int e = tid; e < G.KP * 8; e += 256) {
+    const int k = e >> 3, v = e & 7;
+    sX[k * VUS_LDX + v] = (present && k < G.B && v < nv) ? x[(long)v * xstride + k] : 0.0;
+  }
+}
+// acc (+/-)= op(M) Xs ; sM operand buffer [KP][LD], sX [KP][VUS_LDX]
+template <bool TA, bool NEG>
+VUS_DEV void panel_mma(Panel& P, const double* sM, const double* sX, const Tiles& G) {
+  int ia[2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a) { const int i = (G.warp + 8 * a) * 8 + G.g; ia[a] = i < G.B ? i : G.B - 1; }
+  const bool two = G.warp + 8 < G.T;
+  if (G.warp >= G.T) return;
+#pragma unroll 3
+  for (int k0 = 0; k0 < G.KP; k0 += 4) {
+    const int kk = k0 + G.t;
+    const double b = sX[kk * VUS_LDX + G.g];
+    double a0 = TA ? sM[kk * G.LD + ia[0]] : sM[ia[0] * G.LD + kk];
+    dmma884(P.c[0][0], P.c[0][1], NEG ? -a0 : a0, b);
+    if (two) {
+      double a1 = TA ? sM[kk * G.LD + ia[1]] : sM[ia[1] * G.LD + kk];
+      dmma884(P.c[1][0], P.c[1][1], NEG ? -a1 : a1, b);
+    }
+  }
+}
+// one streamed product: copy block, stage panel, wait, multiply-accumulate.  Ends with a barrier (buffers reusable).
+template <bool TA, bool NEG>
+VUS_DEV void blk_stream(Panel& P, double* buf, double* sX, const double* M, const double* x, long xstride, const Tiles& G, int nv, int tid) {
+  stage_block(buf, M, G);
+  stage_panel(sX, x, xstride, true, G, nv, tid);
+  stage_wait();
+  __syncthreads();
+  panel_mma<TA, NEG>(P, buf, sX, G);
+  __syncthreads();
+}
+// visit (row r, vector v, value) of a Panel
+#define VUS_PANEL_FOREACH(P, G, nv, BODY)                                   \
+  _Pragma("unroll") for (int a_ = 0; a_ < 2; ++a_) {                        \
+    const int r = (G.warp + 8 * a_) * 8 + G.g;                              \
+    if (G.warp + 8 * a_ < G.T && r < G.B) {                                 \
+      _Pragma("unroll") for (int h_ = 0; h_ < 2; ++h_) {                    \
+        const int v = 2 * G.t + h_;                                         \
+        if (v < nv) { const double val = P.c[a_][h_]; BODY }               \
+      }                                                                     \
+    }                                                                       \
+  }
+#else
+// host emulation helpers: out[v][r] += sign * sum_k op(M)[r][k] x[v][k]
+inline void emu_blk_accum(double* out, const double* M, bool ta, const double* x, long xstride, double sign, int B, int nv) {
+  for (int v = 0; v < nv; ++v)
+    for (int r = 0; r < B; ++r) {
+      double s = 0.0;
+      for (int k = 0; k < B; ++k) s += (ta ? M[(long)k * B + r] : M[(long)r * B + k]) * x[(long)v * xstride + k];
+      out[v * B + r] += sign * s;
+    }
+}
+#endif
+
 // forward sweep, per surviving node c: b_c -= Gr_{c-s} b_{c-s} + Gl_{c+s} b_{c+s}
 struct BcrFwdBody {
-  static VUS_DEV void run(const BcrArgs& A, int m, int tid, int nthr, double* sm) {
-    const int B = A.B;
+  static VUS_DEV void run(const BcrArgs& A, int m, int tid, int, double* sm) {
+    const int B = A.B, nv = A.nrhs;
     const long BB = (long)B * B;
     const long c = 2L * m * A.s;
-    double* xs = sm;   // [2][nrhs][B] neighbour rhs
     const long jl = c - A.s, jh = c + A.s;
-    for (int e = tid; e < A.nrhs * B; e += nthr) {
-      const int v = e / B, r = e - v * B;
-      if (jl >= 0) xs[e] = A.X[(long)v * A.xstride + jl * B + r];
-      if (jh < A.Ns) xs[A.nrhs * B + e] = A.X[(long)v * A.xstride + jh * B + r];
-    }
-    VUS_SYNC();
-    if (jl >= 0) cta_rowdot_sub(A.X, A.xstride, c, A.Gr + jl * BB, xs, B, A.nrhs, tid, nthr);
-    VUS_SYNC();
-    if (jh < A.Ns) cta_rowdot_sub(A.X, A.xstride, c, A.Gl + jh * BB, xs + A.nrhs * B, B, A.nrhs, tid, nthr);
+#ifdef VUS_EMU
+    double* dl = sm;
+    for (int e = 0; e < nv * B; ++e) dl[e] = 0.0;
+    if (jl >= 0) emu_blk_accum(dl, A.Gr + jl * BB, false, A.X + jl * B, A.xstride, 1.0, B, nv);
+    if (jh < A.Ns) emu_blk_accum(dl, A.Gl + jh * BB, false, A.X + jh * B, A.xstride, 1.0, B, nv);
+    for (int v = 0; v < nv; ++v)
+      for (int r = 0; r < B; ++r) A.X[(long)v * A.xstride + c * B + r] -= dl[v * B + r];
+    (void)tid;
+#else
+    const Tiles G(B, tid);
+    double* buf = sm;
+    double* sX = sm + bcr_buf_doubles(B);
+    Panel P;
+    P.zero();
+    if (jl >= 0) blk_stream<false, false>(P, buf, sX, A.Gr + jl * BB, A.X + jl * B, A.xstride, G, nv, tid);
+    if (jh < A.Ns) blk_stream<false, false>(P, buf, sX, A.Gl + jh * BB, A.X + jh * B, A.xstride, G, nv, tid);
+    VUS_PANEL_FOREACH(P, G, nv, { A.X[(long)v * A.xstride + c * B + r] -= val; })
+#endif
   }
 };
 // backward sweep, per eliminated node j: x_j = Dinv_j b_j - Gl_j^T x_{j-s} - Gr_j^T x_{j+s}
-// threads (grp, r): column r of each block over a k-range (coalesced rows), partial sums combined through shared memory
 struct BcrBwdBody {
-  static VUS_DEV void run(const BcrArgs& A, int m, int tid, int nthr, double* sm) {
-    const int B = A.B, nrhs = A.nrhs;
+  static VUS_DEV void run(const BcrArgs& A, int m, int tid, int, double* sm) {
+    const int B = A.B, nv = A.nrhs;
     const long BB = (long)B * B;
     const long j = A.s * (2L * m + 1);
     const long jl = j - A.s, jh = j + A.s;
     const bool hl = jl >= 0 && A.s > 0, hh = jh < A.Ns && A.s > 0;
-    int ngrp = nthr / B; if (ngrp < 1) ngrp = 1;
-    double* xs = sm;                       // [3][nrhs][B]: b_j, x_{j-s}, x_{j+s}
-    double* part = sm + 3 * nrhs * B;      // [ngrp][nrhs][B]
-    for (int e = tid; e < nrhs * B; e += nthr) {
-      const int v = e / B, r = e - v * B;
-      xs[e] = A.X[(long)v * A.xstride + j * B + r];
-      xs[nrhs * B + e] = hl ? A.X[(long)v * A.xstride + jl * B + r] : 0.0;
-      xs[2 * nrhs * B + e] = hh ? A.X[(long)v * A.xstride + jh * B + r] : 0.0;
-    }
-    VUS_SYNC();
-    const int kchunk = (B + ngrp - 1) / ngrp;
-    const double* Di = A.Dinv + j * BB;
-    const double* Gl = A.Gl + j * BB;
-    const double* Gr = A.Gr + j * BB;
-    for (int e = tid; e < ngrp * B; e += nthr) {
-      const int grp = e / B, r = e - grp * B;
-      const int k0 = grp * kchunk;
-      int k1 = k0 + kchunk; if (k1 > B) k1 = B;
-      for (int v0 = 0; v0 < nrhs; v0 += 6) {
-        double s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        const int nv = nrhs - v0 < 6 ? nrhs - v0 : 6;
-        for (int k = k0; k < k1; ++k) {
-          const double d = Di[(long)k * B + r];                  // Dinv symmetric: column r read as row k
-          const double gl = hl ? Gl[(long)k * B + r] : 0.0;
-          const double gr = hh ? Gr[(long)k * B + r] : 0.0;
-#pragma unroll
-          for (int v = 0; v < 6; ++v)
-            if (v < nv) s[v] += d * xs[(v0 + v) * B + k] - gl * xs[(nrhs + v0 + v) * B + k] - gr * xs[(2 * nrhs + v0 + v) * B + k];
-        }
-#pragma unroll
-        for (int v = 0; v < 6; ++v)
-          if (v < nv) part[(grp * nrhs + v0 + v) * B + r] = s[v];
-      }
-    }
-    VUS_SYNC();
-    for (int e = tid; e < nrhs * B; e += nthr) {
-      const int v = e / B, r = e - v * B;
-      double s = 0.0;
-      for (int grp = 0; grp < ngrp; ++grp) s += part[(grp * nrhs + v) * B + r];
-      A.X[(long)v * A.xstride + j * B + r] = s;
-    }
+#ifdef VUS_EMU
+    double* dl = sm;
+    for (int e = 0; e < nv * B; ++e) dl[e] = 0.0;
+    emu_blk_accum(dl, A.Dinv + j * BB, false, A.X + j * B, A.xstride, 1.0, B, nv);
+    if (hl) emu_blk_accum(dl, A.Gl + j * BB, true, A.X + jl * B, A.xstride, -1.0, B, nv);
+    if (hh) emu_blk_accum(dl, A.Gr + j * BB, true, A.X + jh * B, A.xstride, -1.0, B, nv);
+    for (int v = 0; v < nv; ++v)
+      for (int r = 0; r < B; ++r) A.X[(long)v * A.xstride + j * B + r] = dl[v * B + r];
+    (void)tid;
+#else
+    const Tiles G(B, tid);
+    double* buf = sm;
+    double* sX = sm + bcr_buf_doubles(B);
+    Panel P;
+    P.zero();
+    blk_stream<false, false>(P, buf, sX, A.Dinv + j * BB, A.X + j * B, A.xstride, G, nv, tid);
+    if (hl) blk_stream<true, true>(P, buf, sX, A.Gl + j * BB, A.X + jl * B, A.xstride, G, nv, tid);
+    if (hh) blk_stream<true, true>(P, buf, sX, A.Gr + j * BB, A.X + jh * B, A.xstride, G, nv, tid);
+    VUS_PANEL_FOREACH(P, G, nv, { A.X[(long)v * A.xstride + j * B + r] = val; })
+#endif
   }
 };
 // root solve: x_0 = Dinv_0 b_0   (the backward body with no neighbours: s = 0, m such that j = 0)
@@ -525,5 +560,44 @@ struct BcrRootSolveBody {
     BcrBwdBody::run(R, 0, tid, nthr, sm);
   }
 };
+
+// =====================================================================================  Kernel 3a: band operator
+// one CTA per supernode I:  y_I = SD_I x_I + SU_I x_{I+1} + SU_{I-1}^T x_{I-1}   for nv vectors
+struct BandMatvecBody {
+  static VUS_DEV void run(const MatvecArgs& A, int I, int tid, int, double* sm) {
+    const int B = A.B, nv = A.nv;
+    const long BB = (long)B * B;
+    const bool up = I + 1 < A.Ns, dn = I > 0;
+#ifdef VUS_EMU
+    double* dl = sm;
+    for (int e = 0; e < nv * B; ++e) dl[e] = 0.0;
+    emu_blk_accum(dl, A.SD + I * BB, false, A.x + (long)I * B, A.xstride, 1.0, B, nv);
+    if (up) emu_blk_accum(dl, A.SU + I * BB, false, A.x + (long)(I + 1) * B, A.xstride, 1.0, B, nv);
+    if (dn) emu_blk_accum(dl, A.SU + (I - 1) * BB, true, A.x + (long)(I - 1) * B, A.xstride, 1.0, B, nv);
+    for (int v = 0; v < nv; ++v)
+      for (int r = 0; r < B; ++r) A.y[(long)v * A.ystride + (long)I * B + r] = dl[v * B + r];
+    (void)tid;
+#else
+    const Tiles G(B, tid);
+    double* buf = sm;
+    double* sX = sm + bcr_buf_doubles(B);
+    Panel P;
+    P.zero();
+    blk_stream<false, false>(P, buf, sX, A.SD + I * BB, A.x + (long)I * B, A.xstride, G, nv, tid);
+    if (up) blk_stream<false, false>(P, buf, sX, A.SU + I * BB, A.x + (long)(I + 1) * B, A.xstride, G, nv, tid);
+    if (dn) blk_stream<true, false>(P, buf, sX, A.SU + (I - 1) * BB, A.x + (long)(I - 1) * B, A.xstride, G, nv, tid);
+    VUS_PANEL_FOREACH(P, G, nv, { A.y[(long)v * A.ystride + (long)I * B + r] = val; })
+#endif
+  }
+};
+
+#ifndef VUS_EMU
+namespace rt {
+template <> struct CoopBounds<BcrFwdBody> { static constexpr int kMaxThreads = 256, kMinBlocks = 3; };
+template <> struct CoopBounds<BcrBwdBody> { static constexpr int kMaxThreads = 256, kMinBlocks = 3; };
+template <> struct CoopBounds<BcrRootSolveBody> { static constexpr int kMaxThreads = 256, kMinBlocks = 3; };
+template <> struct CoopBounds<BandMatvecBody> { static constexpr int kMaxThreads = 256, kMinBlocks = 3; };
+}  // namespace rt
+#endif
 
 }  // namespace vus

@@ -494,6 +494,7 @@ struct DampBody {
 // =====================================================================================
 // Kernel 3a: system operator  y = A x  on the reduced camera system
 // =====================================================================================
+// MatvecArgs / BandMatvecBody (band operator) live in bcr.cuh with the other streaming block kernels
 struct MatvecArgs {
   const double* SD; const double* SU; long Ns; int B;
   const double* x; double* y;        // camera parts, length Ns*B (per vector)
@@ -502,54 +503,6 @@ struct MatvecArgs {
   const int* rem_ptr; const int* rem_col; const double* rem_val; long nnodes; int D;
   // border
   const double* F; const double* Hbb; const double* xb; double* yb; int has_bias;
-};
-// one CTA per supernode: y_I = SD_I x_I + SU_I x_{I+1} + SU_{I-1}^T x_{I-1} for nv vectors.  Blocks are staged in
-// shared memory with coalesced loads, then each thread owns one (vector, row) output.
-struct BandMatvecBody {
-  static VUS_DEV void run(const MatvecArgs& A, int I, int tid, int nthr, double* sm) {
-    const int B = A.B, nv = A.nv;
-    const long BB = (long)B * B;
-    double* M = sm;             // [B*B]
-    double* xs = sm + BB;       // [nv][B]
-    double* acc = xs + nv * B;  // [nv][B]
-    for (int i = tid; i < nv * B; i += nthr) acc[i] = 0.0;
-    // diagonal block (symmetric)
-    for (long i = tid; i < BB; i += nthr) M[i] = A.SD[I * BB + i];
-    for (int i = tid; i < nv * B; i += nthr) xs[i] = A.x[(long)(i / B) * A.xstride + (long)I * B + (i % B)];
-    VUS_SYNC();
-    for (int e = tid; e < nv * B; e += nthr) {
-      const int v = e / B, r = e - v * B;
-      double s = 0.0;
-      for (int c = 0; c < B; ++c) s += M[(long)c * B + r] * xs[v * B + c];     // column r of a symmetric block
-      acc[e] += s;
-    }
-    VUS_SYNC();
-    if (I + 1 < A.Ns) {
-      for (long i = tid; i < BB; i += nthr) M[i] = A.SU[I * BB + i];
-      for (int i = tid; i < nv * B; i += nthr) xs[i] = A.x[(long)(i / B) * A.xstride + (long)(I + 1) * B + (i % B)];
-      VUS_SYNC();
-      for (int e = tid; e < nv * B; e += nthr) {
-        const int v = e / B, r = e - v * B;
-        double s = 0.0;
-        for (int c = 0; c < B; ++c) s += M[(long)r * B + c] * xs[v * B + c];
-        acc[e] += s;
-      }
-      VUS_SYNC();
-    }
-    if (I > 0) {
-      for (long i = tid; i < BB; i += nthr) M[i] = A.SU[(I - 1) * BB + i];
-      for (int i = tid; i < nv * B; i += nthr) xs[i] = A.x[(long)(i / B) * A.xstride + (long)(I - 1) * B + (i % B)];
-      VUS_SYNC();
-      for (int e = tid; e < nv * B; e += nthr) {
-        const int v = e / B, r = e - v * B;
-        double s = 0.0;
-        for (int c = 0; c < B; ++c) s += M[(long)c * B + r] * xs[v * B + c];
-        acc[e] += s;
-      }
-      VUS_SYNC();
-    }
-    for (int e = tid; e < nv * B; e += nthr) A.y[(long)(e / B) * A.ystride + (long)I * B + (e % B)] = acc[e];
-  }
 };
 // per (node, row): remainder blocks + border column
 struct RemBorderMatvecBody {

@@ -467,7 +467,7 @@ void bcr_solve(vus_handle* h, double* X, long xstride, int nrhs, rt::stream_t st
   BcrArgs a = bcr_args(h);
   a.X = X; a.xstride = xstride; a.nrhs = nrhs;
   const int nthr = 256;
-  const size_t smem = (size_t)bcr_solve_smem_doubles(h->B, nrhs, nthr) * sizeof(double);
+  const size_t smem = (size_t)blk_smem_doubles(h->B, nrhs, nthr) * sizeof(double);
   std::vector<long> levels;
   for (long s = 1; s < h->Ns; s <<= 1) levels.push_back(s);
   for (long s : levels) {
@@ -498,8 +498,8 @@ void apply_band(vus_handle* h, double* Y, long ystride, const double* X, long xs
   a.nv = nv; a.xstride = xstride; a.ystride = ystride;
   a.rem_ptr = nullptr; a.rem_col = nullptr; a.rem_val = nullptr; a.nnodes = h->N; a.D = h->D;
   a.F = nullptr; a.Hbb = nullptr; a.xb = nullptr; a.yb = nullptr; a.has_bias = 0;
-  const size_t smem = ((size_t)h->B * h->B + 2 * nv * h->B) * sizeof(double);
-  L_coop<BandMatvecBody>((int)h->Ns, 128, smem, st, a);
+  const size_t smem = (size_t)blk_smem_doubles(h->B, nv, 256) * sizeof(double);
+  L_coop<BandMatvecBody>((int)h->Ns, 256, smem, st, a);
 }
 
 // preconditioner set-up for the current damped system: BCR of the band, Z = M^-1 F, Sb^-1
@@ -543,8 +543,8 @@ void apply_A(vus_handle* h, double* y, const double* x, rt::stream_t st) {
   a.nv = 1; a.xstride = 0; a.ystride = 0;
   a.rem_ptr = h->nrem ? h->rem_ptr.p : nullptr; a.rem_col = h->rem_col.p; a.rem_val = h->H.p + h->rem_off; a.nnodes = h->N; a.D = h->D;
   a.F = h->F.p; a.Hbb = h->Hbb.p; a.xb = x + h->Lc; a.yb = y + h->Lc; a.has_bias = h->has_bias;
-  const size_t smem = ((size_t)h->B * h->B + 2 * h->B) * sizeof(double);
-  L_coop<BandMatvecBody>((int)h->Ns, 128, smem, st, a);
+  const size_t smem = (size_t)blk_smem_doubles(h->B, 1, 256) * sizeof(double);
+  L_coop<BandMatvecBody>((int)h->Ns, 256, smem, st, a);
   if (h->nrem || h->has_bias) L_elem<RemBorderMatvecBody>(h->N * h->D, st, a);
   if (h->has_bias) {
     border_dot(h, x, h->Lc, 1, st);
