@@ -302,7 +302,7 @@ struct StereoAsmArgs {
   const double* Pp; const double* Pl;    // per-observation products written by the stereo linearize kernel
   long nl;
   const int* pose_ptr; const int* pose_obs; const int* pose_ids; long nposes_obs;   // CSR pose -> obs
-  const int* lm_ptr; const int* lm_obs;                                              // CSR landmark -> obs
+  const int* lm_ptr;                                                                 // landmark -> contiguous obs range
 };
 // per (pose-with-observations, e<28): sums the per-observation products the stereo linearize kernel wrote
 // (P_pose[o][e], contiguous in e -> coalesced) over the pose's observations.  e<21: unique B_ii entry (a<=b), 21..26: gradient
@@ -332,7 +332,7 @@ struct StereoLmBody {
     const int e = (int)(w - l * 12);
     if (e >= 9) return;
     double s = 0.0;
-    for (int t = A.lm_ptr[l]; t < A.lm_ptr[l + 1]; ++t) s += A.Pl[(long)A.lm_obs[t] * 12 + e];
+    for (int t = A.lm_ptr[l]; t < A.lm_ptr[l + 1]; ++t) s += A.Pl[(long)t * 12 + e];   // observations are stored landmark-major
     if (e < 6) {
       int a = 0, rem = e;
       while (rem >= 3 - a) { rem -= 3 - a; ++a; }
@@ -358,7 +358,7 @@ struct SchurArgs {
   const int* rem_ptr; const int* rem_col;
   double* gs;                        // reduced gradient (in/out)
   const int* pose_ptr; const int* pose_obs; const int* pose_ids; long nposes_obs;
-  const int* lm_ptr; const int* lm_obs;
+  const int* lm_ptr;
   int* fail;
   // back-substitution
   const double* xc; double* xl;
@@ -421,7 +421,7 @@ struct SchurPoseBody {
         const double w2 = e0 * A.Cinv[2 * A.nl + l] + e1 * A.Cinv[5 * A.nl + l] + e2 * A.Cinv[8 * A.nl + l];
         if (s == 0) gacc += w0 * A.gl[l] + w1 * A.gl[A.nl + l] + w2 * A.gl[2 * A.nl + l];
         for (int q = A.lm_ptr[l]; q < A.lm_ptr[l + 1]; ++q) {
-          const long o2 = A.lm_obs[q];
+          const long o2 = q;                           // observations are stored landmark-major, pose-sorted
           const long j = A.idx[o2];
           if (j < i) continue;
           const double v = w0 * A.E[o2 * 18 + s * 3] + w1 * A.E[o2 * 18 + s * 3 + 1] + w2 * A.E[o2 * 18 + s * 3 + 2];
@@ -461,7 +461,7 @@ struct LmBacksubBody {   // per landmark: xl = Cinv (gl - sum_o E_o^T xc[pose_o]
   static VUS_DEV void run(const SchurArgs& A, long l) {
     double t[3] = {A.gl[l], A.gl[A.nl + l], A.gl[2 * A.nl + l]};
     for (int q = A.lm_ptr[l]; q < A.lm_ptr[l + 1]; ++q) {
-      const long o = A.lm_obs[q];
+      const long o = q;
       const long node = A.idx[o];
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
@@ -653,6 +653,16 @@ VUS_DEV void BorderResidBody::run(const BorderColsArgs& A, long w) {
 }
 struct AddVecBody {     // y[i] += x[i]
   static VUS_DEV void run(const VecArgs& A, long i) { A.y[i] += A.x[i]; }
+};
+
+// dst[c][f] = src[c][perm[f]]  (re-ordering of a component-major table, used once per graph by vus_analyze)
+struct GatherArgs { const double* src; double* dst; const int* perm; long n; int comps; };
+struct GatherBody {
+  static VUS_DEV void run(const GatherArgs& A, long w) {
+    const long f = w % A.n;
+    const long c = w / A.n;
+    A.dst[c * A.n + f] = A.src[c * A.n + A.perm[f]];
+  }
 };
 
 // =====================================================================================

@@ -73,6 +73,7 @@ struct FactorTable {
   long n = 0;
   std::vector<int> h_idx;        // [slots][n]
   std::vector<int64_t> orig;
+  std::vector<int> perm;         // stereo only: table row f holds the caller's row perm[f] (rows are kept landmark-major)
   DBuf<int> idx;
   DBuf<double> meas, sinfo, r, J;
   DBuf<PairDst> pair;
@@ -113,7 +114,7 @@ struct vus_handle {
   DBuf<double> g0, gs, F, Hbb0, Hbb, gb;     // gs = [reduced camera gradient ; gb] (length L)
   // stereo
   long nobs = 0, nposes_obs = 0;
-  DBuf<int> pose_ptr, pose_obs, pose_ids, lm_ptr, lm_obs;
+  DBuf<int> pose_ptr, pose_obs, pose_ids, lm_ptr;
   DBuf<double> C, gl, Cinv, E, Pp, Pl;
   // BCR
   DBuf<double> Dw, U1, U2, Dinv, Gl, Gr, Z, Zr, SbInv;
@@ -250,19 +251,58 @@ int analyze(vus_handle* h, rt::stream_t st) {
   for (long f = 0; f < FD.n; ++f)
     if (FD.h_idx[f] != FD.h_idx[FD.n + f])
       return fail(h, VUS_ERR_UNSUPPORTED, "DVL factor must connect V(i) and X(i) of the same keyframe (batch.py:247)");
-  // stereo CSR structures
+  // stereo: keep the observation table landmark-major, pose-sorted inside a landmark (stable in factor order), so a
+  // landmark's observations -- and the per-observation products the Schur kernels stream -- are contiguous
   h->nobs = FS.n;
-  std::vector<int> lm_ptr(NL + 1, 0), lm_obs(FS.n), pose_cnt(NX, 0);
-  for (long o = 0; o < FS.n; ++o) { lm_ptr[FS.h_idx[FS.n + o] + 1]++; pose_cnt[FS.h_idx[o]]++; }
+  std::vector<int> lm_ptr(NL + 1, 0), pose_cnt(NX, 0);
+  for (long o = 0; o < FS.n; ++o) lm_ptr[FS.h_idx[FS.n + o] + 1]++;
   for (long l = 0; l < NL; ++l) lm_ptr[l + 1] += lm_ptr[l];
-  {
-    std::vector<int> fill(lm_ptr.begin(), lm_ptr.end() - 1);
-    for (long o = 0; o < FS.n; ++o) lm_obs[fill[FS.h_idx[FS.n + o]]++] = (int)o;
+  if (FS.n) {
+    std::vector<int> order(FS.n);
+    {
+      std::vector<int> fill(lm_ptr.begin(), lm_ptr.end() - 1);
+      for (long o = 0; o < FS.n; ++o) order[fill[FS.h_idx[FS.n + o]]++] = (int)o;
+    }
+    bool identity = true;
+    for (long l = 0; l < NL; ++l) {                     // insertion sort by pose: tracks arrive (nearly) sorted
+      int* q = order.data() + lm_ptr[l];
+      const int len = lm_ptr[l + 1] - lm_ptr[l];
+      for (int a = 1; a < len; ++a) {
+        const int v = q[a];
+        const int pv = FS.h_idx[v];
+        int b = a - 1;
+        while (b >= 0 && FS.h_idx[q[b]] > pv) { q[b + 1] = q[b]; --b; }
+        q[b + 1] = v;
+      }
+    }
+    for (long o = 0; o < FS.n && identity; ++o) identity = order[o] == o;
+    if (!identity) {
+      std::vector<int> nidx(2 * FS.n);
+      std::vector<int64_t> norig(FS.n);
+      std::vector<int> nperm(FS.n);
+      for (long o = 0; o < FS.n; ++o) {
+        nidx[o] = FS.h_idx[order[o]]; nidx[FS.n + o] = FS.h_idx[FS.n + order[o]];
+        norig[o] = FS.orig[order[o]];
+        nperm[o] = FS.perm.empty() ? order[o] : FS.perm[order[o]];
+      }
+      FS.h_idx.swap(nidx); FS.orig.swap(norig); FS.perm.swap(nperm);
+      FS.idx.upload(FS.h_idx, st);
+      DBuf<int> dperm; dperm.upload(order, st);
+      DBuf<double> tmp; tmp.alloc((size_t)3 * FS.n);
+      GatherArgs ga; ga.perm = dperm.p; ga.n = FS.n; ga.comps = 3;
+      ga.src = FS.meas.p; ga.dst = tmp.p;
+      L_elem<GatherBody>(3 * FS.n, st, ga);
+      rt::d2d(FS.meas.p, tmp.p, (size_t)3 * FS.n * sizeof(double), st);
+      ga.src = FS.sinfo.p;
+      L_elem<GatherBody>(3 * FS.n, st, ga);
+      rt::d2d(FS.sinfo.p, tmp.p, (size_t)3 * FS.n * sizeof(double), st);
+      rt::sync(st);
+    } else if (FS.perm.empty()) {
+      FS.perm.resize(FS.n);
+      std::iota(FS.perm.begin(), FS.perm.end(), 0);
+    }
   }
-  // sort each landmark's observations by pose (stable in factor order)
-  for (long l = 0; l < NL; ++l)
-    std::stable_sort(lm_obs.begin() + lm_ptr[l], lm_obs.begin() + lm_ptr[l + 1],
-                     [&](int a, int b) { return FS.h_idx[a] < FS.h_idx[b]; });
+  for (long o = 0; o < FS.n; ++o) pose_cnt[FS.h_idx[o]]++;
   std::vector<int> pose_ids, pose_ptr(1, 0), pose_obs(FS.n);
   {
     std::vector<int> slot(NX, -1);
@@ -281,7 +321,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
   for (long f = 0; f < FB.n; ++f) consider(FB.h_idx[f], FB.h_idx[FB.n + f]);
   for (long f = 0; f < FI.n; ++f) consider(FI.h_idx[f], FI.h_idx[2 * FI.n + f]);
   for (long l = 0; l < NL; ++l) {
-    const int a = lm_obs[lm_ptr[l]], b = lm_obs[lm_ptr[l + 1] - 1];
+    const int a = lm_ptr[l], b = lm_ptr[l + 1] - 1;
     consider(FS.h_idx[a], FS.h_idx[b]);
   }
   h->k = (int)std::min<long>(span, kcap);
@@ -300,10 +340,10 @@ int analyze(vus_handle* h, rt::stream_t st) {
   for (long f = 0; f < FB.n; ++f) add_rem(FB.h_idx[f], FB.h_idx[FB.n + f]);
   for (long f = 0; f < FI.n; ++f) add_rem(FI.h_idx[f], FI.h_idx[2 * FI.n + f]);
   for (long l = 0; l < NL; ++l) {
-    const long pf = FS.h_idx[lm_obs[lm_ptr[l]]], pl = FS.h_idx[lm_obs[lm_ptr[l + 1] - 1]];   // observations are pose-sorted
+    const long pf = FS.h_idx[lm_ptr[l]], pl = FS.h_idx[lm_ptr[l + 1] - 1];   // observations are pose-sorted
     if (pl / k - pf / k <= 1) continue;                 // whole track inside the band
     for (int a = lm_ptr[l]; a < lm_ptr[l + 1]; ++a)
-      for (int b = a + 1; b < lm_ptr[l + 1]; ++b) add_rem(FS.h_idx[lm_obs[a]], FS.h_idx[lm_obs[b]]);
+      for (int b = a + 1; b < lm_ptr[l + 1]; ++b) add_rem(FS.h_idx[a], FS.h_idx[b]);
   }
   std::vector<int> rem_ptr(NX + 1, 0), rem_col;
   {
@@ -332,7 +372,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
   // ---- uploads / allocations
   h->rem_ptr.upload(rem_ptr, st); h->rem_col.upload(rem_col, st);
   h->pose_ptr.upload(pose_ptr, st); h->pose_obs.upload(pose_obs, st); h->pose_ids.upload(pose_ids, st);
-  h->lm_ptr.upload(lm_ptr, st); h->lm_obs.upload(lm_obs, st);
+  h->lm_ptr.upload(lm_ptr, st);
   h->H0.alloc(h->hlen); h->H.alloc(h->hlen);
   h->g0.alloc(h->Lc); h->gs.alloc(h->L);
   h->F.alloc(h->Lc * 6); h->Hbb0.alloc(36); h->Hbb.alloc(36); h->gb.alloc(6);
@@ -395,7 +435,7 @@ void assemble_base(vus_handle* h, rt::stream_t st) {
     a.n = S.n; a.idx = S.idx.p; a.J = S.J.p; a.r = S.r.p; a.D = h->D; a.k = h->k; a.B = h->B;
     a.SD = h->H0.p + h->sd_off; a.g = h->g0.p; a.C = h->C.p; a.gl = h->gl.p; a.E = h->E.p; a.nl = h->nvar[3];
     a.pose_ptr = h->pose_ptr.p; a.pose_obs = h->pose_obs.p; a.pose_ids = h->pose_ids.p; a.nposes_obs = h->nposes_obs;
-    a.lm_ptr = h->lm_ptr.p; a.lm_obs = h->lm_obs.p;
+    a.lm_ptr = h->lm_ptr.p;
     a.Pp = h->Pp.p; a.Pl = h->Pl.p;
     L_elem<StereoPoseBody>(h->nposes_obs * 28, st, a);
     L_elem<StereoLmBody>(h->nvar[3] * 12, st, a);
@@ -410,7 +450,7 @@ SchurArgs schur_args(vus_handle* h, double lambda) {
   a.SD = h->H.p + h->sd_off; a.SU = h->H.p + h->su_off; a.REM = h->H.p + h->rem_off;
   a.rem_ptr = h->rem_ptr.p; a.rem_col = h->rem_col.p; a.gs = h->gs.p;
   a.pose_ptr = h->pose_ptr.p; a.pose_obs = h->pose_obs.p; a.pose_ids = h->pose_ids.p; a.nposes_obs = h->nposes_obs;
-  a.lm_ptr = h->lm_ptr.p; a.lm_obs = h->lm_obs.p;
+  a.lm_ptr = h->lm_ptr.p;
   a.fail = h->fail.p; a.xc = h->x.p; a.xl = h->xl.p;
   return a;
 }
@@ -974,6 +1014,18 @@ int vus_linearize(vus_handle* h, void* stream, int type, double* r_out, double* 
   if (r_out) rt::d2h(r_out, T.r.p, (size_t)kFactorM[type] * T.n * sizeof(double), st);
   if (J_out) rt::d2h(J_out, T.J.p, (size_t)kFactorM[type] * kFactorCols[type] * T.n * sizeof(double), st);
   rt::sync(st);
+  if (!T.perm.empty()) {                               // rows are stored landmark-major: hand them back in the caller's order
+    std::vector<double> tmp(T.n);
+    auto unpermute = [&](double* out, int comps) {
+      for (int c = 0; c < comps; ++c) {
+        double* row = out + (size_t)c * T.n;
+        for (long f = 0; f < T.n; ++f) tmp[T.perm[f]] = row[f];
+        std::copy(tmp.begin(), tmp.end(), row);
+      }
+    };
+    if (r_out) unpermute(r_out, kFactorM[type]);
+    if (J_out) unpermute(J_out, kFactorM[type] * kFactorCols[type]);
+  }
   return VUS_OK;
   VUS_CATCH(h)
 }
