@@ -136,36 +136,62 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def roofline(res, lay, nf, ms_class, launches):
-    """Algorithmic bytes per launch-group / CUDA-event device time for each HBM-bound kernel class; returns the
-    dominant one in the contract's format plus the full table."""
+FP64_TENSOR_PEAK_TFLOPS = 37.1   # mma.sync.m8n8k4.f64 issue-rate microbenchmark on this pool's B200 (profiles/r1_dmma_microbench.txt);
+                                  # MEASURED_PEAKS.json carries no FP64 figure, the DFMA pipe measured 34.1 TFLOP/s in the same run
+
+
+def bcr_factor_flops(Ns, B):
+    """Algorithmic flops of one block-cyclic-reduction factorization of an Ns-supernode block-tridiagonal band (bcr.cuh):
+    per eliminated node a B x B inverse (2 B^3) + up to two products (2 B^3 each), per surviving node up to three."""
+    b3 = float(B) ** 3
+    fl = 0.0
+    s = 1
+    while s < Ns:
+        nact = (Ns + s - 1) // s
+        for m in range(nact // 2):
+            j = s * (2 * m + 1)
+            fl += 2 * b3 + 2 * b3 + (2 * b3 if j + s < Ns else 0.0)
+        for m in range((nact + 1) // 2):
+            c = 2 * m * s
+            if c - s >= 0:
+                fl += 2 * b3
+            if c + s < Ns:
+                fl += 2 * b3 + (2 * b3 if c + 2 * s < Ns else 0.0)
+        s *= 2
+    return fl + 2 * b3          # root inverse
+
+
+def roofline(res, lay, nf, ms_class, launches, hbm_peak):
+    """Per kernel class: algorithmic bytes (or flops) / CUDA-event device time summed over the timed region.
+    bcr_factor is FP64-tensor bound (DMMA); every other class is HBM bound.  Returns {class: {...}}."""
     B, Ns, L = lay["B"], lay["Ns"], lay["L"]
     BB8 = B * B * 8
     lin = res["linearizations"]
     tries = res["inner_iterations"]
-    table = {}
-    lin_bytes = sum(ALG_BYTES[k] * nf[k] for k in nf)
-    table["linearize"] = lin_bytes * lin
-    table["error"] = sum((ALG_BYTES[k] - {"prior_pose": 336, "prior_vel": 96, "between": 624, "dvl": 240, "stereo": 240, "imu": 1800}[k]
-                          + 8) * nf[k] for k in nf) * (tries + 1)
-    # BCR solve: one application streams Dinv, Gl, Gr (backward) + GlT, GrT (forward) once, plus the vector
-    # per optimize: (6-rhs border set-up + 1) per try + one per PCG iteration + ...; count applications from launches
     levels = max(1, int(np.ceil(np.log2(max(Ns, 2)))))
-    per_apply_launches = 2 * levels + 1
-    applies = launches["bcr_solve"] / per_apply_launches if per_apply_launches else 0
-    table["bcr_solve"] = applies * (5 * Ns * BB8 + 4 * L * 8)
-    # BCR factor: reads SD + SU, writes Dinv, Gl, Gr, GlT, GrT (+ level couplings ~ 1x)
-    table["bcr_factor"] = tries * (8 * Ns * BB8)
-    # operator: SD + 2 SU per application + vectors
-    mv_launch = launches["matvec"]
-    table["matvec"] = (mv_launch / 3.0) * (3 * Ns * BB8 + 2 * L * 8)
-    # damp + Schur: copy of the base system (read + write) + E, W streams per try
-    table["schur"] = tries * (2 * (2 * Ns * BB8) + nf.get("stereo", 0) * (18 * 8 * 3))
     out = {}
-    for k, b in table.items():
-        ms = ms_class.get(k, 0.0)
-        if ms > 0:
-            out[k] = dict(ms=ms, launches=launches.get(k, 0), alg_bytes=b, gbs=b / ms / 1e6)
+
+    def add(name, bound, work, unit_scale, peak, unit):
+        ms = ms_class.get(name, 0.0)
+        if ms > 0 and work > 0:
+            ach = work / ms / unit_scale
+            out[name] = dict(bound=bound, ms=ms, launches=launches.get(name, 0), work=work, achieved=ach, peak=peak, unit=unit,
+                             frac=ach / peak)
+
+    lin_bytes = sum(ALG_BYTES[k] * nf[k] for k in nf)
+    add("linearize", "hbm", lin_bytes * lin, 1e6, hbm_peak, "GB/s")
+    err_bytes = sum((ALG_BYTES[k] - {"prior_pose": 336, "prior_vel": 96, "between": 624, "dvl": 240, "stereo": 240, "imu": 1800}[k] + 8) * nf[k]
+                    for k in nf)
+    add("error", "hbm", err_bytes * (tries + 1), 1e6, hbm_peak, "GB/s")
+    # BCR solve: one application streams Gr, Gl (forward) and Dinv, Gl, Gr (backward) of every eliminated node once
+    per_apply_launches = 2 * levels + 1
+    applies = launches.get("bcr_solve", 0) / per_apply_launches
+    add("bcr_solve", "hbm", applies * (5 * (Ns - 1) * BB8 + BB8 + 4 * L * 8), 1e6, hbm_peak, "GB/s")
+    # band operator: SD + SU (used twice: as SU and SU^T) per application, full block storage as the accounting basis
+    add("matvec", "hbm", launches.get("matvec", 0) * (3 * Ns - 2) * BB8, 1e6, hbm_peak, "GB/s")
+    # damp + Schur: copy of the base system (read + write), E stream (144 B / observation) read ~once, Cinv
+    add("schur", "hbm", tries * (2 * (2 * Ns - 1) * BB8 + nf.get("stereo", 0) * 144 * 2), 1e6, hbm_peak, "GB/s")
+    add("bcr_factor", "tensor", tries * bcr_factor_flops(Ns, B), 1e9, FP64_TENSOR_PEAK_TFLOPS, "TFLOP/s")
     return out
 
 
@@ -287,15 +313,20 @@ def main():
         return
 
     peak, peak_src = peaks()
-    rf_table = roofline(res, lay, nf, ms_class, launches_class) if ms_class and any(ms_class.values()) else {}
+    rf_table = roofline(res, lay, nf, ms_class, launches_class, peak) if ms_class and any(ms_class.values()) else {}
     rf = None
+    rf_hbm = None
     if rf_table:
-        # dominant HBM-bound kernel class by device time (bcr_factor is FP64-FMA bound: reported in the table, not as the roofline line)
-        cands = {k: v for k, v in rf_table.items() if k != "bcr_factor"}
-        top = max(cands, key=lambda k: cands[k]["ms"])
-        ach = cands[top]["gbs"]
-        rf = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-              "peak_source": peak_src, "device_ms": cands[top]["ms"], "launches": cands[top]["launches"]}
+        def line(name):
+            t = rf_table[name]
+            src = peak_src if t["bound"] == "hbm" else "FP64 DMMA issue-rate microbenchmark, this pool (profiles/r1_dmma_microbench.txt); no FP64 figure in MEASURED_PEAKS.json"
+            return {"bound": t["bound"], "kernel": name, "achieved": t["achieved"], "peak": t["peak"], "unit": t["unit"], "frac": t["frac"],
+                    "traffic": None, "peak_source": src, "device_ms": t["ms"], "launches": t["launches"]}
+        top = max(rf_table, key=lambda k: rf_table[k]["ms"])               # dominant kernel class by device time
+        rf = line(top)
+        hb = {k: v for k, v in rf_table.items() if v["bound"] == "hbm"}
+        if hb:
+            rf_hbm = line(max(hb, key=lambda k: hb[k]["ms"]))              # dominant HBM-bound class
     cpu = None
     if not a.no_cpu_baseline:
         cpu, _ = cpu_oracle_run(a)
@@ -309,7 +340,7 @@ def main():
                    "preintegration": "manifold", "lm_params": "gtsam defaults (batch.py:337)"},
         "time_to_converge_ms": ms / a.steps, "lm_iterations": res["iterations"], "lm_tries": res["inner_iterations"],
         "pcg_iterations": res["pcg_iterations"], "final_error": res["final_error"], "setup_s_upload_plus_analyze": setup_s,
-        "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": rf, "cpu_baseline": cpu,
+        "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": rf, "roofline_hbm": rf_hbm, "cpu_baseline": cpu,
         "phase_ms_last_step": {k: res[k] for k in ("ms_linearize", "ms_assemble", "ms_schur", "ms_factor", "ms_pcg", "ms_update")},
         "kernel_class_device_ms": {k: v for k, v in ms_class.items() if v}, "kernel_class_table": rf_table,
     }

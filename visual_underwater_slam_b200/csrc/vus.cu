@@ -585,7 +585,7 @@ void apply_A(vus_handle* h, double* y, const double* x, rt::stream_t st) {
   a.F = h->F.p; a.Hbb = h->Hbb.p; a.xb = x + h->Lc; a.yb = y + h->Lc; a.has_bias = h->has_bias;
   const size_t smem = (size_t)blk_smem_doubles(h->B, 1, 256) * sizeof(double);
   L_coop<BandMatvecBody>((int)h->Ns, 256, smem, st, a);
-  if (h->nrem || h->has_bias) L_elem<RemBorderMatvecBody>(h->N * h->D, st, a);
+  if (h->nrem || h->has_bias) { ClassGuard kc_b(KC_BORDER); L_elem<RemBorderMatvecBody>(h->N * h->D, st, a); }
   if (h->has_bias) {
     border_dot(h, x, h->Lc, 1, st);
     BorderRowArgs b; b.Hbb = h->Hbb.p; b.xb = x + h->Lc; b.partials = h->bpart.p; b.grid = h->red_grid; b.yb = y + h->Lc;
