@@ -11,8 +11,10 @@
  *   - plain pointers and sizes only; every call returns 0 on success or a negative vus_status;
  *     vus_last_error() returns a message owned by the handle.  No exceptions cross the ABI.
  *   - all numeric tables are FP64 structure-of-arrays, COMPONENT-MAJOR:  table[c * n + i].
- *   - `mem` says where a numeric table lives: VUS_MEM_HOST (the library copies host->device) or
- *     VUS_MEM_DEVICE (a device pointer, e.g. torch.Tensor.data_ptr(); copied device->device).
+ *   - `mem` says where a numeric table lives and how it is laid out: VUS_MEM_HOST (the library copies
+ *     host->device) or VUS_MEM_DEVICE (a device pointer, e.g. torch.Tensor.data_ptr(); copied device->device),
+ *     both component-major; the *_ROWS variants take the natural row-major [n][dim] array (what numpy / gtsam
+ *     callers hold) and transpose it on the device, so the host never re-packs a table.
  *     Key / index / insertion-order arrays are always host memory.
  *   - one handle per GPU, one host thread per handle; all kernels run on the stream passed in.
  */
@@ -27,7 +29,8 @@ extern "C" {
 typedef struct vus_handle vus_handle;
 
 enum vus_status { VUS_OK = 0, VUS_ERR_INVALID = -1, VUS_ERR_UNSUPPORTED = -2, VUS_ERR_CUDA = -3, VUS_ERR_STATE = -4 };
-enum vus_mem { VUS_MEM_HOST = 0, VUS_MEM_DEVICE = 1 };
+enum vus_mem { VUS_MEM_HOST = 0, VUS_MEM_DEVICE = 1,            /* component-major table[c * n + i] */
+               VUS_MEM_HOST_ROWS = 2, VUS_MEM_DEVICE_ROWS = 3 }; /* row-major table[i * dim + c]: transposed on the device */
 
 /* Variable kinds (gtsam::Values entries, batch.py:274, :283-288, :297-298).
  *   POSE  12 comps: R row-major (9) then t (3)      X(i)   gtsam::Pose3

@@ -655,6 +655,24 @@ struct AddVecBody {     // y[i] += x[i]
   static VUS_DEV void run(const VecArgs& A, long i) { A.y[i] += A.x[i]; }
 };
 
+// layout conversion between the caller's row-major [n][dim] tables and the component-major device tables
+struct TransposeArgs { const double* src; double* dst; long n; int dim; int to_soa; };
+struct TransposeBody {
+  static VUS_DEV void run(const TransposeArgs& A, long w) {
+    const long i = w / A.dim;
+    const int c = (int)(w - i * A.dim);
+    if (A.to_soa) A.dst[(long)c * A.n + i] = A.src[w];
+    else A.dst[w] = A.src[(long)c * A.n + i];
+  }
+};
+// sort keys for the landmark-major observation order: (landmark << 32) | pose, value = row
+struct SortKeyArgs { const int* idx; long n; unsigned long long* keys; int* vals; };
+struct SortKeyBody {
+  static VUS_DEV void run(const SortKeyArgs& A, long f) {
+    A.keys[f] = ((unsigned long long)(unsigned)A.idx[A.n + f] << 32) | (unsigned)A.idx[f];
+    A.vals[f] = (int)f;
+  }
+};
 // dst[c][f] = src[c][perm[f]]  (re-ordering of a component-major table, used once per graph by vus_analyze)
 struct GatherArgs { const double* src; double* dst; const int* perm; long n; int comps; };
 struct GatherBody {

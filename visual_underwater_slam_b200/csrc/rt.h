@@ -16,6 +16,7 @@ typedef void* stream_t;
 inline void check_last(const char*) {}
 inline void* dalloc(size_t bytes) { void* p = std::calloc(bytes ? bytes : 1, 1); if (!p) throw std::runtime_error("emu alloc failed"); return p; }
 inline void dfree(void* p) { std::free(p); }
+inline void pool_setup(int) {}
 inline void h2d(void* d, const void* s, size_t n, stream_t) { std::memcpy(d, s, n); }
 inline void d2h(void* d, const void* s, size_t n, stream_t) { std::memcpy(d, s, n); }
 inline void d2d(void* d, const void* s, size_t n, stream_t) { std::memmove(d, s, n); }
@@ -38,8 +39,23 @@ inline void check(cudaError_t e, const char* what) {
   if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
 }
 inline void check_last(const char* what) { check(cudaGetLastError(), what); }
-inline void* dalloc(size_t bytes) { void* p = nullptr; check(cudaMalloc(&p, bytes ? bytes : 8), "cudaMalloc"); return p; }
-inline void dfree(void* p) { if (p) cudaFree(p); }
+// Device memory comes from the default stream-ordered pool with an unlimited release threshold: a handle that is
+// destroyed and re-created (one optimize() per incoming graph) reuses the pool instead of paying cudaMalloc/cudaFree
+// (un)mapping of several GB every time.
+inline void pool_setup(int device) {
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+}
+inline void* dalloc(size_t bytes) {
+  void* p = nullptr;
+  check(cudaMallocAsync(&p, bytes ? bytes : 8, 0), "cudaMallocAsync");
+  check(cudaStreamSynchronize(0), "alloc sync");
+  return p;
+}
+inline void dfree(void* p) { if (p) cudaFreeAsync(p, 0); }
 inline void h2d(void* d, const void* s, size_t n, stream_t st) { if (n) check(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st), "h2d"); }
 inline void d2h(void* d, const void* s, size_t n, stream_t st) { if (n) check(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st), "d2h"); }
 inline void d2d(void* d, const void* s, size_t n, stream_t st) { if (n) check(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st), "d2d"); }

@@ -11,6 +11,9 @@
 #include <cstdio>
 #include <map>
 #include <numeric>
+#ifndef VUS_EMU
+#include <cub/device/device_radix_sort.cuh>
+#endif
 
 using namespace vus;
 using rt::DBuf;
@@ -198,6 +201,33 @@ double graph_error(vus_handle* h, int which, rt::stream_t st) {
   return read_scalar(h, S_TMP, st);
 }
 
+// copy a caller table (host/device, component-major or row-major) into a component-major device table [dim][n]
+void import_table(double* dst, const double* src, long n, int dim, int mem, rt::stream_t st) {
+  const size_t bytes = (size_t)dim * n * sizeof(double);
+  if (!bytes) return;
+  if (mem == VUS_MEM_HOST) { rt::h2d(dst, src, bytes, st); return; }
+  if (mem == VUS_MEM_DEVICE) { rt::d2d(dst, src, bytes, st); return; }
+  DBuf<double> tmp;
+  const double* rows = src;
+  if (mem == VUS_MEM_HOST_ROWS) { tmp.alloc((size_t)dim * n); rt::h2d(tmp.p, src, bytes, st); rows = tmp.p; }
+  TransposeArgs t; t.src = rows; t.dst = dst; t.n = n; t.dim = dim; t.to_soa = 1;
+  L_elem<TransposeBody>((long)dim * n, st, t);
+  rt::sync(st);                                        // tmp is released on return
+}
+void export_table(double* dst, const double* src, long n, int dim, int mem, rt::stream_t st) {
+  const size_t bytes = (size_t)dim * n * sizeof(double);
+  if (!bytes) return;
+  if (mem == VUS_MEM_HOST) { rt::d2h(dst, src, bytes, st); return; }
+  if (mem == VUS_MEM_DEVICE) { rt::d2d(dst, src, bytes, st); return; }
+  DBuf<double> tmp;
+  double* rows = dst;
+  if (mem == VUS_MEM_HOST_ROWS) { tmp.alloc((size_t)dim * n); rows = tmp.p; }
+  TransposeArgs t; t.src = src; t.dst = rows; t.n = n; t.dim = dim; t.to_soa = 0;
+  L_elem<TransposeBody>((long)dim * n, st, t);
+  if (mem == VUS_MEM_HOST_ROWS) rt::d2h(dst, tmp.p, bytes, st);
+  rt::sync(st);
+}
+
 // ------------------------------------------------------------------ symbolic analysis
 struct PairKey { long p, q; };
 
@@ -224,6 +254,11 @@ PairDst band_dst(const vus_handle* h, long p, long q, const std::map<std::pair<l
 }
 
 int analyze(vus_handle* h, rt::stream_t st) {
+  const double t_an0 = now_ms();
+  double t_tick = t_an0;
+  auto tick = [&](const char* what) {
+    if (h->prm.verbose > 1) { const double t = now_ms(); std::fprintf(stderr, "  analyze %-28s %.1f ms\n", what, t - t_tick); t_tick = t; }
+  };
   const long NX = h->nvar[0], NV = h->nvar[1], NB = h->nvar[2], NL = h->nvar[3];
   if (NX == 0) return fail(h, VUS_ERR_INVALID, "no Pose3 variables");
   if (NB > 1) return fail(h, VUS_ERR_UNSUPPORTED, "more than one imuBias variable: only the shared B(0) of batch.py:238/:274 is supported");
@@ -259,11 +294,27 @@ int analyze(vus_handle* h, rt::stream_t st) {
   for (long l = 0; l < NL; ++l) lm_ptr[l + 1] += lm_ptr[l];
   if (FS.n) {
     std::vector<int> order(FS.n);
+#ifndef VUS_EMU
+    {   // stable device radix sort of (landmark, pose) keys: order[f'] = caller row stored at row f'
+      DBuf<unsigned long long> k_in, k_out;
+      DBuf<int> v_in, v_out;
+      k_in.alloc(FS.n); k_out.alloc(FS.n); v_in.alloc(FS.n); v_out.alloc(FS.n);
+      SortKeyArgs ka; ka.idx = FS.idx.p; ka.n = FS.n; ka.keys = k_in.p; ka.vals = v_in.p;
+      L_elem<SortKeyBody>(FS.n, st, ka);
+      int end_bit = 33;
+      while (end_bit < 64 && (NL >> (end_bit - 32)) != 0) ++end_bit;
+      size_t tmp_bytes = 0;
+      rt::check(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in.p, k_out.p, v_in.p, v_out.p, (int)FS.n, 0, end_bit, st), "radix sort size");
+      DBuf<unsigned char> tmp; tmp.alloc(tmp_bytes);
+      rt::check(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k_in.p, k_out.p, v_in.p, v_out.p, (int)FS.n, 0, end_bit, st), "radix sort");
+      rt::d2h(order.data(), v_out.p, FS.n * sizeof(int), st);
+      rt::sync(st);
+    }
+#else
     {
       std::vector<int> fill(lm_ptr.begin(), lm_ptr.end() - 1);
       for (long o = 0; o < FS.n; ++o) order[fill[FS.h_idx[FS.n + o]]++] = (int)o;
     }
-    bool identity = true;
     for (long l = 0; l < NL; ++l) {                     // insertion sort by pose: tracks arrive (nearly) sorted
       int* q = order.data() + lm_ptr[l];
       const int len = lm_ptr[l + 1] - lm_ptr[l];
@@ -275,6 +326,8 @@ int analyze(vus_handle* h, rt::stream_t st) {
         q[b + 1] = v;
       }
     }
+#endif
+    bool identity = true;
     for (long o = 0; o < FS.n && identity; ++o) identity = order[o] == o;
     if (!identity) {
       std::vector<int> nidx(2 * FS.n);
@@ -302,6 +355,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
       std::iota(FS.perm.begin(), FS.perm.end(), 0);
     }
   }
+  tick("stereo landmark-major sort");
   for (long o = 0; o < FS.n; ++o) pose_cnt[FS.h_idx[o]]++;
   std::vector<int> pose_ids, pose_ptr(1, 0), pose_obs(FS.n);
   {
@@ -314,6 +368,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
   h->nposes_obs = (long)pose_ids.size();
   for (long l = 0; l < NL; ++l)
     if (lm_ptr[l + 1] == lm_ptr[l]) return fail(h, VUS_ERR_INVALID, "a landmark has no stereo factor (indeterminate system)");
+  tick("pose CSR");
   // ---- band width k
   const int kcap = h->prm.max_supernode > 0 ? h->prm.max_supernode : 96 / D;
   long span = 1;
@@ -356,6 +411,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
   h->su_off = h->Ns * BB;
   h->rem_off = h->su_off + (h->Ns > 1 ? (h->Ns - 1) * BB : 0);
   h->hlen = h->rem_off + h->nrem * D * D;
+  tick("band width + remainder");
   // ---- per-factor pair destinations
   auto build_pairs = [&](FactorTable& T, int slot_p, int slot_q) {
     std::vector<PairDst> v(T.n);
@@ -369,6 +425,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
   };
   if (FB.n && !build_pairs(FB, 0, 1)) return VUS_ERR_INVALID;
   if (FI.n && !build_pairs(FI, 0, 2)) return VUS_ERR_INVALID;
+  tick("pair destinations");
   // ---- uploads / allocations
   h->rem_ptr.upload(rem_ptr, st); h->rem_col.upload(rem_col, st);
   h->pose_ptr.upload(pose_ptr, st); h->pose_obs.upload(pose_obs, st); h->pose_ids.upload(pose_ids, st);
@@ -397,7 +454,9 @@ int analyze(vus_handle* h, rt::stream_t st) {
   h->e_all.alloc(eoff); h->le_all.alloc(eoff);
   for (int kind = 0; kind < 4; ++kind) h->val[1 - h->cur][kind].alloc((size_t)kVarDim[kind] * h->nvar[kind]);
   rt::sync(st);
+  tick("uploads + allocations");
   h->analyzed = true;
+  if (h->prm.verbose) std::fprintf(stderr, "vus_analyze: %.1f ms (D=%d k=%d Ns=%ld nrem=%ld)\n", now_ms() - t_an0, h->D, h->k, h->Ns, h->nrem);
   return VUS_OK;
 }
 
@@ -836,6 +895,7 @@ int vus_create(int device, vus_handle** out) {
   if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return VUS_ERR_CUDA;
   if (cudaSetDevice(device) != cudaSuccess) return VUS_ERR_CUDA;
 #endif
+  rt::pool_setup(device);
   vus_handle* h = new vus_handle();
   h->device = device;
   vus_default_lm_params(&h->prm);
@@ -848,7 +908,7 @@ void vus_destroy(vus_handle* h) { delete h; }
 const char* vus_last_error(const vus_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
 int vus_set_variables(vus_handle* h, int kind, int64_t n, const uint64_t* keys, const double* data, int mem) {
-  if (!h || kind < 0 || kind >= 4 || n < 0) return fail(h, VUS_ERR_INVALID, "vus_set_variables: bad arguments");
+  if (!h || kind < 0 || kind >= 4 || n < 0 || mem < 0 || mem > 3) return fail(h, VUS_ERR_INVALID, "vus_set_variables: bad arguments");
   VUS_TRY(h)
   for (int64_t i = 1; i < n; ++i)
     if (keys[i] <= keys[i - 1]) return fail(h, VUS_ERR_INVALID, "vus_set_variables: keys must be strictly ascending");
@@ -856,8 +916,7 @@ int vus_set_variables(vus_handle* h, int kind, int64_t n, const uint64_t* keys, 
   h->nvar[kind] = n;
   DBuf<double>& b = h->val[h->cur][kind];
   b.alloc((size_t)kVarDim[kind] * n);
-  if (mem == VUS_MEM_HOST) rt::h2d(b.p, data, (size_t)kVarDim[kind] * n * sizeof(double), 0);
-  else rt::d2d(b.p, data, (size_t)kVarDim[kind] * n * sizeof(double), 0);
+  import_table(b.p, data, n, kVarDim[kind], mem, 0);
   rt::sync(0);
   h->analyzed = false;
   return VUS_OK;
@@ -867,9 +926,7 @@ int vus_set_variables(vus_handle* h, int kind, int64_t n, const uint64_t* keys, 
 int vus_get_variables(vus_handle* h, int kind, double* out, int mem) {
   if (!h || kind < 0 || kind >= 4) return fail(h, VUS_ERR_INVALID, "vus_get_variables: bad arguments");
   VUS_TRY(h)
-  const size_t bytes = (size_t)kVarDim[kind] * h->nvar[kind] * sizeof(double);
-  if (mem == VUS_MEM_HOST) rt::d2h(out, h->val[h->cur][kind].p, bytes, 0);
-  else rt::d2d(out, h->val[h->cur][kind].p, bytes, 0);
+  export_table(out, h->val[h->cur][kind].p, h->nvar[kind], kVarDim[kind], mem, 0);
   rt::sync(0);
   return VUS_OK;
   VUS_CATCH(h)
@@ -912,13 +969,8 @@ int vus_add_factors(vus_handle* h, int type, int64_t n, const int32_t* var_idx, 
   T.idx.upload(T.h_idx, 0);
   T.meas.alloc((size_t)kFactorMeas[type] * n);
   T.sinfo.alloc((size_t)kFactorInfo[type] * n);
-  if (mem == VUS_MEM_HOST) {
-    rt::h2d(T.meas.p, meas, (size_t)kFactorMeas[type] * n * sizeof(double), 0);
-    rt::h2d(T.sinfo.p, sqrt_info, (size_t)kFactorInfo[type] * n * sizeof(double), 0);
-  } else {
-    rt::d2d(T.meas.p, meas, (size_t)kFactorMeas[type] * n * sizeof(double), 0);
-    rt::d2d(T.sinfo.p, sqrt_info, (size_t)kFactorInfo[type] * n * sizeof(double), 0);
-  }
+  import_table(T.meas.p, meas, n, kFactorMeas[type], mem, 0);
+  import_table(T.sinfo.p, sqrt_info, n, kFactorInfo[type], mem, 0);
   rt::sync(0);
   h->nfactors += n;
   h->analyzed = false;

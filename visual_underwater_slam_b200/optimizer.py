@@ -17,6 +17,8 @@ _SLOTS = {"prior_pose": ("x",), "prior_vel": ("v",), "between": ("x1", "x2"), "d
           "stereo": ("x", "l"), "imu": ("xi", "vi", "xj", "vj", "b")}
 _ROWS = {"prior_pose": 6, "prior_vel": 3, "between": 6, "dvl": 3, "stereo": 3, "imu": 9}
 _COLS = {"prior_pose": 6, "prior_vel": 3, "between": 12, "dvl": 9, "stereo": 9, "imu": 24}
+_MEAS = {"prior_pose": 12, "prior_vel": 3, "between": 12, "dvl": 3, "stereo": 3, "imu": 67}
+_INFO = {"prior_pose": 6, "prior_vel": 3, "between": 6, "dvl": 3, "stereo": 3, "imu": 45}
 _KINDS = (("pose", "pose_keys", "poses", 12), ("vel", "vel_keys", "vels", 3), ("bias", "bias_keys", "biases", 6),
           ("lm", "lm_keys", "lms", 3))
 
@@ -95,9 +97,10 @@ class LevenbergMarquardtParams:
         return p
 
 
-def _soa(a, dtype=np.float64):
-    """[n, d] host table -> contiguous component-major [d, n]."""
-    return np.ascontiguousarray(np.asarray(a, dtype=dtype).T)
+def _rows(a, dim):
+    """[n, dim] host table as a C-contiguous float64 array (no copy when it already is one): the library takes
+    row-major tables as they are and transposes them on the device (VUS_MEM_*_ROWS)."""
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1, dim))
 
 
 class Session:
@@ -145,15 +148,15 @@ class Session:
             import torch
             t = torch.from_numpy(arr).cuda()
             self._keep.append(t)
-            return C.c_void_p(t.data_ptr()), 1
+            return C.c_void_p(t.data_ptr()), 3          # VUS_MEM_DEVICE_ROWS
         self._keep.append(arr)
-        return arr.ctypes.data_as(C.c_void_p), 0
+        return arr.ctypes.data_as(C.c_void_p), 2        # VUS_MEM_HOST_ROWS
 
     def _upload(self, prob, device_tensors):
         lib = self.lib
         for kind, (name, kname, dname, dim) in enumerate(_KINDS):
             keys = np.ascontiguousarray(prob[kname], dtype=np.uint64)
-            data = _soa(np.asarray(prob[dname]).reshape(len(keys), dim))
+            data = _rows(prob[dname], dim)
             self.n[name] = len(keys)
             ptr, mem = self._table(data, device_tensors)
             self._check(lib.vus_set_variables(self._h, kind, len(keys), keys.ctypes.data_as(_native.c_u64_p), ptr, mem))
@@ -169,8 +172,8 @@ class Session:
             if n == 0:
                 continue
             idx = np.ascontiguousarray(np.stack([f[s] for s in _SLOTS[name]], 0), dtype=np.int32)
-            meas = _soa(f["meas"])
-            info = _soa(f["sqrt_info"])
+            meas = _rows(f["meas"], _MEAS[name])
+            info = _rows(f["sqrt_info"], _INFO[name])
             orig = np.ascontiguousarray(f["orig"], dtype=np.int64)
             pm, mem = self._table(meas, device_tensors)
             pi, _ = self._table(info, device_tensors)
@@ -254,9 +257,9 @@ class Session:
         out = {}
         self.d2h_bytes = 0
         for kind, (name, kname, dname, dim) in enumerate(_KINDS):
-            buf = np.zeros((dim, self.n[name]))
-            self._check(self.lib.vus_get_variables(self._h, kind, buf.ctypes.data_as(C.c_void_p), 0))
-            out[dname] = buf.T.copy()
+            buf = np.empty((self.n[name], dim))
+            self._check(self.lib.vus_get_variables(self._h, kind, buf.ctypes.data_as(C.c_void_p), 2))
+            out[dname] = buf
             self.d2h_bytes += buf.nbytes
         return out
 
