@@ -422,6 +422,7 @@ struct BcrRootBody {
 // Launch with 256 threads; nv <= 6.
 #define VUS_MAXV 6
 #define VUS_LDX 12
+VUS_HD long blk_slot_doubles(int B) { return bcr_buf_doubles(B) + (long)bcr_kp(B) * VUS_LDX + 8; }   // one block + its panel
 VUS_HD long blk_smem_doubles(int B, int nv, int) {
 #ifdef VUS_EMU
   return (long)4 * nv * B;
@@ -496,7 +497,10 @@ inline void emu_blk_accum(double* out, const double* M, bool ta, const double* x
 #endif
 
 // forward sweep, per surviving node c: b_c -= Gr_{c-s} b_{c-s} + Gl_{c+s} b_{c+s}
-struct BcrFwdBody {
+// DEEP (levels with at most one CTA per SM): one operand buffer + panel per block, all copies in flight at once --
+// a lone CTA otherwise pays the DRAM latency once per block.
+template <bool DEEP>
+struct BcrFwdBodyT {
   static VUS_DEV void run(const BcrArgs& A, int m, int tid, int, double* sm) {
     const int B = A.B, nv = A.nrhs;
     const long BB = (long)B * B;
@@ -512,18 +516,31 @@ struct BcrFwdBody {
     (void)tid;
 #else
     const Tiles G(B, tid);
-    double* buf = sm;
-    double* sX = sm + bcr_buf_doubles(B);
+    const long slot = blk_slot_doubles(B);
     Panel P;
     P.zero();
-    if (jl >= 0) blk_stream<false, false>(P, buf, sX, A.Gr + jl * BB, A.X + jl * B, A.xstride, G, nv, tid);
-    if (jh < A.Ns) blk_stream<false, false>(P, buf, sX, A.Gl + jh * BB, A.X + jh * B, A.xstride, G, nv, tid);
+    if (DEEP) {
+      if (jl >= 0) { stage_block(sm, A.Gr + jl * BB, G); stage_panel(sm + bcr_buf_doubles(B), A.X + jl * B, A.xstride, true, G, nv, tid); }
+      if (jh < A.Ns) { stage_block(sm + slot, A.Gl + jh * BB, G); stage_panel(sm + slot + bcr_buf_doubles(B), A.X + jh * B, A.xstride, true, G, nv, tid); }
+      stage_wait();
+      __syncthreads();
+      if (jl >= 0) panel_mma<false, false>(P, sm, sm + bcr_buf_doubles(B), G);
+      if (jh < A.Ns) panel_mma<false, false>(P, sm + slot, sm + slot + bcr_buf_doubles(B), G);
+    } else {
+      double* buf = sm;
+      double* sX = sm + bcr_buf_doubles(B);
+      if (jl >= 0) blk_stream<false, false>(P, buf, sX, A.Gr + jl * BB, A.X + jl * B, A.xstride, G, nv, tid);
+      if (jh < A.Ns) blk_stream<false, false>(P, buf, sX, A.Gl + jh * BB, A.X + jh * B, A.xstride, G, nv, tid);
+    }
     VUS_PANEL_FOREACH(P, G, nv, { A.X[(long)v * A.xstride + c * B + r] -= val; })
 #endif
   }
 };
+typedef BcrFwdBodyT<false> BcrFwdBody;
+typedef BcrFwdBodyT<true> BcrFwdDeepBody;
 // backward sweep, per eliminated node j: x_j = Dinv_j b_j - Gl_j^T x_{j-s} - Gr_j^T x_{j+s}
-struct BcrBwdBody {
+template <bool DEEP>
+struct BcrBwdBodyT {
   static VUS_DEV void run(const BcrArgs& A, int m, int tid, int, double* sm) {
     const int B = A.B, nv = A.nrhs;
     const long BB = (long)B * B;
@@ -541,17 +558,31 @@ struct BcrBwdBody {
     (void)tid;
 #else
     const Tiles G(B, tid);
-    double* buf = sm;
-    double* sX = sm + bcr_buf_doubles(B);
+    const long slot = blk_slot_doubles(B), po = bcr_buf_doubles(B);
     Panel P;
     P.zero();
-    blk_stream<false, false>(P, buf, sX, A.Dinv + j * BB, A.X + j * B, A.xstride, G, nv, tid);
-    if (hl) blk_stream<true, true>(P, buf, sX, A.Gl + j * BB, A.X + jl * B, A.xstride, G, nv, tid);
-    if (hh) blk_stream<true, true>(P, buf, sX, A.Gr + j * BB, A.X + jh * B, A.xstride, G, nv, tid);
+    if (DEEP) {
+      stage_block(sm, A.Dinv + j * BB, G); stage_panel(sm + po, A.X + j * B, A.xstride, true, G, nv, tid);
+      if (hl) { stage_block(sm + slot, A.Gl + j * BB, G); stage_panel(sm + slot + po, A.X + jl * B, A.xstride, true, G, nv, tid); }
+      if (hh) { stage_block(sm + 2 * slot, A.Gr + j * BB, G); stage_panel(sm + 2 * slot + po, A.X + jh * B, A.xstride, true, G, nv, tid); }
+      stage_wait();
+      __syncthreads();
+      panel_mma<false, false>(P, sm, sm + po, G);
+      if (hl) panel_mma<true, true>(P, sm + slot, sm + slot + po, G);
+      if (hh) panel_mma<true, true>(P, sm + 2 * slot, sm + 2 * slot + po, G);
+    } else {
+      double* buf = sm;
+      double* sX = sm + po;
+      blk_stream<false, false>(P, buf, sX, A.Dinv + j * BB, A.X + j * B, A.xstride, G, nv, tid);
+      if (hl) blk_stream<true, true>(P, buf, sX, A.Gl + j * BB, A.X + jl * B, A.xstride, G, nv, tid);
+      if (hh) blk_stream<true, true>(P, buf, sX, A.Gr + j * BB, A.X + jh * B, A.xstride, G, nv, tid);
+    }
     VUS_PANEL_FOREACH(P, G, nv, { A.X[(long)v * A.xstride + j * B + r] = val; })
 #endif
   }
 };
+typedef BcrBwdBodyT<false> BcrBwdBody;
+typedef BcrBwdBodyT<true> BcrBwdDeepBody;
 // root solve: x_0 = Dinv_0 b_0   (the backward body with no neighbours: s = 0, m such that j = 0)
 struct BcrRootSolveBody {
   static VUS_DEV void run(const BcrArgs& A, int, int tid, int nthr, double* sm) {
@@ -595,6 +626,8 @@ struct BandMatvecBody {
 namespace rt {
 template <> struct CoopBounds<BcrFwdBody> { static constexpr int kMaxThreads = 256, kMinBlocks = 3; };
 template <> struct CoopBounds<BcrBwdBody> { static constexpr int kMaxThreads = 256, kMinBlocks = 3; };
+template <> struct CoopBounds<BcrFwdDeepBody> { static constexpr int kMaxThreads = 256, kMinBlocks = 1; };
+template <> struct CoopBounds<BcrBwdDeepBody> { static constexpr int kMaxThreads = 256, kMinBlocks = 1; };
 template <> struct CoopBounds<BcrRootSolveBody> { static constexpr int kMaxThreads = 256, kMinBlocks = 3; };
 template <> struct CoopBounds<BandMatvecBody> { static constexpr int kMaxThreads = 256, kMinBlocks = 3; };
 }  // namespace rt

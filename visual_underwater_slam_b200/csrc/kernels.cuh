@@ -251,6 +251,73 @@ struct AsmBody {
   }
 };
 
+// ImuFactor assembly, tiled: one CTA stages the whitened Jacobians (9 x 24) and residuals of 32 consecutive factors in
+// shared memory with coalesced loads (J is component-major, so a warp reads 32 factors' component c in one request),
+// then lane = factor, warps stride over the 297 distinct outputs of a factor:
+//   45 H_pp (a <= b, mirrored) | 45 H_qq | 81 H_pq | 54 F_p | 54 F_q | 18 gradient      (bias-bias block: ImuBiasBody)
+// Destinations are those of AsmBody<VUS_F_IMU>; chain neighbours share diagonal blocks, hence the atomics.
+#define VUS_IMU_TILE 32
+struct ImuAsmBody {
+  static VUS_DEV void run(const AsmArgs& A, int tile, int tid, int nthr, double* sm) {
+    const long n = A.n;
+    const long f0 = (long)tile * VUS_IMU_TILE;
+    const int nf = (int)((n - f0 < VUS_IMU_TILE) ? (n - f0) : VUS_IMU_TILE);
+    double* sJ = sm;                              // [216][32]
+    double* sR = sm + 216 * VUS_IMU_TILE;         // [9][32]
+    for (int e = tid; e < 225 * VUS_IMU_TILE; e += nthr) {
+      const int c = e / VUS_IMU_TILE, fl = e - c * VUS_IMU_TILE;
+      double v = 0.0;
+      if (fl < nf) v = c < 216 ? A.J[(long)c * n + f0 + fl] : A.r[(long)(c - 216) * n + f0 + fl];
+      sm[e] = v;
+    }
+    VUS_SYNC();
+    const int D = A.D;
+    for (int w = tid; w < 297 * VUS_IMU_TILE; w += nthr) {
+      const int e = w / VUS_IMU_TILE, fl = w - e * VUS_IMU_TILE;
+      if (fl >= nf) continue;
+      const long f = f0 + fl;
+      const long p = A.idx[f], q = A.idx[2 * n + f];
+      int a, b, kind;                             // kind 0 pp, 1 qq, 2 pq, 3 Fp, 4 Fq, 5 gradient
+      if (e < 90) {
+        int t = e < 45 ? e : e - 45;
+        a = 0;
+        while (t >= 9 - a) { t -= 9 - a; ++a; }
+        b = a + t;
+        kind = e < 45 ? 0 : 1;
+        if (kind == 1) { a += 9; b += 9; }
+      } else if (e < 171) { const int t = e - 90; a = t / 9; b = 9 + t % 9; kind = 2; }
+      else if (e < 225) { const int t = e - 171; a = t / 6; b = 18 + t % 6; kind = 3; }
+      else if (e < 279) { const int t = e - 225; a = 9 + t / 6; b = 18 + t % 6; kind = 4; }
+      else { a = e - 279; b = 0; kind = 5; }
+      double h = 0.0;
+      if (kind == 5) {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) h += sJ[(r * 24 + a) * VUS_IMU_TILE + fl] * sR[r * VUS_IMU_TILE + fl];
+        atomic_add(&A.g[(a < 9 ? p : q) * D + (a < 9 ? a : a - 9)], -h);
+        continue;
+      }
+#pragma unroll
+      for (int r = 0; r < 9; ++r) h += sJ[(r * 24 + a) * VUS_IMU_TILE + fl] * sJ[(r * 24 + b) * VUS_IMU_TILE + fl];
+      if (kind <= 1) {
+        const long node = kind == 0 ? p : q;
+        const int la = kind == 0 ? a : a - 9, lb = kind == 0 ? b : b - 9;
+        atomic_add(&A.Hval[diag_off(node, la, lb, D, A.k, A.B)], h);
+        if (la != lb) atomic_add(&A.Hval[diag_off(node, lb, la, D, A.k, A.B)], h);
+      } else if (kind == 2) {
+        const int la = a, lb = b - 9;
+        const PairDst d = A.pair[f];
+        if (d.transposed) atomic_add(&A.Hval[d.off + (long)lb * d.ld + la], h);
+        else atomic_add(&A.Hval[d.off + (long)la * d.ld + lb], h);
+        if (d.moff >= 0) atomic_add(&A.Hval[d.moff + (long)lb * d.mld + la], h);
+      } else {
+        const long node = kind == 3 ? p : q;
+        const int la = kind == 3 ? a : a - 9;
+        atomic_add(&A.F[(node * D + la) * 6 + (b - 18)], h);
+      }
+    }
+  }
+};
+
 // shared-bias block: Hbb = sum_f Jb^T Jb (36) and gb = -sum_f Jb^T r (6) over ALL imu factors -- every factor hits the
 // same 42 addresses, so this is a two-stage block reduction instead of atomics.  partials [grid][42]
 struct ImuBiasArgs { long n; const double* J; const double* r; double* partials; int grid; double* Hbb; double* gb; };
@@ -420,10 +487,14 @@ struct SchurPoseBody {
         const double w1 = e0 * A.Cinv[A.nl + l] + e1 * A.Cinv[4 * A.nl + l] + e2 * A.Cinv[7 * A.nl + l];
         const double w2 = e0 * A.Cinv[2 * A.nl + l] + e1 * A.Cinv[5 * A.nl + l] + e2 * A.Cinv[8 * A.nl + l];
         if (s == 0) gacc += w0 * A.gl[l] + w1 * A.gl[A.nl + l] + w2 * A.gl[2 * A.nl + l];
-        for (int q = A.lm_ptr[l]; q < A.lm_ptr[l + 1]; ++q) {
-          const long o2 = q;                           // observations are stored landmark-major, pose-sorted
+        // observations are stored landmark-major and pose-sorted: the partners with j >= i start at o itself
+        // (or at an earlier observation of the same pose, if the landmark was seen twice from pose i)
+        int q0 = (int)o;
+        const int qbeg = A.lm_ptr[l], qend = A.lm_ptr[l + 1];
+        while (q0 > qbeg && A.idx[q0 - 1] == i) --q0;
+        for (int q = q0; q < qend; ++q) {
+          const long o2 = q;
           const long j = A.idx[o2];
-          if (j < i) continue;
           const double v = w0 * A.E[o2 * 18 + s * 3] + w1 * A.E[o2 * 18 + s * 3 + 1] + w2 * A.E[o2 * 18 + s * 3 + 2];
           const long J = j / k;
           if (J <= I + 1) {

@@ -480,7 +480,14 @@ void assemble_base(vus_handle* h, rt::stream_t st) {
   launch_asm<VUS_F_PRIOR_VEL>(h, st);
   launch_asm<VUS_F_BETWEEN>(h, st);
   launch_asm<VUS_F_DVL>(h, st);
-  launch_asm<VUS_F_IMU>(h, st);
+  if (h->ft[VUS_F_IMU].n) {
+    FactorTable& I = h->ft[VUS_F_IMU];
+    AsmArgs a;
+    a.type = VUS_F_IMU; a.n = I.n; a.idx = I.idx.p; a.J = I.J.p; a.r = I.r.p;
+    a.D = h->D; a.k = h->k; a.B = h->B;
+    a.Hval = h->H0.p; a.g = h->g0.p; a.F = h->F.p; a.Hbb = h->Hbb0.p; a.gb = h->gb.p; a.pair = I.pair.p;
+    L_coop<ImuAsmBody>((int)((I.n + VUS_IMU_TILE - 1) / VUS_IMU_TILE), 256, (size_t)225 * VUS_IMU_TILE * sizeof(double), st, a);
+  }
   if (h->ft[VUS_F_IMU].n) {
     FactorTable& I = h->ft[VUS_F_IMU];
     ImuBiasArgs b; b.n = I.n; b.J = I.J.p; b.r = I.r.p; b.partials = h->bpart.p; b.grid = h->red_grid; b.Hbb = h->Hbb0.p; b.gb = h->gb.p;
@@ -569,17 +576,24 @@ void bcr_solve(vus_handle* h, double* X, long xstride, int nrhs, rt::stream_t st
   const size_t smem = (size_t)blk_smem_doubles(h->B, nrhs, nthr) * sizeof(double);
   std::vector<long> levels;
   for (long s = 1; s < h->Ns; s <<= 1) levels.push_back(s);
+  // levels with at most one CTA per SM use the DEEP bodies (every block of a node in flight at once)
+  const size_t smem_deep = (size_t)3 * blk_slot_doubles(h->B) * sizeof(double);
+  const int deep_max = smem_deep <= 220 * 1024 ? rt::sm_count() : 0;
   for (long s : levels) {
     const long nact = (h->Ns + s - 1) / s;
     a.s = s;
-    L_coop<BcrFwdBody>((int)((nact + 1) / 2), nthr, smem, st, a);
+    const int grid = (int)((nact + 1) / 2);
+    if (grid <= deep_max) L_coop<BcrFwdDeepBody>(grid, nthr, smem_deep, st, a);
+    else L_coop<BcrFwdBody>(grid, nthr, smem, st, a);
   }
   L_coop<BcrRootSolveBody>(1, nthr, smem, st, a);
   for (auto it = levels.rbegin(); it != levels.rend(); ++it) {
     const long s = *it;
     const long nact = (h->Ns + s - 1) / s;
     a.s = s;
-    L_coop<BcrBwdBody>((int)(nact / 2), nthr, smem, st, a);
+    const int grid = (int)(nact / 2);
+    if (grid <= deep_max) L_coop<BcrBwdDeepBody>(grid, nthr, smem_deep, st, a);
+    else L_coop<BcrBwdBody>(grid, nthr, smem, st, a);
   }
 }
 
