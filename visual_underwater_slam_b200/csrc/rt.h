@@ -3,6 +3,7 @@
 // VUS_EMU build (tests only): malloc / memcpy / sequential loops.
 #pragma once
 #include "vus_common.h"
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -93,10 +94,10 @@ template <class Body, class Args>
 inline void launch_coop(int grid, int block, size_t smem_bytes, stream_t st, const Args& a) {
   if (grid <= 0) return;
   if (smem_bytes > 48 * 1024) {
-    static size_t configured = 0;   // per (Body,Args) instantiation
-    if (smem_bytes > configured) {
+    static std::atomic<size_t> configured{0};   // per (Body,Args) instantiation
+    if (smem_bytes > configured.load()) {
       check(cudaFuncSetAttribute(k_coop<Body, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes), "smem attr");
-      configured = smem_bytes;
+      configured.store(smem_bytes);
     }
   }
   k_coop<Body, Args><<<grid, block, smem_bytes, st>>>(a);

@@ -20,15 +20,17 @@ using rt::DBuf;
 
 namespace {
 
-long g_launches = 0;
+// launch counter / class / profiler are per host thread: one host thread drives one handle (include/vus.h), several
+// handles may run concurrently from several threads (independent trajectories on one GPU)
+thread_local long g_launches = 0;
 
 // kernel classes for the per-class device timing (vus_lm_result.ms_class / launches_class)
 enum { KC_LINEARIZE = 0, KC_ERROR, KC_LINERR, KC_ASSEMBLE, KC_STEREO_ASM, KC_SCHUR, KC_BCR_FACTOR, KC_BCR_SOLVE,
        KC_MATVEC, KC_BORDER, KC_VECTOR, KC_RETRACT, KC_COUNT };
-int g_class = KC_VECTOR;
+thread_local int g_class = KC_VECTOR;
 struct ClassGuard { int prev; explicit ClassGuard(int c) : prev(g_class) { g_class = c; } ~ClassGuard() { g_class = prev; } };
 
-struct Profiler {
+struct Profiler {   // one instance per host thread (g_prof below)
   bool on = false;
   double ms[16] = {0};
   long count[16] = {0};
@@ -53,7 +55,8 @@ struct Profiler {
   void collect() {}
 #endif
   void reset() { collect(); for (int i = 0; i < 16; ++i) { ms[i] = 0; count[i] = 0; } }
-} g_prof;
+};
+thread_local Profiler g_prof;
 
 template <class Body, class Args>
 void L_elem(long n, rt::stream_t st, const Args& a) {
