@@ -49,11 +49,6 @@ struct BcrArgs {
 
 #ifndef VUS_EMU
 // =====================================================================================  sm_100a: DMMA tile engine
-VUS_DEV void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
 // A 256-thread CTA = 8 warps in a 4 x 2 grid; warp (wr, wc) owns the 8x8 tiles ti in [3wr, 3wr+3), tj in [6wc, 6wc+6)
 // of a (<= 96 x 96) block.  Inside a tile lane (g = lane/4, t = lane%4) holds (row g, cols 2t, 2t+1).
 struct Tiles {

@@ -464,61 +464,89 @@ VUS_DEV int rem_find(const int* rem_ptr, const int* rem_col, long node, int col)
 // walking pose i's observations and, per landmark, its (pose-sorted) observation list.  In-band blocks (same or next
 // supernode, j - i < 2k) accumulate in shared memory and are written once; off-band blocks go straight to REM.
 // Each block (i,j) and its mirror are written by this CTA only: no atomics, deterministic summation order.
-struct SchurPoseBody {
+#define VUS_SCHUR_GROUPS 4
+// Thread (grp, rs): entry rs = (r, s) of every block S(i, j >= i), over the observations t = grp (mod ngrp) of pose i --
+// the groups shorten each thread's chain of dependent loads; their partial blocks are summed in a fixed order.
+template <bool OFFBAND_ONLY>
+struct SchurPoseScalar {
   static VUS_DEV void run(const SchurArgs& A, int pi, int tid, int nthr, double* sm) {
     const long i = A.pose_ids[pi];
     const int D = A.D, k = A.k, B = A.B;
     const long BB = (long)B * B;
     const int ndj = 2 * k;
-    double* acc = sm;                 // [ndj][36]
-    double* touched = sm + ndj * 36;  // [ndj]
-    for (int e = tid; e < ndj * 37; e += nthr) sm[e] = 0.0;
+    int ngrp = nthr / 36;
+    if (ngrp > VUS_SCHUR_GROUPS) ngrp = VUS_SCHUR_GROUPS;
+    if (ngrp < 1) ngrp = 1;
+    const int gstride = ndj * 37;       // per group: acc [ndj][36] | touched [ndj]
+    for (int e = tid; e < ngrp * gstride; e += nthr) sm[e] = 0.0;
     VUS_SYNC();
     const long I = i / k;
     const int ri = (int)(i - I * k);
-    for (int rs = tid; rs < 36; rs += nthr) {
+    for (int w = tid; w < ngrp * 36; w += nthr) {
+      const int grp = w / 36, rs = w - grp * 36;
       const int r = rs / 6, s = rs - r * 6;
+      double* acc = sm + grp * gstride;
+      double* touched = acc + ndj * 36;
       double gacc = 0.0;
-      for (int t = A.pose_ptr[pi]; t < A.pose_ptr[pi + 1]; ++t) {
+      for (int t = A.pose_ptr[pi] + grp; t < A.pose_ptr[pi + 1]; t += ngrp) {
         const long o = A.pose_obs[t];
         const long l = A.idx[A.n + o];
         const double e0 = A.E[o * 18 + r * 3], e1 = A.E[o * 18 + r * 3 + 1], e2 = A.E[o * 18 + r * 3 + 2];
         const double w0 = e0 * A.Cinv[l] + e1 * A.Cinv[3 * A.nl + l] + e2 * A.Cinv[6 * A.nl + l];
         const double w1 = e0 * A.Cinv[A.nl + l] + e1 * A.Cinv[4 * A.nl + l] + e2 * A.Cinv[7 * A.nl + l];
         const double w2 = e0 * A.Cinv[2 * A.nl + l] + e1 * A.Cinv[5 * A.nl + l] + e2 * A.Cinv[8 * A.nl + l];
-        if (s == 0) gacc += w0 * A.gl[l] + w1 * A.gl[A.nl + l] + w2 * A.gl[2 * A.nl + l];
+        if (!OFFBAND_ONLY && s == 0) gacc += w0 * A.gl[l] + w1 * A.gl[A.nl + l] + w2 * A.gl[2 * A.nl + l];
         // observations are stored landmark-major and pose-sorted: the partners with j >= i start at o itself
         // (or at an earlier observation of the same pose, if the landmark was seen twice from pose i)
         int q0 = (int)o;
         const int qbeg = A.lm_ptr[l], qend = A.lm_ptr[l + 1];
         while (q0 > qbeg && A.idx[q0 - 1] == i) --q0;
-        for (int q = q0; q < qend; ++q) {
-          const long o2 = q;
-          const long j = A.idx[o2];
-          const double v = w0 * A.E[o2 * 18 + s * 3] + w1 * A.E[o2 * 18 + s * 3 + 1] + w2 * A.E[o2 * 18 + s * 3 + 2];
-          const long J = j / k;
-          if (J <= I + 1) {
-            const int dj = (int)(j - i);
-            acc[dj * 36 + rs] += v;
-            if (rs == 0) touched[dj] = 1.0;
-          } else {                                   // off-band co-observation: remainder blocks (i,j) and (j,i)
-            const int t1 = rem_find(A.rem_ptr, A.rem_col, i, (int)j), t2 = rem_find(A.rem_ptr, A.rem_col, j, (int)i);
-            A.REM[(long)t1 * D * D + r * D + s] -= v;
-            A.REM[(long)t2 * D * D + s * D + r] -= v;
+        for (int qb = q0; qb < qend; qb += 4) {           // partners in batches of 4: all loads of a batch are independent
+          long jj[4];
+          double ev[4][3];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int q = qb + u < qend ? qb + u : qend - 1;
+            jj[u] = qb + u < qend ? (long)A.idx[q] : -1;
+            ev[u][0] = A.E[(long)q * 18 + s * 3]; ev[u][1] = A.E[(long)q * 18 + s * 3 + 1]; ev[u][2] = A.E[(long)q * 18 + s * 3 + 2];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const long j = jj[u];
+            if (j < 0) continue;
+            const double v = w0 * ev[u][0] + w1 * ev[u][1] + w2 * ev[u][2];
+            const long J = j / k;
+            if (J <= I + 1) {
+              if (OFFBAND_ONLY) continue;
+              const int dj = (int)(j - i);
+              acc[dj * 36 + rs] += v;
+              if (rs == 0) touched[dj] = 1.0;
+            } else {                                 // off-band co-observation: remainder blocks (i,j) and (j,i)
+              const int t1 = rem_find(A.rem_ptr, A.rem_col, i, (int)j), t2 = rem_find(A.rem_ptr, A.rem_col, j, (int)i);
+              atomic_add(&A.REM[(long)t1 * D * D + r * D + s], -v);
+              atomic_add(&A.REM[(long)t2 * D * D + s * D + r], -v);
+            }
           }
         }
       }
-      if (s == 0) A.gs[i * D + r] -= gacc;
+      if (!OFFBAND_ONLY && s == 0) sm[ngrp * gstride + grp * 6 + r] = gacc;
     }
     VUS_SYNC();
+    if (OFFBAND_ONLY) return;
+    for (int e = tid; e < 6; e += nthr) {
+      double gsum = 0.0;
+      for (int grp = 0; grp < ngrp; ++grp) gsum += sm[ngrp * gstride + grp * 6 + e];
+      A.gs[i * D + e] -= gsum;
+    }
     for (int e = tid; e < ndj * 36; e += nthr) {
       const int dj = e / 36, rs = e - dj * 36;
-      if (touched[dj] == 0.0) continue;
+      double v = 0.0, any = 0.0;
+      for (int grp = 0; grp < ngrp; ++grp) { v += sm[grp * gstride + e]; any += sm[grp * gstride + ndj * 36 + dj]; }
+      if (any == 0.0) continue;
       const int r = rs / 6, s = rs - r * 6;
       const long j = i + dj;
       const long J = j / k;
       const int rj = (int)(j - J * k);
-      const double v = acc[e];
       if (J == I) {
         A.SD[I * BB + (long)(ri * D + r) * B + rj * D + s] -= v;
         if (dj) A.SD[I * BB + (long)(rj * D + s) * B + ri * D + r] -= v;
@@ -528,6 +556,13 @@ struct SchurPoseBody {
     }
   }
 };
+typedef SchurPoseScalar<false> SchurPoseBody;
+#ifdef VUS_EMU
+VUS_HD int schur_pose_threads() { return 64; }
+#else
+VUS_HD int schur_pose_threads() { return 160; }      // 4 observation groups x 36 entries (+ padding to a warp multiple)
+#endif
+VUS_HD long schur_pose_smem_doubles(int k) { return (long)VUS_SCHUR_GROUPS * (2 * k * 37 + 6); }
 struct LmBacksubBody {   // per landmark: xl = Cinv (gl - sum_o E_o^T xc[pose_o])
   static VUS_DEV void run(const SchurArgs& A, long l) {
     double t[3] = {A.gl[l], A.gl[A.nl + l], A.gl[2 * A.nl + l]};

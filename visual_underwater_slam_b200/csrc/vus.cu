@@ -536,7 +536,7 @@ void form_system(vus_handle* h, double lambda, rt::stream_t st) {
   if (h->nobs) {
     SchurArgs a = schur_args(h, lambda);
     L_elem<LmInvertBody>(a.nl, st, a);
-    L_coop<SchurPoseBody>((int)h->nposes_obs, 64, (size_t)2 * h->k * 37 * sizeof(double), st, a);
+    L_coop<SchurPoseBody>((int)h->nposes_obs, schur_pose_threads(), (size_t)schur_pose_smem_doubles(h->k) * sizeof(double), st, a);
   }
 }
 

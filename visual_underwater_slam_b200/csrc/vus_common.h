@@ -36,3 +36,12 @@
 enum { VUS_F_PRIOR_POSE = 0, VUS_F_PRIOR_VEL = 1, VUS_F_BETWEEN = 2, VUS_F_DVL = 3, VUS_F_STEREO = 4, VUS_F_IMU = 5, VUS_F_NTYPES = 6 };
 // variable kinds
 enum { VUS_V_POSE = 0, VUS_V_VEL = 1, VUS_V_BIAS = 2, VUS_V_LM = 3, VUS_V_NKINDS = 4 };
+
+#ifndef VUS_EMU
+// FP64 tensor-core tile product D(8x8) += A(8x4) B(4x8)  (SASS: DMMA).  Lane (g = lane/4, t = lane%4) supplies
+// A[g][t], B[t][g] and holds D[g][2t], D[g][2t+1].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+#endif
