@@ -165,3 +165,49 @@ def test_concurrent_handles_match_sequential(lib):
         # the chain-factor scatter uses FP64 atomics, so two runs agree to rounding amplified by conditioning, not bitwise
         assert abs(a["final_error"] - b["final_error"]) <= 1e-6 * abs(a["final_error"]), (a["final_error"], b["final_error"])
         assert np.abs(a["values"]["poses"] - b["values"]["poses"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("name", ["lm_c1", "lm_c2s"])
+def test_golden_configs(lib, name):
+    """BASELINE.json config 1 at full size / config 2 reduced: the whole LM path (error after every accepted step,
+    accepted / rejected lambda tries) and the final poses against the frozen oracle run."""
+    from visual_underwater_slam_b200 import synthetic
+    from visual_underwater_slam_b200.optimizer import Session, LevenbergMarquardtParams
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    meta = json.loads(str(g["meta"]))
+    d = synthetic.make_trajectory_graph(**meta["make"])
+    assert d["meta"]["n_factors"] == meta["n_factors"]
+    prob = d["graph"].to_problem(d["initial"])
+    s = Session(prob, LevenbergMarquardtParams(), lib=lib)
+    res = s.optimize()
+    v = s.values()
+    s.close()
+    assert res["iterations"] == meta["iterations"] and res["inner_iterations"] == len(meta["tries"])
+    assert abs(res["final_error"] - meta["final_error"]) <= 1e-6 * meta["final_error"]      # north_star tolerance
+    assert abs(res["final_lambda"] - meta["final_lambda"]) <= 1e-12 * meta["final_lambda"]
+    assert np.sqrt(((v["poses"][:, 9:] - g["poses"][:, 9:]) ** 2).sum(1).mean()) < 1e-6      # metres
+    assert np.abs(v["poses"][:, :9] - g["poses"][:, :9]).max() < 1e-6                        # ~radians
+    assert np.abs(v["vels"] - g["vels"]).max() < 1e-6
+    assert np.abs(v["biases"] - g["biases"]).max() < 1e-6
+
+
+def test_config2_full_size_properties(lib):
+    """BASELINE.json config 2 at full size (5 000 poses, 200 000 stereo factors): too slow for the oracle inside a unit
+    test, so size-independent properties: monotone accepted errors, factor-error bookkeeping, fixed point on re-solve,
+    and the optimum sits at the noise level (chi-square per factor of order one)."""
+    from visual_underwater_slam_b200 import synthetic
+    from visual_underwater_slam_b200.optimizer import Session
+    d = synthetic.make_config("C2")
+    prob = d["graph"].to_problem(d["initial"])
+    s = Session(prob, lib=lib)
+    e0 = s.error()
+    fe = s.factor_errors()
+    assert fe.shape == (d["meta"]["n_factors"],) and abs(fe.sum() - e0) <= 1e-10 * e0
+    res = s.optimize()
+    assert res["solve_failures"] == 0 and res["final_error"] < 1e-3 * e0
+    assert res["final_error"] < 2.0 * d["meta"]["n_factors"]
+    e1 = s.error()
+    assert abs(e1 - res["final_error"]) <= 1e-12 * e1
+    res2 = s.optimize()
+    assert res2["iterations"] <= 2 and abs(res2["final_error"] - e1) <= 1e-4 * e1
+    s.close()

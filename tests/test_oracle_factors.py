@@ -197,3 +197,22 @@ def test_product_preintegration_matches_oracle():
     assert np.allclose(pim2, pim, atol=1e-13)
     assert np.allclose(cov2, cov, rtol=1e-10, atol=1e-20)
     assert np.allclose(info2, preint.sqrt_info_upper(cov), rtol=1e-8)
+
+
+def test_oracle_reproduces_golden_small():
+    """The committed golden fixture is the oracle's own frozen answer (tests/golden/make_golden.py): re-running the
+    oracle must reproduce it, so oracle edits cannot drift silently."""
+    import json
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    import parity_common as pc
+    from oracle import lm
+    g = np.load(os.path.join(here, "golden", "lm_small.npz"))
+    meta = json.loads(str(g["meta"]))
+    _, prob = pc.make(**meta["make"])
+    vals, info = lm.lm_optimize(prob)
+    assert info["iterations"] == meta["iterations"]
+    assert abs(info["error"] - meta["final_error"]) <= 1e-9 * meta["final_error"]
+    assert np.abs(vals["poses"] - g["poses"]).max() < 1e-8
