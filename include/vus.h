@@ -114,6 +114,23 @@ int vus_set_calibration(vus_handle* h, const double K[6]);       /* Cal3_S2Stere
 int vus_set_gravity(vus_handle* h, const double g[3]);           /* PreintegrationParams n_gravity (batch.py:181) */
 int vus_set_lm_params(vus_handle* h, const vus_lm_params* p);
 
+/* ---- one graph split across GPUs by contiguous pose range (BASELINE.json config 5) -------------------
+ * Each rank holds a LOCAL graph: its owned poses first, then the halo poses (owned by other ranks) that its factors
+ * touch; every factor that touches an owned pose is present (cut factors are duplicated on both sides, so each rank
+ * assembles complete Hessian rows for its owned poses and nothing has to be reduced).  Per factor type the factors this
+ * rank owns come first (n_owned_factors): only those enter the error sums.  Pose graphs only (PRIOR_POSE / BETWEEN).
+ * The collectives are supplied by the caller -- torch.distributed over NCCL in the shipped host code, gloo in the CPU
+ * tests -- so the library does not link a communication stack:
+ *   VUS_COMM_ALLREDUCE_SUM  buf = `count` doubles in device memory, summed over ranks in place
+ *   VUS_COMM_HALO           buf = a node vector in device memory, `count` (= D) doubles per local node: fill the halo
+ *                           nodes' entries with their owners' entries
+ * The callback is invoked after the library synchronised its stream and must return (0 = ok) once the result is visible
+ * to the device.  Every rank takes identical accept / reject decisions from the all-reduced scalars.              */
+enum vus_comm_op { VUS_COMM_ALLREDUCE_SUM = 0, VUS_COMM_HALO = 1 };
+typedef int (*vus_comm_fn)(void* ctx, int op, void* buf, int64_t count);
+int vus_set_partition(vus_handle* h, int64_t n_owned_nodes, const int64_t n_owned_factors[6]);
+int vus_set_comm(vus_handle* h, vus_comm_fn fn, void* ctx);
+
 /* symbolic phase: node ordering, supernode band layout, off-band blocks, Schur destination lists */
 int vus_analyze(vus_handle* h);
 /* band description after analyze: D (node dof), k (nodes per supernode), Ns, nrem, ndst */

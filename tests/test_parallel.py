@@ -73,3 +73,81 @@ def test_two_rank_gloo_equals_one_rank(tmp_path):
     p1 = np.load(str(one) + ".rank0.npy")
     p2 = np.concatenate([np.load(str(two) + ".rank%d.npy" % r) for r in range(2)], 0)
     assert np.array_equal(p1, p2)
+
+
+PART_WORKER = r'''
+import os, sys, json
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from visual_underwater_slam_b200 import _native, parallel, synthetic
+from visual_underwater_slam_b200.optimizer import Session
+lib = _native.bind(os.path.join(sys.argv[1], "tests", "emu", "libvus_emu.so"))
+world = int(os.environ["WORLD_SIZE"]); rank = int(os.environ["RANK"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+d = synthetic.make_pose_graph(int(sys.argv[2]), seed=5, n_loops=int(sys.argv[3]))
+prob = d["graph"].to_problem(d["initial"])
+part = parallel.partition_pose_graph(prob, world)[rank]
+ps = parallel.PartitionedSolver(part, lib=lib)
+res = ps.optimize()
+poses = ps.gather_poses()
+if rank == 0:
+    np.save(sys.argv[4], poses)
+    json.dump(dict(iterations=res["iterations"], tries=res["inner_iterations"], final_error=res["final_error"],
+                   initial_error=res["initial_error"], pcg=res["pcg_iterations"], comm=ps.comm_calls), open(sys.argv[4] + ".json", "w"))
+ps.close()
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def _run_part(world, n, loops, out, tmp_path):
+    script = tmp_path / "part_worker.py"
+    script.write_text(PART_WORKER)
+    port = 29500 + ((os.getpid() + 7 * world) % 500)
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, WORLD_SIZE=str(world), RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT, str(n), str(loops), str(out)], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        o, _ = p.communicate(timeout=900)
+        assert p.returncode == 0, o
+
+
+def test_partition_lists_are_consistent():
+    from visual_underwater_slam_b200 import synthetic
+    d = synthetic.make_pose_graph(300, seed=5, n_loops=40)
+    prob = d["graph"].to_problem(d["initial"])
+    for world in (2, 3, 4):
+        parts = parallel.partition_pose_graph(prob, world)
+        n_between = len(prob["between"]["orig"])
+        owned = np.concatenate([P["global_factor_index"]["between"][:P["n_own_between"]] for P in parts])
+        assert sorted(owned.tolist()) == list(range(n_between))          # every factor is owned exactly once
+        assert sum(P["nf_owned"][0] for P in parts) == len(prob["prior_pose"]["orig"])
+        for r, P in enumerate(parts):
+            a, b = P["owned"]
+            assert np.all((P["halo_global"] < a) | (P["halo_global"] >= b))
+            for peer, ix in P["send"].items():                            # what I send is what the peer expects, in its halo order
+                off, cnt = parts[peer]["recv"][r]
+                assert np.array_equal(ix + a, parts[peer]["halo_global"][off:off + cnt])
+            # local indices of every factor are in range and touch an owned pose
+            bt = P["prob"]["between"]
+            assert np.all((bt["x1"] < P["n_owned"]) | (bt["x2"] < P["n_owned"]))
+
+
+def test_partitioned_two_rank_gloo_matches_one_rank(tmp_path):
+    """BASELINE config 5 in miniature on CPU: a pose graph with loop closures split over 2 ranks (halo exchange +
+    all-reduced PCG / LM scalars through gloo) reaches the 1-rank LM path and optimum."""
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "visual_underwater_slam_b200", "csrc"), "emu"], check=True)
+    import json
+    one, two = tmp_path / "p1.npy", tmp_path / "p2.npy"
+    _run_part(1, 240, 30, one, tmp_path)
+    _run_part(2, 240, 30, two, tmp_path)
+    m1, m2 = json.load(open(str(one) + ".json")), json.load(open(str(two) + ".json"))
+    assert m1["iterations"] == m2["iterations"] and m1["tries"] == m2["tries"]
+    assert abs(m1["final_error"] - m2["final_error"]) <= 1e-6 * m1["final_error"]
+    assert m2["final_error"] < 0.2 * m2["initial_error"]
+    assert m2["comm"]["halo"] > 0 and m2["comm"]["allreduce"] > 0
+    p1, p2 = np.load(one), np.load(two)
+    assert p1.shape == p2.shape == (240, 12)
+    assert np.abs(p1[:, 9:] - p2[:, 9:]).max() < 1e-6 and np.abs(p1[:, :9] - p2[:, :9]).max() < 1e-6

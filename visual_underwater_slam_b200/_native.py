@@ -40,6 +40,9 @@ class LmResult(C.Structure):
         return d
 
 
+COMM_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64)     # vus_comm_fn
+COMM_ALLREDUCE_SUM, COMM_HALO = 0, 1
+
 EXPORTS = {
     "vus_default_lm_params": (None, [C.POINTER(LmParams)]),
     "vus_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
@@ -53,6 +56,8 @@ EXPORTS = {
     "vus_set_calibration": (C.c_int, [C.c_void_p, c_double_p]),
     "vus_set_gravity": (C.c_int, [C.c_void_p, c_double_p]),
     "vus_set_lm_params": (C.c_int, [C.c_void_p, C.POINTER(LmParams)]),
+    "vus_set_partition": (C.c_int, [C.c_void_p, C.c_int64, c_i64_p]),
+    "vus_set_comm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vus_analyze": (C.c_int, [C.c_void_p]),
     "vus_get_layout": (C.c_int, [C.c_void_p, c_i64_p]),
     "vus_optimize": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(LmResult)]),

@@ -113,7 +113,7 @@ struct LinErrBody {
 // =====================================================================================
 enum { RED_STORE = 0, RED_PAP = 1, RED_RZ = 2, RED_RZ0 = 3 };
 // scalar slots
-enum { S_RZ = 0, S_PAP = 1, S_ALPHA = 2, S_BETA = 3, S_RR = 4, S_TMP = 5, S_NEG_ALPHA = 6, S_COUNT = 16 };
+enum { S_RZ = 0, S_PAP = 1, S_ALPHA = 2, S_BETA = 3, S_RR = 4, S_TMP = 5, S_NEG_ALPHA = 6, S_COMM = 8, S_COUNT = 16 };
 
 struct RedArgs {
   const double* a; const double* b;   // sum a[i]*b[i] (b null -> sum a[i])
@@ -139,6 +139,12 @@ struct Red1Body {
     if (tid == 0) A.partials[bid] = sm[0];
   }
 };
+VUS_DEV void red_post(double* s, int slot, int op, double v) {
+  if (op == RED_STORE) s[slot] = v;
+  else if (op == RED_PAP) { s[S_PAP] = v; const double al = (v != 0.0) ? s[S_RZ] / v : 0.0; s[S_ALPHA] = al; s[S_NEG_ALPHA] = -al; }
+  else if (op == RED_RZ) { const double old = s[S_RZ]; s[S_BETA] = (old != 0.0) ? v / old : 0.0; s[S_RZ] = v; }
+  else if (op == RED_RZ0) { s[S_RZ] = v; s[S_BETA] = 0.0; }
+}
 struct Red2Args {
   const double* partials; int grid;
   double* scal;      // scalar block
@@ -154,15 +160,12 @@ struct Red2Body {
       for (int t = tid; t < s; t += nthr) sm[t] += sm[t + s];
       VUS_SYNC();
     }
-    if (tid == 0) {
-      const double v = sm[0];
-      double* s = A.scal;
-      if (A.op == RED_STORE) s[A.slot] = v;
-      else if (A.op == RED_PAP) { s[S_PAP] = v; const double al = (v != 0.0) ? s[S_RZ] / v : 0.0; s[S_ALPHA] = al; s[S_NEG_ALPHA] = -al; }
-      else if (A.op == RED_RZ) { const double old = s[S_RZ]; s[S_BETA] = (old != 0.0) ? v / old : 0.0; s[S_RZ] = v; }
-      else if (A.op == RED_RZ0) { s[S_RZ] = v; s[S_BETA] = 0.0; }
-    }
+    if (tid == 0) red_post(A.scal, A.slot, A.op, sm[0]);
   }
+};
+// the same post-op on a value that was all-reduced across ranks first (partitioned graphs)
+struct RedPostBody {
+  static VUS_DEV void run(const Red2Args& A, long) { red_post(A.scal, A.slot, A.op, A.scal[S_COMM]); }
 };
 
 // =====================================================================================

@@ -128,6 +128,13 @@ struct vus_handle {
   DBuf<double> x, r, z, p, Ap, d, xl, scal, partials, bpart, e_all, le_all;
   DBuf<int> fail;
   int red_grid = 0;
+  // pose-range partition (one rank of a graph split across GPUs): local nodes = [owned | halo]
+  long n_owned = -1;             // -1: not partitioned
+  int64_t nf_owned[VUS_F_NTYPES] = {0, 0, 0, 0, 0, 0};
+  long Lr = 0;                   // length of the vector prefix that enters dot products (owned dofs)
+  DBuf<double> e_mask;           // 1 for factors this rank owns, 0 for duplicates of a neighbour's factor
+  vus_comm_fn comm = nullptr;
+  void* comm_ctx = nullptr;
   // stats
   vus_lm_result res;
 };
@@ -184,11 +191,29 @@ void run_factors(vus_handle* h, int which, bool with_J, rt::stream_t st) {
 }
 
 // deterministic sum / dot -> scal[slot] with post-op
+void comm_call(vus_handle* h, int op, void* buf, long count, rt::stream_t st) {
+  rt::sync(st);                                        // the collective runs on the caller's (torch) stream
+  if (h->comm(h->comm_ctx, op, buf, (int64_t)count) != 0) throw std::runtime_error("communication callback failed");
+}
 void reduce(vus_handle* h, const double* a, const double* b, long n, int slot, int op, rt::stream_t st) {
   RedArgs r1; r1.a = a; r1.b = b; r1.n = n; r1.partials = h->partials.p; r1.grid = h->red_grid;
   L_coop<Red1Body>(h->red_grid, 256, 256 * sizeof(double), st, r1);
   Red2Args r2; r2.partials = h->partials.p; r2.grid = h->red_grid; r2.scal = h->scal.p; r2.slot = slot; r2.op = op;
-  L_coop<Red2Body>(1, 256, 256 * sizeof(double), st, r2);
+  if (!h->comm) {
+    L_coop<Red2Body>(1, 256, 256 * sizeof(double), st, r2);
+    return;
+  }
+  Red2Args rl = r2; rl.slot = S_COMM; rl.op = RED_STORE;             // local partial -> all-reduce -> post-op
+  L_coop<Red2Body>(1, 256, 256 * sizeof(double), st, rl);
+  comm_call(h, VUS_COMM_ALLREDUCE_SUM, h->scal.p + S_COMM, 1, st);
+  L_elem<RedPostBody>(1, st, r2);
+}
+// fill the halo entries of a node vector (D doubles per node) from their owners
+void halo(vus_handle* h, double* vec, rt::stream_t st) {
+  if (h->comm && h->n_owned >= 0 && h->n_owned < h->N) comm_call(h, VUS_COMM_HALO, vec, h->D, st);
+}
+void zero_halo(vus_handle* h, double* vec, rt::stream_t st) {
+  if (h->n_owned >= 0 && h->Lc > h->Lr) rt::dzero(vec + h->Lr, (size_t)(h->Lc - h->Lr) * sizeof(double), st);
 }
 
 double read_scalar(vus_handle* h, int slot, rt::stream_t st) {
@@ -200,7 +225,7 @@ double read_scalar(vus_handle* h, int slot, rt::stream_t st) {
 
 double graph_error(vus_handle* h, int which, rt::stream_t st) {
   run_factors(h, which, false, st);
-  reduce(h, h->e_all.p, nullptr, h->nfactors, S_TMP, RED_STORE, st);
+  reduce(h, h->e_all.p, h->n_owned >= 0 ? h->e_mask.p : nullptr, h->nfactors, S_TMP, RED_STORE, st);
   return read_scalar(h, S_TMP, st);
 }
 
@@ -440,6 +465,21 @@ int analyze(vus_handle* h, rt::stream_t st) {
   h->Dw.alloc(h->Ns * BB); h->U1.alloc(h->Ns * BB); h->U2.alloc(h->Ns * BB);
   h->Dinv.alloc(h->Ns * BB); h->Gl.alloc(h->Ns * BB); h->Gr.alloc(h->Ns * BB);
   h->Z.alloc(6 * h->Lc); h->Zr.alloc(6 * h->Lc); h->SbInv.alloc(36);
+  if (h->n_owned >= 0) {
+    if (h->has_bias || FS.n || NV) return fail(h, VUS_ERR_UNSUPPORTED, "pose-range partition supports pose graphs (PriorFactorPose3 / BetweenFactorPose3) only");
+    if (h->n_owned > NX) return fail(h, VUS_ERR_INVALID, "vus_set_partition: more owned nodes than nodes");
+    h->Lr = h->n_owned * D;
+    std::vector<double> mask((size_t)h->nfactors, 0.0);
+    long off = 0;
+    for (int t = 0; t < VUS_F_NTYPES; ++t) {
+      if (h->nf_owned[t] > h->ft[t].n) return fail(h, VUS_ERR_INVALID, "vus_set_partition: more owned factors than factors");
+      for (long f = 0; f < h->nf_owned[t]; ++f) mask[off + f] = 1.0;
+      off += h->ft[t].n;
+    }
+    h->e_mask.upload(mask, st);
+  } else {
+    h->Lr = h->L;
+  }
   h->x.alloc(h->L); h->d.alloc(h->L); h->r.alloc(h->L); h->z.alloc(h->L); h->p.alloc(h->L); h->Ap.alloc(h->L);
   h->xl.alloc(3 * NL);
   h->scal.alloc(S_COUNT); h->scal.zero(st);
@@ -693,8 +733,9 @@ int pcg(vus_handle* h, rt::stream_t st, bool* converged) {
   const long L = h->L;
   VecArgs v; v.z = nullptr; v.scal = h->scal.p; v.slot = 0; v.n = L; v.Z = nullptr; v.xb = nullptr; v.zstride = 0;
   h->x.zero(st);
+  zero_halo(h, h->gs.p, st);                           // halo rows belong to another rank's system
   rt::d2d(h->r.p, h->gs.p, L * sizeof(double), st);
-  reduce(h, h->r.p, h->r.p, L, S_RR, RED_STORE, st);
+  reduce(h, h->r.p, h->r.p, h->Lr, S_RR, RED_STORE, st);
   const double rr0 = read_scalar(h, S_RR, st);
   *converged = true;
   if (!(rr0 > 0.0)) return 0;
@@ -707,17 +748,19 @@ int pcg(vus_handle* h, rt::stream_t st, bool* converged) {
     h->d.zero(st);
     precond_apply(h, h->z.p, h->r.p, st);
     rt::d2d(h->p.p, h->z.p, L * sizeof(double), st);
-    reduce(h, h->r.p, h->z.p, L, S_RZ, RED_RZ0, st);
+    reduce(h, h->r.p, h->z.p, h->Lr, S_RZ, RED_RZ0, st);
     int since_best = 0;
     double best = rr_outer;
     bool bad = false;
     while (it < h->prm.pcg_max_iterations) {
+      halo(h, h->p.p, st);
       apply_A(h, h->Ap.p, h->p.p, st);
-      reduce(h, h->p.p, h->Ap.p, L, S_PAP, RED_PAP, st);
+      zero_halo(h, h->Ap.p, st);
+      reduce(h, h->p.p, h->Ap.p, h->Lr, S_PAP, RED_PAP, st);
       axpy(h, h->d.p, h->p.p, S_ALPHA, st);
       axpy(h, h->r.p, h->Ap.p, S_NEG_ALPHA, st);
       ++it;
-      reduce(h, h->r.p, h->r.p, L, S_RR, RED_STORE, st);
+      reduce(h, h->r.p, h->r.p, h->Lr, S_RR, RED_STORE, st);
       const double rr = read_scalar(h, S_RR, st);
       if (h->prm.verbose > 1) std::fprintf(stderr, "    pcg %d.%d rel_res %.3e\n", outer, it, std::sqrt(rr / rr0));
       if (!(rr == rr)) { bad = true; break; }
@@ -725,17 +768,19 @@ int pcg(vus_handle* h, rt::stream_t st, bool* converged) {
       if (rr < best) { best = rr; since_best = 0; }
       else if (++since_best >= 40) break;              // CG residuals are not monotone: only a long stall ends the recursion
       precond_apply(h, h->z.p, h->r.p, st);
-      reduce(h, h->r.p, h->z.p, L, S_RZ, RED_RZ, st);
+      reduce(h, h->r.p, h->z.p, h->Lr, S_RZ, RED_RZ, st);
       xpby(h, h->p.p, h->z.p, S_BETA, st);
     }
     if (bad) break;
     // ---- x += d ; true residual
     v.y = h->x.p; v.x = h->d.p;
     L_elem<AddBody>(L, st, v);
+    halo(h, h->x.p, st);
     apply_A(h, h->r.p, h->x.p, st);
     v.y = h->r.p; v.x = h->gs.p;
     L_elem<RsubBody>(L, st, v);
-    reduce(h, h->r.p, h->r.p, L, S_RR, RED_STORE, st);
+    zero_halo(h, h->r.p, st);
+    reduce(h, h->r.p, h->r.p, h->Lr, S_RR, RED_STORE, st);
     const double rr_true = read_scalar(h, S_RR, st);
     if (h->prm.verbose > 1) std::fprintf(stderr, "    pcg outer %d true rel_res %.3e\n", outer, std::sqrt(rr_true / rr0));
     if (rr_true <= tol2) { *converged = true; break; }
@@ -750,6 +795,14 @@ int read_fail(vus_handle* h, rt::stream_t st) {
   rt::d2h(&f, h->fail.p, sizeof(int), st);
   rt::sync(st);
   if (f) h->fail.zero(st);
+  if (h->comm) {                                       // every rank must take the same decision
+    double v = f ? 1.0 : 0.0;
+    rt::h2d(h->scal.p + S_COMM, &v, sizeof(double), st);
+    comm_call(h, VUS_COMM_ALLREDUCE_SUM, h->scal.p + S_COMM, 1, st);
+    rt::d2h(&v, h->scal.p + S_COMM, sizeof(double), st);
+    rt::sync(st);
+    f = v > 0.0;
+  }
   return f;
 }
 
@@ -763,6 +816,7 @@ bool solve_damped(vus_handle* h, double lambda, rt::stream_t st, int* iters, boo
   if (read_fail(h, st)) { *iters = 0; return false; }
   bool conv = false;
   *iters = pcg(h, st, &conv);
+  halo(h, h->x.p, st);                                 // the step of the halo poses comes from their owners
   if (h->nobs) {
     SchurArgs a = schur_args(h, lambda);
     L_elem<LmBacksubBody>(a.nl, st, a);
@@ -786,7 +840,7 @@ double linear_error(vus_handle* h, rt::stream_t st) {
   ClassGuard kc_guard(KC_LINERR);
   launch_linerr<VUS_F_PRIOR_POSE>(h, st); launch_linerr<VUS_F_PRIOR_VEL>(h, st); launch_linerr<VUS_F_BETWEEN>(h, st);
   launch_linerr<VUS_F_DVL>(h, st); launch_linerr<VUS_F_STEREO>(h, st); launch_linerr<VUS_F_IMU>(h, st);
-  reduce(h, h->le_all.p, nullptr, h->nfactors, S_TMP, RED_STORE, st);
+  reduce(h, h->le_all.p, h->n_owned >= 0 ? h->e_mask.p : nullptr, h->nfactors, S_TMP, RED_STORE, st);
   return read_scalar(h, S_TMP, st);
 }
 
@@ -1008,6 +1062,20 @@ int vus_set_gravity(vus_handle* h, const double g[3]) {
 int vus_set_lm_params(vus_handle* h, const vus_lm_params* p) {
   if (!h || !p) return VUS_ERR_INVALID;
   h->prm = *p;
+  return VUS_OK;
+}
+
+int vus_set_partition(vus_handle* h, int64_t n_owned_nodes, const int64_t n_owned_factors[6]) {
+  if (!h || n_owned_nodes < 0 || !n_owned_factors) return fail(h, VUS_ERR_INVALID, "vus_set_partition: bad arguments");
+  h->n_owned = n_owned_nodes;
+  for (int t = 0; t < VUS_F_NTYPES; ++t) h->nf_owned[t] = n_owned_factors[t];
+  h->analyzed = false;
+  return VUS_OK;
+}
+
+int vus_set_comm(vus_handle* h, vus_comm_fn fn, void* ctx) {
+  if (!h) return VUS_ERR_INVALID;
+  h->comm = fn; h->comm_ctx = ctx;
   return VUS_OK;
 }
 

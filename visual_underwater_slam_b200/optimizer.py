@@ -106,7 +106,7 @@ def _rows(a, dim):
 class Session:
     """One vus_handle: uploads a packed problem (graph.to_problem), analyses it, exposes the C-ABI calls."""
 
-    def __init__(self, prob, params=None, lib=None, device=0, device_tensors=False):
+    def __init__(self, prob, params=None, lib=None, device=0, device_tensors=False, partition=None, comm=None):
         self.lib = lib if lib is not None else _native.load()
         self.prob = prob
         self._h = C.c_void_p()
@@ -120,6 +120,12 @@ class Session:
         try:
             self._upload(prob, device_tensors)
             self.set_params(params or LevenbergMarquardtParams())
+            if partition is not None:                   # (n_owned_nodes, [owned factors per type]) -- parallel.py
+                nf = (C.c_int64 * 6)(*[int(x) for x in partition[1]])
+                self._check(self.lib.vus_set_partition(self._h, int(partition[0]), nf))
+            if comm is not None:                        # a _native.COMM_FN instance (kept alive by the caller and here)
+                self._comm = comm
+                self._check(self.lib.vus_set_comm(self._h, C.cast(comm, C.c_void_p), None))
             self._check(self.lib.vus_analyze(self._h))
         except Exception:
             self.close()

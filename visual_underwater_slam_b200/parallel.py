@@ -10,7 +10,13 @@ weak and the N-rank result is bit-identical to the 1-rank result for every traje
 Inside a rank the trajectories of a shard are small (launch-latency bound), so several handles run concurrently from a
 thread pool, each on its own CUDA stream (ctypes releases the GIL during the C-ABI calls; one host thread per handle, as
 include/vus.h requires).
+
+The second mode (BASELINE.json config 5) splits ONE pose graph by contiguous pose range: `partition_pose_graph` builds
+every rank's local graph ([owned | halo] poses, owned + duplicated cut factors) and its halo send / receive lists,
+`PartitionedSolver` drives one handle per rank and supplies the two collectives the C-ABI asks for (vus_set_comm): the
+all-reduce of the PCG / LM scalars and the halo exchange of node vectors, both through torch.distributed.
 """
+import ctypes as C
 from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 from .optimizer import Session, LevenbergMarquardtParams
@@ -85,3 +91,158 @@ def solve_sharded(make_problem, n_trajectories, params=None, lib=None, device=0,
         f, l = shard_range(n_trajectories, r, world)
         parts.append(recv[r][:l - f].cpu().numpy())
     return np.concatenate(parts, 0), local, (first, last)
+
+
+# ======================================================================================================================
+# one pose graph across ranks: contiguous pose ranges + halo exchange
+# ======================================================================================================================
+def partition_pose_graph(prob, world):
+    """Split a packed pose-graph problem (poses, prior_pose, between only) into `world` local problems.
+
+    Rank r owns poses shard_range(n, r, world).  Its local graph holds every factor touching an owned pose; a factor is
+    OWNED by the rank of its lowest pose (its error is counted there), the other copy is a duplicate.  Local pose order
+    is [owned (ascending) | halo (ascending global index)]; owned factors come first in every table.
+    -> list over ranks of dict(prob, n_owned, nf_owned, owned (first, last), halo_global [nh], send {peer: local idx},
+       recv {peer: (offset in halo, count)})."""
+    for t in ("prior_vel", "dvl", "stereo", "imu"):
+        if len(prob[t]["orig"]):
+            raise NotImplementedError("pose-range partition supports pose graphs (PriorFactorPose3 / BetweenFactorPose3) only")
+    n = len(prob["pose_keys"])
+    x1, x2 = np.asarray(prob["between"]["x1"], np.int64), np.asarray(prob["between"]["x2"], np.int64)
+    xp = np.asarray(prob["prior_pose"]["x"], np.int64)
+    lo = np.minimum(x1, x2)
+    parts = []
+    for r in range(world):
+        a, b = shard_range(n, r, world)
+        in1, in2 = (x1 >= a) & (x1 < b), (x2 >= a) & (x2 < b)
+        sel = np.nonzero(in1 | in2)[0]
+        mine = (lo[sel] >= a) & (lo[sel] < b)
+        sel = np.concatenate([sel[mine], sel[~mine]])                  # owned factors first (stable)
+        n_own_b = int(mine.sum())
+        ends = np.concatenate([x1[sel], x2[sel]])
+        halo = np.unique(ends[(ends < a) | (ends >= b)])
+        loc = np.full(n, -1, np.int64)
+        loc[a:b] = np.arange(b - a)
+        loc[halo] = (b - a) + np.arange(len(halo))
+        selp = np.nonzero((xp >= a) & (xp < b))[0]
+        nloc = (b - a) + len(halo)
+        glob = np.concatenate([np.arange(a, b), halo])
+        from .symbol import symbols
+        lp = dict(prob)
+        lp["pose_keys"] = symbols("x", np.arange(nloc))
+        lp["poses"] = np.ascontiguousarray(prob["poses"][glob])
+        bt = prob["between"]
+        lp["between"] = dict(meas=np.ascontiguousarray(bt["meas"][sel]), sqrt_info=np.ascontiguousarray(bt["sqrt_info"][sel]),
+                             orig=np.arange(len(selp), len(selp) + len(sel), dtype=np.int64),
+                             x1=loc[x1[sel]].astype(np.int32), x2=loc[x2[sel]].astype(np.int32))
+        pp = prob["prior_pose"]
+        lp["prior_pose"] = dict(meas=np.ascontiguousarray(pp["meas"][selp]), sqrt_info=np.ascontiguousarray(pp["sqrt_info"][selp]),
+                                orig=np.arange(len(selp), dtype=np.int64), x=loc[xp[selp]].astype(np.int32))
+        lp["n_factors"] = len(selp) + len(sel)
+        parts.append(dict(prob=lp, n_owned=b - a, nf_owned=[len(selp), 0, n_own_b, 0, 0, 0], owned=(a, b), halo_global=halo,
+                          global_factor_index=dict(prior_pose=selp, between=sel), n_own_between=n_own_b))
+    for r, P in enumerate(parts):                                       # halo lists: who sends what to whom
+        P["recv"], P["send"] = {}, {}
+        owners = np.array([owner_of(int(g), n, world) for g in P["halo_global"]], np.int64) if len(P["halo_global"]) else np.zeros(0, np.int64)
+        for s_ in range(world):
+            idx = np.nonzero(owners == s_)[0]
+            if len(idx):
+                P["recv"][s_] = (int(idx[0]), int(len(idx)))            # halo is sorted by global index -> contiguous per owner
+    for r, P in enumerate(parts):
+        for s_, Q in enumerate(parts):
+            if s_ == r or r not in Q["recv"]:
+                continue
+            off, cnt = Q["recv"][r]
+            P["send"][s_] = (Q["halo_global"][off:off + cnt] - P["owned"][0]).astype(np.int64)   # my local indices, in s_'s halo order
+    return parts
+
+
+class PartitionedSolver:
+    """One rank of a pose graph split by pose range.  `part` is this rank's entry of partition_pose_graph(); the process
+    group must already exist (nccl on GPUs, gloo for the CPU tests)."""
+
+    def __init__(self, part, params=None, lib=None, device=0, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import _native
+        self.torch, self.dist, self.group = torch, dist, group
+        self.part = part
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.cuda = self.world > 1 and dist.get_backend(group) == "nccl" or (lib is None and torch.cuda.is_available())
+        self.device = torch.device("cuda", device) if self.cuda else torch.device("cpu")
+        self.D = 6
+        self.n_owned = part["n_owned"]
+        self.n_local = self.n_owned + len(part["halo_global"])
+        self._send_idx = {p: torch.as_tensor(ix, device=self.device) for p, ix in part["send"].items()}
+        self.comm_calls = {"allreduce": 0, "halo": 0}
+        self._cb = _native.COMM_FN(self._comm)
+        self.session = Session(part["prob"], params, lib=lib, device=device, partition=(self.n_owned, part["nf_owned"]),
+                               comm=self._cb if self.world > 1 else None)
+
+    # ---- device memory handed over by the library as a torch tensor (no copy)
+    def _view(self, ptr, count):
+        torch = self.torch
+        if self.cuda:
+            class _Arr:
+                __cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+            return torch.as_tensor(_Arr(), device=self.device)
+        buf = (C.c_double * count).from_address(int(ptr))
+        return torch.from_numpy(np.ctypeslib.as_array(buf))
+
+    def _comm(self, ctx, op, buf, count):
+        try:
+            from . import _native
+            dist, torch = self.dist, self.torch
+            if op == _native.COMM_ALLREDUCE_SUM:
+                self.comm_calls["allreduce"] += 1
+                dist.all_reduce(self._view(buf, int(count)), group=self.group)
+            else:
+                self.comm_calls["halo"] += 1
+                D = int(count)
+                vec = self._view(buf, self.n_local * D).view(self.n_local, D)
+                ops, keep = [], []
+                for peer, ix in self._send_idx.items():
+                    out = vec.index_select(0, ix).contiguous()
+                    keep.append(out)
+                    ops.append(dist.P2POp(dist.isend, out, peer, group=self.group))
+                for peer, (off, cnt) in self.part["recv"].items():
+                    ops.append(dist.P2POp(dist.irecv, vec[self.n_owned + off:self.n_owned + off + cnt], peer, group=self.group))
+                if ops:
+                    for w in dist.batch_isend_irecv(ops):
+                        w.wait()
+            if self.cuda:
+                torch.cuda.synchronize(self.device)
+            return 0
+        except Exception as exc:                        # never let an exception cross the C boundary
+            import traceback
+            traceback.print_exc()
+            self.error = exc
+            return 1
+
+    def optimize(self):
+        return self.session.optimize()
+
+    def owned_poses(self):
+        return self.session.values()["poses"][:self.n_owned]
+
+    def gather_poses(self):
+        """All ranks' owned poses, in global order, on every rank (result read-out, not part of the solve)."""
+        mine = self.torch.from_numpy(np.ascontiguousarray(self.owned_poses()))
+        if self.world == 1:
+            return mine.numpy()
+        sizes = [shard_range(self._n_global(), r, self.world) for r in range(self.world)]
+        width = max(b - a for a, b in sizes)
+        send = self.torch.zeros((width, 12), dtype=self.torch.float64, device=self.device)
+        send[:self.n_owned] = mine.to(self.device)
+        recv = [self.torch.empty_like(send) for _ in range(self.world)]
+        self.dist.all_gather(recv, send, group=self.group)
+        return np.concatenate([recv[r][:b - a].cpu().numpy() for r, (a, b) in enumerate(sizes)], 0)
+
+    def _n_global(self):
+        t = self.torch.tensor([self.n_owned], dtype=self.torch.int64, device=self.device)
+        self.dist.all_reduce(t, group=self.group)
+        return int(t.item())
+
+    def close(self):
+        self.session.close()
