@@ -150,6 +150,19 @@ int vus_linearize(vus_handle* h, void* stream, int type, double* r_out, double* 
  * solves (J^T J + lambda I) delta = -J^T r; delta_pose [nx][6], delta_vel [nv][3], delta_bias [nb][6], delta_lm [nl][3] (host, AoS) */
 int vus_solve_step(vus_handle* h, void* stream, double lambda, double* d_pose, double* d_vel, double* d_bias, double* d_lm,
                    int32_t* pcg_iterations);
+/* ---- front-end loops that feed the graph; tables are row-major (mem = VUS_MEM_*_ROWS) --------
+ * gtsam.PreintegratedImuMeasurements.integrateMeasurement x k + resetIntegration per keyframe interval
+ * (batch.py:289-293; covariances of batch.py:183-185): acc, gyro [n][k][3], constant dt (batch.py:290 passes 0.005).
+ * Emits what vus_add_factors(VUS_FACTOR_IMU) takes: pim_out [n][67] (packed PIM), sqrt_info_out [n][45] (upper R,
+ * R^T R = preintMeasCov^-1).  Manifold preintegration. */
+int vus_preintegrate_imu(vus_handle* h, void* stream, int64_t n, int32_t k, const double* acc, const double* gyro, double dt,
+                         const double bias_hat[6], const double acc_cov[9], const double gyro_cov[9], const double int_cov[9],
+                         double* pim_out, double* sqrt_info_out, int mem);
+/* landmark initial values from stereo measurements (get_landmarks, batch.py:144-176, in gtsam's StereoCamera
+ * convention uL > uR): points_out[o] = X(pose_idx[o]) * backproject(uL, uR, v) with the calibration of
+ * vus_set_calibration and the CURRENT pose values.  pose_idx is host memory; meas [n][3], points_out [n][3]. */
+int vus_backproject_stereo(vus_handle* h, void* stream, int64_t n, const int32_t* pose_idx, const double* meas, double* points_out, int mem);
+
 /* test hook for the band solver (kernel 3b): linearize + assemble + damp/Schur at the current values, copy out the
  * block-tridiagonal band (SD [Ns][B][B], SU [Ns-1][B][B], host, may be NULL), factor it by block cyclic reduction and
  * solve nrhs right-hand sides in place (x_inout [nrhs][Ns*B], host).  Returns 1 if a pivot was not positive. */

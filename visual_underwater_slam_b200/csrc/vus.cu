@@ -6,6 +6,7 @@
 #include "../../include/vus.h"
 #include "rt.h"
 #include "kernels.cuh"
+#include "frontend.cuh"
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -1217,6 +1218,64 @@ int vus_debug_band_solve(vus_handle* h, void* stream, double lambda, double* SD_
   }
   rt::sync(st);
   return read_fail(h, st) ? 1 : VUS_OK;
+  VUS_CATCH(h)
+}
+
+int vus_preintegrate_imu(vus_handle* h, void* stream, int64_t n, int32_t k, const double* acc, const double* gyro, double dt,
+                         const double bias_hat[6], const double acc_cov[9], const double gyro_cov[9], const double int_cov[9],
+                         double* pim_out, double* sqrt_info_out, int mem) {
+  if (!h || n < 0 || k <= 0 || !(dt > 0.0) || !acc || !gyro || !pim_out || !sqrt_info_out || (mem != VUS_MEM_HOST_ROWS && mem != VUS_MEM_DEVICE_ROWS))
+    return fail(h, VUS_ERR_INVALID, "vus_preintegrate_imu: bad arguments (tables are row-major: mem = VUS_MEM_HOST_ROWS or VUS_MEM_DEVICE_ROWS)");
+  VUS_TRY(h)
+  rt::stream_t st = (rt::stream_t)stream;
+  if (n == 0) return VUS_OK;
+  const size_t in_bytes = (size_t)n * k * 3 * sizeof(double);
+  DBuf<double> dacc, dgyr, pim, sinfo;
+  PreintArgs P;
+  P.n = n; P.k = k; P.dt = dt;
+  if (mem == VUS_MEM_HOST_ROWS) {
+    dacc.alloc((size_t)n * k * 3); dgyr.alloc((size_t)n * k * 3);
+    rt::h2d(dacc.p, acc, in_bytes, st); rt::h2d(dgyr.p, gyro, in_bytes, st);
+    P.acc = dacc.p; P.gyro = dgyr.p;
+  } else { P.acc = acc; P.gyro = gyro; }
+  for (int i = 0; i < 6; ++i) P.bhat[i] = bias_hat ? bias_hat[i] : 0.0;
+  for (int i = 0; i < 9; ++i) { P.aC[i] = acc_cov[i]; P.wC[i] = gyro_cov[i]; P.iC[i] = int_cov[i]; }
+  pim.alloc((size_t)67 * n); sinfo.alloc((size_t)45 * n);
+  P.pim = pim.p; P.sinfo = sinfo.p;
+  if (!h->fail.p) { h->fail.alloc(1); h->fail.zero(st); }
+  P.fail = h->fail.p;
+  L_elem<PreintBody>(n, st, P);
+  export_table(pim_out, pim.p, n, 67, mem, st);
+  export_table(sqrt_info_out, sinfo.p, n, 45, mem, st);
+  rt::sync(st);
+  if (read_fail(h, st)) return fail(h, VUS_ERR_INVALID, "vus_preintegrate_imu: a preintegrated covariance is not positive definite");
+  return VUS_OK;
+  VUS_CATCH(h)
+}
+
+int vus_backproject_stereo(vus_handle* h, void* stream, int64_t n, const int32_t* pose_idx, const double* meas, double* points_out, int mem) {
+  if (!h || n < 0 || !pose_idx || !meas || !points_out || (mem != VUS_MEM_HOST_ROWS && mem != VUS_MEM_DEVICE_ROWS))
+    return fail(h, VUS_ERR_INVALID, "vus_backproject_stereo: bad arguments (tables are row-major)");
+  if (!h->nvar[0]) return fail(h, VUS_ERR_STATE, "vus_backproject_stereo: set the pose variables first");
+  VUS_TRY(h)
+  rt::stream_t st = (rt::stream_t)stream;
+  if (n == 0) return VUS_OK;
+  for (int64_t o = 0; o < n; ++o)
+    if (pose_idx[o] < 0 || pose_idx[o] >= h->nvar[0]) return fail(h, VUS_ERR_INVALID, "vus_backproject_stereo: pose index out of range");
+  DBuf<int> didx; didx.upload(pose_idx, (size_t)n, st);
+  DBuf<double> dmeas, out;
+  dmeas.alloc((size_t)3 * n); out.alloc((size_t)3 * n);
+  import_table(dmeas.p, meas, n, 3, mem, st);
+  BackprojArgs A;
+  A.n = n; A.pose_idx = didx.p; A.pose = h->val[h->cur][0].p; A.nx = h->nvar[0]; A.meas = dmeas.p; A.out = out.p;
+  for (int i = 0; i < 6; ++i) A.K[i] = h->K[i];
+  if (!h->fail.p) { h->fail.alloc(1); h->fail.zero(st); }
+  A.fail = h->fail.p;
+  L_elem<BackprojBody>(n, st, A);
+  export_table(points_out, out.p, n, 3, mem, st);
+  rt::sync(st);
+  if (read_fail(h, st)) return fail(h, VUS_ERR_INVALID, "vus_backproject_stereo: non-positive disparity (uL - uR <= 0)");
+  return VUS_OK;
   VUS_CATCH(h)
 }
 

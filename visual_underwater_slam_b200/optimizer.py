@@ -321,3 +321,44 @@ class LevenbergMarquardtOptimizer:
     def stats(self):
         """Per-phase timings, PCG iterations, kernel launches of the last optimize()."""
         return dict(self._result or {})
+
+
+# ---------------------------------------------------------------------------------------------- front-end rows (SURVEY.md 8f)
+def preintegrate_imu(acc, gyro, dt, params, bias_hat=None, lib=None, device=0, stream=None):
+    """Device version of navigation.preintegrate_batch (the integrateMeasurement loop of batch.py:289-293):
+    acc, gyro [n, k, 3], constant dt -> (pim [n, 67], sqrt_info_triu [n, 45]) ready for graph.add_imu_factors."""
+    lib = lib if lib is not None else _native.load()
+    acc = np.ascontiguousarray(acc, dtype=np.float64)
+    gyro = np.ascontiguousarray(gyro, dtype=np.float64)
+    n, k, _ = acc.shape
+    if gyro.shape != acc.shape:
+        raise ValueError("preintegrate_imu: acc and gyro must both be [n, k, 3]")
+    h = C.c_void_p()
+    if lib.vus_create(int(device), C.byref(h)) != 0:
+        raise RuntimeError("vus_create failed: no usable CUDA device; this path has no CPU fallback")
+    try:
+        pim = np.empty((n, 67))
+        info = np.empty((n, 45))
+        P = _native.c_double_p
+        b = np.zeros(6) if bias_hat is None else np.ascontiguousarray(bias_hat, dtype=np.float64).reshape(6)
+        cov = [np.ascontiguousarray(c, dtype=np.float64).reshape(9) for c in
+               (params.accelerometerCovariance, params.gyroscopeCovariance, params.integrationCovariance)]
+        rc = lib.vus_preintegrate_imu(h, stream, n, k, acc.ctypes.data_as(C.c_void_p), gyro.ctypes.data_as(C.c_void_p), float(dt),
+                                      b.ctypes.data_as(P), cov[0].ctypes.data_as(P), cov[1].ctypes.data_as(P), cov[2].ctypes.data_as(P),
+                                      pim.ctypes.data_as(C.c_void_p), info.ctypes.data_as(C.c_void_p), 2)
+        if rc != 0:
+            raise RuntimeError(lib.vus_last_error(h).decode() or f"libvus error {rc}")
+        return pim, info
+    finally:
+        lib.vus_destroy(h)
+
+
+def backproject_stereo(session, pose_idx, meas, stream=None):
+    """Landmark initial values from stereo measurements (get_landmarks, batch.py:144-176) at the session's current
+    poses and calibration: pose_idx [n] (indices into the pose table), meas [n, 3] (uL, uR, v) -> points [n, 3]."""
+    idx = np.ascontiguousarray(pose_idx, dtype=np.int32)
+    z = np.ascontiguousarray(meas, dtype=np.float64).reshape(len(idx), 3)
+    out = np.empty((len(idx), 3))
+    session._check(session.lib.vus_backproject_stereo(session._h, stream, len(idx), idx.ctypes.data_as(_native.c_i32_p),
+                                                      z.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), 2))
+    return out
