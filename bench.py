@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=3)
     ap.add_argument("--drift-scale", type=float, default=0.1, help="initial odometry drift: per-step sigma = scale x (0.002 rad, 0.01 m)")
     ap.add_argument("--cpu-poses", type=int, default=2500, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--max-supernode", type=int, default=0, help="cap on poses per supernode (0 = from the graph)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="do not time individual kernels with CUDA events")
@@ -229,6 +230,7 @@ def main():
     n_factors = sum(nf.values())
     params = LevenbergMarquardtParams()
     params.profileKernels = not a.no_profile
+    params.maxSupernode = a.max_supernode
 
     t0 = time.perf_counter()
     sess = Session(prob, params, device=local_rank)

@@ -401,6 +401,9 @@ int analyze(vus_handle* h, rt::stream_t st) {
   // ---- band width k
   const int kcap = h->prm.max_supernode > 0 ? h->prm.max_supernode : 96 / D;
   long span = 1;
+  // spans up to kcap widen the band; longer links (loop closures, very long tracks) stay in the off-band remainder.
+  // NOTE: the band is only guaranteed positive definite when every landmark track fits in it (the Schur complement
+  // subtracts from the blocks it touches); tracks longer than kcap poses degrade the preconditioner.
   auto consider = [&](long p, long q) { long s = p > q ? p - q : q - p; if (s <= kcap && s > span) span = s; };
   for (long f = 0; f < FB.n; ++f) consider(FB.h_idx[f], FB.h_idx[FB.n + f]);
   for (long f = 0; f < FI.n; ++f) consider(FI.h_idx[f], FI.h_idx[2 * FI.n + f]);
