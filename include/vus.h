@@ -16,7 +16,10 @@
  *     both component-major; the *_ROWS variants take the natural row-major [n][dim] array (what numpy / gtsam
  *     callers hold) and transpose it on the device, so the host never re-packs a table.
  *     Key / index / insertion-order arrays are always host memory.
- *   - one handle per GPU, one host thread per handle; all kernels run on the stream passed in.
+ *   - one host thread per handle (several handles may run concurrently from several threads); all kernels run on
+ *     the stream passed in, or on a stream the handle owns when NULL is passed.  The library captures its fixed
+ *     launch sequences into CUDA graphs on that stream: do not share one stream between handles that run at the
+ *     same time, and do not pass the legacy default stream expecting capture (NULL selects the handle's own).
  */
 #ifndef VUS_H_
 #define VUS_H_

@@ -153,13 +153,12 @@ def test_larger_properties(lib):
 
 def test_concurrent_handles_match_sequential(lib):
     """BASELINE config 4 in miniature: independent trajectories solved concurrently on one GPU (one handle + one CUDA
-    stream per host thread) give exactly what solving them one after another gives."""
+    stream per handle) give exactly what solving them one after another gives."""
     import torch
     from visual_underwater_slam_b200 import parallel
     probs = [pc.make(60, n_loops=2, loop_min_gap=15, seed=10 + t)[1] for t in range(6)]
     seq = parallel.solve_local(probs, lib=lib, threads=1)
-    streams = [torch.cuda.Stream() for _ in range(3)]
-    con = parallel.solve_local(probs, lib=lib, threads=3, streams=[s.cuda_stream for s in streams])
+    con = parallel.solve_local(probs, lib=lib, threads=3)
     for a, b in zip(seq, con):
         assert a["iterations"] == b["iterations"] and a["inner_iterations"] == b["inner_iterations"]
         # the chain-factor scatter uses FP64 atomics, so two runs agree to rounding amplified by conditioning, not bitwise

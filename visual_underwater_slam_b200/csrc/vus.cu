@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <map>
 #include <numeric>
+#include <tuple>
 #ifndef VUS_EMU
 #include <cub/device/device_radix_sort.cuh>
 #endif
@@ -76,6 +77,43 @@ void L_coop(int grid, int block, size_t smem, rt::stream_t st, const Args& a) {
   if (g_prof.on) g_prof.end(st);
 }
 
+// A fixed sequence of launches (one band factorization, one band solve of a given right-hand side) replayed as a CUDA
+// graph: one host call instead of ~30, so the solve does not depend on how fast the host can enqueue kernels.
+struct GraphCache {
+  bool warm = false;
+  long launches = 0;
+#ifndef VUS_EMU
+  cudaGraphExec_t exec = nullptr;
+  void reset() { if (exec) cudaGraphExecDestroy(exec); exec = nullptr; warm = false; launches = 0; }
+#else
+  void reset() { warm = false; launches = 0; }
+#endif
+};
+
+template <class F>
+void run_graphed(GraphCache& gc, rt::stream_t st, F&& body) {
+#ifndef VUS_EMU
+  if (!g_prof.on && st != 0) {
+    if (!gc.exec) {
+      if (!gc.warm) { body(); gc.warm = true; return; }       // first use runs eagerly (sets kernel attributes)
+      const long l0 = g_launches;
+      cudaGraph_t graph = nullptr;
+      rt::check(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal), "graph capture begin");
+      body();
+      rt::check(cudaStreamEndCapture(st, &graph), "graph capture end");
+      gc.launches = g_launches - l0;
+      g_launches = l0;
+      rt::check(cudaGraphInstantiate(&gc.exec, graph, 0), "graph instantiate");
+      cudaGraphDestroy(graph);
+    }
+    rt::check(cudaGraphLaunch(gc.exec, st), "graph launch");
+    g_launches += gc.launches;
+    return;
+  }
+#endif
+  body();
+}
+
 struct FactorTable {
   long n = 0;
   std::vector<int> h_idx;        // [slots][n]
@@ -88,6 +126,7 @@ struct FactorTable {
 };
 
 const int kVarDim[4] = {12, 3, 6, 3};
+
 
 double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -136,6 +175,17 @@ struct vus_handle {
   DBuf<double> e_mask;           // 1 for factors this rank owns, 0 for duplicates of a neighbour's factor
   vus_comm_fn comm = nullptr;
   void* comm_ctx = nullptr;
+  // CUDA graphs of the fixed launch sequences + the stream used when the caller passes NULL (capture needs a real stream)
+  GraphCache g_factor;
+  std::map<std::tuple<const double*, long, int>, GraphCache> g_solve;
+  rt::stream_t own_stream = 0;
+  void drop_graphs() { g_factor.reset(); for (auto& kv : g_solve) kv.second.reset(); g_solve.clear(); }
+  ~vus_handle() {
+    drop_graphs();
+#ifndef VUS_EMU
+    if (own_stream) cudaStreamDestroy(own_stream);
+#endif
+  }
   // stats
   vus_lm_result res;
 };
@@ -284,6 +334,7 @@ PairDst band_dst(const vus_handle* h, long p, long q, const std::map<std::pair<l
 
 int analyze(vus_handle* h, rt::stream_t st) {
   const double t_an0 = now_ms();
+  h->drop_graphs();
   double t_tick = t_an0;
   auto tick = [&](const char* what) {
     if (h->prm.verbose > 1) { const double t = now_ms(); std::fprintf(stderr, "  analyze %-28s %.1f ms\n", what, t - t_tick); t_tick = t; }
@@ -595,7 +646,11 @@ BcrArgs bcr_args(vus_handle* h) {
   return a;
 }
 
+void bcr_factor_launches(vus_handle* h, rt::stream_t st);
 void bcr_factor(vus_handle* h, rt::stream_t st) {
+  run_graphed(h->g_factor, st, [&] { bcr_factor_launches(h, st); });
+}
+void bcr_factor_launches(vus_handle* h, rt::stream_t st) {
   ClassGuard kc_guard(KC_BCR_FACTOR);
   const long BB = (long)h->B * h->B;
   rt::d2d(h->Dw.p, h->H.p + h->sd_off, h->Ns * BB * sizeof(double), st);
@@ -615,7 +670,13 @@ void bcr_factor(vus_handle* h, rt::stream_t st) {
 }
 
 // in-place solve of the band system for nrhs vectors X[v*xstride + ...]
-void bcr_solve(vus_handle* h, double* X, long xstride, int nrhs, rt::stream_t st) {
+void bcr_solve_launches(vus_handle* h, double* X, long xstride, int nrhs, rt::stream_t st);
+void bcr_solve(vus_handle* h, double* X, long xstride, int nrhs, rt::stream_t st, bool cacheable = true) {
+  if (!cacheable) { bcr_solve_launches(h, X, xstride, nrhs, st); return; }
+  GraphCache& gc = h->g_solve[std::make_tuple((const double*)X, xstride, nrhs)];
+  run_graphed(gc, st, [&] { bcr_solve_launches(h, X, xstride, nrhs, st); });
+}
+void bcr_solve_launches(vus_handle* h, double* X, long xstride, int nrhs, rt::stream_t st) {
   ClassGuard kc_guard(KC_BCR_SOLVE);
   BcrArgs a = bcr_args(h);
   a.X = X; a.xstride = xstride; a.nrhs = nrhs;
@@ -973,6 +1034,9 @@ int vus_create(int device, vus_handle** out) {
   rt::pool_setup(device);
   vus_handle* h = new vus_handle();
   h->device = device;
+#ifndef VUS_EMU
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) h->own_stream = 0;
+#endif
   vus_default_lm_params(&h->prm);
   *out = h;
   return VUS_OK;
@@ -1110,7 +1174,7 @@ int vus_optimize(vus_handle* h, void* stream, vus_lm_result* result) {
   if (!h) return VUS_ERR_INVALID;
   if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_optimize: call vus_analyze first");
   VUS_TRY(h)
-  const int rc = optimize(h, (rt::stream_t)stream);
+  const int rc = optimize(h, stream ? (rt::stream_t)stream : h->own_stream);
   if (result) *result = h->res;
   return rc;
   VUS_CATCH(h)
@@ -1120,7 +1184,7 @@ int vus_error(vus_handle* h, void* stream, double* out) {
   if (!h || !out) return VUS_ERR_INVALID;
   if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_error: call vus_analyze first");
   VUS_TRY(h)
-  *out = graph_error(h, h->cur, (rt::stream_t)stream);
+  *out = graph_error(h, h->cur, stream ? (rt::stream_t)stream : h->own_stream);
   return VUS_OK;
   VUS_CATCH(h)
 }
@@ -1129,7 +1193,7 @@ int vus_factor_errors(vus_handle* h, void* stream, double* out) {
   if (!h || !out) return VUS_ERR_INVALID;
   if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_factor_errors: call vus_analyze first");
   VUS_TRY(h)
-  rt::stream_t st = (rt::stream_t)stream;
+  rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
   run_factors(h, h->cur, false, st);
   std::vector<double> tmp(h->nfactors);
   rt::d2h(tmp.data(), h->e_all.p, h->nfactors * sizeof(double), st);
@@ -1149,7 +1213,7 @@ int vus_linearize(vus_handle* h, void* stream, int type, double* r_out, double* 
   if (!h || type < 0 || type >= VUS_F_NTYPES) return VUS_ERR_INVALID;
   if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_linearize: call vus_analyze first");
   VUS_TRY(h)
-  rt::stream_t st = (rt::stream_t)stream;
+  rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
   run_factors(h, h->cur, true, st);
   FactorTable& T = h->ft[type];
   if (r_out) rt::d2h(r_out, T.r.p, (size_t)kFactorM[type] * T.n * sizeof(double), st);
@@ -1176,7 +1240,7 @@ int vus_solve_step(vus_handle* h, void* stream, double lambda, double* d_pose, d
   if (!h) return VUS_ERR_INVALID;
   if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_solve_step: call vus_analyze first");
   VUS_TRY(h)
-  rt::stream_t st = (rt::stream_t)stream;
+  rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
   run_factors(h, h->cur, true, st);
   assemble_base(h, st);
   int its = 0;
@@ -1203,7 +1267,7 @@ int vus_debug_band_solve(vus_handle* h, void* stream, double lambda, double* SD_
   if (!h) return VUS_ERR_INVALID;
   if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_debug_band_solve: call vus_analyze first");
   VUS_TRY(h)
-  rt::stream_t st = (rt::stream_t)stream;
+  rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
   const long BB = (long)h->B * h->B;
   run_factors(h, h->cur, true, st);
   assemble_base(h, st);
@@ -1215,7 +1279,7 @@ int vus_debug_band_solve(vus_handle* h, void* stream, double lambda, double* SD_
     DBuf<double> X;
     X.alloc((size_t)nrhs * h->Lc);
     rt::h2d(X.p, x_inout, (size_t)nrhs * h->Lc * sizeof(double), st);
-    bcr_solve(h, X.p, h->Lc, nrhs, st);
+    bcr_solve(h, X.p, h->Lc, nrhs, st, false);
     rt::d2h(x_inout, X.p, (size_t)nrhs * h->Lc * sizeof(double), st);
     rt::sync(st);
   }
@@ -1230,7 +1294,7 @@ int vus_preintegrate_imu(vus_handle* h, void* stream, int64_t n, int32_t k, cons
   if (!h || n < 0 || k <= 0 || !(dt > 0.0) || !acc || !gyro || !pim_out || !sqrt_info_out || (mem != VUS_MEM_HOST_ROWS && mem != VUS_MEM_DEVICE_ROWS))
     return fail(h, VUS_ERR_INVALID, "vus_preintegrate_imu: bad arguments (tables are row-major: mem = VUS_MEM_HOST_ROWS or VUS_MEM_DEVICE_ROWS)");
   VUS_TRY(h)
-  rt::stream_t st = (rt::stream_t)stream;
+  rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
   if (n == 0) return VUS_OK;
   const size_t in_bytes = (size_t)n * k * 3 * sizeof(double);
   DBuf<double> dacc, dgyr, pim, sinfo;
@@ -1261,7 +1325,7 @@ int vus_backproject_stereo(vus_handle* h, void* stream, int64_t n, const int32_t
     return fail(h, VUS_ERR_INVALID, "vus_backproject_stereo: bad arguments (tables are row-major)");
   if (!h->nvar[0]) return fail(h, VUS_ERR_STATE, "vus_backproject_stereo: set the pose variables first");
   VUS_TRY(h)
-  rt::stream_t st = (rt::stream_t)stream;
+  rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
   if (n == 0) return VUS_OK;
   for (int64_t o = 0; o < n; ++o)
     if (pose_idx[o] < 0 || pose_idx[o] >= h->nvar[0]) return fail(h, VUS_ERR_INVALID, "vus_backproject_stereo: pose index out of range");
@@ -1286,7 +1350,7 @@ int vus_time_linearize(vus_handle* h, void* stream, int reps, double* ms_per_rep
   if (!h || !ms_per_rep || reps <= 0) return VUS_ERR_INVALID;
   if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_time_linearize: call vus_analyze first");
   VUS_TRY(h)
-  rt::stream_t st = (rt::stream_t)stream;
+  rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
   run_factors(h, h->cur, true, st);
   rt::sync(st);
 #ifndef VUS_EMU

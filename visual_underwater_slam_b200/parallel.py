@@ -8,8 +8,9 @@ per-trajectory summary (final error, iterations, lambda) at the end -- there is 
 weak and the N-rank result is bit-identical to the 1-rank result for every trajectory.
 
 Inside a rank the trajectories of a shard are small (launch-latency bound), so several handles run concurrently from a
-thread pool, each on its own CUDA stream (ctypes releases the GIL during the C-ABI calls; one host thread per handle, as
-include/vus.h requires).
+thread pool, each on its handle's own CUDA stream (ctypes releases the GIL during the C-ABI calls; one host thread per
+handle, as include/vus.h requires; a stream must never be shared by two handles that run at the same time -- the
+library captures its fixed launch sequences into CUDA graphs on it).
 
 The second mode (BASELINE.json config 5) splits ONE pose graph by contiguous pose range: `partition_pose_graph` builds
 every rank's local graph ([owned | halo] poses, owned + duplicated cut factors) and its halo send / receive lists,
@@ -38,19 +39,16 @@ def owner_of(item, n_items, world):
     return item // (base + 1) if item < cut else extra + (item - cut) // max(base, 1)
 
 
-def solve_local(problems, params=None, lib=None, device=0, threads=4, streams=None, keep_values=True):
+def solve_local(problems, params=None, lib=None, device=0, threads=4, keep_values=True):
     """Solve a list of independent packed problems (graph.to_problem) on this rank's GPU.
     -> list of dict(summary fields..., values=tables or None), in input order."""
     params = params or LevenbergMarquardtParams()
 
     def work(arg):
         i, prob = arg
-        stream = None
-        if streams is not None:
-            stream = streams[i % len(streams)]
         s = Session(prob, params, lib=lib, device=device)
         try:
-            res = s.optimize(stream=stream)
+            res = s.optimize()                          # every handle runs on its own (library-owned) CUDA stream
             out = {k: res[k] for k in SUMMARY_FIELDS}
             out["values"] = s.values() if keep_values else None
             return out
