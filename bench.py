@@ -4,7 +4,7 @@
 One "step" = one full `optimize()` (LM to convergence, gtsam defaults) of the BASELINE.json workload
 "100k-pose underwater trajectory graph with IMU preintegration and 2M stereo factors" (config C3; synthetic,
 generator in visual_underwater_slam_b200/synthetic.py).  At N > 1 every rank solves its own independent
-trajectory graph of the same size (the path shards by trajectory with no data-path collective): weak scaling.
+instance of that graph (the path shards by trajectory with no data-path collective): weak scaling.
 
   value        Sum over ranks of (factors x LM linearizations) / time-to-converge, inputs resident in HBM
   e2e          same metric through the public C-ABI session with HOST tables: host->device copy of every table,
@@ -53,13 +53,14 @@ def parse():
 
 def workload_name(a):
     return (f"C3-style synthetic DVL/IMU/stereo trajectory graph: {a.poses} poses, {a.landmarks} landmarks x 10 obs, "
-            f"{a.loops} loop closures, seed {a.seed}(+rank), manifold preintegration, stereo pixel noise 1 px, "
+            f"{a.loops} loop closures, seed {a.seed}, manifold preintegration, stereo pixel noise 1 px, "
             f"initial drift scale {a.drift_scale}")
 
 
 def make_problem(a, rank):
     from visual_underwater_slam_b200 import synthetic
-    d = synthetic.make_trajectory_graph(a.poses, seed=a.seed + rank, n_landmarks=a.landmarks, n_loops=a.loops, pixel_noise=1.0,
+    # every rank solves its own instance of the SAME synthetic graph (identical work per GPU: clean weak scaling)
+    d = synthetic.make_trajectory_graph(a.poses, seed=a.seed, n_landmarks=a.landmarks, n_loops=a.loops, pixel_noise=1.0,
                                         drift_scale=a.drift_scale)
     return d, d["graph"].to_problem(d["initial"])
 
@@ -100,6 +101,8 @@ class ClockSampler:
         self.proc = None
 
     def start(self):
+        if os.environ.get("VUS_BENCH_NO_SMI"):
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
