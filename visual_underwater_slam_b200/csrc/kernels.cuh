@@ -663,8 +663,31 @@ struct BorderDot1Body {
 // =====================================================================================
 // small dense bias-border algebra (one thread)
 // =====================================================================================
+// out[a][b] = sum_i Z_a[i] R_b[i]  (Z^T R, both [6][len] column sets); stage-1 partials [grid][36]
+struct ColDotArgs { const double* Z; const double* R; long len; long stride; double* partials; int grid; };
+struct ColDot1Body {
+  static VUS_DEV void run(const ColDotArgs& A, int bid, int tid, int nthr, double* sm) {
+    const long chunk = (A.len + A.grid - 1) / A.grid;
+    const long i0 = (long)bid * chunk;
+    long i1 = i0 + chunk;
+    if (i1 > A.len) i1 = A.len;
+    for (int e = 0; e < 36; ++e) {
+      const int a = e / 6, b = e - a * 6;
+      double acc = 0.0;
+      for (long i = i0 + tid; i < i1; i += nthr) acc += A.Z[(long)a * A.stride + i] * A.R[(long)b * A.stride + i];
+      sm[tid] = acc;
+      VUS_SYNC();
+      for (int s = nthr >> 1; s > 0; s >>= 1) {
+        for (int t = tid; t < s; t += nthr) sm[t] += sm[t + s];
+        VUS_SYNC();
+      }
+      if (tid == 0) A.partials[(long)bid * 36 + e] = sm[0];
+      VUS_SYNC();
+    }
+  }
+};
 // Sb = Hbb - F^T Z (from partials of BorderDot over the 6 Z columns), SbInv = Sb^-1
-struct BorderSchurArgs { const double* Hbb; const double* partials; int grid; int nv; double* SbInv; int* fail; };
+struct BorderSchurArgs { const double* Hbb; const double* partials; int grid; int nv; double* SbInv; int* fail; const double* corr; };
 struct BorderSchurBody {
   static VUS_DEV void run(const BorderSchurArgs& A, long) {
     double S[36];
@@ -676,6 +699,16 @@ struct BorderSchurBody {
         for (int b = 0; b < A.grid; ++b) s += A.partials[(long)b * (A.nv * 6) + v * 6 + c];
         S[c * 6 + v] -= s;
       }
+    // second-order correction for the finite accuracy of Z: with R = F - M Z,  F^T M^-1 F = F^T Z + Z^T R + O(|dZ|^2)
+    if (A.corr) {
+      for (int e = 0; e < 36; ++e) {
+        double s = 0.0;
+        for (int b = 0; b < A.grid; ++b) s += A.corr[(long)b * 36 + e];
+        const int a = e / 6, c = e - a * 6;
+        S[a * 6 + c] -= 0.5 * s;                 // symmetrised: Z^T R is symmetric up to rounding
+        S[c * 6 + a] -= 0.5 * s;
+      }
+    }
     for (int p = 0; p < 6; ++p) {            // Gauss-Jordan
       const double piv = S[p * 6 + p];
       if (!(piv > 0.0)) *A.fail = 1;

@@ -165,7 +165,7 @@ struct vus_handle {
   // BCR
   DBuf<double> Dw, U1, U2, Dinv, Gl, Gr, Z, Zr, SbInv;
   // PCG
-  DBuf<double> x, r, z, p, Ap, d, xl, scal, partials, bpart, e_all, le_all;
+  DBuf<double> x, r, z, p, Ap, d, xl, scal, partials, bpart, bpart2, e_all, le_all;
   DBuf<int> fail;
   int red_grid = 0;
   // pose-range partition (one rank of a graph split across GPUs): local nodes = [owned | halo]
@@ -541,6 +541,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
   h->red_grid = std::min<long>(std::max<long>(1, (std::max(h->L, h->nfactors) + 4095) / 4096), 2L * rt::sm_count());
   h->partials.alloc(h->red_grid);
   h->bpart.alloc((size_t)h->red_grid * 42);
+  h->bpart2.alloc((size_t)h->red_grid * 36);
   h->fail.alloc(1); h->fail.zero(st);
   long eoff = 0;
   for (int t = 0; t < VUS_F_NTYPES; ++t) {
@@ -730,15 +731,20 @@ void precond_setup(vus_handle* h, rt::stream_t st) {
     BorderColsArgs c; c.F = h->F.p; c.Z = h->Z.p; c.len = h->Lc; c.zstride = h->Lc; c.R = h->Zr.p;
     L_elem<BorderColsBody>(h->Lc * 6, st, c);
     bcr_solve(h, h->Z.p, h->Lc, 6, st);
-    // one step of iterative refinement, Z += M^-1 (F - M Z): the bias Schur complement Hbb - F^T Z cancels to ~1e-8
-    // of its terms on short trajectories (the bias is barely observable), far below the raw accuracy of the band solve
+    // The bias Schur complement Hbb - F^T M^-1 F cancels to ~1e-8 of its terms on short trajectories (the bias is barely
+    // observable), far below the raw ~1e-7 accuracy of the band solve.  With the residual R = F - M Z of the computed
+    // Z,  F^T M^-1 F = F^T Z + Z^T R + O(|dZ|^2): one 6-vector band product and a 6x6 dot product restore the
+    // complement to second order without a second band solve (Z itself only feeds the preconditioner).
     apply_band(h, h->Zr.p, h->Lc, h->Z.p, h->Lc, 6, st);
     L_elem<BorderResidBody>(h->Lc * 6, st, c);
-    bcr_solve(h, h->Zr.p, h->Lc, 6, st);
-    { VecArgs v; v.y = h->Z.p; v.x = h->Zr.p; v.z = nullptr; v.scal = nullptr; v.slot = 0; v.n = 6 * h->Lc; v.Z = nullptr; v.xb = nullptr; v.zstride = 0;
-      ClassGuard kc_v(KC_VECTOR); L_elem<AddVecBody>(6 * h->Lc, st, v); }
     border_dot(h, h->Z.p, h->Lc, 6, st);
+    {
+      ClassGuard kc_b(KC_BORDER);
+      ColDotArgs d; d.Z = h->Z.p; d.R = h->Zr.p; d.len = h->Lc; d.stride = h->Lc; d.partials = h->bpart2.p; d.grid = h->red_grid;
+      L_coop<ColDot1Body>(h->red_grid, 256, 256 * sizeof(double), st, d);
+    }
     BorderSchurArgs s; s.Hbb = h->Hbb.p; s.partials = h->bpart.p; s.grid = h->red_grid; s.nv = 6; s.SbInv = h->SbInv.p; s.fail = h->fail.p;
+    s.corr = h->bpart2.p;
     L_elem<BorderSchurBody>(1, st, s);
   }
 }
