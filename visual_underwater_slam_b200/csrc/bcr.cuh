@@ -157,13 +157,13 @@ VUS_DEV void acc_load_global(Acc& c, const double* src, const Tiles& G) {
 // memory (double buffered: two barriers per step).  `sm` needs VUS_GJ_DOUBLES doubles.
 VUS_DEV void mma_gj_inverse(Acc& c, double* sm, const Tiles& G, int* fail) {
   const int LDP = VUS_GJ_LDP, LDQ = VUS_GJ_LDQ;
-  double* Pw = sm + 2 * VUS_GJ_SET + G.warp * 64;
   const int g = G.g, t = G.t;
   for (int p = 0; p < G.T; ++p) {
     double* Rraw = sm + (p & 1) * VUS_GJ_SET;
     double* Rnew = Rraw + 8 * LDP;
     double* Craw = Rnew + 8 * LDP;
     double* Cnew = Craw + 96 * LDQ;
+    double* Pw = sm + 2 * VUS_GJ_SET + (p & 1) * 64;   // inverse of the pivot tile, double buffered like the panels
     // (a) owners publish the raw pivot row / column panels
 #pragma unroll
     for (int a = 0; a < 3; ++a)
@@ -180,8 +180,9 @@ VUS_DEV void mma_gj_inverse(Acc& c, double* sm, const Tiles& G, int* fail) {
           if (a < G.na) { const int row = (G.ti0 + a) * 8 + g; Craw[row * LDQ + 2 * t] = c[a][b][0]; Craw[row * LDQ + 2 * t + 1] = c[a][b][1]; }
       }
     __syncthreads();
-    // (b) every warp inverts the 8x8 pivot tile redundantly: lane r (mod 8) owns row r, pivot rows travel by shuffle
-    {
+    // (b) ONE warp inverts the 8x8 pivot tile (lane r mod 8 owns row r, pivot rows travel by shuffle); the others wait at
+    //     the barrier, leaving the issue slots to the co-resident CTA instead of repeating the same serial chain 8 times
+    if (G.warp == (p & 7)) {
       const int r = G.lane & 7;
       double row[8];
 #pragma unroll
@@ -203,13 +204,12 @@ VUS_DEV void mma_gj_inverse(Acc& c, double* sm, const Tiles& G, int* fail) {
           for (int q2 = 0; q2 < 8; ++q2) row[q2] = (q2 == q) ? -f : row[q2] - f * prow[q2];
         }
       }
-      __syncwarp();
       if (G.lane < 8) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) Pw[r * 8 + q] = row[q];
       }
-      __syncwarp();
     }
+    __syncthreads();
     // (c) new panels, spread over the warps:  Rnew[q] = P Rraw[q],  Cnew[q] = -Craw[q] P   (q != p)
     for (int item = G.warp; item < 2 * G.T; item += 8) {
       const int q = item < G.T ? item : item - G.T;
