@@ -37,15 +37,22 @@ VUS_HD long bcr_smem_doubles(int B) {
   return a > VUS_GJ_DOUBLES ? a : VUS_GJ_DOUBLES;
 }
 
+// Every array the reduction itself produces (Dw, level couplings, Dinv, Gl, Gr) is stored PADDED, one [KP][LD] tile
+// per supernode with zero padding -- exactly the shared-memory operand layout -- so a block is 16-byte aligned and
+// moves global -> shared as ONE bulk copy (cp.async.bulk, SASS UBLKCP: the TMA engine), completion on an mbarrier.
+// The level-1 inputs (SD, SU of the assembled system) stay plain B x B and are staged with 8-byte cp.async.
 struct BcrArgs {
   long Ns; int B; long s;          // level stride
-  double* Dw;                      // working diagonal blocks [Ns]
-  const double* Ucur; double* Unext;   // couplings at this level / next level, indexed by node id
-  double* Dinv; double* Gl; double* Gr;   // per eliminated node
+  const double* Dsrc; int d_ld; long d_stride;    // diagonal blocks read at this level (level 1: SD, plain; else Dw, padded)
+  double* Dw;                      // working diagonal blocks [Ns], padded
+  const double* Ucur; int u_ld; long u_stride;    // couplings at this level (level 1: SU, plain; else padded)
+  double* Unext;                   // couplings of the next level, padded
+  double* Dinv; double* Gl; double* Gr;   // per eliminated node, padded
   int* fail;
   // solve
   double* X; long xstride; int nrhs;
 };
+VUS_HD long bcr_bbp(int B) { return bcr_buf_doubles(B); }          // doubles per padded block
 
 #ifndef VUS_EMU
 // =====================================================================================  sm_100a: DMMA tile engine
@@ -69,6 +76,33 @@ VUS_DEV void acc_zero(Acc& c) {
 #pragma unroll
     for (int b = 0; b < 6; ++b) c[a][b][0] = c[a][b][1] = 0.0;
 }
+// ---- bulk (TMA) global -> shared copy of one padded block, completion on an mbarrier in shared memory
+VUS_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+struct Mbar {
+  unsigned long long* bar; unsigned parity;
+  VUS_DEV void init(unsigned long long* b, int tid) {        // call once per kernel, followed by a barrier
+    bar = b; parity = 0;
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  // thread 0 only, after a barrier that retired every earlier generic access to the destinations
+  VUS_DEV void expect(unsigned bytes) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  }
+  VUS_DEV void copy(double* dst, const double* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+  }
+  VUS_DEV void wait() {                                       // all threads
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+    parity ^= 1;
+  }
+};
+
 // acc += op(A) op(B)  (NEG: acc -= op(A) op(B)); sA / sB operand buffers [KP][LD] (zero padded); TA: A^T is stored, TB: B^T is stored
 template <bool TA, bool TB, bool NEG>
 VUS_DEV void mma_gemm(Acc& c, const double* sA, const double* sB, const Tiles& G) {
@@ -112,7 +146,7 @@ VUS_DEV void stage_block(double* s, const double* g, const Tiles& G) {
 VUS_DEV void stage_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
 // accumulator tiles -> global row-major block; dst = alpha * acc (+ dst if ADD); optional second destination
 template <bool ADD>
-VUS_DEV void acc_store_global(double* dst, const Acc& c, double alpha, const Tiles& G) {
+VUS_DEV void acc_store_global(double* dst, int ld, const Acc& c, double alpha, const Tiles& G) {
 #pragma unroll
   for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -120,7 +154,7 @@ VUS_DEV void acc_store_global(double* dst, const Acc& c, double alpha, const Til
       if (a >= G.na || b >= G.nb) continue;
       const int i = (G.ti0 + a) * 8 + G.g, j = (G.tj0 + b) * 8 + 2 * G.t;
       if (i >= G.B) continue;
-      double* p = dst + (long)i * G.B + j;
+      double* p = dst + (long)i * ld + j;
       if (j < G.B) p[0] = ADD ? p[0] + alpha * c[a][b][0] : alpha * c[a][b][0];
       if (j + 1 < G.B) p[1] = ADD ? p[1] + alpha * c[a][b][1] : alpha * c[a][b][1];
     }
@@ -139,15 +173,15 @@ VUS_DEV void acc_store_smem(double* s, const Acc& c, const Tiles& G) {
     }
 }
 // global row-major SPD block -> accumulator tiles, identity on the padding
-VUS_DEV void acc_load_global(Acc& c, const double* src, const Tiles& G) {
+VUS_DEV void acc_load_global(Acc& c, const double* src, int ld, const Tiles& G) {
 #pragma unroll
   for (int a = 0; a < 3; ++a)
 #pragma unroll
     for (int b = 0; b < 6; ++b) {
       const int i = (G.ti0 + a) * 8 + G.g, j = (G.tj0 + b) * 8 + 2 * G.t;
       const bool in = a < G.na && b < G.nb && i < G.B;
-      c[a][b][0] = (in && j < G.B) ? src[(long)i * G.B + j] : (i == j ? 1.0 : 0.0);
-      c[a][b][1] = (in && j + 1 < G.B) ? src[(long)i * G.B + j + 1] : (i == j + 1 ? 1.0 : 0.0);
+      c[a][b][0] = (in && j < G.B) ? src[(long)i * ld + j] : (i == j ? 1.0 : 0.0);
+      c[a][b][1] = (in && j + 1 < G.B) ? src[(long)i * ld + j + 1] : (i == j + 1 ? 1.0 : 0.0);
     }
 }
 
@@ -258,89 +292,124 @@ VUS_DEV void mma_gj_inverse(Acc& c, double* sm, const Tiles& G, int* fail) {
   __syncthreads();
 }
 
+// one operand of a factor kernel: padded blocks arrive by one bulk copy, the plain level-1 inputs by 8-byte cp.async
+struct Staged { bool bulk; };
+VUS_DEV Staged stage_any(double* buf, const double* src, int ld, const Tiles& G, Mbar& mb, int tid) {
+  Staged st;
+  st.bulk = ld == G.LD;
+  if (st.bulk) {
+    if (tid == 0) { const unsigned bytes = (unsigned)(bcr_buf_doubles(G.B) * sizeof(double)); mb.expect(bytes); mb.copy(buf, src, bytes); }
+  } else {
+    stage_block(buf, src, G);
+  }
+  return st;
+}
+VUS_DEV void stage_done(const Staged& st, Mbar& mb) {            // then __syncthreads() before the operand is read
+  if (st.bulk) mb.wait(); else stage_wait();
+}
+
 // per eliminated node j = s*(2m+1): Dinv_j, Gl_j = U[j-s] Dinv_j, Gr_j = U[j]^T Dinv_j      (256 threads)
 struct BcrElimBody {
   static VUS_DEV void run(const BcrArgs& A, int m, int tid, int, double* sm) {
+    __shared__ unsigned long long bar_;
     const Tiles G(A.B, tid);
-    const long BB = (long)A.B * A.B;
+    const long BBP = bcr_bbp(A.B);
     const long j = A.s * (2L * m + 1);
     double* buf0 = sm;
     double* buf1 = sm + bcr_buf_doubles(A.B);
+    Mbar mb;
+    mb.init(&bar_, tid);
     Acc c;
-    acc_load_global(c, A.Dw + j * BB, G);
-    mma_gj_inverse(c, sm, G, A.fail);
-    acc_store_global<false>(A.Dinv + j * BB, c, 1.0, G);
+    acc_load_global(c, A.Dsrc + j * A.d_stride, A.d_ld, G);
+    mma_gj_inverse(c, sm, G, A.fail);                    // ends with a barrier (also publishes the mbarrier init)
+    acc_store_global<false>(A.Dinv + j * BBP, G.LD, c, 1.0, G);
     acc_store_smem(buf1, c, G);
-    stage_block(buf0, A.Ucur + (j - A.s) * BB, G);
-    stage_wait();
+    Staged st = stage_any(buf0, A.Ucur + (j - A.s) * A.u_stride, A.u_ld, G, mb, tid);
+    stage_done(st, mb);
     __syncthreads();
     acc_zero(c);
     mma_gemm<false, false, false>(c, buf0, buf1, G);
     if (j + A.s < A.Ns) {
       __syncthreads();
-      stage_block(buf0, A.Ucur + j * BB, G);           // in flight while Gl is written out
-      acc_store_global<false>(A.Gl + j * BB, c, 1.0, G);
-      stage_wait();
+      st = stage_any(buf0, A.Ucur + j * A.u_stride, A.u_ld, G, mb, tid);   // in flight while Gl is written out
+      acc_store_global<false>(A.Gl + j * BBP, G.LD, c, 1.0, G);
+      stage_done(st, mb);
       __syncthreads();
       acc_zero(c);
       mma_gemm<true, false, false>(c, buf0, buf1, G);
-      acc_store_global<false>(A.Gr + j * BB, c, 1.0, G);
+      acc_store_global<false>(A.Gr + j * BBP, G.LD, c, 1.0, G);
     } else {
-      acc_store_global<false>(A.Gl + j * BB, c, 1.0, G);
+      acc_store_global<false>(A.Gl + j * BBP, G.LD, c, 1.0, G);
     }
   }
 };
-// per surviving node c = 2*m*s: Dw_c -= Gr_{c-s} U_{c-s} + Gl_{c+s} U_c^T ; Unext_c = -Gl_{c+s} U_{c+s}
+// per surviving node c = 2*m*s: Dw_c = D_c - Gr_{c-s} U_{c-s} - Gl_{c+s} U_c^T ; Unext_c = -Gl_{c+s} U_{c+s}
 struct BcrUpdateBody {
   static VUS_DEV void run(const BcrArgs& A, int m, int tid, int, double* sm) {
+    __shared__ unsigned long long bar_;
     const Tiles G(A.B, tid);
-    const long BB = (long)A.B * A.B;
+    const long BBP = bcr_bbp(A.B);
+    const unsigned blk_bytes = (unsigned)(BBP * sizeof(double));
     const long c = 2L * m * A.s;
     double* buf0 = sm;
     double* buf1 = sm + bcr_buf_doubles(A.B);
     const bool lo = c - A.s >= 0, hi = c + A.s < A.Ns;
-    if (lo) {
-      stage_block(buf0, A.Gr + (c - A.s) * BB, G);
-      stage_block(buf1, A.Ucur + (c - A.s) * BB, G);
+    const bool ubulk = A.u_ld == G.LD;
+    Mbar mb;
+    mb.init(&bar_, tid);
+    __syncthreads();
+    if (lo) {                                            // Gr is always padded -> bulk; U bulk from level 2 on
+      if (tid == 0) {
+        mb.expect(ubulk ? 2 * blk_bytes : blk_bytes);
+        mb.copy(buf0, A.Gr + (c - A.s) * BBP, blk_bytes);
+        if (ubulk) mb.copy(buf1, A.Ucur + (c - A.s) * A.u_stride, blk_bytes);
+      }
+      if (!ubulk) stage_block(buf1, A.Ucur + (c - A.s) * A.u_stride, G);
     }
     Acc acc;
-    acc_load_global(acc, A.Dw + c * BB, G);            // D_c rides in the accumulators; the products are subtracted
+    acc_load_global(acc, A.Dsrc + c * A.d_stride, A.d_ld, G);    // D_c rides in the accumulators; the products are subtracted
     if (lo) {
-      stage_wait();
+      mb.wait();
+      if (!ubulk) stage_wait();
       __syncthreads();
       mma_gemm<false, false, true>(acc, buf0, buf1, G);
       __syncthreads();
     }
     if (hi) {
       const long j = c + A.s;
-      stage_block(buf0, A.Gl + j * BB, G);
-      stage_block(buf1, A.Ucur + c * BB, G);
-      stage_wait();
+      if (tid == 0) {
+        mb.expect(ubulk ? 2 * blk_bytes : blk_bytes);
+        mb.copy(buf0, A.Gl + j * BBP, blk_bytes);
+        if (ubulk) mb.copy(buf1, A.Ucur + c * A.u_stride, blk_bytes);
+      }
+      if (!ubulk) stage_block(buf1, A.Ucur + c * A.u_stride, G);
+      mb.wait();
+      if (!ubulk) stage_wait();
       __syncthreads();
       mma_gemm<false, true, true>(acc, buf0, buf1, G);
       if (j + A.s < A.Ns) {
         __syncthreads();
-        stage_block(buf1, A.Ucur + j * BB, G);          // in flight while D_c is written out
-        acc_store_global<false>(A.Dw + c * BB, acc, 1.0, G);
-        stage_wait();
+        Staged st = stage_any(buf1, A.Ucur + j * A.u_stride, A.u_ld, G, mb, tid);   // in flight while D_c is written out
+        acc_store_global<false>(A.Dw + c * BBP, G.LD, acc, 1.0, G);
+        stage_done(st, mb);
         __syncthreads();
         acc_zero(acc);
         mma_gemm<false, false, true>(acc, buf0, buf1, G);
-        acc_store_global<false>(A.Unext + c * BB, acc, 1.0, G);
+        acc_store_global<false>(A.Unext + c * BBP, G.LD, acc, 1.0, G);
         return;
       }
     }
-    acc_store_global<false>(A.Dw + c * BB, acc, 1.0, G);
+    acc_store_global<false>(A.Dw + c * BBP, G.LD, acc, 1.0, G);
   }
 };
-// root: Dinv_0 = inv(Dw_0)
+// root: Dinv_0 = inv(D_0)
 struct BcrRootBody {
   static VUS_DEV void run(const BcrArgs& A, int, int tid, int, double* sm) {
     const Tiles G(A.B, tid);
     Acc c;
-    acc_load_global(c, A.Dw, G);
+    acc_load_global(c, A.Dsrc, A.d_ld, G);
     mma_gj_inverse(c, sm, G, A.fail);
-    acc_store_global<false>(A.Dinv, c, 1.0, G);
+    acc_store_global<false>(A.Dinv, G.LD, c, 1.0, G);
   }
 };
 
@@ -353,57 +422,72 @@ template <> struct CoopBounds<BcrRootBody> { static constexpr int kMaxThreads = 
 
 #else
 // =====================================================================================  host emulation (tests only)
-inline void emu_spd_inverse(const double* M, double* out, int B, int* fail) {
-  for (int e = 0; e < B * B; ++e) out[e] = M[e];
-  std::vector<double> rowp(B), colp(B);
+inline void emu_spd_inverse(const double* M, int ldm, double* out, int ldo, int B, int* fail) {
+  std::vector<double> w((size_t)B * B), rowp(B), colp(B);
+  for (int i = 0; i < B; ++i)
+    for (int j = 0; j < B; ++j) w[(size_t)i * B + j] = M[(long)i * ldm + j];
   for (int p = 0; p < B; ++p) {
-    for (int i = 0; i < B; ++i) { colp[i] = out[(long)i * B + p]; rowp[i] = out[(long)p * B + i]; }
+    for (int i = 0; i < B; ++i) { colp[i] = w[(size_t)i * B + p]; rowp[i] = w[(size_t)p * B + i]; }
     const double piv = rowp[p];
     if (!(piv > 0.0)) *fail = 1;
     const double d = 1.0 / piv;
     for (int i = 0; i < B; ++i) {
-      double* row = out + (long)i * B;
+      double* row = w.data() + (size_t)i * B;
       if (i == p) { for (int j = 0; j < B; ++j) row[j] = (j == p) ? d : rowp[j] * d; }
       else { const double ci = colp[i] * d; for (int j = 0; j < B; ++j) row[j] = (j == p) ? -ci : row[j] - ci * rowp[j]; }
     }
   }
+  for (int i = 0; i < B; ++i)
+    for (int j = 0; j < B; ++j) out[(long)i * ldo + j] = w[(size_t)i * B + j];
 }
-// C = beta*C + alpha * op(A) op(B), all row-major B x B
-inline void emu_gemm(double* C, const double* A, bool ta, const double* Bm, bool tb, int B, double alpha, double beta) {
+// C = Cin + alpha * op(A) op(B)   (Cin may be null); every operand is a B x B block with its own row stride
+inline void emu_gemm(double* C, int ldc, const double* Cin, int ldi, const double* A, int lda, bool ta, const double* Bm, int ldb, bool tb,
+                     int B, double alpha) {
   std::vector<double> out((size_t)B * B);
   for (int i = 0; i < B; ++i)
     for (int j = 0; j < B; ++j) {
       double s = 0.0;
-      for (int k = 0; k < B; ++k) s += (ta ? A[(long)k * B + i] : A[(long)i * B + k]) * (tb ? Bm[(long)j * B + k] : Bm[(long)k * B + j]);
-      out[(long)i * B + j] = alpha * s + (beta != 0.0 ? beta * C[(long)i * B + j] : 0.0);
+      for (int k = 0; k < B; ++k) s += (ta ? A[(long)k * lda + i] : A[(long)i * lda + k]) * (tb ? Bm[(long)j * ldb + k] : Bm[(long)k * ldb + j]);
+      out[(size_t)i * B + j] = alpha * s + (Cin ? Cin[(long)i * ldi + j] : 0.0);
     }
-  for (long e = 0; e < (long)B * B; ++e) C[e] = out[e];
+  for (int i = 0; i < B; ++i)
+    for (int j = 0; j < B; ++j) C[(long)i * ldc + j] = out[(size_t)i * B + j];
 }
 struct BcrElimBody {
   static VUS_DEV void run(const BcrArgs& A, int m, int, int, double*) {
-    const int B = A.B;
-    const long BB = (long)B * B;
+    const int B = A.B, LD = bcr_ld(B);
+    const long BBP = bcr_bbp(B);
     const long j = A.s * (2L * m + 1);
-    emu_spd_inverse(A.Dw + j * BB, A.Dinv + j * BB, B, A.fail);
-    emu_gemm(A.Gl + j * BB, A.Ucur + (j - A.s) * BB, false, A.Dinv + j * BB, false, B, 1.0, 0.0);
-    if (j + A.s < A.Ns) emu_gemm(A.Gr + j * BB, A.Ucur + j * BB, true, A.Dinv + j * BB, false, B, 1.0, 0.0);
+    emu_spd_inverse(A.Dsrc + j * A.d_stride, A.d_ld, A.Dinv + j * BBP, LD, B, A.fail);
+    emu_gemm(A.Gl + j * BBP, LD, nullptr, 0, A.Ucur + (j - A.s) * A.u_stride, A.u_ld, false, A.Dinv + j * BBP, LD, false, B, 1.0);
+    if (j + A.s < A.Ns) emu_gemm(A.Gr + j * BBP, LD, nullptr, 0, A.Ucur + j * A.u_stride, A.u_ld, true, A.Dinv + j * BBP, LD, false, B, 1.0);
   }
 };
 struct BcrUpdateBody {
   static VUS_DEV void run(const BcrArgs& A, int m, int, int, double*) {
-    const int B = A.B;
-    const long BB = (long)B * B;
+    const int B = A.B, LD = bcr_ld(B);
+    const long BBP = bcr_bbp(B);
     const long c = 2L * m * A.s;
-    if (c - A.s >= 0) emu_gemm(A.Dw + c * BB, A.Gr + (c - A.s) * BB, false, A.Ucur + (c - A.s) * BB, false, B, -1.0, 1.0);
+    const double* Cin = A.Dsrc + c * A.d_stride;
+    int ldi = A.d_ld;
+    double* D = A.Dw + c * BBP;
+    if (c - A.s >= 0) {
+      emu_gemm(D, LD, Cin, ldi, A.Gr + (c - A.s) * BBP, LD, false, A.Ucur + (c - A.s) * A.u_stride, A.u_ld, false, B, -1.0);
+      Cin = D; ldi = LD;
+    }
     if (c + A.s < A.Ns) {
       const long j = c + A.s;
-      emu_gemm(A.Dw + c * BB, A.Gl + j * BB, false, A.Ucur + c * BB, true, B, -1.0, 1.0);
-      if (j + A.s < A.Ns) emu_gemm(A.Unext + c * BB, A.Gl + j * BB, false, A.Ucur + j * BB, false, B, -1.0, 0.0);
+      emu_gemm(D, LD, Cin, ldi, A.Gl + j * BBP, LD, false, A.Ucur + c * A.u_stride, A.u_ld, true, B, -1.0);
+      Cin = D; ldi = LD;
+      if (j + A.s < A.Ns) emu_gemm(A.Unext + c * BBP, LD, nullptr, 0, A.Gl + j * BBP, LD, false, A.Ucur + j * A.u_stride, A.u_ld, false, B, -1.0);
     }
+    if (Cin != D)                                            // isolated node: plain copy
+      for (int i = 0; i < B; ++i)
+        for (int jj = 0; jj < B; ++jj) D[(long)i * LD + jj] = Cin[(long)i * ldi + jj];
   }
 };
 struct BcrRootBody {
-  static VUS_DEV void run(const BcrArgs& A, int, int, int, double*) { emu_spd_inverse(A.Dw, A.Dinv, A.B, A.fail); }
+  static VUS_DEV void run(const BcrArgs& A, int, int, int, double*) { emu_spd_inverse(A.Dsrc, A.d_ld, A.Dinv, bcr_ld(A.B), A.B, A.fail); }
 };
 #endif
 
@@ -459,11 +543,16 @@ VUS_DEV void panel_mma(Panel& P, const double* sM, const double* sX, const Tiles
   }
 }
 // one streamed product: copy block, stage panel, wait, multiply-accumulate.  Ends with a barrier (buffers reusable).
-template <bool TA, bool NEG>
-VUS_DEV void blk_stream(Panel& P, double* buf, double* sX, const double* M, const double* x, long xstride, const Tiles& G, int nv, int tid) {
-  stage_block(buf, M, G);
+// BULK: the block is padded in global memory and arrives by one bulk (TMA) copy; else 8-byte cp.async of a plain block.
+template <bool TA, bool NEG, bool BULK>
+VUS_DEV void blk_stream(Panel& P, double* buf, double* sX, const double* M, const double* x, long xstride, const Tiles& G, int nv, int tid, Mbar& mb) {
+  if (BULK) {
+    if (tid == 0) { const unsigned bytes = (unsigned)(bcr_buf_doubles(G.B) * sizeof(double)); mb.expect(bytes); mb.copy(buf, M, bytes); }
+  } else {
+    stage_block(buf, M, G);
+  }
   stage_panel(sX, x, xstride, true, G, nv, tid);
-  stage_wait();
+  if (BULK) mb.wait(); else stage_wait();
   __syncthreads();
   panel_mma<TA, NEG>(P, buf, sX, G);
   __syncthreads();
@@ -481,11 +570,11 @@ VUS_DEV void blk_stream(Panel& P, double* buf, double* sX, const double* M, cons
   }
 #else
 // host emulation helpers: out[v][r] += sign * sum_k op(M)[r][k] x[v][k]
-inline void emu_blk_accum(double* out, const double* M, bool ta, const double* x, long xstride, double sign, int B, int nv) {
+inline void emu_blk_accum(double* out, const double* M, int ld, bool ta, const double* x, long xstride, double sign, int B, int nv) {
   for (int v = 0; v < nv; ++v)
     for (int r = 0; r < B; ++r) {
       double s = 0.0;
-      for (int k = 0; k < B; ++k) s += (ta ? M[(long)k * B + r] : M[(long)r * B + k]) * x[(long)v * xstride + k];
+      for (int k = 0; k < B; ++k) s += (ta ? M[(long)k * ld + r] : M[(long)r * ld + k]) * x[(long)v * xstride + k];
       out[v * B + r] += sign * s;
     }
 }
@@ -498,34 +587,45 @@ template <bool DEEP>
 struct BcrFwdBodyT {
   static VUS_DEV void run(const BcrArgs& A, int m, int tid, int, double* sm) {
     const int B = A.B, nv = A.nrhs;
-    const long BB = (long)B * B;
+    const long BBP = bcr_bbp(B);
     const long c = 2L * m * A.s;
     const long jl = c - A.s, jh = c + A.s;
 #ifdef VUS_EMU
+    const int LD = bcr_ld(B);
     double* dl = sm;
     for (int e = 0; e < nv * B; ++e) dl[e] = 0.0;
-    if (jl >= 0) emu_blk_accum(dl, A.Gr + jl * BB, false, A.X + jl * B, A.xstride, 1.0, B, nv);
-    if (jh < A.Ns) emu_blk_accum(dl, A.Gl + jh * BB, false, A.X + jh * B, A.xstride, 1.0, B, nv);
+    if (jl >= 0) emu_blk_accum(dl, A.Gr + jl * BBP, LD, false, A.X + jl * B, A.xstride, 1.0, B, nv);
+    if (jh < A.Ns) emu_blk_accum(dl, A.Gl + jh * BBP, LD, false, A.X + jh * B, A.xstride, 1.0, B, nv);
     for (int v = 0; v < nv; ++v)
       for (int r = 0; r < B; ++r) A.X[(long)v * A.xstride + c * B + r] -= dl[v * B + r];
     (void)tid;
 #else
+    __shared__ unsigned long long bar_;
     const Tiles G(B, tid);
-    const long slot = blk_slot_doubles(B);
+    const long slot = blk_slot_doubles(B), po = bcr_buf_doubles(B);
+    const unsigned blk_bytes = (unsigned)(BBP * sizeof(double));
+    Mbar mb;
+    mb.init(&bar_, tid);
+    __syncthreads();
     Panel P;
     P.zero();
     if (DEEP) {
-      if (jl >= 0) { stage_block(sm, A.Gr + jl * BB, G); stage_panel(sm + bcr_buf_doubles(B), A.X + jl * B, A.xstride, true, G, nv, tid); }
-      if (jh < A.Ns) { stage_block(sm + slot, A.Gl + jh * BB, G); stage_panel(sm + slot + bcr_buf_doubles(B), A.X + jh * B, A.xstride, true, G, nv, tid); }
-      stage_wait();
+      if (tid == 0) {
+        mb.expect(((jl >= 0) + (jh < A.Ns)) * blk_bytes);
+        if (jl >= 0) mb.copy(sm, A.Gr + jl * BBP, blk_bytes);
+        if (jh < A.Ns) mb.copy(sm + slot, A.Gl + jh * BBP, blk_bytes);
+      }
+      if (jl >= 0) stage_panel(sm + po, A.X + jl * B, A.xstride, true, G, nv, tid);
+      if (jh < A.Ns) stage_panel(sm + slot + po, A.X + jh * B, A.xstride, true, G, nv, tid);
+      mb.wait();
       __syncthreads();
-      if (jl >= 0) panel_mma<false, false>(P, sm, sm + bcr_buf_doubles(B), G);
-      if (jh < A.Ns) panel_mma<false, false>(P, sm + slot, sm + slot + bcr_buf_doubles(B), G);
+      if (jl >= 0) panel_mma<false, false>(P, sm, sm + po, G);
+      if (jh < A.Ns) panel_mma<false, false>(P, sm + slot, sm + slot + po, G);
     } else {
       double* buf = sm;
-      double* sX = sm + bcr_buf_doubles(B);
-      if (jl >= 0) blk_stream<false, false>(P, buf, sX, A.Gr + jl * BB, A.X + jl * B, A.xstride, G, nv, tid);
-      if (jh < A.Ns) blk_stream<false, false>(P, buf, sX, A.Gl + jh * BB, A.X + jh * B, A.xstride, G, nv, tid);
+      double* sX = sm + po;
+      if (jl >= 0) blk_stream<false, false, true>(P, buf, sX, A.Gr + jl * BBP, A.X + jl * B, A.xstride, G, nv, tid, mb);
+      if (jh < A.Ns) blk_stream<false, false, true>(P, buf, sX, A.Gl + jh * BBP, A.X + jh * B, A.xstride, G, nv, tid, mb);
     }
     VUS_PANEL_FOREACH(P, G, nv, { A.X[(long)v * A.xstride + c * B + r] -= val; })
 #endif
@@ -538,29 +638,41 @@ template <bool DEEP>
 struct BcrBwdBodyT {
   static VUS_DEV void run(const BcrArgs& A, int m, int tid, int, double* sm) {
     const int B = A.B, nv = A.nrhs;
-    const long BB = (long)B * B;
+    const long BBP = bcr_bbp(B);
     const long j = A.s * (2L * m + 1);
     const long jl = j - A.s, jh = j + A.s;
     const bool hl = jl >= 0 && A.s > 0, hh = jh < A.Ns && A.s > 0;
 #ifdef VUS_EMU
+    const int LD = bcr_ld(B);
     double* dl = sm;
     for (int e = 0; e < nv * B; ++e) dl[e] = 0.0;
-    emu_blk_accum(dl, A.Dinv + j * BB, false, A.X + j * B, A.xstride, 1.0, B, nv);
-    if (hl) emu_blk_accum(dl, A.Gl + j * BB, true, A.X + jl * B, A.xstride, -1.0, B, nv);
-    if (hh) emu_blk_accum(dl, A.Gr + j * BB, true, A.X + jh * B, A.xstride, -1.0, B, nv);
+    emu_blk_accum(dl, A.Dinv + j * BBP, LD, false, A.X + j * B, A.xstride, 1.0, B, nv);
+    if (hl) emu_blk_accum(dl, A.Gl + j * BBP, LD, true, A.X + jl * B, A.xstride, -1.0, B, nv);
+    if (hh) emu_blk_accum(dl, A.Gr + j * BBP, LD, true, A.X + jh * B, A.xstride, -1.0, B, nv);
     for (int v = 0; v < nv; ++v)
       for (int r = 0; r < B; ++r) A.X[(long)v * A.xstride + j * B + r] = dl[v * B + r];
     (void)tid;
 #else
+    __shared__ unsigned long long bar_;
     const Tiles G(B, tid);
     const long slot = blk_slot_doubles(B), po = bcr_buf_doubles(B);
+    const unsigned blk_bytes = (unsigned)(BBP * sizeof(double));
+    Mbar mb;
+    mb.init(&bar_, tid);
+    __syncthreads();
     Panel P;
     P.zero();
     if (DEEP) {
-      stage_block(sm, A.Dinv + j * BB, G); stage_panel(sm + po, A.X + j * B, A.xstride, true, G, nv, tid);
-      if (hl) { stage_block(sm + slot, A.Gl + j * BB, G); stage_panel(sm + slot + po, A.X + jl * B, A.xstride, true, G, nv, tid); }
-      if (hh) { stage_block(sm + 2 * slot, A.Gr + j * BB, G); stage_panel(sm + 2 * slot + po, A.X + jh * B, A.xstride, true, G, nv, tid); }
-      stage_wait();
+      if (tid == 0) {
+        mb.expect((1 + hl + hh) * blk_bytes);
+        mb.copy(sm, A.Dinv + j * BBP, blk_bytes);
+        if (hl) mb.copy(sm + slot, A.Gl + j * BBP, blk_bytes);
+        if (hh) mb.copy(sm + 2 * slot, A.Gr + j * BBP, blk_bytes);
+      }
+      stage_panel(sm + po, A.X + j * B, A.xstride, true, G, nv, tid);
+      if (hl) stage_panel(sm + slot + po, A.X + jl * B, A.xstride, true, G, nv, tid);
+      if (hh) stage_panel(sm + 2 * slot + po, A.X + jh * B, A.xstride, true, G, nv, tid);
+      mb.wait();
       __syncthreads();
       panel_mma<false, false>(P, sm, sm + po, G);
       if (hl) panel_mma<true, true>(P, sm + slot, sm + slot + po, G);
@@ -568,9 +680,9 @@ struct BcrBwdBodyT {
     } else {
       double* buf = sm;
       double* sX = sm + po;
-      blk_stream<false, false>(P, buf, sX, A.Dinv + j * BB, A.X + j * B, A.xstride, G, nv, tid);
-      if (hl) blk_stream<true, true>(P, buf, sX, A.Gl + j * BB, A.X + jl * B, A.xstride, G, nv, tid);
-      if (hh) blk_stream<true, true>(P, buf, sX, A.Gr + j * BB, A.X + jh * B, A.xstride, G, nv, tid);
+      blk_stream<false, false, true>(P, buf, sX, A.Dinv + j * BBP, A.X + j * B, A.xstride, G, nv, tid, mb);
+      if (hl) blk_stream<true, true, true>(P, buf, sX, A.Gl + j * BBP, A.X + jl * B, A.xstride, G, nv, tid, mb);
+      if (hh) blk_stream<true, true, true>(P, buf, sX, A.Gr + j * BBP, A.X + jh * B, A.xstride, G, nv, tid, mb);
     }
     VUS_PANEL_FOREACH(P, G, nv, { A.X[(long)v * A.xstride + j * B + r] = val; })
 #endif
@@ -597,9 +709,9 @@ struct BandMatvecBody {
 #ifdef VUS_EMU
     double* dl = sm;
     for (int e = 0; e < nv * B; ++e) dl[e] = 0.0;
-    emu_blk_accum(dl, A.SD + I * BB, false, A.x + (long)I * B, A.xstride, 1.0, B, nv);
-    if (up) emu_blk_accum(dl, A.SU + I * BB, false, A.x + (long)(I + 1) * B, A.xstride, 1.0, B, nv);
-    if (dn) emu_blk_accum(dl, A.SU + (I - 1) * BB, true, A.x + (long)(I - 1) * B, A.xstride, 1.0, B, nv);
+    emu_blk_accum(dl, A.SD + I * BB, B, false, A.x + (long)I * B, A.xstride, 1.0, B, nv);
+    if (up) emu_blk_accum(dl, A.SU + I * BB, B, false, A.x + (long)(I + 1) * B, A.xstride, 1.0, B, nv);
+    if (dn) emu_blk_accum(dl, A.SU + (I - 1) * BB, B, true, A.x + (long)(I - 1) * B, A.xstride, 1.0, B, nv);
     for (int v = 0; v < nv; ++v)
       for (int r = 0; r < B; ++r) A.y[(long)v * A.ystride + (long)I * B + r] = dl[v * B + r];
     (void)tid;
@@ -609,9 +721,11 @@ struct BandMatvecBody {
     double* sX = sm + bcr_buf_doubles(B);
     Panel P;
     P.zero();
-    blk_stream<false, false>(P, buf, sX, A.SD + I * BB, A.x + (long)I * B, A.xstride, G, nv, tid);
-    if (up) blk_stream<false, false>(P, buf, sX, A.SU + I * BB, A.x + (long)(I + 1) * B, A.xstride, G, nv, tid);
-    if (dn) blk_stream<true, false>(P, buf, sX, A.SU + (I - 1) * BB, A.x + (long)(I - 1) * B, A.xstride, G, nv, tid);
+    Mbar mb;                                                 // unused: the assembled system is stored plain (B x B)
+    mb.bar = nullptr; mb.parity = 0;
+    blk_stream<false, false, false>(P, buf, sX, A.SD + I * BB, A.x + (long)I * B, A.xstride, G, nv, tid, mb);
+    if (up) blk_stream<false, false, false>(P, buf, sX, A.SU + I * BB, A.x + (long)(I + 1) * B, A.xstride, G, nv, tid, mb);
+    if (dn) blk_stream<true, false, false>(P, buf, sX, A.SU + (I - 1) * BB, A.x + (long)(I - 1) * B, A.xstride, G, nv, tid, mb);
     VUS_PANEL_FOREACH(P, G, nv, { A.y[(long)v * A.ystride + (long)I * B + r] = val; })
 #endif
   }

@@ -517,8 +517,10 @@ int analyze(vus_handle* h, rt::stream_t st) {
   h->g0.alloc(h->Lc); h->gs.alloc(h->L);
   h->F.alloc(h->Lc * 6); h->Hbb0.alloc(36); h->Hbb.alloc(36); h->gb.alloc(6);
   h->C.alloc(9 * NL); h->gl.alloc(3 * NL); h->Cinv.alloc(9 * NL); h->E.alloc(18 * FS.n); h->Pp.alloc(28 * FS.n); h->Pl.alloc(12 * FS.n);
-  h->Dw.alloc(h->Ns * BB); h->U1.alloc(h->Ns * BB); h->U2.alloc(h->Ns * BB);
-  h->Dinv.alloc(h->Ns * BB); h->Gl.alloc(h->Ns * BB); h->Gr.alloc(h->Ns * BB);
+  {   // the reduction's own blocks are padded [KP][LD] tiles; the padding must be (and stays) zero
+    const size_t nb = (size_t)h->Ns * bcr_bbp(h->B);
+    for (DBuf<double>* b : {&h->Dw, &h->U1, &h->U2, &h->Dinv, &h->Gl, &h->Gr}) { b->alloc(nb); b->zero(st); }
+  }
   h->Z.alloc(6 * h->Lc); h->Zr.alloc(6 * h->Lc); h->SbInv.alloc(36);
   if (h->n_owned >= 0) {
     if (h->has_bias || FS.n || NV) return fail(h, VUS_ERR_UNSUPPORTED, "pose-range partition supports pose graphs (PriorFactorPose3 / BetweenFactorPose3) only");
@@ -641,7 +643,9 @@ size_t bcr_smem(int B) { return (size_t)bcr_smem_doubles(B) * sizeof(double); }
 
 BcrArgs bcr_args(vus_handle* h) {
   BcrArgs a;
-  a.Ns = h->Ns; a.B = h->B; a.s = 1; a.Dw = h->Dw.p; a.Ucur = nullptr; a.Unext = nullptr;
+  a.Ns = h->Ns; a.B = h->B; a.s = 1;
+  a.Dsrc = nullptr; a.d_ld = 0; a.d_stride = 0; a.Dw = h->Dw.p;
+  a.Ucur = nullptr; a.u_ld = 0; a.u_stride = 0; a.Unext = nullptr;
   a.Dinv = h->Dinv.p; a.Gl = h->Gl.p; a.Gr = h->Gr.p; a.fail = h->fail.p;
   a.X = nullptr; a.xstride = 0; a.nrhs = 1;
   return a;
@@ -653,19 +657,23 @@ void bcr_factor(vus_handle* h, rt::stream_t st) {
 }
 void bcr_factor_launches(vus_handle* h, rt::stream_t st) {
   ClassGuard kc_guard(KC_BCR_FACTOR);
-  const long BB = (long)h->B * h->B;
-  rt::d2d(h->Dw.p, h->H.p + h->sd_off, h->Ns * BB * sizeof(double), st);
+  const long BB = (long)h->B * h->B, BBP = bcr_bbp(h->B);
+  const int LD = bcr_ld(h->B);
   BcrArgs a = bcr_args(h);
-  const double* ucur = h->H.p + h->su_off;
+  // level 1 reads the assembled system in place (plain B x B blocks); deeper levels read the padded working arrays
+  a.Dsrc = h->H.p + h->sd_off; a.d_ld = h->B; a.d_stride = BB;
+  a.Ucur = h->H.p + h->su_off; a.u_ld = h->B; a.u_stride = BB;
   double* bufs[2] = {h->U1.p, h->U2.p};
   int w = 0;
   for (long s = 1; s < h->Ns; s <<= 1) {
     const long nact = (h->Ns + s - 1) / s;
     const int nel = (int)(nact / 2), nsv = (int)((nact + 1) / 2);
-    a.s = s; a.Ucur = ucur; a.Unext = bufs[w];
+    a.s = s; a.Unext = bufs[w];
     L_coop<BcrElimBody>(nel, 256, bcr_smem(h->B), st, a);
     L_coop<BcrUpdateBody>(nsv, 256, bcr_smem(h->B), st, a);
-    ucur = bufs[w]; w ^= 1;
+    a.Dsrc = h->Dw.p; a.d_ld = LD; a.d_stride = BBP;
+    a.Ucur = bufs[w]; a.u_ld = LD; a.u_stride = BBP;
+    w ^= 1;
   }
   L_coop<BcrRootBody>(1, 256, bcr_smem(h->B), st, a);
 }
