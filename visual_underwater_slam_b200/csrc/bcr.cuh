@@ -40,7 +40,7 @@ VUS_HD long bcr_smem_doubles(int B) {
 // Every array the reduction itself produces (Dw, level couplings, Dinv, Gl, Gr) is stored PADDED, one [KP][LD] tile
 // per supernode with zero padding -- exactly the shared-memory operand layout -- so a block is 16-byte aligned and
 // moves global -> shared as ONE bulk copy (cp.async.bulk, SASS UBLKCP: the TMA engine), completion on an mbarrier.
-// The level-1 inputs (SD, SU of the assembled system) stay plain B x B and are staged with 8-byte cp.async.
+// The assembled system (SD, SU) uses the same tile layout, so level 1 and the band operator stream it the same way.
 struct BcrArgs {
   long Ns; int B; long s;          // level stride
   const double* Dsrc; int d_ld; long d_stride;    // diagonal blocks read at this level (level 1: SD, plain; else Dw, padded)
@@ -704,28 +704,31 @@ struct BcrRootSolveBody {
 struct BandMatvecBody {
   static VUS_DEV void run(const MatvecArgs& A, int I, int tid, int, double* sm) {
     const int B = A.B, nv = A.nv;
-    const long BB = (long)B * B;
+    const long BBP = bcr_bbp(B);
     const bool up = I + 1 < A.Ns, dn = I > 0;
 #ifdef VUS_EMU
+    const int LD = bcr_ld(B);
     double* dl = sm;
     for (int e = 0; e < nv * B; ++e) dl[e] = 0.0;
-    emu_blk_accum(dl, A.SD + I * BB, B, false, A.x + (long)I * B, A.xstride, 1.0, B, nv);
-    if (up) emu_blk_accum(dl, A.SU + I * BB, B, false, A.x + (long)(I + 1) * B, A.xstride, 1.0, B, nv);
-    if (dn) emu_blk_accum(dl, A.SU + (I - 1) * BB, B, true, A.x + (long)(I - 1) * B, A.xstride, 1.0, B, nv);
+    emu_blk_accum(dl, A.SD + I * BBP, LD, false, A.x + (long)I * B, A.xstride, 1.0, B, nv);
+    if (up) emu_blk_accum(dl, A.SU + I * BBP, LD, false, A.x + (long)(I + 1) * B, A.xstride, 1.0, B, nv);
+    if (dn) emu_blk_accum(dl, A.SU + (I - 1) * BBP, LD, true, A.x + (long)(I - 1) * B, A.xstride, 1.0, B, nv);
     for (int v = 0; v < nv; ++v)
       for (int r = 0; r < B; ++r) A.y[(long)v * A.ystride + (long)I * B + r] = dl[v * B + r];
     (void)tid;
 #else
+    __shared__ unsigned long long bar_;
     const Tiles G(B, tid);
     double* buf = sm;
     double* sX = sm + bcr_buf_doubles(B);
+    Mbar mb;
+    mb.init(&bar_, tid);
+    __syncthreads();
     Panel P;
     P.zero();
-    Mbar mb;                                                 // unused: the assembled system is stored plain (B x B)
-    mb.bar = nullptr; mb.parity = 0;
-    blk_stream<false, false, false>(P, buf, sX, A.SD + I * BB, A.x + (long)I * B, A.xstride, G, nv, tid, mb);
-    if (up) blk_stream<false, false, false>(P, buf, sX, A.SU + I * BB, A.x + (long)(I + 1) * B, A.xstride, G, nv, tid, mb);
-    if (dn) blk_stream<true, false, false>(P, buf, sX, A.SU + (I - 1) * BB, A.x + (long)(I - 1) * B, A.xstride, G, nv, tid, mb);
+    blk_stream<false, false, true>(P, buf, sX, A.SD + I * BBP, A.x + (long)I * B, A.xstride, G, nv, tid, mb);
+    if (up) blk_stream<false, false, true>(P, buf, sX, A.SU + I * BBP, A.x + (long)(I + 1) * B, A.xstride, G, nv, tid, mb);
+    if (dn) blk_stream<true, false, true>(P, buf, sX, A.SU + (I - 1) * BBP, A.x + (long)(I - 1) * B, A.xstride, G, nv, tid, mb);
     VUS_PANEL_FOREACH(P, G, nv, { A.y[(long)v * A.ystride + (long)I * B + r] = val; })
 #endif
   }

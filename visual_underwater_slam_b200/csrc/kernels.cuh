@@ -188,15 +188,18 @@ struct AsmArgs {
   int type; long n;
   const int* idx; const double* J; const double* r;
   int D, k, B;
+  int ld; long bs;      // row / block stride of the padded supernode tiles
   double* Hval;         // base of SD | SU | REM
   double* g; double* F; double* Hbb; double* gb;
   const PairDst* pair;  // [n] for between / imu
 };
 
-VUS_HD long diag_off(long node, int la, int lb, int D, int k, int B) {
+// element (la, lb) of the diagonal node block of `node` inside SD; ld / bs = row stride / block stride of the padded
+// supernode tiles ([KP][LD], bcr.cuh)
+VUS_HD long diag_off(long node, int la, int lb, int D, int k, int ld, long bs) {
   const long I = node / k;
   const int rp = (int)(node % k);
-  return I * (long)B * B + (long)(rp * D + la) * B + rp * D + lb;
+  return I * bs + (long)(rp * D + la) * ld + rp * D + lb;
 }
 
 template <int TYPE>
@@ -242,7 +245,7 @@ struct AsmBody {
     for (int r = 0; r < M; ++r) h += A.J[(r * C + a) * n + f] * A.J[(r * C + b) * n + f];
     if (ga == gb) {
       if (ga == 2) return;                           // bias-bias block: ImuBiasBody
-      atomic_add(&A.Hval[diag_off(ga == 0 ? p : q, la, lb, D, A.k, A.B)], h);
+      atomic_add(&A.Hval[diag_off(ga == 0 ? p : q, la, lb, D, A.k, A.ld, A.bs)], h);
     } else if (gb == 2) {                          // (node, bias) border
       atomic_add(&A.F[((ga == 0 ? p : q) * D + la) * 6 + lb], h);
     } else {                                       // (p, q) coupling
@@ -304,8 +307,8 @@ struct ImuAsmBody {
       if (kind <= 1) {
         const long node = kind == 0 ? p : q;
         const int la = kind == 0 ? a : a - 9, lb = kind == 0 ? b : b - 9;
-        atomic_add(&A.Hval[diag_off(node, la, lb, D, A.k, A.B)], h);
-        if (la != lb) atomic_add(&A.Hval[diag_off(node, lb, la, D, A.k, A.B)], h);
+        atomic_add(&A.Hval[diag_off(node, la, lb, D, A.k, A.ld, A.bs)], h);
+        if (la != lb) atomic_add(&A.Hval[diag_off(node, lb, la, D, A.k, A.ld, A.bs)], h);
       } else if (kind == 2) {
         const int la = a, lb = b - 9;
         const PairDst d = A.pair[f];
@@ -366,6 +369,7 @@ struct StereoAsmArgs {
   const int* idx;              // [2][n] pose, landmark
   const double* J; const double* r;      // 3x9 / 3
   int D, k, B;
+  int ld; long bs;             // row / block stride of the padded supernode tiles
   double* SD; double* g;       // camera diag blocks / gradient
   double* C; double* gl;       // [9][nl], [3][nl]
   double* E;                   // [n][18]   E_o = Jp^T Jl (6x3 row-major)
@@ -388,8 +392,8 @@ struct StereoPoseBody {
       int a = 0, rem = e;
       while (rem >= 6 - a) { rem -= 6 - a; ++a; }
       const int b = a + rem;
-      A.SD[diag_off(node, a, b, A.D, A.k, A.B)] += s;
-      if (a != b) A.SD[diag_off(node, b, a, A.D, A.k, A.B)] += s;
+      A.SD[diag_off(node, a, b, A.D, A.k, A.ld, A.bs)] += s;
+      if (a != b) A.SD[diag_off(node, b, a, A.D, A.k, A.ld, A.bs)] += s;
     } else {
       A.g[node * A.D + (e - 21)] -= s;
     }
@@ -424,6 +428,7 @@ struct SchurArgs {
   const double* E;                   // [n][18]  E_o = Jp^T Jl (6x3 row-major)
   double lambda;
   int D, k, B;
+  int ld; long bs;                   // row / block stride of the padded supernode tiles
   double* SD; double* SU; double* REM;   // damped system being formed (Schur complement subtracted in place)
   const int* rem_ptr; const int* rem_col;
   double* gs;                        // reduced gradient (in/out)
@@ -474,8 +479,8 @@ template <bool OFFBAND_ONLY>
 struct SchurPoseScalar {
   static VUS_DEV void run(const SchurArgs& A, int pi, int tid, int nthr, double* sm) {
     const long i = A.pose_ids[pi];
-    const int D = A.D, k = A.k, B = A.B;
-    const long BB = (long)B * B;
+    const int D = A.D, k = A.k, B = A.ld;      // B: row stride of the tiles
+    const long BB = A.bs;
     const int ndj = 2 * k;
     int ngrp = nthr / 36;
     if (ngrp > VUS_SCHUR_GROUPS) ngrp = VUS_SCHUR_GROUPS;
@@ -586,13 +591,13 @@ struct LmBacksubBody {   // per landmark: xl = Cinv (gl - sum_o E_o^T xc[pose_o]
 };
 
 // add lambda (and identity on padding dofs) to the diagonal of SD and Hbb
-struct DampArgs { double* SD; double* Hbb; long ndof; long nreal; int B; double lambda; };
+struct DampArgs { double* SD; double* Hbb; long ndof; long nreal; int B; double lambda; int ld; long bs; };
 struct DampBody {
   static VUS_DEV void run(const DampArgs& A, long i) {
     if (i < A.ndof) {
       const long I = i / A.B;
       const int r = (int)(i % A.B);
-      A.SD[I * (long)A.B * A.B + (long)r * A.B + r] += (i < A.nreal) ? A.lambda : 1.0;
+      A.SD[I * A.bs + (long)r * A.ld + r] += (i < A.nreal) ? A.lambda : 1.0;
     } else {
       const int c = (int)(i - A.ndof);
       A.Hbb[c * 6 + c] += A.lambda;

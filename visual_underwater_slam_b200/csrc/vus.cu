@@ -313,10 +313,10 @@ struct PairKey { long p, q; };
 PairDst band_dst(const vus_handle* h, long p, long q, const std::map<std::pair<long, long>, long>& rem_index) {
   // destination of block (p,q), p != q allowed to be in any order
   PairDst d; d.pad = 0;
-  const int D = h->D, k = h->k, B = h->B;
+  const int D = h->D, k = h->k, B = bcr_ld(h->B);          // B: row stride of the padded supernode tiles
   const long I = p / k, J = q / k;
   const int rp = (int)(p % k), rq = (int)(q % k);
-  const long BB = (long)B * B;
+  const long BB = bcr_bbp(h->B);
   if (I == J) {
     d.off = h->sd_off + I * BB + (long)(rp * D) * B + rq * D; d.ld = B; d.transposed = 0;
     d.moff = h->sd_off + I * BB + (long)(rq * D) * B + rp * D; d.mld = B;
@@ -470,7 +470,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
   h->Npad = h->Ns * k;
   h->Lc = h->Npad * D;
   h->L = h->Lc + (h->has_bias ? 6 : 0);
-  const long BB = (long)h->B * h->B;
+  const long BB = bcr_bbp(h->B);                     // SD / SU are padded [KP][LD] tiles (bulk-copy layout, bcr.cuh)
   auto inband = [&](long p, long q) { long I = p / k, J = q / k; return (I - J <= 1) && (J - I <= 1); };
   // ---- off-band remainder blocks
   std::map<std::pair<long, long>, long> rem_index;
@@ -568,7 +568,7 @@ void launch_asm(vus_handle* h, rt::stream_t st) {
   if (!F.n) return;
   AsmArgs a;
   a.type = T; a.n = F.n; a.idx = F.idx.p; a.J = F.J.p; a.r = F.r.p;
-  a.D = h->D; a.k = h->k; a.B = h->B;
+  a.D = h->D; a.k = h->k; a.B = h->B; a.ld = bcr_ld(h->B); a.bs = bcr_bbp(h->B);
   a.Hval = h->H0.p; a.g = h->g0.p; a.F = h->F.p; a.Hbb = h->Hbb0.p; a.gb = h->gb.p; a.pair = F.pair.p;
   const long items = (long)(kFactorCols[T] * kFactorCols[T] + kFactorCols[T]) * F.n;
   L_elem<AsmBody<T>>(items, st, a);
@@ -585,7 +585,7 @@ void assemble_base(vus_handle* h, rt::stream_t st) {
     FactorTable& I = h->ft[VUS_F_IMU];
     AsmArgs a;
     a.type = VUS_F_IMU; a.n = I.n; a.idx = I.idx.p; a.J = I.J.p; a.r = I.r.p;
-    a.D = h->D; a.k = h->k; a.B = h->B;
+    a.D = h->D; a.k = h->k; a.B = h->B; a.ld = bcr_ld(h->B); a.bs = bcr_bbp(h->B);
     a.Hval = h->H0.p; a.g = h->g0.p; a.F = h->F.p; a.Hbb = h->Hbb0.p; a.gb = h->gb.p; a.pair = I.pair.p;
     L_coop<ImuAsmBody>((int)((I.n + VUS_IMU_TILE - 1) / VUS_IMU_TILE), 256, (size_t)225 * VUS_IMU_TILE * sizeof(double), st, a);
   }
@@ -599,7 +599,7 @@ void assemble_base(vus_handle* h, rt::stream_t st) {
   if (S.n) {
     ClassGuard kc_stereo(KC_STEREO_ASM);
     StereoAsmArgs a;
-    a.n = S.n; a.idx = S.idx.p; a.J = S.J.p; a.r = S.r.p; a.D = h->D; a.k = h->k; a.B = h->B;
+    a.n = S.n; a.idx = S.idx.p; a.J = S.J.p; a.r = S.r.p; a.D = h->D; a.k = h->k; a.B = h->B; a.ld = bcr_ld(h->B); a.bs = bcr_bbp(h->B);
     a.SD = h->H0.p + h->sd_off; a.g = h->g0.p; a.C = h->C.p; a.gl = h->gl.p; a.E = h->E.p; a.nl = h->nvar[3];
     a.pose_ptr = h->pose_ptr.p; a.pose_obs = h->pose_obs.p; a.pose_ids = h->pose_ids.p; a.nposes_obs = h->nposes_obs;
     a.lm_ptr = h->lm_ptr.p;
@@ -613,7 +613,7 @@ SchurArgs schur_args(vus_handle* h, double lambda) {
   FactorTable& S = h->ft[VUS_F_STEREO];
   SchurArgs a;
   a.n = S.n; a.nl = h->nvar[3]; a.idx = S.idx.p; a.C = h->C.p; a.gl = h->gl.p; a.Cinv = h->Cinv.p; a.E = h->E.p;
-  a.lambda = lambda; a.D = h->D; a.k = h->k; a.B = h->B;
+  a.lambda = lambda; a.D = h->D; a.k = h->k; a.B = h->B; a.ld = bcr_ld(h->B); a.bs = bcr_bbp(h->B);
   a.SD = h->H.p + h->sd_off; a.SU = h->H.p + h->su_off; a.REM = h->H.p + h->rem_off;
   a.rem_ptr = h->rem_ptr.p; a.rem_col = h->rem_col.p; a.gs = h->gs.p;
   a.pose_ptr = h->pose_ptr.p; a.pose_obs = h->pose_obs.p; a.pose_ids = h->pose_ids.p; a.nposes_obs = h->nposes_obs;
@@ -629,7 +629,7 @@ void form_system(vus_handle* h, double lambda, rt::stream_t st) {
   rt::d2d(h->Hbb.p, h->Hbb0.p, 36 * sizeof(double), st);
   rt::d2d(h->gs.p, h->g0.p, h->Lc * sizeof(double), st);
   if (h->has_bias) rt::d2d(h->gs.p + h->Lc, h->gb.p, 6 * sizeof(double), st);
-  DampArgs d; d.SD = h->H.p + h->sd_off; d.Hbb = h->Hbb.p; d.ndof = h->Lc; d.nreal = h->N * h->D; d.B = h->B; d.lambda = lambda;
+  DampArgs d; d.SD = h->H.p + h->sd_off; d.Hbb = h->Hbb.p; d.ndof = h->Lc; d.nreal = h->N * h->D; d.B = h->B; d.lambda = lambda; d.ld = bcr_ld(h->B); d.bs = bcr_bbp(h->B);
   L_elem<DampBody>(h->Lc + (h->has_bias ? 6 : 0), st, d);
   if (h->nobs) {
     SchurArgs a = schur_args(h, lambda);
@@ -657,12 +657,12 @@ void bcr_factor(vus_handle* h, rt::stream_t st) {
 }
 void bcr_factor_launches(vus_handle* h, rt::stream_t st) {
   ClassGuard kc_guard(KC_BCR_FACTOR);
-  const long BB = (long)h->B * h->B, BBP = bcr_bbp(h->B);
+  const long BBP = bcr_bbp(h->B);
   const int LD = bcr_ld(h->B);
   BcrArgs a = bcr_args(h);
-  // level 1 reads the assembled system in place (plain B x B blocks); deeper levels read the padded working arrays
-  a.Dsrc = h->H.p + h->sd_off; a.d_ld = h->B; a.d_stride = BB;
-  a.Ucur = h->H.p + h->su_off; a.u_ld = h->B; a.u_stride = BB;
+  // level 1 reads the assembled system in place; deeper levels read the working arrays (all padded tiles)
+  a.Dsrc = h->H.p + h->sd_off; a.d_ld = LD; a.d_stride = BBP;
+  a.Ucur = h->H.p + h->su_off; a.u_ld = LD; a.u_stride = BBP;
   double* bufs[2] = {h->U1.p, h->U2.p};
   int w = 0;
   for (long s = 1; s < h->Ns; s <<= 1) {
@@ -784,7 +784,7 @@ void apply_A(vus_handle* h, double* y, const double* x, rt::stream_t st) {
   if (h->has_bias) {
     border_dot(h, x, h->Lc, 1, st);
     BorderRowArgs b; b.Hbb = h->Hbb.p; b.xb = x + h->Lc; b.partials = h->bpart.p; b.grid = h->red_grid; b.yb = y + h->Lc;
-    L_elem<BorderRowBody>(1, st, b);
+    { ClassGuard kc_b(KC_BORDER); L_elem<BorderRowBody>(1, st, b); }
   }
 }
 
@@ -1282,12 +1282,21 @@ int vus_debug_band_solve(vus_handle* h, void* stream, double lambda, double* SD_
   if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_debug_band_solve: call vus_analyze first");
   VUS_TRY(h)
   rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
-  const long BB = (long)h->B * h->B;
+  const long BB = (long)h->B * h->B, BBP = bcr_bbp(h->B);
+  const int LD = bcr_ld(h->B);
   run_factors(h, h->cur, true, st);
   assemble_base(h, st);
   form_system(h, lambda, st);
-  if (SD_out) rt::d2h(SD_out, h->H.p + h->sd_off, h->Ns * BB * sizeof(double), st);
-  if (SU_out && h->Ns > 1) rt::d2h(SU_out, h->H.p + h->su_off, (h->Ns - 1) * BB * sizeof(double), st);
+  auto unpad = [&](double* out, const double* dev, long nblk) {     // padded device tiles -> dense B x B blocks
+    std::vector<double> tmp((size_t)nblk * BBP);
+    rt::d2h(tmp.data(), dev, tmp.size() * sizeof(double), st);
+    rt::sync(st);
+    for (long b = 0; b < nblk; ++b)
+      for (int i = 0; i < h->B; ++i)
+        for (int j = 0; j < h->B; ++j) out[b * BB + (long)i * h->B + j] = tmp[b * BBP + (long)i * LD + j];
+  };
+  if (SD_out) unpad(SD_out, h->H.p + h->sd_off, h->Ns);
+  if (SU_out && h->Ns > 1) unpad(SU_out, h->H.p + h->su_off, h->Ns - 1);
   bcr_factor(h, st);
   if (x_inout && nrhs > 0) {
     DBuf<double> X;
