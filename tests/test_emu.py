@@ -72,3 +72,27 @@ def test_known_answer_noise_free(emu):
     assert np.abs(v["poses"] - d["truth"]["poses"]).max() < 1e-6
     assert np.abs(v["vels"] - d["truth"]["vels"]).max() < 1e-6
     s.close()
+
+
+def test_tracks_longer_than_the_band_stay_exact(emu):
+    """Landmark tracks that do not fit in the band (here: supernodes capped below the 10-pose track length) keep their
+    Schur term implicit in the operator: the damped solve is still the exact one, only PCG works harder."""
+    from visual_underwater_slam_b200.optimizer import LevenbergMarquardtParams, Session
+    from oracle import lm
+    _, prob = pc.make(60, n_lm=120)
+    vals = lm.values_of(prob)
+    lay = lm.Layout(prob)
+    J, b = lm.linearize(prob, vals, lay)
+    delta = lm.solve_damped(J, b, 1e-3, lay)
+    p = LevenbergMarquardtParams()
+    p.maxSupernode = 4
+    p.pcgMaxIterations = 2000
+    s = Session(prob, p, lib=emu)
+    assert s.layout()["k"] < 9
+    st = s.solve_step(1e-3)
+    s.close()
+    mine = np.concatenate([st["bias"].ravel(), st["lm"].ravel(), st["vel"].ravel(), st["pose"].ravel()])
+    H = (J.T @ J).tocsr()
+    g = J.T @ b
+    assert np.linalg.norm(H @ mine + 1e-3 * mine - g) <= 1e-9 * np.linalg.norm(g)
+    assert np.linalg.norm(mine - delta) <= 1e-5 * np.linalg.norm(delta)

@@ -434,9 +434,13 @@ struct SchurArgs {
   double* gs;                        // reduced gradient (in/out)
   const int* pose_ptr; const int* pose_obs; const int* pose_ids; long nposes_obs;
   const int* lm_ptr;
+  const int* lm_long;                // 1: the landmark's track does not fit in the band -> its Schur term stays implicit
   int* fail;
   // back-substitution
   const double* xc; double* xl;
+  // implicit Schur term of the long-track landmarks (operator only)
+  long nlong; const int* long_ids; double* ulong;     // ulong [3][nlong]
+  const double* xin; double* yout;
 };
 struct LmInvertBody {    // per landmark
   static VUS_DEV void run(const SchurArgs& A, long l) {
@@ -504,6 +508,7 @@ struct SchurPoseScalar {
         const double w1 = e0 * A.Cinv[A.nl + l] + e1 * A.Cinv[4 * A.nl + l] + e2 * A.Cinv[7 * A.nl + l];
         const double w2 = e0 * A.Cinv[2 * A.nl + l] + e1 * A.Cinv[5 * A.nl + l] + e2 * A.Cinv[8 * A.nl + l];
         if (!OFFBAND_ONLY && s == 0) gacc += w0 * A.gl[l] + w1 * A.gl[A.nl + l] + w2 * A.gl[2 * A.nl + l];
+        if (A.lm_long[l]) continue;                  // long track: only the gradient is reduced here (LongSchur*Body)
         // observations are stored landmark-major and pose-sorted: the partners with j >= i start at o itself
         // (or at an earlier observation of the same pose, if the landmark was seen twice from pose i)
         int q0 = (int)o;
@@ -529,11 +534,7 @@ struct SchurPoseScalar {
               const int dj = (int)(j - i);
               acc[dj * 36 + rs] += v;
               if (rs == 0) touched[dj] = 1.0;
-            } else {                                 // off-band co-observation: remainder blocks (i,j) and (j,i)
-              const int t1 = rem_find(A.rem_ptr, A.rem_col, i, (int)j), t2 = rem_find(A.rem_ptr, A.rem_col, j, (int)i);
-              atomic_add(&A.REM[(long)t1 * D * D + r * D + s], -v);
-              atomic_add(&A.REM[(long)t2 * D * D + s * D + r], -v);
-            }
+            }                                        // (every partner of a short track is in-band by construction)
           }
         }
       }
@@ -571,6 +572,47 @@ VUS_HD int schur_pose_threads() { return 64; }
 VUS_HD int schur_pose_threads() { return 160; }      // 4 observation groups x 36 entries (+ padding to a warp multiple)
 #endif
 VUS_HD long schur_pose_smem_doubles(int k) { return (long)VUS_SCHUR_GROUPS * (2 * k * 37 + 6); }
+// Landmarks whose track is longer than the band cannot be folded into the block-tridiagonal matrix without making it
+// indefinite (the Schur complement subtracts from every block it touches).  They are still eliminated EXACTLY, but
+// their term  - E_l (C_l + lambda I)^-1 E_l^T  is applied implicitly inside the operator and left out of the band
+// preconditioner (which therefore stays an upper bound of the operator in the SPD order).
+// pass 1, per long landmark:  u_l = Cinv_l * sum_o E_o^T x[pose_o]
+struct LongSchur1Body {
+  static VUS_DEV void run(const SchurArgs& A, long q) {
+    const long l = A.long_ids[q];
+    double t[3] = {0.0, 0.0, 0.0};
+    for (int o = A.lm_ptr[l]; o < A.lm_ptr[l + 1]; ++o) {
+      const long node = A.idx[o];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        const double x = A.xin[node * A.D + a];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) t[c] += A.E[(long)o * 18 + a * 3 + c] * x;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      A.ulong[c * A.nlong + q] = A.Cinv[(c * 3) * A.nl + l] * t[0] + A.Cinv[(c * 3 + 1) * A.nl + l] * t[1] + A.Cinv[(c * 3 + 2) * A.nl + l] * t[2];
+  }
+};
+// pass 2, per (pose with observations, dof a): y_i[a] -= sum over its observations o of long landmarks of E_o[a][:] u_l
+// (gather through the pose -> observation lists: fixed summation order, no atomics); lm_long holds 1 + position in long_ids
+struct LongSchur2Body {
+  static VUS_DEV void run(const SchurArgs& A, long w) {
+    const long pi = w / 6;
+    const int a = (int)(w - pi * 6);
+    const long node = A.pose_ids[pi];
+    double s = 0.0;
+    for (int t = A.pose_ptr[pi]; t < A.pose_ptr[pi + 1]; ++t) {
+      const long o = A.pose_obs[t];
+      const int q = A.lm_long[A.idx[A.n + o]];
+      if (!q) continue;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) s += A.E[o * 18 + a * 3 + c] * A.ulong[c * A.nlong + (q - 1)];
+    }
+    if (s != 0.0) A.yout[node * A.D + a] -= s;
+  }
+};
 struct LmBacksubBody {   // per landmark: xl = Cinv (gl - sum_o E_o^T xc[pose_o])
   static VUS_DEV void run(const SchurArgs& A, long l) {
     double t[3] = {A.gl[l], A.gl[A.nl + l], A.gl[2 * A.nl + l]};

@@ -160,7 +160,10 @@ struct vus_handle {
   DBuf<double> g0, gs, F, Hbb0, Hbb, gb;     // gs = [reduced camera gradient ; gb] (length L)
   // stereo
   long nobs = 0, nposes_obs = 0;
-  DBuf<int> pose_ptr, pose_obs, pose_ids, lm_ptr;
+  DBuf<int> pose_ptr, pose_obs, pose_ids, lm_ptr, lm_long, long_ids;
+  long nlong = 0;
+  DBuf<double> ulong;
+  double cur_lambda = 0.0;
   DBuf<double> C, gl, Cinv, E, Pp, Pl;
   // BCR
   DBuf<double> Dw, U1, U2, Dinv, Gl, Gr, Z, Zr, SbInv;
@@ -477,12 +480,17 @@ int analyze(vus_handle* h, rt::stream_t st) {
   auto add_rem = [&](long p, long q) { if (p != q && !inband(p, q)) { rem_index[{p, q}] = 0; rem_index[{q, p}] = 0; } };
   for (long f = 0; f < FB.n; ++f) add_rem(FB.h_idx[f], FB.h_idx[FB.n + f]);
   for (long f = 0; f < FI.n; ++f) add_rem(FI.h_idx[f], FI.h_idx[2 * FI.n + f]);
+  // landmarks whose track does not fit inside the band keep their Schur term implicit (LongSchur*Body)
+  std::vector<int> lm_long(NL, 0), long_ids;
   for (long l = 0; l < NL; ++l) {
     const long pf = FS.h_idx[lm_ptr[l]], pl = FS.h_idx[lm_ptr[l + 1] - 1];   // observations are pose-sorted
     if (pl / k - pf / k <= 1) continue;                 // whole track inside the band
-    for (int a = lm_ptr[l]; a < lm_ptr[l + 1]; ++a)
-      for (int b = a + 1; b < lm_ptr[l + 1]; ++b) add_rem(FS.h_idx[a], FS.h_idx[b]);
+    long_ids.push_back((int)l);
+    lm_long[l] = (int)long_ids.size();                  // 1 + position in long_ids
   }
+  h->nlong = (long)long_ids.size();
+  h->lm_long.upload(lm_long, st);
+  if (h->nlong) { h->long_ids.upload(long_ids, st); h->ulong.alloc((size_t)3 * h->nlong); }
   std::vector<int> rem_ptr(NX + 1, 0), rem_col;
   {
     long id = 0;
@@ -617,14 +625,16 @@ SchurArgs schur_args(vus_handle* h, double lambda) {
   a.SD = h->H.p + h->sd_off; a.SU = h->H.p + h->su_off; a.REM = h->H.p + h->rem_off;
   a.rem_ptr = h->rem_ptr.p; a.rem_col = h->rem_col.p; a.gs = h->gs.p;
   a.pose_ptr = h->pose_ptr.p; a.pose_obs = h->pose_obs.p; a.pose_ids = h->pose_ids.p; a.nposes_obs = h->nposes_obs;
-  a.lm_ptr = h->lm_ptr.p;
+  a.lm_ptr = h->lm_ptr.p; a.lm_long = h->lm_long.p;
   a.fail = h->fail.p; a.xc = h->x.p; a.xl = h->xl.p;
+  a.nlong = h->nlong; a.long_ids = h->long_ids.p; a.ulong = h->ulong.p; a.xin = nullptr; a.yout = nullptr;
   return a;
 }
 
 // damped + Schur-reduced system for this lambda
 void form_system(vus_handle* h, double lambda, rt::stream_t st) {
   ClassGuard kc_guard(KC_SCHUR);
+  h->cur_lambda = lambda;
   rt::d2d(h->H.p, h->H0.p, h->hlen * sizeof(double), st);
   rt::d2d(h->Hbb.p, h->Hbb0.p, 36 * sizeof(double), st);
   rt::d2d(h->gs.p, h->g0.p, h->Lc * sizeof(double), st);
@@ -781,6 +791,13 @@ void apply_A(vus_handle* h, double* y, const double* x, rt::stream_t st) {
   const size_t smem = (size_t)blk_smem_doubles(h->B, 1, 256) * sizeof(double);
   L_coop<BandMatvecBody>((int)h->Ns, 256, smem, st, a);
   if (h->nrem || h->has_bias) { ClassGuard kc_b(KC_BORDER); L_elem<RemBorderMatvecBody>(h->N * h->D, st, a); }
+  if (h->nlong) {                                      // implicit Schur term of the long-track landmarks
+    ClassGuard kc_s(KC_SCHUR);
+    SchurArgs sa = schur_args(h, h->cur_lambda);
+    sa.xin = x; sa.yout = y;
+    L_elem<LongSchur1Body>(h->nlong, st, sa);
+    L_elem<LongSchur2Body>(h->nposes_obs * 6, st, sa);
+  }
   if (h->has_bias) {
     border_dot(h, x, h->Lc, 1, st);
     BorderRowArgs b; b.Hbb = h->Hbb.p; b.xb = x + h->Lc; b.partials = h->bpart.p; b.grid = h->red_grid; b.yb = y + h->Lc;
