@@ -429,8 +429,7 @@ struct SchurArgs {
   double lambda;
   int D, k, B;
   int ld; long bs;                   // row / block stride of the padded supernode tiles
-  double* SD; double* SU; double* REM;   // damped system being formed (Schur complement subtracted in place)
-  const int* rem_ptr; const int* rem_col;
+  double* SD; double* SU;            // damped system being formed (Schur complement subtracted in place)
   double* gs;                        // reduced gradient (in/out)
   const int* pose_ptr; const int* pose_obs; const int* pose_ids; long nposes_obs;
   const int* lm_ptr;
@@ -460,27 +459,10 @@ struct LmInvertBody {    // per landmark
     for (int e = 0; e < 9; ++e) A.Cinv[e * A.nl + l] = inv[e];
   }
 };
-// position of column `col` in the sorted remainder row of `node`, -1 if absent
-VUS_DEV int rem_find(const int* rem_ptr, const int* rem_col, long node, int col) {
-  int lo = rem_ptr[node], hi = rem_ptr[node + 1] - 1;
-  while (lo <= hi) {
-    const int mid = (lo + hi) >> 1;
-    const int c = rem_col[mid];
-    if (c == col) return mid;
-    if (c < col) lo = mid + 1; else hi = mid - 1;
-  }
-  return -1;
-}
-// One CTA per pose i that has observations.  Thread rs = (r,s) owns element (r,s) of every 6x6 block S(i,j), j >= i:
-//   S(i,j) -= sum over landmarks l seen from both i and j of (E_o Cinv_l) E_o'^T ,   gs_i -= sum_o (E_o Cinv_l) gl_l
-// walking pose i's observations and, per landmark, its (pose-sorted) observation list.  In-band blocks (same or next
-// supernode, j - i < 2k) accumulate in shared memory and are written once; off-band blocks go straight to REM.
-// Each block (i,j) and its mirror are written by this CTA only: no atomics, deterministic summation order.
 #define VUS_SCHUR_GROUPS 4
 // Thread (grp, rs): entry rs = (r, s) of every block S(i, j >= i), over the observations t = grp (mod ngrp) of pose i --
 // the groups shorten each thread's chain of dependent loads; their partial blocks are summed in a fixed order.
-template <bool OFFBAND_ONLY>
-struct SchurPoseScalar {
+struct SchurPoseBody {
   static VUS_DEV void run(const SchurArgs& A, int pi, int tid, int nthr, double* sm) {
     const long i = A.pose_ids[pi];
     const int D = A.D, k = A.k, B = A.ld;      // B: row stride of the tiles
@@ -507,7 +489,7 @@ struct SchurPoseScalar {
         const double w0 = e0 * A.Cinv[l] + e1 * A.Cinv[3 * A.nl + l] + e2 * A.Cinv[6 * A.nl + l];
         const double w1 = e0 * A.Cinv[A.nl + l] + e1 * A.Cinv[4 * A.nl + l] + e2 * A.Cinv[7 * A.nl + l];
         const double w2 = e0 * A.Cinv[2 * A.nl + l] + e1 * A.Cinv[5 * A.nl + l] + e2 * A.Cinv[8 * A.nl + l];
-        if (!OFFBAND_ONLY && s == 0) gacc += w0 * A.gl[l] + w1 * A.gl[A.nl + l] + w2 * A.gl[2 * A.nl + l];
+        if (s == 0) gacc += w0 * A.gl[l] + w1 * A.gl[A.nl + l] + w2 * A.gl[2 * A.nl + l];
         if (A.lm_long[l]) continue;                  // long track: only the gradient is reduced here (LongSchur*Body)
         // observations are stored landmark-major and pose-sorted: the partners with j >= i start at o itself
         // (or at an earlier observation of the same pose, if the landmark was seen twice from pose i)
@@ -530,7 +512,6 @@ struct SchurPoseScalar {
             const double v = w0 * ev[u][0] + w1 * ev[u][1] + w2 * ev[u][2];
             const long J = j / k;
             if (J <= I + 1) {
-              if (OFFBAND_ONLY) continue;
               const int dj = (int)(j - i);
               acc[dj * 36 + rs] += v;
               if (rs == 0) touched[dj] = 1.0;
@@ -538,10 +519,9 @@ struct SchurPoseScalar {
           }
         }
       }
-      if (!OFFBAND_ONLY && s == 0) sm[ngrp * gstride + grp * 6 + r] = gacc;
+      if (s == 0) sm[ngrp * gstride + grp * 6 + r] = gacc;
     }
     VUS_SYNC();
-    if (OFFBAND_ONLY) return;
     for (int e = tid; e < 6; e += nthr) {
       double gsum = 0.0;
       for (int grp = 0; grp < ngrp; ++grp) gsum += sm[ngrp * gstride + grp * 6 + e];
@@ -565,7 +545,6 @@ struct SchurPoseScalar {
     }
   }
 };
-typedef SchurPoseScalar<false> SchurPoseBody;
 #ifdef VUS_EMU
 VUS_HD int schur_pose_threads() { return 64; }
 #else

@@ -622,8 +622,7 @@ SchurArgs schur_args(vus_handle* h, double lambda) {
   SchurArgs a;
   a.n = S.n; a.nl = h->nvar[3]; a.idx = S.idx.p; a.C = h->C.p; a.gl = h->gl.p; a.Cinv = h->Cinv.p; a.E = h->E.p;
   a.lambda = lambda; a.D = h->D; a.k = h->k; a.B = h->B; a.ld = bcr_ld(h->B); a.bs = bcr_bbp(h->B);
-  a.SD = h->H.p + h->sd_off; a.SU = h->H.p + h->su_off; a.REM = h->H.p + h->rem_off;
-  a.rem_ptr = h->rem_ptr.p; a.rem_col = h->rem_col.p; a.gs = h->gs.p;
+  a.SD = h->H.p + h->sd_off; a.SU = h->H.p + h->su_off; a.gs = h->gs.p;
   a.pose_ptr = h->pose_ptr.p; a.pose_obs = h->pose_obs.p; a.pose_ids = h->pose_ids.p; a.nposes_obs = h->nposes_obs;
   a.lm_ptr = h->lm_ptr.p; a.lm_long = h->lm_long.p;
   a.fail = h->fail.p; a.xc = h->x.p; a.xl = h->xl.p;
