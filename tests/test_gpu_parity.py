@@ -210,3 +210,52 @@ def test_config2_full_size_properties(lib):
     res2 = s.optimize()
     assert res2["iterations"] <= 2 and abs(res2["final_error"] - e1) <= 1e-4 * e1
     s.close()
+
+
+def test_config3_full_size_properties(lib):
+    """BASELINE.json config 3 at full size (100 000 poses, 2 M stereo factors, 2.2 M factors): size-independent
+    properties -- bookkeeping of the per-factor errors in insertion order, monotone decrease, a noise-level optimum
+    (chi-square per factor of order one), fixed point on re-solve, identical result on a second run."""
+    from visual_underwater_slam_b200 import synthetic
+    from visual_underwater_slam_b200.optimizer import Session
+    d = synthetic.make_config("C3")
+    prob = d["graph"].to_problem(d["initial"])
+    n = d["meta"]["n_factors"]
+    assert n == 2 + 2 * 99999 + 2000000
+    s = Session(prob, lib=lib)
+    s.save_values()
+    e0 = s.error()
+    fe = s.factor_errors()
+    assert fe.shape == (n,) and abs(fe.sum() - e0) <= 1e-10 * e0
+    assert fe[0] == 0.0                                   # factor 0 is the pose prior at its own mean (batch.py:281)
+    res = s.optimize()
+    assert res["solve_failures"] == 0 and res["final_error"] < 1e-4 * e0 and res["final_error"] < 0.5 * n
+    v1 = s.values()["poses"]
+    res2 = s.optimize()
+    assert res2["iterations"] <= 2 and abs(res2["final_error"] - res["final_error"]) <= 1e-4 * res["final_error"]
+    s.restore_values()
+    res3 = s.optimize()
+    assert res3["iterations"] == res["iterations"] and res3["inner_iterations"] == res["inner_iterations"]
+    assert abs(res3["final_error"] - res["final_error"]) <= 1e-9 * res["final_error"]
+    assert np.abs(s.values()["poses"] - v1).max() < 1e-6
+    s.close()
+
+
+def test_partitioned_solver_single_rank_matches_session(lib):
+    """The pose-range partition code path (owned prefix, masked error sums, halo hooks) with one rank must reproduce the
+    plain solve of the same pose graph (BASELINE config 5 in miniature; the 2-rank runs are in tests/test_parallel.py)."""
+    from visual_underwater_slam_b200 import synthetic, parallel
+    from visual_underwater_slam_b200.optimizer import Session
+    d = synthetic.make_pose_graph(3000, seed=5, n_loops=60, noise_scale=0.05)
+    prob = d["graph"].to_problem(d["initial"])
+    s = Session(prob, lib=lib)
+    ref = s.optimize()
+    pref = s.values()["poses"]
+    s.close()
+    part = parallel.partition_pose_graph(prob, 1)[0]
+    assert part["n_owned"] == 3000 and len(part["halo_global"]) == 0
+    ps = parallel.PartitionedSolver(part, lib=lib)
+    res = ps.optimize()
+    assert res["iterations"] == ref["iterations"] and abs(res["final_error"] - ref["final_error"]) <= 1e-9 * ref["final_error"]
+    assert np.abs(ps.owned_poses() - pref).max() < 1e-8
+    ps.close()
