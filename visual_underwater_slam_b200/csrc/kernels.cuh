@@ -44,6 +44,31 @@ struct LinBody {
   }
 };
 
+// Stereo linearize with the fused assembly products: one CTA per 128 consecutive observations.  The component-major
+// outputs (r, J, e2) are already coalesced; the three per-observation record arrays (E 18, Pp 28, Pl 12 doubles) would
+// be written with a 144 / 224 / 96-byte stride between neighbouring threads, so every thread parks its records in
+// shared memory (odd row strides: conflict-free) and the CTA streams them out as contiguous runs.
+#define VUS_LIN_TILE 128
+#define VUS_LIN_ROW 61                 // 19 + 29 + 13: E | Pp | Pl with one padding double each (odd strides)
+struct LinStereoTileBody {
+  static VUS_DEV void run(const LinArgs& a, int tile, int tid, int nthr, double* sm) {
+    const long f0 = (long)tile * VUS_LIN_TILE;
+    const long n = a.F.n;
+    const int nf = (int)(n - f0 < VUS_LIN_TILE ? n - f0 : VUS_LIN_TILE);
+    for (int fl = tid; fl < nf; fl += nthr) {
+      double* row = sm + fl * VUS_LIN_ROW;
+      const long f = f0 + fl;
+      LinOut O = a.O;                                   // f_stereo indexes its record arrays by f: aim them at this row
+      O.sE = row - f * 18; O.sPp = row + 19 - f * 28; O.sPl = row + 48 - f * 12;
+      f_stereo<true>(a.V, a.F, O, f, a.K);
+    }
+    VUS_SYNC();
+    for (int e = tid; e < nf * 18; e += nthr) { const int fl = e / 18, c = e - fl * 18; a.O.sE[f0 * 18 + e] = sm[fl * VUS_LIN_ROW + c]; }
+    for (int e = tid; e < nf * 28; e += nthr) { const int fl = e / 28, c = e - fl * 28; a.O.sPp[f0 * 28 + e] = sm[fl * VUS_LIN_ROW + 19 + c]; }
+    for (int e = tid; e < nf * 12; e += nthr) { const int fl = e / 12, c = e - fl * 12; a.O.sPl[f0 * 12 + e] = sm[fl * VUS_LIN_ROW + 48 + c]; }
+  }
+};
+
 // delta layout: camera part xc[node * D + dof] (pose dofs 0-5, velocity dofs 6-8), bias xb[6], landmarks xl[c * nl + l]
 struct DeltaView {
   const double* xc; const double* xb; const double* xl; long nl; int D;
@@ -510,12 +535,9 @@ struct SchurPoseBody {
             const long j = jj[u];
             if (j < 0) continue;
             const double v = w0 * ev[u][0] + w1 * ev[u][1] + w2 * ev[u][2];
-            const long J = j / k;
-            if (J <= I + 1) {
-              const int dj = (int)(j - i);
-              acc[dj * 36 + rs] += v;
-              if (rs == 0) touched[dj] = 1.0;
-            }                                        // (every partner of a short track is in-band by construction)
+            const int dj = (int)(j - i);             // every partner of a short track is in-band by construction: dj < 2k
+            acc[dj * 36 + rs] += v;
+            if (rs == 0) touched[dj] = 1.0;
           }
         }
       }

@@ -239,7 +239,8 @@ void run_factors(vus_handle* h, int which, bool with_J, rt::stream_t st) {
     for (int i = 0; i < 6; ++i) a.K[i] = h->K[i];
     for (int i = 0; i < 3; ++i) a.g[i] = h->grav[i];
     a.type = t;
-    if (with_J) launch_lin_type<true>(h, t, a, st);
+    if (fused) L_coop<LinStereoTileBody>((int)((T.n + VUS_LIN_TILE - 1) / VUS_LIN_TILE), VUS_LIN_TILE, (size_t)VUS_LIN_TILE * VUS_LIN_ROW * sizeof(double), st, a);
+    else if (with_J) launch_lin_type<true>(h, t, a, st);
     else launch_lin_type<false>(h, t, a, st);
   }
 }
