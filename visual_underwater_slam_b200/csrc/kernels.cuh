@@ -684,25 +684,44 @@ struct RemBorderMatvecBody {
 };
 // out[v][c] = sum_i F[i][c] * Y[v][i]  (F^T Y) for nv vectors, two-stage; stage 1 partials [grid][nv*6]
 struct BorderDotArgs { const double* F; const double* Y; long len; long ystride; int nv; double* partials; int grid; };
-struct BorderDot1Body {
+// block reduction of six per-thread values at a time: part[c] (c < 6) summed over the CTA into out[c]
+VUS_DEV void cta_sum6(const double* part, double* out, int tid, int nthr, double* sm) {
+  for (int c = 0; c < 6; ++c) sm[c * nthr + tid] = part[c];
+  VUS_SYNC();
+  for (int s = nthr >> 1; s > 0; s >>= 1) {
+    for (int t = tid; t < s; t += nthr)
+      for (int c = 0; c < 6; ++c) sm[c * nthr + t] += sm[c * nthr + t + s];
+    VUS_SYNC();
+  }
+  if (tid == 0)
+    for (int c = 0; c < 6; ++c) out[c] = sm[c * nthr];
+  VUS_SYNC();
+}
+struct BorderDot1Body {       // one pass over F and the nv vectors; needs 6 * nthr doubles of shared memory
   static VUS_DEV void run(const BorderDotArgs& A, int bid, int tid, int nthr, double* sm) {
     const long chunk = (A.len + A.grid - 1) / A.grid;
     const long i0 = (long)bid * chunk;
     long i1 = i0 + chunk;
     if (i1 > A.len) i1 = A.len;
-    for (int v = 0; v < A.nv; ++v)
-      for (int c = 0; c < 6; ++c) {
-        double acc = 0.0;
-        for (long i = i0 + tid; i < i1; i += nthr) acc += A.F[i * 6 + c] * A.Y[(long)v * A.ystride + i];
-        sm[tid] = acc;
-        VUS_SYNC();
-        for (int s = nthr >> 1; s > 0; s >>= 1) {
-          for (int t = tid; t < s; t += nthr) sm[t] += sm[t + s];
-          VUS_SYNC();
+    double acc[6][6];
+    for (int v = 0; v < 6; ++v)
+      for (int c = 0; c < 6; ++c) acc[v][c] = 0.0;
+    for (long i = i0 + tid; i < i1; i += nthr) {
+      double f[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) f[c] = A.F[i * 6 + c];
+#pragma unroll
+      for (int v = 0; v < 6; ++v) {
+        if (v < A.nv) {
+          const double y = A.Y[(long)v * A.ystride + i];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) acc[v][c] += f[c] * y;
         }
-        if (tid == 0) A.partials[(long)bid * (A.nv * 6) + v * 6 + c] = sm[0];
-        VUS_SYNC();
       }
+    }
+#pragma unroll
+    for (int v = 0; v < 6; ++v)
+      if (v < A.nv) cta_sum6(acc[v], A.partials + (long)bid * (A.nv * 6) + v * 6, tid, nthr, sm);
   }
 };
 
@@ -713,48 +732,57 @@ struct BorderDot1Body {
 // =====================================================================================
 // out[a][b] = sum_i Z_a[i] R_b[i]  (Z^T R, both [6][len] column sets); stage-1 partials [grid][36]
 struct ColDotArgs { const double* Z; const double* R; long len; long stride; double* partials; int grid; };
-struct ColDot1Body {
+struct ColDot1Body {          // one pass over the 6 + 6 columns; needs 6 * nthr doubles of shared memory
   static VUS_DEV void run(const ColDotArgs& A, int bid, int tid, int nthr, double* sm) {
     const long chunk = (A.len + A.grid - 1) / A.grid;
     const long i0 = (long)bid * chunk;
     long i1 = i0 + chunk;
     if (i1 > A.len) i1 = A.len;
-    for (int e = 0; e < 36; ++e) {
-      const int a = e / 6, b = e - a * 6;
-      double acc = 0.0;
-      for (long i = i0 + tid; i < i1; i += nthr) acc += A.Z[(long)a * A.stride + i] * A.R[(long)b * A.stride + i];
-      sm[tid] = acc;
-      VUS_SYNC();
-      for (int s = nthr >> 1; s > 0; s >>= 1) {
-        for (int t = tid; t < s; t += nthr) sm[t] += sm[t + s];
-        VUS_SYNC();
-      }
-      if (tid == 0) A.partials[(long)bid * 36 + e] = sm[0];
-      VUS_SYNC();
+    double acc[6][6];
+    for (int a = 0; a < 6; ++a)
+      for (int b = 0; b < 6; ++b) acc[a][b] = 0.0;
+    for (long i = i0 + tid; i < i1; i += nthr) {
+      double z[6], r[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { z[c] = A.Z[(long)c * A.stride + i]; r[c] = A.R[(long)c * A.stride + i]; }
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = 0; b < 6; ++b) acc[a][b] += z[a] * r[b];
     }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) cta_sum6(acc[a], A.partials + (long)bid * 36 + a * 6, tid, nthr, sm);
   }
 };
 // Sb = Hbb - F^T Z (from partials of BorderDot over the 6 Z columns), SbInv = Sb^-1
 struct BorderSchurArgs { const double* Hbb; const double* partials; int grid; int nv; double* SbInv; int* fail; const double* corr; };
-struct BorderSchurBody {
-  static VUS_DEV void run(const BorderSchurArgs& A, long) {
+// column sums of a [grid][stride] partial table into shared memory: out[e] = sum_b partials[b*stride + e], e < nout
+// (thread per column, coalesced across columns; replaces one thread walking the whole table)
+VUS_DEV void sum_partials(double* out, const double* partials, int grid, int stride, int nout, int tid, int nthr) {
+  for (int e = tid; e < nout; e += nthr) {
+    double s = 0.0;
+    for (int b = 0; b < grid; ++b) s += partials[(long)b * stride + e];
+    out[e] = s;
+  }
+}
+struct BorderSchurBody {      // one CTA
+  static VUS_DEV void run(const BorderSchurArgs& A, int, int tid, int nthr, double* sm) {
+    double* ftz = sm;             // [36]  entry v*6+c = (F^T Z)[c][v]
+    double* ztr = sm + 36;        // [36]
+    sum_partials(ftz, A.partials, A.grid, A.nv * 6, 36, tid, nthr);
+    if (A.corr) sum_partials(ztr, A.corr, A.grid, 36, 36, tid, nthr);
+    VUS_SYNC();
+    if (tid != 0) return;
     double S[36];
     for (int e = 0; e < 36; ++e) S[e] = A.Hbb[e];
-    // partial layout [grid][nv*6]: entry (v,c) = sum_i F[i][c] Z_v[i] = (F^T Z)[c][v]
     for (int v = 0; v < 6; ++v)
-      for (int c = 0; c < 6; ++c) {
-        double s = 0.0;
-        for (int b = 0; b < A.grid; ++b) s += A.partials[(long)b * (A.nv * 6) + v * 6 + c];
-        S[c * 6 + v] -= s;
-      }
+      for (int c = 0; c < 6; ++c) S[c * 6 + v] -= ftz[v * 6 + c];
     // second-order correction for the finite accuracy of Z: with R = F - M Z,  F^T M^-1 F = F^T Z + Z^T R + O(|dZ|^2)
     if (A.corr) {
       for (int e = 0; e < 36; ++e) {
-        double s = 0.0;
-        for (int b = 0; b < A.grid; ++b) s += A.corr[(long)b * 36 + e];
         const int a = e / 6, c = e - a * 6;
-        S[a * 6 + c] -= 0.5 * s;                 // symmetrised: Z^T R is symmetric up to rounding
-        S[c * 6 + a] -= 0.5 * s;
+        S[a * 6 + c] -= 0.5 * ztr[e];            // symmetrised: Z^T R is symmetric up to rounding
+        S[c * 6 + a] -= 0.5 * ztr[e];
       }
     }
     for (int p = 0; p < 6; ++p) {            // Gauss-Jordan
@@ -777,28 +805,25 @@ struct BorderSchurBody {
 };
 // xb = SbInv (rb - F^T y)   with F^T y from partials (nv = 1)
 struct BorderSolveArgs { const double* SbInv; const double* rb; const double* partials; int grid; double* xb; };
-struct BorderSolveBody {
-  static VUS_DEV void run(const BorderSolveArgs& A, long) {
-    double t[6];
-    for (int c = 0; c < 6; ++c) {
+struct BorderSolveBody {      // one CTA
+  static VUS_DEV void run(const BorderSolveArgs& A, int, int tid, int nthr, double* sm) {
+    sum_partials(sm, A.partials, A.grid, 6, 6, tid, nthr);
+    VUS_SYNC();
+    for (int r = tid; r < 6; r += nthr) {
       double s = 0.0;
-      for (int b = 0; b < A.grid; ++b) s += A.partials[(long)b * 6 + c];
-      t[c] = A.rb[c] - s;
-    }
-    for (int r = 0; r < 6; ++r) {
-      double s = 0.0;
-      for (int c = 0; c < 6; ++c) s += A.SbInv[r * 6 + c] * t[c];
+      for (int c = 0; c < 6; ++c) s += A.SbInv[r * 6 + c] * (A.rb[c] - sm[c]);
       A.xb[r] = s;
     }
   }
 };
 // yb = F^T x (partials) + Hbb xb
 struct BorderRowArgs { const double* Hbb; const double* xb; const double* partials; int grid; double* yb; };
-struct BorderRowBody {
-  static VUS_DEV void run(const BorderRowArgs& A, long) {
-    for (int r = 0; r < 6; ++r) {
-      double s = 0.0;
-      for (int b = 0; b < A.grid; ++b) s += A.partials[(long)b * 6 + r];
+struct BorderRowBody {        // one CTA
+  static VUS_DEV void run(const BorderRowArgs& A, int, int tid, int nthr, double* sm) {
+    sum_partials(sm, A.partials, A.grid, 6, 6, tid, nthr);
+    VUS_SYNC();
+    for (int r = tid; r < 6; r += nthr) {
+      double s = sm[r];
       for (int c = 0; c < 6; ++c) s += A.Hbb[r * 6 + c] * A.xb[c];
       A.yb[r] = s;
     }

@@ -727,7 +727,7 @@ void bcr_solve_launches(vus_handle* h, double* X, long xstride, int nrhs, rt::st
 void border_dot(vus_handle* h, const double* Y, long ystride, int nv, rt::stream_t st) {
   ClassGuard kc_guard(KC_BORDER);
   BorderDotArgs a; a.F = h->F.p; a.Y = Y; a.len = h->Lc; a.ystride = ystride; a.nv = nv; a.partials = h->bpart.p; a.grid = h->red_grid;
-  L_coop<BorderDot1Body>(h->red_grid, 256, 256 * sizeof(double), st, a);
+  L_coop<BorderDot1Body>(h->red_grid, 256, 6 * 256 * sizeof(double), st, a);
 }
 
 // Y = band(SD, SU) X for nv vectors (no remainder, no border)
@@ -759,11 +759,11 @@ void precond_setup(vus_handle* h, rt::stream_t st) {
     {
       ClassGuard kc_b(KC_BORDER);
       ColDotArgs d; d.Z = h->Z.p; d.R = h->Zr.p; d.len = h->Lc; d.stride = h->Lc; d.partials = h->bpart2.p; d.grid = h->red_grid;
-      L_coop<ColDot1Body>(h->red_grid, 256, 256 * sizeof(double), st, d);
+      L_coop<ColDot1Body>(h->red_grid, 256, 6 * 256 * sizeof(double), st, d);
     }
     BorderSchurArgs s; s.Hbb = h->Hbb.p; s.partials = h->bpart.p; s.grid = h->red_grid; s.nv = 6; s.SbInv = h->SbInv.p; s.fail = h->fail.p;
     s.corr = h->bpart2.p;
-    L_elem<BorderSchurBody>(1, st, s);
+    L_coop<BorderSchurBody>(1, 128, 72 * sizeof(double), st, s);
   }
 }
 
@@ -774,7 +774,7 @@ void precond_apply(vus_handle* h, double* z, const double* r, rt::stream_t st) {
   if (h->has_bias) {
     border_dot(h, z, h->Lc, 1, st);
     BorderSolveArgs b; b.SbInv = h->SbInv.p; b.rb = r + h->Lc; b.partials = h->bpart.p; b.grid = h->red_grid; b.xb = z + h->Lc;
-    L_elem<BorderSolveBody>(1, st, b);
+    L_coop<BorderSolveBody>(1, 32, 8 * sizeof(double), st, b);
     VecArgs v; v.y = z; v.x = z; v.z = nullptr; v.scal = nullptr; v.slot = 0; v.n = h->Lc; v.Z = h->Z.p; v.xb = z + h->Lc; v.zstride = h->Lc;
     L_elem<SubZxbBody>(h->Lc, st, v);
   }
@@ -801,7 +801,7 @@ void apply_A(vus_handle* h, double* y, const double* x, rt::stream_t st) {
   if (h->has_bias) {
     border_dot(h, x, h->Lc, 1, st);
     BorderRowArgs b; b.Hbb = h->Hbb.p; b.xb = x + h->Lc; b.partials = h->bpart.p; b.grid = h->red_grid; b.yb = y + h->Lc;
-    { ClassGuard kc_b(KC_BORDER); L_elem<BorderRowBody>(1, st, b); }
+    { ClassGuard kc_b(KC_BORDER); L_coop<BorderRowBody>(1, 32, 8 * sizeof(double), st, b); }
   }
 }
 
