@@ -228,7 +228,12 @@ VUS_DEV void mma_gj_inverse(Acc& c, double* sm, const Tiles& G, int* fail) {
         for (int q2 = 0; q2 < 8; ++q2) prow[q2] = __shfl_sync(0xffffffffu, row[q2], q);
         const double piv = prow[q];
         if (G.lane == 0 && !(piv > 0.0)) *fail = 1;
-        const double d = 1.0 / piv;
+        // reciprocal by hardware seed + two Newton steps (full FP64 accuracy for normal pivots): the IEEE division's
+        // slow-path checks sit on the serial chain of every sweep
+        double d;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(d) : "d"(piv));
+        d = fma(fma(-piv, d, 1.0), d, d);
+        d = fma(fma(-piv, d, 1.0), d, d);
         const double f = row[q] * d;
         if (r == q) {
 #pragma unroll
