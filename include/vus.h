@@ -153,6 +153,16 @@ int vus_linearize(vus_handle* h, void* stream, int type, double* r_out, double* 
  * solves (J^T J + lambda I) delta = -J^T r; delta_pose [nx][6], delta_vel [nv][3], delta_bias [nb][6], delta_lm [nl][3] (host, AoS) */
 int vus_solve_step(vus_handle* h, void* stream, double lambda, double* d_pose, double* d_vel, double* d_bias, double* d_lm,
                    int32_t* pcg_iterations);
+/* gtsam::Marginals(graph, values).marginalCovariance(key) / .jointMarginalCovariance(keys)  (what users
+ * of batch.py:337's result ask for next).  Linearizes at the CURRENT values (no damping), and returns the joint
+ * covariance of nq variables -- query q is variable idx[q] of kind kinds[q] (vus_var_kind) -- as one dense symmetric
+ * matrix cov_out [M][M] (host, row-major), M = sum of the queries' tangent dimensions (POSE 6: rotation then
+ * translation, gtsam's Pose3 tangent order; VEL 3; BIAS 6; LM 3), blocks in query order.  Each column is one exact
+ * solve of the undamped normal equations with a unit right-hand side (landmarks by their Schur complement, camera
+ * block by the band factorization + PCG).  Returns VUS_ERR_STATE when the undamped system is not positive definite
+ * (gtsam throws IndeterminantLinearSystemException there). */
+int vus_marginal_covariance(vus_handle* h, void* stream, int64_t nq, const int32_t* kinds, const int32_t* idx, double* cov_out);
+
 /* ---- front-end loops that feed the graph; tables are row-major (mem = VUS_MEM_*_ROWS) --------
  * gtsam.PreintegratedImuMeasurements.integrateMeasurement x k + resetIntegration per keyframe interval
  * (batch.py:289-293; covariances of batch.py:183-185): acc, gyro [n][k][3], constant dt (batch.py:290 passes 0.005).

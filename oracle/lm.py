@@ -269,3 +269,24 @@ def lm_optimize(prob, params=None, schur=True, verbose=False):
             break
     info.update(iterations=iterations, error=err, lam=lam)
     return vals, info
+
+
+def marginal_covariance(prob, vals, queries):
+    """gtsam::Marginals(graph, values).jointMarginalCovariance(keys).fullMatrix()  (gtsam/nonlinear/Marginals.cpp:
+    linearize at `values`, eliminate, read the marginal off the Bayes tree) restated as the corresponding block of
+    (J^T J)^-1, computed column by column with an exact sparse solve.  queries = [(kind, index)], kind in 'x','v','b','l';
+    the tangent order of a Pose3 block is gtsam's (rotation, translation)."""
+    lay = Layout(prob)
+    J, _ = linearize(prob, vals, lay)
+    lu = _splu_sym((J.T @ J).tocsc())
+    cols = []
+    for kind, idx in queries:
+        c0, d = lay.cols(kind, [idx])
+        cols.extend(range(int(c0[0]), int(c0[0]) + d))
+    cols = np.asarray(cols)
+    cov = np.empty((len(cols), len(cols)))
+    for j, c in enumerate(cols):
+        e = np.zeros(lay.n)
+        e[c] = 1.0
+        cov[:, j] = lu.solve(e)[cols]
+    return 0.5 * (cov + cov.T)

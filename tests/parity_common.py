@@ -5,6 +5,8 @@ import numpy as np
 from visual_underwater_slam_b200 import synthetic
 from visual_underwater_slam_b200.optimizer import Session, LevenbergMarquardtParams, FACTOR_TYPES
 from oracle import lm
+from visual_underwater_slam_b200 import NonlinearFactorGraph, Values
+from visual_underwater_slam_b200.symbol import symbolChr, symbolIndex
 
 
 def make(n_poses, n_lm=0, n_loops=0, seed=1, **kw):
@@ -113,3 +115,67 @@ def check_band_solve(lib, prob, lam, nrhs=3, tol=1e-5, params=None):
         return err
     finally:
         s.close()
+
+
+def check_marginals(lib, prob, queries, rtol=1e-6):
+    """gtsam.Marginals: the joint covariance of `queries` [(kind, index)] at the problem's values against the oracle's
+    (J^T J)^-1 blocks.  Tolerance relative to the largest entry of each block pair (covariances span 1e-12 .. 1e2)."""
+    short = {"pose": "x", "vel": "v", "bias": "b", "lm": "l"}
+    dims = {"pose": 6, "vel": 3, "bias": 6, "lm": 3}
+    s = Session(prob, lib=lib)
+    try:
+        mine = s.marginal_covariance(queries)
+    finally:
+        s.close()
+    ref = lm.marginal_covariance(prob, lm.values_of(prob), [(short[k], i) for k, i in queries])
+    assert mine.shape == ref.shape
+    assert np.abs(mine - mine.T).max() == 0.0
+    off = np.concatenate([[0], np.cumsum([dims[k] for k, _ in queries])])
+    worst = 0.0
+    for a in range(len(queries)):
+        for b in range(len(queries)):
+            A, R = mine[off[a]:off[a + 1], off[b]:off[b + 1]], ref[off[a]:off[a + 1], off[b]:off[b + 1]]
+            scale = np.sqrt(np.abs(ref[off[a]:off[a + 1], off[a]:off[a + 1]]).max() * np.abs(ref[off[b]:off[b + 1], off[b]:off[b + 1]]).max())
+            worst = max(worst, np.abs(A - R).max() / scale)
+    assert worst <= rtol, worst
+    return mine, ref
+
+
+def split_for_incremental(d, cuts):
+    """Cut a synthetic trajectory graph into the (new factors, new values) pairs an incremental front-end would hand over
+    (isam.py:341): segment s holds the factors whose newest pose / velocity index is < cuts[s] (and not in an earlier
+    segment), and the variables those factors mention for the first time."""
+    g, init = d["graph"], d["initial"]
+    adders = {"prior_pose": lambda G, k, m, i: G.add_prior_pose_factors(k[:, 0], m, i),
+              "prior_vel": lambda G, k, m, i: G.add_prior_vector_factors(k[:, 0], m, i),
+              "between": lambda G, k, m, i: G.add_between_factors(k[:, 0], k[:, 1], m, i),
+              "dvl": lambda G, k, m, i: G.add_dvl_factors(k[:, 0], k[:, 1], m, i),
+              "stereo": lambda G, k, m, i: G.add_stereo_factors(k[:, 0], k[:, 1], m, i, g.calib),
+              "imu": lambda G, k, m, i: G.add_imu_factors(k[:, 0], k[:, 1], k[:, 2], k[:, 3], k[:, 4], m, i, g.gravity)}
+    seen = set()
+    out = []
+    lo = 0
+    for hi in cuts:
+        G, V = NonlinearFactorGraph(), Values()
+        newkeys = []
+        for t in FACTOR_TYPES:
+            tab = g.table(t)
+            if len(tab["orig"]) == 0:
+                continue
+            keys = tab["keys"]
+            chain = np.array([[symbolIndex(int(k)) if symbolChr(int(k)) in "xv" else -1 for k in row] for row in keys])
+            newest = chain.max(1)
+            sel = (newest >= lo) & (newest < hi)
+            if not sel.any():
+                continue
+            adders[t](G, keys[sel], tab["meas"][sel], tab["sqrt_info"][sel])
+            newkeys.extend(int(k) for k in np.unique(keys[sel]))
+        for kind in ("pose", "vel", "bias", "lm"):
+            ks, data = init.table(kind)
+            pick = np.array([int(k) in set(newkeys) and int(k) not in seen for k in ks], dtype=bool)
+            if pick.any():
+                V.insert_bulk(kind, ks[pick], data[pick])
+        seen.update(newkeys)
+        out.append((G, V))
+        lo = hi
+    return out

@@ -96,3 +96,40 @@ def test_tracks_longer_than_the_band_stay_exact(emu):
     g = J.T @ b
     assert np.linalg.norm(H @ mine + 1e-3 * mine - g) <= 1e-9 * np.linalg.norm(g)
     assert np.linalg.norm(mine - delta) <= 1e-5 * np.linalg.norm(delta)
+
+
+def test_marginals_chain_and_bias(emu):
+    _, prob = pc.make(50, n_loops=2, loop_min_gap=20)
+    pc.check_marginals(emu, prob, [("pose", 0), ("pose", 37), ("vel", 12), ("bias", 0)])
+
+
+def test_marginals_stereo_landmarks(emu):
+    _, prob = pc.make(40, n_lm=60)
+    pc.check_marginals(emu, prob, [("lm", 7), ("pose", 20), ("lm", 41), ("vel", 39)])
+
+
+def test_incremental_resolve_matches_oracle_warm_start(emu):
+    """ISAM2 facade (isam.py:341-342): after every update the estimate is the LM optimum of the accumulated
+    graph started from the previous estimate -- checked against the oracle run from the same warm start."""
+    import visual_underwater_slam_b200 as gtsam
+    from oracle import lm
+    d, _ = pc.make(60, n_lm=40, n_loops=2, loop_min_gap=20)
+    isam = gtsam.ISAM2(lib=emu)
+    acc_graph, acc_init = gtsam.NonlinearFactorGraph(), gtsam.Values()
+    n_seen = 0
+    for G, V in pc.split_for_incremental(d, [25, 45, 60]):
+        warm = gtsam.Values(isam.calculateEstimate())
+        warm.insert(V)
+        acc_graph.push_back(G)
+        res = isam.update(G, V)
+        n_seen += G.size()
+        assert isam.getFactorsUnsafe().size() == n_seen == acc_graph.size()
+        prob = acc_graph.to_problem(warm)
+        vals, info = lm.lm_optimize(prob)
+        est = isam.calculateEstimate()
+        assert abs(res.getErrorAfter() - info["error"]) <= 1e-6 * info["error"]
+        assert np.abs(est.table("pose")[1] - vals["poses"]).max() < 1e-6
+        assert np.abs(est.table("vel")[1] - vals["vels"]).max() < 1e-6
+    assert n_seen == d["graph"].size()
+    c = isam.marginalCovariance(gtsam.symbol_shorthand.X(59))
+    assert c.shape == (6, 6) and np.all(np.linalg.eigvalsh(c) > 0)

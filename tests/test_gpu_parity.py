@@ -260,3 +260,25 @@ def test_partitioned_solver_single_rank_matches_session(lib):
     assert res["iterations"] == ref["iterations"] and abs(res["final_error"] - ref["final_error"]) <= 1e-6 * ref["final_error"]
     assert np.abs(ps.owned_poses() - pref).max() < 1e-5
     ps.close()
+
+
+def test_marginals_parity(lib):
+    """gtsam.Marginals: covariance blocks against the oracle's (J^T J)^-1 on chain + loops, and on a
+    stereo graph (landmark marginals through the Schur complement); supernode band (B = 81) on the second one."""
+    _, prob = pc.make(300, n_loops=6, loop_min_gap=60)
+    pc.check_marginals(lib, prob, [("pose", 0), ("pose", 299), ("vel", 150), ("bias", 0)])
+    _, prob = pc.make(200, n_lm=400)
+    pc.check_marginals(lib, prob, [("lm", 17), ("pose", 120), ("lm", 333), ("vel", 5), ("bias", 0)])
+
+
+def test_marginals_public_api(lib):
+    import visual_underwater_slam_b200 as gtsam
+    from visual_underwater_slam_b200.symbol import X, L
+    d, prob = pc.make(60, n_lm=80)
+    res = gtsam.LevenbergMarquardtOptimizer(d["graph"], d["initial"], gtsam.LevenbergMarquardtParams()).optimize()
+    m = gtsam.Marginals(d["graph"], res)
+    c = m.marginalCovariance(X(30))
+    assert c.shape == (6, 6) and np.all(np.linalg.eigvalsh(c) > 0)
+    jm = m.jointMarginalCovariance([X(30), L(int(prob["lm_keys"][3]) & 0xFFFFFFFF)])
+    assert jm.fullMatrix().shape == (9, 9) and np.allclose(jm.at(X(30), X(30)), c, rtol=1e-9, atol=1e-15)
+    assert np.allclose(m.marginalInformation(X(30)) @ c, np.eye(6), atol=1e-8)

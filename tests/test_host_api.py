@@ -190,3 +190,17 @@ def test_c_abi_exports_every_declared_symbol(emu):
         lib = ctypes.CDLL(path)
         for name in declared:
             assert hasattr(lib, name), (path, name)
+
+
+def test_marginals_facade_keys_and_errors(emu):
+    """gtsam.Marginals facade: key lookup, joint blocks in the order asked, unknown keys raise."""
+    d = synthetic.make_trajectory_graph(30, seed=3, n_landmarks=20, pixel_noise=1.0)
+    m = gtsam.Marginals(d["graph"], d["initial"], lib=emu)
+    c = m.marginalCovariance(X(10))
+    assert c.shape == (6, 6) and np.all(np.linalg.eigvalsh(c) > 0)
+    jm = m.jointMarginalCovariance([V(4), X(10), B(0)])
+    assert jm.fullMatrix().shape == (15, 15)
+    assert np.allclose(jm.at(X(10), X(10)), c, rtol=1e-8, atol=1e-16)
+    assert np.array_equal(jm.at(V(4), B(0)), jm.at(B(0), V(4)).T)
+    with pytest.raises(KeyError):
+        m.marginalCovariance(X(999))

@@ -65,6 +65,7 @@ EXPORTS = {
     "vus_factor_errors": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p]),
     "vus_linearize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_double_p, c_double_p]),
     "vus_solve_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, c_double_p, c_double_p, c_double_p, c_double_p, c_i32_p]),
+    "vus_marginal_covariance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_i32_p, c_i32_p, c_double_p]),
     "vus_preintegrate_imu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, c_double_p,
                                        c_double_p, c_double_p, c_double_p, C.c_void_p, C.c_void_p, C.c_int]),
     "vus_backproject_stereo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, c_i32_p, C.c_void_p, C.c_void_p, C.c_int]),

@@ -1036,6 +1036,84 @@ int optimize(vus_handle* h, rt::stream_t st) {
   return VUS_OK;
 }
 
+// ------------------------------------------------------------------ gtsam::Marginals
+// right-hand side = one unit vector of the FULL system (camera dof `pos`, or column `col` of landmark l, whose reduced
+// right-hand side is -E_o C_l^-1 e_col on the poses of its track).  One thread: a track is a handful of observations.
+struct UnitRhsArgs { double* gs; double* gl; const double* E; const double* Cinv; const int* idx; const int* lm_ptr; long nl, l, pos; int col, D; };
+struct UnitRhsBody {
+  static VUS_DEV void run(const UnitRhsArgs& A, long) {
+    if (A.pos >= 0) { A.gs[A.pos] = 1.0; return; }
+    A.gl[A.col * A.nl + A.l] = 1.0;
+    for (int q = A.lm_ptr[A.l]; q < A.lm_ptr[A.l + 1]; ++q) {
+      const long node = A.idx[q];
+      for (int a = 0; a < 6; ++a) {
+        double s = 0.0;
+        for (int c = 0; c < 3; ++c) s += A.E[(long)q * 18 + a * 3 + c] * A.Cinv[(c * 3 + A.col) * A.nl + A.l];
+        A.gs[node * A.D + a] -= s;
+      }
+    }
+  }
+};
+
+int marginal_covariance(vus_handle* h, rt::stream_t st, long nq, const int32_t* kinds, const int32_t* idx, double* out) {
+  const int kTan[4] = {6, 3, 6, 3};
+  std::vector<long> off(nq + 1, 0);
+  bool any_lm = false;
+  for (long q = 0; q < nq; ++q) {
+    const int kd = kinds[q];
+    if (kd < 0 || kd > 3 || idx[q] < 0 || idx[q] >= h->nvar[kd]) return fail(h, VUS_ERR_INVALID, "vus_marginal_covariance: query out of range");
+    if (kd == VUS_VAR_BIAS && !h->has_bias) return fail(h, VUS_ERR_INVALID, "vus_marginal_covariance: the graph has no factor on the bias");
+    if (kd == VUS_VAR_VEL && h->D < 9) return fail(h, VUS_ERR_INVALID, "vus_marginal_covariance: the graph has no factor on velocities");
+    any_lm |= kd == VUS_VAR_LM;
+    off[q + 1] = off[q] + kTan[kd];
+  }
+  const long M = off[nq];
+  const long nl = h->nvar[3];
+  // undamped system at the current values, factored once
+  run_factors(h, h->cur, true, st);
+  assemble_base(h, st);
+  form_system(h, 0.0, st);
+  precond_setup(h, st);
+  if (read_fail(h, st)) return fail(h, VUS_ERR_STATE, "vus_marginal_covariance: the undamped system is not positive definite (indeterminate linear system)");
+  std::vector<double> cov((size_t)M * M, 0.0);
+  double buf[6];
+  for (long q = 0; q < nq; ++q) {
+    const int kd = kinds[q];
+    for (int j = 0; j < kTan[kd]; ++j) {
+      h->gs.zero(st);
+      if (nl) h->gl.zero(st);
+      UnitRhsArgs u;
+      u.gs = h->gs.p; u.gl = h->gl.p; u.E = h->E.p; u.Cinv = h->Cinv.p; u.idx = h->ft[VUS_F_STEREO].idx.p; u.lm_ptr = h->lm_ptr.p;
+      u.nl = nl; u.l = idx[q]; u.col = j; u.D = h->D; u.pos = -1;
+      if (kd == VUS_VAR_POSE) u.pos = (long)idx[q] * h->D + j;
+      else if (kd == VUS_VAR_VEL) u.pos = (long)idx[q] * h->D + 6 + j;
+      else if (kd == VUS_VAR_BIAS) u.pos = h->Lc + j;
+      L_elem<UnitRhsBody>(1, st, u);
+      bool conv = false;
+      pcg(h, st, &conv);
+      if (any_lm) {
+        SchurArgs a = schur_args(h, 0.0);
+        L_elem<LmBacksubBody>(a.nl, st, a);
+      }
+      const long colj = off[q] + j;
+      for (long p = 0; p < nq; ++p) {
+        const int kp = kinds[p];
+        if (kp == VUS_VAR_LM) {
+          for (int c = 0; c < 3; ++c) rt::d2h(buf + c, h->xl.p + c * nl + idx[p], sizeof(double), st);
+        } else {
+          const long pos = kp == VUS_VAR_BIAS ? h->Lc : (long)idx[p] * h->D + (kp == VUS_VAR_VEL ? 6 : 0);
+          rt::d2h(buf, h->x.p + pos, kTan[kp] * sizeof(double), st);
+        }
+        rt::sync(st);
+        for (int c = 0; c < kTan[kp]; ++c) cov[(size_t)(off[p] + c) * M + colj] = buf[c];
+      }
+    }
+  }
+  for (long a = 0; a < M; ++a)
+    for (long b = 0; b < M; ++b) out[a * M + b] = 0.5 * (cov[(size_t)a * M + b] + cov[(size_t)b * M + a]);
+  return VUS_OK;
+}
+
 }  // namespace
 
 // =====================================================================================
@@ -1291,6 +1369,15 @@ int vus_solve_step(vus_handle* h, void* stream, double lambda, double* d_pose, d
   for (long l = 0; l < h->nvar[3]; ++l)
     for (int c = 0; c < 3; ++c) if (d_lm) d_lm[l * 3 + c] = xl[c * h->nvar[3] + l];
   return VUS_OK;
+  VUS_CATCH(h)
+}
+
+int vus_marginal_covariance(vus_handle* h, void* stream, int64_t nq, const int32_t* kinds, const int32_t* idx, double* cov_out) {
+  if (!h || nq <= 0 || !kinds || !idx || !cov_out) return VUS_ERR_INVALID;
+  if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_marginal_covariance: call vus_analyze first");
+  if (h->n_owned >= 0) return fail(h, VUS_ERR_UNSUPPORTED, "vus_marginal_covariance: not available on a partitioned graph");
+  VUS_TRY(h)
+  return marginal_covariance(h, stream ? (rt::stream_t)stream : h->own_stream, nq, kinds, idx, cov_out);
   VUS_CATCH(h)
 }
 

@@ -35,6 +35,9 @@ class NonlinearFactorGraph:
 
     # ------------------------------------------------------------------ gtsam API
     def add(self, factor):
+        if isinstance(factor, NonlinearFactorGraph):          # push_back(graph): isam.py:341 hands whole graphs over
+            self._merge(factor)
+            return
         if isinstance(factor, F.CustomFactor):
             lowered = factor.as_dvl()
             if lowered is None:
@@ -54,6 +57,30 @@ class NonlinearFactorGraph:
         self._n += 1
 
     push_back = add
+
+    def _merge(self, other):
+        """Append every factor of `other`, keeping its insertion order after this graph's factors."""
+        if other._custom:
+            for idx, f in other._custom:
+                self._custom.append((self._n + idx, f))
+        if other.calib is not None:
+            self._set_once("calib", other.calib, "Cal3_S2Stereo")
+        if other.gravity is not None:
+            self._set_once("gravity", other.gravity, "n_gravity")
+        for t in FACTOR_TYPES:
+            tab = other.table(t)
+            if len(tab["orig"]) == 0:
+                continue
+            self._flush(t)
+            self._chunks[t].append(dict(keys=tab["keys"].copy(), meas=tab["meas"].copy(), sqrt_info=tab["sqrt_info"].copy(),
+                                        orig=tab["orig"] + self._n))
+        self._n += other._n
+
+    def resize(self, n):
+        """gtsam's graph.resize(0) (isam.py clears its staging graph after every update)."""
+        if n != 0:
+            raise NotImplementedError("NonlinearFactorGraph.resize: only resize(0) is supported")
+        self.__init__()
 
     def size(self):
         return self._n

@@ -242,6 +242,16 @@ class Session:
             self._check(rc)
         return SD, SU[:Ns - 1], x, bool(rc)
 
+    def marginal_covariance(self, queries, stream=None):
+        """Joint covariance of [(kind, index)] (kind in 'pose','vel','bias','lm') at the current values: dense [M, M]."""
+        kinds = np.ascontiguousarray([("pose", "vel", "bias", "lm").index(k) for k, _ in queries], dtype=np.int32)
+        idx = np.ascontiguousarray([i for _, i in queries], dtype=np.int32)
+        M = int(sum((6, 3, 6, 3)[k] for k in kinds))
+        out = np.zeros((M, M))
+        self._check(self.lib.vus_marginal_covariance(self._h, stream, len(kinds), kinds.ctypes.data_as(_native.c_i32_p),
+                                                     idx.ctypes.data_as(_native.c_i32_p), out.ctypes.data_as(_native.c_double_p)))
+        return out
+
     def optimize(self, stream=None):
         res = LmResult()
         self._check(self.lib.vus_optimize(self._h, stream, C.byref(res)))
@@ -321,6 +331,57 @@ class LevenbergMarquardtOptimizer:
     def stats(self):
         """Per-phase timings, PCG iterations, kernel launches of the last optimize()."""
         return dict(self._result or {})
+
+
+class JointMarginal:
+    """gtsam.JointMarginal: the joint covariance (or information) of several variables, blocks in the order asked."""
+
+    def __init__(self, keys, dims, full):
+        self._keys = list(keys)
+        self._off = np.concatenate([[0], np.cumsum(dims)]).astype(int)
+        self._full = full
+
+    def fullMatrix(self):
+        return self._full
+
+    def at(self, k1, k2):
+        i, j = self._keys.index(int(k1)), self._keys.index(int(k2))
+        return self._full[self._off[i]:self._off[i + 1], self._off[j]:self._off[j + 1]]
+
+
+class Marginals:
+    """gtsam.Marginals(graph, solution): marginal covariances of the optimised variables -- what a user of
+    batch.py:337's result asks for next.  Linearizes at `solution`; every covariance column is one exact undamped solve
+    on the device (vus_marginal_covariance)."""
+
+    def __init__(self, graph, solution, lib=None):
+        self._prob = graph.to_problem(solution)
+        self._session = Session(self._prob, lib=lib)
+        self._where = {}
+        for name, kname in (("pose", "pose_keys"), ("vel", "vel_keys"), ("bias", "bias_keys"), ("lm", "lm_keys")):
+            for i, k in enumerate(self._prob[kname]):
+                self._where[int(k)] = (name, i)
+
+    def _query(self, key):
+        try:
+            return self._where[int(key)]
+        except KeyError:
+            raise KeyError(f"Marginals: key {int(key)} is not in the solution") from None
+
+    def marginalCovariance(self, key):
+        return self._session.marginal_covariance([self._query(key)])
+
+    def marginalInformation(self, key):
+        return np.linalg.inv(self.marginalCovariance(key))
+
+    def jointMarginalCovariance(self, keys):
+        q = [self._query(k) for k in keys]
+        dims = [dict(pose=6, vel=3, bias=6, lm=3)[k] for k, _ in q]
+        return JointMarginal([int(k) for k in keys], dims, self._session.marginal_covariance(q))
+
+    def jointMarginalInformation(self, keys):
+        jm = self.jointMarginalCovariance(keys)
+        return JointMarginal(jm._keys, np.diff(jm._off), np.linalg.inv(jm.fullMatrix()))
 
 
 # ---------------------------------------------------------------------------------------------- front-end rows (SURVEY.md 8f)

@@ -25,7 +25,12 @@ class Values:
                 self.insert_bulk(k, keys, data)
 
     # ------------------------------------------------------------------ gtsam API
-    def insert(self, key, value):
+    def insert(self, key, value=None):
+        if isinstance(key, Values):                           # Values.insert(Values)
+            for k in KINDS:
+                keys, data = key.table(k)
+                self.insert_bulk(k, keys, data)
+            return
         key = int(key)
         if key in self._index:
             raise RuntimeError(f"Attempting to add a key-value pair with key \"{symbolChr(key)}"
@@ -57,6 +62,9 @@ class Values:
         self._keys[kind].append(keys.copy())
         self._index.update(dict.fromkeys(kl, kind))
         self._cache = None
+
+    def clear(self):
+        self.__init__()
 
     def exists(self, key):
         return int(key) in self._index
