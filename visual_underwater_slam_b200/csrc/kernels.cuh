@@ -888,6 +888,22 @@ struct SortKeyBody {
     A.vals[f] = (int)f;
   }
 };
+// the same re-ordering for the int32 index table [slots][n]; flags a non-identity order
+struct GatherIdxArgs { const int* src; int* dst; const int* perm; long n; int slots; int* moved; };
+struct GatherIdxBody {
+  static VUS_DEV void run(const GatherIdxArgs& A, long w) {
+    const long f = w % A.n;
+    const long c = w / A.n;
+    const int s = A.perm[f];
+    A.dst[c * A.n + f] = A.src[c * A.n + s];
+    if (c == 0 && s != (int)f) *A.moved = 1;
+  }
+};
+// sort keys for the pose-major observation lists: key = pose of row f, value = row
+struct PoseKeyArgs { const int* idx; long n; unsigned* keys; int* vals; };
+struct PoseKeyBody {
+  static VUS_DEV void run(const PoseKeyArgs& A, long f) { A.keys[f] = (unsigned)A.idx[f]; A.vals[f] = (int)f; }
+};
 // dst[c][f] = src[c][perm[f]]  (re-ordering of a component-major table, used once per graph by vus_analyze)
 struct GatherArgs { const double* src; double* dst; const int* perm; long n; int comps; };
 struct GatherBody {

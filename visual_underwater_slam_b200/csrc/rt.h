@@ -118,6 +118,8 @@ struct DBuf {
   void upload(const T* h, size_t count, stream_t st) { alloc(count); h2d(p, h, count * sizeof(T), st); }
   void upload(const std::vector<T>& h, stream_t st) { upload(h.data(), h.size(), st); }
   void zero(stream_t st) { dzero(p, n * sizeof(T), st); }
+  void swap(DBuf& o) { std::swap(p, o.p); std::swap(n, o.n); }
+  void release() { dfree(p); p = nullptr; n = 0; }
 };
 
 }}  // namespace vus::rt

@@ -122,10 +122,28 @@ struct FactorTable {
   DBuf<int> idx;
   DBuf<double> meas, sinfo, r, J;
   DBuf<PairDst> pair;
+  DBuf<int> d_order;             // stereo only: pending row re-ordering whose orig / perm bookkeeping has not been derived yet
   long e_off = 0;                // offset into the concatenated per-factor error buffer
 };
 
 const int kVarDim[4] = {12, 3, 6, 3};
+
+// Caller-order bookkeeping of a re-ordered table: row f now holds what row order[f] held.  Only the calls that hand
+// per-factor results back in the caller's order need it, so vus_analyze leaves the order on the device.
+void finish_order(FactorTable& T, rt::stream_t st) {
+  if (!T.d_order.p) return;
+  std::vector<int> order(T.n);
+  rt::d2h(order.data(), T.d_order.p, T.n * sizeof(int), st);
+  rt::sync(st);
+  std::vector<int64_t> norig(T.n);
+  std::vector<int> nperm(T.n);
+  for (long o = 0; o < T.n; ++o) {
+    norig[o] = T.orig[order[o]];
+    nperm[o] = T.perm.empty() ? order[o] : T.perm[order[o]];
+  }
+  T.orig.swap(norig); T.perm.swap(nperm);
+  T.d_order.release();
+}
 
 
 double now_ms() {
@@ -374,27 +392,66 @@ int analyze(vus_handle* h, rt::stream_t st) {
   // landmark's observations -- and the per-observation products the Schur kernels stream -- are contiguous
   h->nobs = FS.n;
   std::vector<int> lm_ptr(NL + 1, 0), pose_cnt(NX, 0);
+  bool pose_obs_on_device = false;
+#ifndef VUS_EMU
+  if (FS.n) {
+    // Stable device radix sort of (landmark, pose) keys gives the landmark-major row order; the index / measurement /
+    // noise tables are re-ordered on the device and only the re-ordered indices come back to the host.  The caller-order
+    // bookkeeping (orig, perm) is not needed by optimize(): it is derived from the order on first use (finish_order).
+    finish_order(FS, st);
+    DBuf<unsigned long long> k_in, k_out;
+    DBuf<int> v_in, v_out, nidx, moved;
+    k_in.alloc(FS.n); k_out.alloc(FS.n); v_in.alloc(FS.n); v_out.alloc(FS.n); nidx.alloc(2 * FS.n); moved.alloc(1); moved.zero(st);
+    SortKeyArgs ka; ka.idx = FS.idx.p; ka.n = FS.n; ka.keys = k_in.p; ka.vals = v_in.p;
+    L_elem<SortKeyBody>(FS.n, st, ka);
+    int end_bit = 33;
+    while (end_bit < 64 && (NL >> (end_bit - 32)) != 0) ++end_bit;
+    size_t tmp_bytes = 0, tmp_bytes2 = 0;
+    rt::check(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in.p, k_out.p, v_in.p, v_out.p, (int)FS.n, 0, end_bit, st), "radix sort size");
+    int pose_bits = 1;
+    while (pose_bits < 32 && (NX >> pose_bits) != 0) ++pose_bits;
+    DBuf<unsigned> pk_in, pk_out;
+    DBuf<int> pv_in, pobs;
+    pk_in.alloc(FS.n); pk_out.alloc(FS.n); pv_in.alloc(FS.n); pobs.alloc(FS.n);
+    rt::check(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes2, pk_in.p, pk_out.p, pv_in.p, pobs.p, (int)FS.n, 0, pose_bits, st), "radix sort size");
+    DBuf<unsigned char> tmp; tmp.alloc(std::max(tmp_bytes, tmp_bytes2));
+    rt::check(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k_in.p, k_out.p, v_in.p, v_out.p, (int)FS.n, 0, end_bit, st), "radix sort");
+    GatherIdxArgs gi; gi.src = FS.idx.p; gi.dst = nidx.p; gi.perm = v_out.p; gi.n = FS.n; gi.slots = 2; gi.moved = moved.p;
+    L_elem<GatherIdxBody>(2 * FS.n, st, gi);
+    // pose-major observation lists of the re-ordered rows (stable: rows of one pose stay in row order)
+    PoseKeyArgs pa; pa.idx = nidx.p; pa.n = FS.n; pa.keys = pk_in.p; pa.vals = pv_in.p;
+    L_elem<PoseKeyBody>(FS.n, st, pa);
+    rt::check(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes2, pk_in.p, pk_out.p, pv_in.p, pobs.p, (int)FS.n, 0, pose_bits, st), "radix sort");
+    int h_moved = 0;
+    rt::d2h(&h_moved, moved.p, sizeof(int), st);
+    rt::d2h(FS.h_idx.data(), nidx.p, 2 * FS.n * sizeof(int), st);
+    rt::sync(st);
+    if (h_moved) {
+      FS.idx.swap(nidx);
+      DBuf<double> tmpd; tmpd.alloc((size_t)3 * FS.n);
+      GatherArgs ga; ga.perm = v_out.p; ga.n = FS.n; ga.comps = 3;
+      ga.src = FS.meas.p; ga.dst = tmpd.p;
+      L_elem<GatherBody>(3 * FS.n, st, ga);
+      FS.meas.swap(tmpd);
+      ga.src = FS.sinfo.p; ga.dst = tmpd.p;
+      L_elem<GatherBody>(3 * FS.n, st, ga);
+      FS.sinfo.swap(tmpd);
+      FS.d_order.swap(v_out);                           // orig / perm follow lazily
+      rt::sync(st);
+    } else if (FS.perm.empty()) {
+      FS.perm.resize(FS.n);
+      std::iota(FS.perm.begin(), FS.perm.end(), 0);
+    }
+    h->pose_obs.swap(pobs);
+    pose_obs_on_device = true;
+  }
+  for (long o = 0; o < FS.n; ++o) lm_ptr[FS.h_idx[FS.n + o] + 1]++;
+  for (long l = 0; l < NL; ++l) lm_ptr[l + 1] += lm_ptr[l];
+#else
   for (long o = 0; o < FS.n; ++o) lm_ptr[FS.h_idx[FS.n + o] + 1]++;
   for (long l = 0; l < NL; ++l) lm_ptr[l + 1] += lm_ptr[l];
   if (FS.n) {
     std::vector<int> order(FS.n);
-#ifndef VUS_EMU
-    {   // stable device radix sort of (landmark, pose) keys: order[f'] = caller row stored at row f'
-      DBuf<unsigned long long> k_in, k_out;
-      DBuf<int> v_in, v_out;
-      k_in.alloc(FS.n); k_out.alloc(FS.n); v_in.alloc(FS.n); v_out.alloc(FS.n);
-      SortKeyArgs ka; ka.idx = FS.idx.p; ka.n = FS.n; ka.keys = k_in.p; ka.vals = v_in.p;
-      L_elem<SortKeyBody>(FS.n, st, ka);
-      int end_bit = 33;
-      while (end_bit < 64 && (NL >> (end_bit - 32)) != 0) ++end_bit;
-      size_t tmp_bytes = 0;
-      rt::check(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in.p, k_out.p, v_in.p, v_out.p, (int)FS.n, 0, end_bit, st), "radix sort size");
-      DBuf<unsigned char> tmp; tmp.alloc(tmp_bytes);
-      rt::check(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k_in.p, k_out.p, v_in.p, v_out.p, (int)FS.n, 0, end_bit, st), "radix sort");
-      rt::d2h(order.data(), v_out.p, FS.n * sizeof(int), st);
-      rt::sync(st);
-    }
-#else
     {
       std::vector<int> fill(lm_ptr.begin(), lm_ptr.end() - 1);
       for (long o = 0; o < FS.n; ++o) order[fill[FS.h_idx[FS.n + o]]++] = (int)o;
@@ -410,7 +467,6 @@ int analyze(vus_handle* h, rt::stream_t st) {
         q[b + 1] = v;
       }
     }
-#endif
     bool identity = true;
     for (long o = 0; o < FS.n && identity; ++o) identity = order[o] == o;
     if (!identity) {
@@ -439,15 +495,19 @@ int analyze(vus_handle* h, rt::stream_t st) {
       std::iota(FS.perm.begin(), FS.perm.end(), 0);
     }
   }
+#endif
   tick("stereo landmark-major sort");
   for (long o = 0; o < FS.n; ++o) pose_cnt[FS.h_idx[o]]++;
-  std::vector<int> pose_ids, pose_ptr(1, 0), pose_obs(FS.n);
+  std::vector<int> pose_ids, pose_ptr(1, 0), pose_obs;
   {
     std::vector<int> slot(NX, -1);
     for (long i = 0; i < NX; ++i)
       if (pose_cnt[i]) { slot[i] = (int)pose_ids.size(); pose_ids.push_back((int)i); pose_ptr.push_back(pose_ptr.back() + pose_cnt[i]); }
-    std::vector<int> fill(pose_ptr.begin(), pose_ptr.end() - 1);
-    for (long o = 0; o < FS.n; ++o) pose_obs[fill[slot[FS.h_idx[o]]]++] = (int)o;
+    if (!pose_obs_on_device) {
+      pose_obs.resize(FS.n);
+      std::vector<int> fill(pose_ptr.begin(), pose_ptr.end() - 1);
+      for (long o = 0; o < FS.n; ++o) pose_obs[fill[slot[FS.h_idx[o]]]++] = (int)o;
+    }
   }
   h->nposes_obs = (long)pose_ids.size();
   for (long l = 0; l < NL; ++l)
@@ -520,7 +580,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
   tick("pair destinations");
   // ---- uploads / allocations
   h->rem_ptr.upload(rem_ptr, st); h->rem_col.upload(rem_col, st);
-  h->pose_ptr.upload(pose_ptr, st); h->pose_obs.upload(pose_obs, st); h->pose_ids.upload(pose_ids, st);
+  h->pose_ptr.upload(pose_ptr, st); if (!pose_obs_on_device) h->pose_obs.upload(pose_obs, st); h->pose_ids.upload(pose_ids, st);
   h->lm_ptr.upload(lm_ptr, st);
   h->H0.alloc(h->hlen); h->H.alloc(h->hlen);
   h->g0.alloc(h->Lc); h->gs.alloc(h->L);
@@ -1304,6 +1364,7 @@ int vus_factor_errors(vus_handle* h, void* stream, double* out) {
   VUS_TRY(h)
   rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
   run_factors(h, h->cur, false, st);
+  finish_order(h->ft[VUS_F_STEREO], st);
   std::vector<double> tmp(h->nfactors);
   rt::d2h(tmp.data(), h->e_all.p, h->nfactors * sizeof(double), st);
   rt::sync(st);
@@ -1325,6 +1386,7 @@ int vus_linearize(vus_handle* h, void* stream, int type, double* r_out, double* 
   rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
   run_factors(h, h->cur, true, st);
   FactorTable& T = h->ft[type];
+  finish_order(T, st);
   if (r_out) rt::d2h(r_out, T.r.p, (size_t)kFactorM[type] * T.n * sizeof(double), st);
   if (J_out) rt::d2h(J_out, T.J.p, (size_t)kFactorM[type] * kFactorCols[type] * T.n * sizeof(double), st);
   rt::sync(st);
