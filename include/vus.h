@@ -134,6 +134,22 @@ typedef int (*vus_comm_fn)(void* ctx, int op, void* buf, int64_t count);
 int vus_set_partition(vus_handle* h, int64_t n_owned_nodes, const int64_t n_owned_factors[6]);
 int vus_set_comm(vus_handle* h, vus_comm_fn fn, void* ctx);
 
+/* ---- a batch of INDEPENDENT trajectories in one handle (BASELINE.json config 4: 4096 x 500-pose graphs, a block per GPU)
+ * The reference runs one gtsam.LevenbergMarquardtOptimizer per graph (batch.py:337); a 500-pose solve cannot fill a B200,
+ * so the caller concatenates the trajectories of a shard into one graph -- component c owns the contiguous pose / velocity
+ * index range [node_start[c], node_start[c+1]) and, if the graphs have one, the bias with index c -- and the library
+ * runs gtsam's LM loop for every component at once: each component keeps its own lambda, error, accept / reject /
+ * convergence decisions and PCG scalars, exactly as ncomp separate optimizers would.  No factor may connect two
+ * components; stereo factors are not supported in this mode.  Call before vus_analyze; vus_optimize then fills the
+ * summed errors / the largest iteration count into vus_lm_result and vus_get_component_results the per-trajectory ones. */
+typedef struct vus_component_result {
+  int32_t iterations;            /* accepted LM steps of this trajectory */
+  int32_t inner_iterations;      /* its lambda tries */
+  double initial_error, final_error, final_lambda;
+} vus_component_result;
+int vus_set_components(vus_handle* h, int64_t ncomp, const int64_t* node_start /* [ncomp + 1] */);
+int vus_get_component_results(vus_handle* h, vus_component_result* out /* [ncomp] */);
+
 /* symbolic phase: node ordering, supernode band layout, off-band blocks, Schur destination lists */
 int vus_analyze(vus_handle* h);
 /* band description after analyze: D (node dof), k (nodes per supernode), Ns, nrem, ndst */

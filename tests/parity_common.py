@@ -179,3 +179,26 @@ def split_for_incremental(d, cuts):
         out.append((G, V))
         lo = hi
     return out
+
+
+def check_batched_parity(lib, problems):
+    """BASELINE config 4: independent trajectories solved as ONE block-diagonal system (vus_set_components) against the
+    oracle run on every trajectory separately -- same LM path (accepted steps, lambda tries, final lambda) per
+    trajectory and the north_star tolerances on error and values."""
+    from visual_underwater_slam_b200 import parallel
+    res = parallel.solve_batched(problems, lib=lib)
+    assert len(res) == len(problems)
+    for p, r in zip(problems, res):
+        vals, info = lm.lm_optimize(p)
+        assert r["iterations"] == info["iterations"], (r["iterations"], info["iterations"])
+        assert r["inner_iterations"] == len(info["trace"]["tries"])
+        assert abs(r["final_error"] - info["error"]) <= 1e-6 * info["error"]
+        assert abs(r["final_lambda"] - info["lam"]) <= 1e-12 * info["lam"]
+        v = r["values"]
+        assert np.sqrt(((v["poses"][:, 9:] - vals["poses"][:, 9:]) ** 2).sum(1).mean()) < 1e-6
+        assert np.abs(v["poses"][:, :9] - vals["poses"][:, :9]).max() < 1e-6
+        if len(vals["vels"]):
+            assert np.abs(v["vels"] - vals["vels"]).max() < 1e-6
+        if len(vals["biases"]):
+            assert np.abs(v["biases"] - vals["biases"]).max() < 1e-6
+    return res

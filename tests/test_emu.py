@@ -133,3 +133,31 @@ def test_incremental_resolve_matches_oracle_warm_start(emu):
     assert n_seen == d["graph"].size()
     c = isam.marginalCovariance(gtsam.symbol_shorthand.X(59))
     assert c.shape == (6, 6) and np.all(np.linalg.eigvalsh(c) > 0)
+
+
+def test_batched_trajectories_match_separate_optimizers(emu):
+    """Ragged batch (different lengths, loop closures, LM paths with rejected tries) in one handle."""
+    probs = [pc.make(40 + 7 * t, n_loops=2, loop_min_gap=15, seed=10 + t)[1] for t in range(3)]
+    res = pc.check_batched_parity(emu, probs)
+    assert len({r["inner_iterations"] for r in res}) > 1        # the trajectories really took different LM paths
+
+
+def test_batched_pose_graphs_without_bias(emu):
+    from visual_underwater_slam_b200 import synthetic
+    probs = []
+    for t in range(3):
+        d = synthetic.make_pose_graph(60 + 10 * t, seed=20 + t, n_loops=4)
+        probs.append(d["graph"].to_problem(d["initial"]))
+    pc.check_batched_parity(emu, probs)
+
+
+def test_batched_rejects_cross_component_factor(emu):
+    from visual_underwater_slam_b200 import parallel
+    from visual_underwater_slam_b200.optimizer import Session
+    probs = [pc.make(20, seed=30 + t)[1] for t in range(2)]
+    prob, node_start = parallel.concat_problems(probs)
+    for slot in ("xj", "vj"):                                     # ImuFactor from keyframe 0 of trajectory 0 to keyframe 5 of trajectory 1
+        prob["imu"][slot] = prob["imu"][slot].copy()
+        prob["imu"][slot][0] = 25
+    with pytest.raises(RuntimeError, match="connects two components"):
+        Session(prob, lib=emu, components=node_start)

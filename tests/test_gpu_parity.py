@@ -282,3 +282,22 @@ def test_marginals_public_api(lib):
     jm = m.jointMarginalCovariance([X(30), L(int(prob["lm_keys"][3]) & 0xFFFFFFFF)])
     assert jm.fullMatrix().shape == (9, 9) and np.allclose(jm.at(X(30), X(30)), c, rtol=1e-9, atol=1e-15)
     assert np.allclose(m.marginalInformation(X(30)) @ c, np.eye(6), atol=1e-8)
+
+
+def test_batched_trajectories_parity(lib):
+    """BASELINE config 4 (independent trajectories, one block-diagonal system per GPU): every trajectory follows the
+    oracle's LM path of its own graph -- ragged lengths, loop closures, own bias."""
+    probs = [pc.make(120 + 30 * t, n_loops=3, loop_min_gap=40, seed=40 + t)[1] for t in range(4)]
+    pc.check_batched_parity(lib, probs)
+
+
+def test_batched_matches_one_handle_per_trajectory(lib):
+    """Size-independent property at a size the oracle is too slow for: the batched solve and one handle per trajectory
+    take the same LM path and reach the same error for every trajectory."""
+    from visual_underwater_slam_b200 import parallel
+    probs = [pc.make(300, n_loops=5, loop_min_gap=80, seed=60 + t)[1] for t in range(48)]
+    bat = parallel.solve_batched(probs, lib=lib, keep_values=False)
+    one = parallel.solve_local(probs, lib=lib, threads=4, keep_values=False)
+    for b, o in zip(bat, one):
+        assert b["iterations"] == o["iterations"] and b["inner_iterations"] == o["inner_iterations"]
+        assert abs(b["final_error"] - o["final_error"]) <= 1e-9 * o["final_error"]

@@ -40,6 +40,11 @@ class LmResult(C.Structure):
         return d
 
 
+class ComponentResult(C.Structure):                     # vus_component_result
+    _fields_ = [("iterations", C.c_int32), ("inner_iterations", C.c_int32), ("initial_error", C.c_double),
+                ("final_error", C.c_double), ("final_lambda", C.c_double)]
+
+
 COMM_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64)     # vus_comm_fn
 COMM_ALLREDUCE_SUM, COMM_HALO = 0, 1
 
@@ -58,6 +63,8 @@ EXPORTS = {
     "vus_set_lm_params": (C.c_int, [C.c_void_p, C.POINTER(LmParams)]),
     "vus_set_partition": (C.c_int, [C.c_void_p, C.c_int64, c_i64_p]),
     "vus_set_comm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vus_set_components": (C.c_int, [C.c_void_p, C.c_int64, c_i64_p]),
+    "vus_get_component_results": (C.c_int, [C.c_void_p, C.POINTER(ComponentResult)]),
     "vus_analyze": (C.c_int, [C.c_void_p]),
     "vus_get_layout": (C.c_int, [C.c_void_p, c_i64_p]),
     "vus_optimize": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(LmResult)]),

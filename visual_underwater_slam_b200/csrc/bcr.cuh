@@ -43,6 +43,7 @@ VUS_HD long bcr_smem_doubles(int B) {
 // The assembled system (SD, SU) uses the same tile layout, so level 1 and the band operator stream it the same way.
 struct BcrArgs {
   long Ns; int B; long s;          // level stride
+  long root_stride;                // the nodes left after the last level are the multiples of root_stride (>= Ns: node 0 only)
   const double* Dsrc; int d_ld; long d_stride;    // diagonal blocks read at this level (level 1: SD, plain; else Dw, padded)
   double* Dw;                      // working diagonal blocks [Ns], padded
   const double* Ucur; int u_ld; long u_stride;    // couplings at this level (level 1: SU, plain; else padded)
@@ -409,12 +410,13 @@ struct BcrUpdateBody {
 };
 // root: Dinv_0 = inv(D_0)
 struct BcrRootBody {
-  static VUS_DEV void run(const BcrArgs& A, int, int tid, int, double* sm) {
+  static VUS_DEV void run(const BcrArgs& A, int m, int tid, int, double* sm) {
     const Tiles G(A.B, tid);
+    const long j = (long)m * A.root_stride;
     Acc c;
-    acc_load_global(c, A.Dsrc, A.d_ld, G);
+    acc_load_global(c, A.Dsrc + j * A.d_stride, A.d_ld, G);
     mma_gj_inverse(c, sm, G, A.fail);
-    acc_store_global<false>(A.Dinv, G.LD, c, 1.0, G);
+    acc_store_global<false>(A.Dinv + j * bcr_bbp(A.B), G.LD, c, 1.0, G);
   }
 };
 
@@ -492,7 +494,10 @@ struct BcrUpdateBody {
   }
 };
 struct BcrRootBody {
-  static VUS_DEV void run(const BcrArgs& A, int, int, int, double*) { emu_spd_inverse(A.Dsrc, A.d_ld, A.Dinv, bcr_ld(A.B), A.B, A.fail); }
+  static VUS_DEV void run(const BcrArgs& A, int m, int, int, double*) {
+    const long j = (long)m * A.root_stride;
+    emu_spd_inverse(A.Dsrc + j * A.d_stride, A.d_ld, A.Dinv + j * bcr_bbp(A.B), bcr_ld(A.B), A.B, A.fail);
+  }
 };
 #endif
 
@@ -644,7 +649,7 @@ struct BcrBwdBodyT {
   static VUS_DEV void run(const BcrArgs& A, int m, int tid, int, double* sm) {
     const int B = A.B, nv = A.nrhs;
     const long BBP = bcr_bbp(B);
-    const long j = A.s * (2L * m + 1);
+    const long j = A.s > 0 ? A.s * (2L * m + 1) : (long)m * A.root_stride;     // s = 0: a root
     const long jl = j - A.s, jh = j + A.s;
     const bool hl = jl >= 0 && A.s > 0, hh = jh < A.Ns && A.s > 0;
 #ifdef VUS_EMU
@@ -695,12 +700,12 @@ struct BcrBwdBodyT {
 };
 typedef BcrBwdBodyT<false> BcrBwdBody;
 typedef BcrBwdBodyT<true> BcrBwdDeepBody;
-// root solve: x_0 = Dinv_0 b_0   (the backward body with no neighbours: s = 0, m such that j = 0)
+// root solve: x_j = Dinv_j b_j for the root(s) j = m * root_stride   (the backward body with no neighbours: s = 0)
 struct BcrRootSolveBody {
-  static VUS_DEV void run(const BcrArgs& A, int, int tid, int nthr, double* sm) {
+  static VUS_DEV void run(const BcrArgs& A, int m, int tid, int nthr, double* sm) {
     BcrArgs R = A;
     R.s = 0;
-    BcrBwdBody::run(R, 0, tid, nthr, sm);
+    BcrBwdBody::run(R, m, tid, nthr, sm);
   }
 };
 
@@ -736,6 +741,94 @@ struct BandMatvecBody {
     if (dn) blk_stream<true, false, true>(P, buf, sX, A.SU + (I - 1) * BBP, A.x + (long)(I - 1) * B, A.xstride, G, nv, tid, mb);
     VUS_PANEL_FOREACH(P, G, nv, { A.y[(long)v * A.ystride + (long)I * B + r] = val; })
 #endif
+  }
+};
+
+// =====================================================================================  small blocks (B <= 16)
+// Pure chain graphs (no landmark tracks: k = 1, B = D = 6 or 9 -- BASELINE configs 1, 4, 5) have hundreds of thousands of
+// tiny supernodes; a 256-thread CTA with a TMA pipeline per 9 x 9 block spends its time on CTA launch and barrier
+// latency.  Here one thread owns one (supernode, row, vector) item and a CTA covers VUS_SMALLB_G supernodes: a tile is
+// read once, by neighbouring lanes (rows are contiguous; transposed operands are read along the lanes), straight from
+// global memory.  Same recurrences as the streaming bodies above; single source for the device and the emulation.
+#define VUS_SMALLB_MAX 16
+#define VUS_SMALLB_G 16
+struct SmallFwdBody {      // per surviving node c = 2 m s:  b_c -= Gr_{c-s} b_{c-s} + Gl_{c+s} b_{c+s}
+  static VUS_DEV void run(const BcrArgs& A, int blk, int tid, int nthr, double*) {
+    const int B = A.B, nv = A.nrhs, LD = bcr_ld(B);
+    const long BBP = bcr_bbp(B);
+    const long nsv = ((A.Ns + A.s - 1) / A.s + 1) / 2;
+    for (int e = tid; e < VUS_SMALLB_G * B * nv; e += nthr) {
+      const int r = e % B, g = (e / B) % VUS_SMALLB_G, v = e / (B * VUS_SMALLB_G);
+      const long m = (long)blk * VUS_SMALLB_G + g;
+      if (m >= nsv) continue;
+      const long c = 2L * m * A.s, jl = c - A.s, jh = c + A.s;
+      const double* X = A.X + (long)v * A.xstride;
+      double acc = 0.0;
+      if (jl >= 0) {
+        const double* G = A.Gr + jl * BBP + (long)r * LD;
+        for (int k = 0; k < B; ++k) acc += G[k] * X[jl * B + k];
+      }
+      if (jh < A.Ns) {
+        const double* G = A.Gl + jh * BBP + (long)r * LD;
+        for (int k = 0; k < B; ++k) acc += G[k] * X[jh * B + k];
+      }
+      A.X[(long)v * A.xstride + c * B + r] -= acc;
+    }
+  }
+};
+struct SmallBwdBody {      // per eliminated node j = s (2 m + 1):  x_j = Dinv_j b_j - Gl_j^T x_{j-s} - Gr_j^T x_{j+s};  s = 0: the root
+  static VUS_DEV void run(const BcrArgs& A, int blk, int tid, int nthr, double* sm) {
+    const int B = A.B, nv = A.nrhs, LD = bcr_ld(B);
+    const long BBP = bcr_bbp(B);
+    const long nel = A.s > 0 ? ((A.Ns + A.s - 1) / A.s) / 2 : (A.Ns + A.root_stride - 1) / A.root_stride;
+    for (int e = tid; e < VUS_SMALLB_G * B * nv; e += nthr) {
+      const int r = e % B, g = (e / B) % VUS_SMALLB_G, v = e / (B * VUS_SMALLB_G);
+      const long m = (long)blk * VUS_SMALLB_G + g;
+      if (m >= nel) continue;
+      const long j = A.s > 0 ? A.s * (2L * m + 1) : m * A.root_stride, jl = j - A.s, jh = j + A.s;
+      const double* X = A.X + (long)v * A.xstride;
+      const double* Dj = A.Dinv + j * BBP + (long)r * LD;
+      double acc = 0.0;
+      for (int k = 0; k < B; ++k) acc += Dj[k] * X[j * B + k];
+      if (A.s > 0 && jl >= 0) {
+        const double* G = A.Gl + j * BBP + r;
+        for (int k = 0; k < B; ++k) acc -= G[(long)k * LD] * X[jl * B + k];
+      }
+      if (A.s > 0 && jh < A.Ns) {
+        const double* G = A.Gr + j * BBP + r;
+        for (int k = 0; k < B; ++k) acc -= G[(long)k * LD] * X[jh * B + k];
+      }
+      sm[e] = acc;
+    }
+    VUS_SYNC();                                           // x_j overwrites b_j: every row of the node is computed first
+    for (int e = tid; e < VUS_SMALLB_G * B * nv; e += nthr) {
+      const int r = e % B, g = (e / B) % VUS_SMALLB_G, v = e / (B * VUS_SMALLB_G);
+      const long m = (long)blk * VUS_SMALLB_G + g;
+      if (m >= nel) continue;
+      A.X[(long)v * A.xstride + (A.s > 0 ? A.s * (2L * m + 1) : m * A.root_stride) * B + r] = sm[e];
+    }
+  }
+};
+struct SmallMatvecBody {   // work item (v, I, r):  y_I[r] = SD_I[r,:] x_I + SU_I[r,:] x_{I+1} + SU_{I-1}[:,r] x_{I-1}
+  static VUS_DEV void run(const MatvecArgs& A, long w) {
+    const int B = A.B, LD = bcr_ld(B);
+    const long BBP = bcr_bbp(B);
+    const int r = (int)(w % B);
+    const long I = (w / B) % A.Ns;
+    const int v = (int)(w / ((long)B * A.Ns));
+    const double* x = A.x + (long)v * A.xstride;
+    const double* d = A.SD + I * BBP + (long)r * LD;
+    double acc = 0.0;
+    for (int k = 0; k < B; ++k) acc += d[k] * x[I * B + k];
+    if (I + 1 < A.Ns) {
+      const double* u = A.SU + I * BBP + (long)r * LD;
+      for (int k = 0; k < B; ++k) acc += u[k] * x[(I + 1) * B + k];
+    }
+    if (I > 0) {
+      const double* u = A.SU + (I - 1) * BBP + r;
+      for (int k = 0; k < B; ++k) acc += u[(long)k * LD] * x[(I - 1) * B + k];
+    }
+    A.y[(long)v * A.ystride + I * B + r] = acc;
   }
 };
 

@@ -117,7 +117,7 @@ struct LinErrBody {
     } else {
       const long xi = ix[f], vi = ix[n + f], xj = ix[2 * n + f], vj = ix[3 * n + f];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) { d[c] = a.X.xc[xi * D + c]; d[9 + c] = a.X.xc[xj * D + c]; d[18 + c] = a.X.xb[c]; }
+      for (int c = 0; c < 6; ++c) { d[c] = a.X.xc[xi * D + c]; d[9 + c] = a.X.xc[xj * D + c]; d[18 + c] = a.X.xb[6 * (long)ix[4 * n + f] + c]; }
 #pragma unroll
       for (int c = 0; c < 3; ++c) { d[6 + c] = a.X.xc[vi * D + 6 + c]; d[15 + c] = a.X.xc[vj * D + 6 + c]; }
     }
@@ -954,10 +954,11 @@ struct RetractBody {    // work items: nx poses, then nv velocities, then nl lan
     }
     w -= A.nl;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) A.bias_out[c * A.nb + w] = A.bias[c * A.nb + w] + A.xb[c];
+    for (int c = 0; c < 6; ++c) A.bias_out[c * A.nb + w] = A.bias[c * A.nb + w] + A.xb[6 * w + c];
   }
 };
 
 }  // namespace vus
 
 #include "bcr.cuh"
+#include "batch.cuh"

@@ -196,6 +196,14 @@ struct vus_handle {
   DBuf<double> e_mask;           // 1 for factors this rank owns, 0 for duplicates of a neighbour's factor
   vus_comm_fn comm = nullptr;
   void* comm_ctx = nullptr;
+  // batched mode: independent components (trajectories) in one block-diagonal system (batch.cuh)
+  int ncomp = 1;
+  long bcr_stop = 1L << 62;      // cyclic reduction needs no stride beyond the longest component (in supernodes)
+  std::vector<long> comp_start;  // [ncomp + 1] node ranges, vus_set_components
+  DBuf<int> node_comp, cf_ptr, cf_list, ci_ptr, ci_list;
+  DBuf<long> seg;
+  DBuf<double> scal_b, lam_c, acc_c, cdots, cdots2, err_c;
+  std::vector<vus_component_result> comp_res;
   // CUDA graphs of the fixed launch sequences + the stream used when the caller passes NULL (capture needs a real stream)
   GraphCache g_factor;
   std::map<std::tuple<const double*, long, int>, GraphCache> g_solve;
@@ -354,6 +362,55 @@ PairDst band_dst(const vus_handle* h, long p, long q, const std::map<std::pair<l
   return d;
 }
 
+// batched mode: component of every node, dof segments, per-component factor lists (errors) and IMU lists (bias blocks)
+int analyze_components(vus_handle* h, rt::stream_t st) {
+  const int nc = h->ncomp;
+  const long NX = h->nvar[0];
+  std::vector<int> node_comp(h->Npad, nc - 1);
+  std::vector<long> seg(nc + 1);
+  for (int c = 0; c < nc; ++c) {
+    if (h->comp_start[c + 1] <= h->comp_start[c]) return fail(h, VUS_ERR_INVALID, "vus_set_components: empty component");
+    for (long i = h->comp_start[c]; i < h->comp_start[c + 1]; ++i) node_comp[i] = c;
+    seg[c] = h->comp_start[c] * h->D;
+  }
+  long longest = 1;
+  for (int c = 0; c < nc; ++c) longest = std::max(longest, h->comp_start[c + 1] - h->comp_start[c]);
+  h->bcr_stop = (longest + h->k - 1) / h->k + 1;          // supernodes a component can touch
+  seg[nc] = NX * h->D;                                   // padding nodes carry identity rows and zero vectors
+  const int slot_kind[VUS_F_NTYPES][5] = {{0}, {1}, {0, 0}, {1, 0}, {0, 3}, {0, 1, 0, 1, 2}};
+  std::vector<int> fcomp(h->nfactors), cf_ptr(nc + 1, 0), ci_ptr(nc + 1, 0);
+  for (int t = 0; t < VUS_F_NTYPES; ++t) {
+    FactorTable& T = h->ft[t];
+    for (long f = 0; f < T.n; ++f) {
+      const int c = node_comp[T.h_idx[f]];
+      for (int sl = 1; sl < kFactorSlots[t]; ++sl) {
+        const int v = T.h_idx[sl * T.n + f];
+        const int cv = slot_kind[t][sl] == 2 ? v : node_comp[v];
+        if (cv != c) return fail(h, VUS_ERR_INVALID, "batched graph: a factor connects two components");
+      }
+      fcomp[T.e_off + f] = c;
+      cf_ptr[c + 1]++;
+      if (t == VUS_F_IMU) ci_ptr[c + 1]++;
+    }
+  }
+  for (int c = 0; c < nc; ++c) { cf_ptr[c + 1] += cf_ptr[c]; ci_ptr[c + 1] += ci_ptr[c]; }
+  std::vector<int> cf_list(h->nfactors), ci_list(h->ft[VUS_F_IMU].n);
+  {
+    std::vector<int> fill(cf_ptr.begin(), cf_ptr.end() - 1);
+    for (long e = 0; e < h->nfactors; ++e) cf_list[fill[fcomp[e]]++] = (int)e;
+    std::vector<int> filli(ci_ptr.begin(), ci_ptr.end() - 1);
+    const FactorTable& I = h->ft[VUS_F_IMU];
+    for (long f = 0; f < I.n; ++f) ci_list[filli[fcomp[I.e_off + f]]++] = (int)f;
+  }
+  h->node_comp.upload(node_comp, st); h->seg.upload(seg, st);
+  h->cf_ptr.upload(cf_ptr, st); h->cf_list.upload(cf_list, st);
+  h->ci_ptr.upload(ci_ptr, st); h->ci_list.upload(ci_list, st);
+  h->scal_b.alloc((size_t)nc * SB_STRIDE); h->scal_b.zero(st);
+  h->lam_c.alloc(nc); h->acc_c.alloc(nc); h->cdots.alloc((size_t)nc * 36); h->cdots2.alloc((size_t)nc * 36); h->err_c.alloc(nc);
+  rt::sync(st);
+  return VUS_OK;
+}
+
 int analyze(vus_handle* h, rt::stream_t st) {
   const double t_an0 = now_ms();
   h->drop_graphs();
@@ -363,7 +420,13 @@ int analyze(vus_handle* h, rt::stream_t st) {
   };
   const long NX = h->nvar[0], NV = h->nvar[1], NB = h->nvar[2], NL = h->nvar[3];
   if (NX == 0) return fail(h, VUS_ERR_INVALID, "no Pose3 variables");
-  if (NB > 1) return fail(h, VUS_ERR_UNSUPPORTED, "more than one imuBias variable: only the shared B(0) of batch.py:238/:274 is supported");
+  if (h->ncomp <= 1 && NB > 1) return fail(h, VUS_ERR_UNSUPPORTED, "more than one imuBias variable: only the shared B(0) of batch.py:238/:274 is supported (or one per component, vus_set_components)");
+  if (h->ncomp > 1) {
+    if (NB != 0 && NB != h->ncomp) return fail(h, VUS_ERR_INVALID, "batched graph: one imuBias per component (or none)");
+    if (h->ft[VUS_F_STEREO].n) return fail(h, VUS_ERR_UNSUPPORTED, "batched graph: stereo factors are not supported");
+    if (h->n_owned >= 0) return fail(h, VUS_ERR_UNSUPPORTED, "batched graph: cannot be combined with a pose-range partition");
+    if (h->comp_start.back() != NX) return fail(h, VUS_ERR_INVALID, "vus_set_components: node ranges must cover every pose");
+  }
   h->D = NV > 0 ? 9 : 6;
   if (NV > 0) {
     if (NV != NX) return fail(h, VUS_ERR_UNSUPPORTED, "every pose X(i) needs a velocity V(i) (batch.py:283-288)");
@@ -533,7 +596,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
   h->Ns = (NX + k - 1) / k;
   h->Npad = h->Ns * k;
   h->Lc = h->Npad * D;
-  h->L = h->Lc + (h->has_bias ? 6 : 0);
+  h->L = h->Lc + 6 * NB;
   const long BB = bcr_bbp(h->B);                     // SD / SU are padded [KP][LD] tiles (bulk-copy layout, bcr.cuh)
   auto inband = [&](long p, long q) { long I = p / k, J = q / k; return (I - J <= 1) && (J - I <= 1); };
   // ---- off-band remainder blocks
@@ -584,13 +647,13 @@ int analyze(vus_handle* h, rt::stream_t st) {
   h->lm_ptr.upload(lm_ptr, st);
   h->H0.alloc(h->hlen); h->H.alloc(h->hlen);
   h->g0.alloc(h->Lc); h->gs.alloc(h->L);
-  h->F.alloc(h->Lc * 6); h->Hbb0.alloc(36); h->Hbb.alloc(36); h->gb.alloc(6);
+  h->F.alloc(h->Lc * 6); h->Hbb0.alloc(36 * std::max<long>(NB, 1)); h->Hbb.alloc(36 * std::max<long>(NB, 1)); h->gb.alloc(6 * std::max<long>(NB, 1));
   h->C.alloc(9 * NL); h->gl.alloc(3 * NL); h->Cinv.alloc(9 * NL); h->E.alloc(18 * FS.n); h->Pp.alloc(28 * FS.n); h->Pl.alloc(12 * FS.n);
   {   // the reduction's own blocks are padded [KP][LD] tiles; the padding must be (and stays) zero
     const size_t nb = (size_t)h->Ns * bcr_bbp(h->B);
     for (DBuf<double>* b : {&h->Dw, &h->U1, &h->U2, &h->Dinv, &h->Gl, &h->Gr}) { b->alloc(nb); b->zero(st); }
   }
-  h->Z.alloc(6 * h->Lc); h->Zr.alloc(6 * h->Lc); h->SbInv.alloc(36);
+  h->Z.alloc(6 * h->Lc); h->Zr.alloc(6 * h->Lc); h->SbInv.alloc(36 * std::max<long>(NB, 1));
   if (h->n_owned >= 0) {
     if (h->has_bias || FS.n || NV) return fail(h, VUS_ERR_UNSUPPORTED, "pose-range partition supports pose graphs (PriorFactorPose3 / BetweenFactorPose3) only");
     if (h->n_owned > NX) return fail(h, VUS_ERR_INVALID, "vus_set_partition: more owned nodes than nodes");
@@ -622,6 +685,10 @@ int analyze(vus_handle* h, rt::stream_t st) {
     T.J.alloc((size_t)kFactorM[t] * kFactorCols[t] * T.n);
   }
   h->e_all.alloc(eoff); h->le_all.alloc(eoff);
+  if (h->ncomp > 1) {
+    const int rc = analyze_components(h, st);
+    if (rc != VUS_OK) return rc;
+  }
   for (int kind = 0; kind < 4; ++kind) h->val[1 - h->cur][kind].alloc((size_t)kVarDim[kind] * h->nvar[kind]);
   rt::sync(st);
   tick("uploads + allocations");
@@ -660,9 +727,16 @@ void assemble_base(vus_handle* h, rt::stream_t st) {
   }
   if (h->ft[VUS_F_IMU].n) {
     FactorTable& I = h->ft[VUS_F_IMU];
+    if (h->ncomp > 1) {
+      if (h->has_bias) {
+        BImuBiasArgs bb; bb.n = I.n; bb.J = I.J.p; bb.r = I.r.p; bb.ptr = h->ci_ptr.p; bb.list = h->ci_list.p; bb.Hbb = h->Hbb0.p; bb.gb = h->gb.p;
+        L_coop<BImuBiasBody>(h->ncomp, 128, 128 * sizeof(double), st, bb);
+      }
+    } else {
     ImuBiasArgs b; b.n = I.n; b.J = I.J.p; b.r = I.r.p; b.partials = h->bpart.p; b.grid = h->red_grid; b.Hbb = h->Hbb0.p; b.gb = h->gb.p;
     L_coop<ImuBias1Body>(h->red_grid, 256, 256 * sizeof(double), st, b);
     L_elem<ImuBias2Body>(42, st, b);
+    }
   }
   FactorTable& S = h->ft[VUS_F_STEREO];
   if (S.n) {
@@ -709,11 +783,19 @@ void form_system(vus_handle* h, double lambda, rt::stream_t st) {
 }
 
 // ------------------------------------------------------------------ kernel 3 drivers
+// The reduction stops at the first stride that no coupling can span: the whole chain for one graph; the longest component
+// for a batch of independent trajectories (their couplings across component boundaries are zero), where the nodes left
+// -- the multiples of that stride, one or none per component -- are all roots and are inverted / solved in one launch.
+long bcr_root_stride(const vus_handle* h) {
+  long s = 1;
+  while (s < h->Ns && s < h->bcr_stop) s <<= 1;
+  return s;
+}
 size_t bcr_smem(int B) { return (size_t)bcr_smem_doubles(B) * sizeof(double); }
 
 BcrArgs bcr_args(vus_handle* h) {
   BcrArgs a;
-  a.Ns = h->Ns; a.B = h->B; a.s = 1;
+  a.Ns = h->Ns; a.B = h->B; a.s = 1; a.root_stride = bcr_root_stride(h);
   a.Dsrc = nullptr; a.d_ld = 0; a.d_stride = 0; a.Dw = h->Dw.p;
   a.Ucur = nullptr; a.u_ld = 0; a.u_stride = 0; a.Unext = nullptr;
   a.Dinv = h->Dinv.p; a.Gl = h->Gl.p; a.Gr = h->Gr.p; a.fail = h->fail.p;
@@ -735,7 +817,8 @@ void bcr_factor_launches(vus_handle* h, rt::stream_t st) {
   a.Ucur = h->H.p + h->su_off; a.u_ld = LD; a.u_stride = BBP;
   double* bufs[2] = {h->U1.p, h->U2.p};
   int w = 0;
-  for (long s = 1; s < h->Ns; s <<= 1) {
+  const long s_root = bcr_root_stride(h);
+  for (long s = 1; s < s_root; s <<= 1) {
     const long nact = (h->Ns + s - 1) / s;
     const int nel = (int)(nact / 2), nsv = (int)((nact + 1) / 2);
     a.s = s; a.Unext = bufs[w];
@@ -745,7 +828,7 @@ void bcr_factor_launches(vus_handle* h, rt::stream_t st) {
     a.Ucur = bufs[w]; a.u_ld = LD; a.u_stride = BBP;
     w ^= 1;
   }
-  L_coop<BcrRootBody>(1, 256, bcr_smem(h->B), st, a);
+  L_coop<BcrRootBody>((int)((h->Ns + s_root - 1) / s_root), 256, bcr_smem(h->B), st, a);
 }
 
 // in-place solve of the band system for nrhs vectors X[v*xstride + ...]
@@ -760,9 +843,26 @@ void bcr_solve_launches(vus_handle* h, double* X, long xstride, int nrhs, rt::st
   BcrArgs a = bcr_args(h);
   a.X = X; a.xstride = xstride; a.nrhs = nrhs;
   const int nthr = 256;
-  const size_t smem = (size_t)blk_smem_doubles(h->B, nrhs, nthr) * sizeof(double);
   std::vector<long> levels;
-  for (long s = 1; s < h->Ns; s <<= 1) levels.push_back(s);
+  const long s_root = bcr_root_stride(h);
+  const int nroot = (int)((h->Ns + s_root - 1) / s_root);
+  for (long s = 1; s < s_root; s <<= 1) levels.push_back(s);
+  if (h->B <= VUS_SMALLB_MAX) {                          // tiny supernodes: thread per (node, row), VUS_SMALLB_G nodes per CTA
+    const size_t sm_small = (size_t)VUS_SMALLB_G * h->B * nrhs * sizeof(double);
+    auto grid_of = [](long n) { return (int)((n + VUS_SMALLB_G - 1) / VUS_SMALLB_G); };
+    for (long s : levels) {
+      a.s = s;
+      L_coop<SmallFwdBody>(grid_of(((h->Ns + s - 1) / s + 1) / 2), nthr, 0, st, a);
+    }
+    a.s = 0;
+    L_coop<SmallBwdBody>(grid_of(nroot), nthr, sm_small, st, a);
+    for (auto it = levels.rbegin(); it != levels.rend(); ++it) {
+      a.s = *it;
+      L_coop<SmallBwdBody>(grid_of(((h->Ns + a.s - 1) / a.s) / 2), nthr, sm_small, st, a);
+    }
+    return;
+  }
+  const size_t smem = (size_t)blk_smem_doubles(h->B, nrhs, nthr) * sizeof(double);
   // levels with at most one CTA per SM use the DEEP bodies (every block of a node in flight at once)
   const size_t smem_deep = (size_t)3 * blk_slot_doubles(h->B) * sizeof(double);
   const int deep_max = smem_deep <= 220 * 1024 ? rt::sm_count() : 0;
@@ -773,7 +873,7 @@ void bcr_solve_launches(vus_handle* h, double* X, long xstride, int nrhs, rt::st
     if (grid <= deep_max) L_coop<BcrFwdDeepBody>(grid, nthr, smem_deep, st, a);
     else L_coop<BcrFwdBody>(grid, nthr, smem, st, a);
   }
-  L_coop<BcrRootSolveBody>(1, nthr, smem, st, a);
+  L_coop<BcrRootSolveBody>(nroot, nthr, smem, st, a);
   for (auto it = levels.rbegin(); it != levels.rend(); ++it) {
     const long s = *it;
     const long nact = (h->Ns + s - 1) / s;
@@ -798,6 +898,7 @@ void apply_band(vus_handle* h, double* Y, long ystride, const double* X, long xs
   a.nv = nv; a.xstride = xstride; a.ystride = ystride;
   a.rem_ptr = nullptr; a.rem_col = nullptr; a.rem_val = nullptr; a.nnodes = h->N; a.D = h->D;
   a.F = nullptr; a.Hbb = nullptr; a.xb = nullptr; a.yb = nullptr; a.has_bias = 0;
+  if (h->B <= VUS_SMALLB_MAX) { L_elem<SmallMatvecBody>(h->Ns * h->B * nv, st, a); return; }
   const size_t smem = (size_t)blk_smem_doubles(h->B, nv, 256) * sizeof(double);
   L_coop<BandMatvecBody>((int)h->Ns, 256, smem, st, a);
 }
@@ -848,8 +949,12 @@ void apply_A(vus_handle* h, double* y, const double* x, rt::stream_t st) {
   a.nv = 1; a.xstride = 0; a.ystride = 0;
   a.rem_ptr = h->nrem ? h->rem_ptr.p : nullptr; a.rem_col = h->rem_col.p; a.rem_val = h->H.p + h->rem_off; a.nnodes = h->N; a.D = h->D;
   a.F = h->F.p; a.Hbb = h->Hbb.p; a.xb = x + h->Lc; a.yb = y + h->Lc; a.has_bias = h->has_bias;
-  const size_t smem = (size_t)blk_smem_doubles(h->B, 1, 256) * sizeof(double);
-  L_coop<BandMatvecBody>((int)h->Ns, 256, smem, st, a);
+  if (h->B <= VUS_SMALLB_MAX) {
+    L_elem<SmallMatvecBody>(h->Ns * h->B, st, a);
+  } else {
+    const size_t smem = (size_t)blk_smem_doubles(h->B, 1, 256) * sizeof(double);
+    L_coop<BandMatvecBody>((int)h->Ns, 256, smem, st, a);
+  }
   if (h->nrem || h->has_bias) { ClassGuard kc_b(KC_BORDER); L_elem<RemBorderMatvecBody>(h->N * h->D, st, a); }
   if (h->nlong) {                                      // implicit Schur term of the long-track landmarks
     ClassGuard kc_s(KC_SCHUR);
@@ -992,10 +1097,14 @@ void launch_linerr(vus_handle* h, rt::stream_t st) {
   a.out = h->le_all.p + F.e_off; a.type = T;
   L_elem<LinErrBody<T>>(F.n, st, a);
 }
-double linear_error(vus_handle* h, rt::stream_t st) {
+void linear_error_launches(vus_handle* h, rt::stream_t st) {
   ClassGuard kc_guard(KC_LINERR);
   launch_linerr<VUS_F_PRIOR_POSE>(h, st); launch_linerr<VUS_F_PRIOR_VEL>(h, st); launch_linerr<VUS_F_BETWEEN>(h, st);
   launch_linerr<VUS_F_DVL>(h, st); launch_linerr<VUS_F_STEREO>(h, st); launch_linerr<VUS_F_IMU>(h, st);
+}
+double linear_error(vus_handle* h, rt::stream_t st) {
+  linear_error_launches(h, st);
+  ClassGuard kc_guard(KC_LINERR);
   reduce(h, h->le_all.p, h->n_owned >= 0 ? h->e_mask.p : nullptr, h->nfactors, S_TMP, RED_STORE, st);
   return read_scalar(h, S_TMP, st);
 }
@@ -1088,6 +1197,270 @@ int optimize(vus_handle* h, rt::stream_t st) {
   R.iterations = iterations;
   R.final_error = err;
   R.final_lambda = lambda;
+  R.ms_total = now_ms() - t_begin;
+  R.kernel_launches = g_launches - launches0;
+  g_prof.collect();
+  g_prof.on = false;
+  for (int i = 0; i < 16; ++i) { R.ms_class[i] = g_prof.ms[i]; R.launches_class[i] = g_prof.count[i]; }
+  return VUS_OK;
+}
+
+// ------------------------------------------------------------------ batched mode (batch.cuh): many independent trajectories
+BCtx bctx(vus_handle* h) {
+  BCtx c; c.node_comp = h->node_comp.p; c.seg = h->seg.p; c.ncomp = h->ncomp; c.D = h->D; c.has_bias = h->has_bias; c.Lc = h->Lc;
+  return c;
+}
+void form_system_b(vus_handle* h, rt::stream_t st) {       // damping from h->lam_c
+  ClassGuard kc_guard(KC_SCHUR);
+  const long nb = h->nvar[2];
+  rt::d2d(h->H.p, h->H0.p, h->hlen * sizeof(double), st);
+  rt::d2d(h->gs.p, h->g0.p, h->Lc * sizeof(double), st);
+  if (nb) {
+    rt::d2d(h->Hbb.p, h->Hbb0.p, 36 * nb * sizeof(double), st);
+    rt::d2d(h->gs.p + h->Lc, h->gb.p, 6 * nb * sizeof(double), st);
+  }
+  BDampArgs d; d.C = bctx(h); d.SD = h->H.p + h->sd_off; d.Hbb = h->Hbb.p; d.nreal = h->N * h->D; d.B = h->B; d.lam = h->lam_c.p;
+  d.ld = bcr_ld(h->B); d.bs = bcr_bbp(h->B);
+  L_elem<BDampBody>(h->Lc + 6 * nb, st, d);
+}
+void bdot(vus_handle* h, const double* a, const double* b, int slot, int op, rt::stream_t st) {
+  BDotArgs r; r.C = bctx(h); r.a = a; r.b = b; r.scal = h->scal_b.p; r.slot = slot; r.op = op; r.tol = h->prm.pcg_rel_tol;
+  L_coop<BDotBody>(h->ncomp, 128, 128 * sizeof(double), st, r);
+}
+void bborder_dot(vus_handle* h, const double* Y, long ystride, int nv, double* out, rt::stream_t st) {
+  ClassGuard kc_guard(KC_BORDER);
+  BBorderDotArgs a; a.C = bctx(h); a.F = h->F.p; a.Y = Y; a.ystride = ystride; a.nv = nv; a.out = out;
+  L_coop<BBorderDotBody>(h->ncomp, 128, 6 * 128 * sizeof(double), st, a);
+}
+void precond_setup_b(vus_handle* h, rt::stream_t st) {
+  bcr_factor(h, st);
+  if (!h->has_bias) return;
+  BorderColsArgs c; c.F = h->F.p; c.Z = h->Z.p; c.len = h->Lc; c.zstride = h->Lc; c.R = h->Zr.p;
+  L_elem<BorderColsBody>(h->Lc * 6, st, c);
+  bcr_solve(h, h->Z.p, h->Lc, 6, st);
+  apply_band(h, h->Zr.p, h->Lc, h->Z.p, h->Lc, 6, st);     // second-order correction of every component's complement
+  L_elem<BorderResidBody>(h->Lc * 6, st, c);
+  bborder_dot(h, h->Z.p, h->Lc, 6, h->cdots.p, st);
+  ClassGuard kc_b(KC_BORDER);
+  BColDotArgs d; d.C = bctx(h); d.Z = h->Z.p; d.R = h->Zr.p; d.stride = h->Lc; d.out = h->cdots2.p;
+  L_coop<BColDotBody>(h->ncomp, 128, 6 * 128 * sizeof(double), st, d);
+  BBorderSchurArgs sa; sa.ncomp = h->ncomp; sa.Hbb = h->Hbb.p; sa.ftz = h->cdots.p; sa.ztr = h->cdots2.p; sa.SbInv = h->SbInv.p; sa.fail = h->fail.p;
+  L_elem<BBorderSchurBody>(h->ncomp, st, sa);
+}
+void precond_apply_b(vus_handle* h, double* z, const double* r, rt::stream_t st) {
+  rt::d2d(z, r, h->L * sizeof(double), st);
+  bcr_solve(h, z, h->Lc, 1, st);
+  if (!h->has_bias) return;
+  bborder_dot(h, z, h->Lc, 1, h->cdots.p, st);
+  ClassGuard kc_b(KC_BORDER);
+  BBorderSmallArgs b; b.M = h->SbInv.p; b.rb = r + h->Lc; b.dots = h->cdots.p; b.out = z + h->Lc;
+  L_elem<BBorderSolveBody>(6L * h->ncomp, st, b);
+  BVecArgs v; v.C = bctx(h); v.y = z; v.x = z; v.scal = nullptr; v.slot = 0; v.Z = h->Z.p; v.xb = z + h->Lc; v.zstride = h->Lc;
+  L_elem<BSubZxbBody>(h->Lc, st, v);
+}
+void apply_A_b(vus_handle* h, double* y, const double* x, rt::stream_t st) {
+  apply_band(h, y, 0, x, 0, 1, st);
+  ClassGuard kc_b(KC_BORDER);
+  if (h->nrem || h->has_bias) {
+    BRemBorderArgs a; a.C = bctx(h); a.rem_ptr = h->nrem ? h->rem_ptr.p : nullptr; a.rem_col = h->rem_col.p; a.rem_val = h->H.p + h->rem_off;
+    a.F = h->F.p; a.x = x; a.xb = x + h->Lc; a.y = y;
+    L_elem<BRemBorderBody>(h->N * h->D, st, a);
+  }
+  if (h->has_bias) {
+    bborder_dot(h, x, h->Lc, 1, h->cdots.p, st);
+    BBorderSmallArgs b; b.M = h->Hbb.p; b.rb = x + h->Lc; b.dots = h->cdots.p; b.out = y + h->Lc;
+    L_elem<BBorderRowBody>(6L * h->ncomp, st, b);
+  }
+}
+void baxpy(vus_handle* h, double* y, const double* x, int slot, rt::stream_t st) {
+  BVecArgs v; v.C = bctx(h); v.y = y; v.x = x; v.scal = h->scal_b.p; v.slot = slot; v.Z = nullptr; v.xb = nullptr; v.zstride = 0;
+  L_elem<BAxpyBody>(h->L, st, v);
+}
+void bxpby(vus_handle* h, double* y, const double* x, int slot, rt::stream_t st) {
+  BVecArgs v; v.C = bctx(h); v.y = y; v.x = x; v.scal = h->scal_b.p; v.slot = slot; v.Z = nullptr; v.xb = nullptr; v.zstride = 0;
+  L_elem<BXpbyBody>(h->L, st, v);
+}
+// worst ratio rr_c / tol2_c over the components (<= 1: every component met its tolerance); NaN-safe
+double worst_ratio(vus_handle* h, std::vector<double>& sb, rt::stream_t st, bool* bad) {
+  rt::d2h(sb.data(), h->scal_b.p, sb.size() * sizeof(double), st);
+  rt::sync(st);
+  double w = 0.0;
+  for (int c = 0; c < h->ncomp; ++c) {
+    const double rr = sb[(size_t)c * SB_STRIDE + S_RR], t2 = sb[(size_t)c * SB_STRIDE + SB_TOL2];
+    if (!(rr == rr)) { *bad = true; return INFINITY; }
+    if (rr <= t2) continue;
+    w = std::max(w, t2 > 0.0 ? rr / t2 : INFINITY);
+  }
+  return w;
+}
+// PCG with per-component scalars: the block-diagonal system is solved as ncomp independent CG recursions advanced in
+// lock step (one set of kernels for all of them); a component whose residual met the tolerance stops moving.
+int pcg_b(vus_handle* h, rt::stream_t st, bool* converged) {
+  const long L = h->L;
+  VecArgs v; v.z = nullptr; v.scal = nullptr; v.slot = 0; v.n = L; v.Z = nullptr; v.xb = nullptr; v.zstride = 0;
+  std::vector<double> sb((size_t)h->ncomp * SB_STRIDE);
+  h->x.zero(st);
+  rt::d2d(h->r.p, h->gs.p, L * sizeof(double), st);
+  bdot(h, h->r.p, h->r.p, S_RR, BOP_RR0, st);
+  bool bad = false;
+  double worst = worst_ratio(h, sb, st, &bad);
+  *converged = !bad && worst <= 1.0;
+  if (*converged || bad) return 0;
+  int it = 0;
+  double worst_outer = worst;
+  for (int outer = 0; outer < 6 && !*converged; ++outer) {
+    h->d.zero(st);
+    precond_apply_b(h, h->z.p, h->r.p, st);
+    rt::d2d(h->p.p, h->z.p, L * sizeof(double), st);
+    bdot(h, h->r.p, h->z.p, S_RZ, BOP_RZ0, st);
+    int since_best = 0;
+    double best = worst_outer;
+    while (it < h->prm.pcg_max_iterations) {
+      apply_A_b(h, h->Ap.p, h->p.p, st);
+      bdot(h, h->p.p, h->Ap.p, S_PAP, BOP_PAP, st);
+      baxpy(h, h->d.p, h->p.p, S_ALPHA, st);
+      baxpy(h, h->r.p, h->Ap.p, S_NEG_ALPHA, st);
+      ++it;
+      bdot(h, h->r.p, h->r.p, S_RR, BOP_STORE, st);
+      worst = worst_ratio(h, sb, st, &bad);
+      if (h->prm.verbose > 1) std::fprintf(stderr, "    pcg_b %d.%d worst rr/tol2 %.3e\n", outer, it, worst);
+      if (bad || worst <= 1.0) break;
+      if (worst < best) { best = worst; since_best = 0; }
+      else if (++since_best >= 40) break;
+      precond_apply_b(h, h->z.p, h->r.p, st);
+      bdot(h, h->r.p, h->z.p, S_RZ, BOP_RZ, st);
+      bxpby(h, h->p.p, h->z.p, S_BETA, st);
+    }
+    if (bad) break;
+    v.y = h->x.p; v.x = h->d.p;
+    L_elem<AddBody>(L, st, v);
+    apply_A_b(h, h->r.p, h->x.p, st);
+    v.y = h->r.p; v.x = h->gs.p;
+    L_elem<RsubBody>(L, st, v);
+    bdot(h, h->r.p, h->r.p, S_RR, BOP_STORE, st);
+    const double worst_true = worst_ratio(h, sb, st, &bad);
+    if (h->prm.verbose > 1) std::fprintf(stderr, "    pcg_b outer %d true worst rr/tol2 %.3e\n", outer, worst_true);
+    if (bad) break;
+    if (worst_true <= 1.0) { *converged = true; break; }
+    if (!(worst_true < 0.25 * worst_outer) || it >= h->prm.pcg_max_iterations) break;
+    worst_outer = worst_true;
+  }
+  return it;
+}
+void comp_sums(vus_handle* h, const double* e, std::vector<double>& out, rt::stream_t st) {
+  BErrSumArgs a; a.e = e; a.ptr = h->cf_ptr.p; a.list = h->cf_list.p; a.out = h->err_c.p;
+  L_coop<BErrSumBody>(h->ncomp, 128, 128 * sizeof(double), st, a);
+  out.resize(h->ncomp);
+  rt::d2h(out.data(), h->err_c.p, h->ncomp * sizeof(double), st);
+  rt::sync(st);
+}
+// gtsam's LM loop run for every component at once: each round linearizes at the current values, every
+// active component tries its own lambda, and the accept / reject / stop decisions of optimize() are taken per component.
+// A component whose try fails is re-solved next round from the same values (hence the same linearization) with 10 x lambda.
+int optimize_batched(vus_handle* h, rt::stream_t st) {
+  vus_lm_result& R = h->res;
+  R = vus_lm_result();
+  const vus_lm_params& P = h->prm;
+  const int nc = h->ncomp;
+  const long launches0 = g_launches;
+  g_prof.reset();
+  g_prof.on = P.profile_kernels != 0;
+  const double t_begin = now_ms();
+  std::vector<double> lam(nc, P.lambda_initial), err, cur_err, new_err, new_lin, accept(nc, 0.0);
+  std::vector<char> active(nc, 0);
+  h->comp_res.assign(nc, vus_component_result());
+  run_factors(h, h->cur, false, st);
+  comp_sums(h, h->e_all.p, err, st);
+  int n_active = 0;
+  for (int c = 0; c < nc; ++c) {
+    h->comp_res[c].initial_error = err[c];
+    R.initial_error += err[c];
+    active[c] = !(err[c] <= P.error_tol) && P.max_iterations > 0 && std::isfinite(err[c]);
+    n_active += active[c];
+  }
+  cur_err = err;
+  while (n_active > 0) {
+    run_factors(h, h->cur, true, st);
+    assemble_base(h, st);
+    R.linearizations++;
+    R.factors_linearized += h->nfactors;
+    rt::h2d(h->lam_c.p, lam.data(), nc * sizeof(double), st);
+    form_system_b(h, st);
+    precond_setup_b(h, st);
+    const bool solved = !read_fail(h, st);
+    if (solved) {
+      bool conv = false;
+      R.pcg_iterations += pcg_b(h, st, &conv);
+      linear_error_launches(h, st);
+      comp_sums(h, h->le_all.p, new_lin, st);
+      retract(h, st);
+      run_factors(h, 1 - h->cur, false, st);
+      comp_sums(h, h->e_all.p, new_err, st);
+    } else {
+      R.solve_failures++;
+    }
+    R.inner_iterations++;
+    for (int c = 0; c < nc; ++c) {
+      accept[c] = 0.0;
+      if (!active[c]) continue;
+      vus_component_result& cr = h->comp_res[c];
+      cr.inner_iterations++;
+      bool success = false, stop = false;
+      double ne = INFINITY;
+      if (solved) {
+        const double old_lin = err[c];
+        const double lin_change = old_lin - new_lin[c];
+        if (lin_change >= 0) {
+          ne = new_err[c];
+          const double cost_change = err[c] - ne;
+          if (lin_change > VUS_EPS * old_lin) success = cost_change / lin_change > P.min_model_fidelity;
+          if (std::fabs(cost_change) < P.relative_error_tol * err[c]) stop = true;
+        }
+      }
+      if (P.verbose > 1) std::fprintf(stderr, "  comp %d try lam=%.3e new_err=%.9e success=%d\n", c, lam[c], ne, (int)success);
+      bool outer_done = false;                         // the tryLambda loop of this component ended
+      if (success) {
+        accept[c] = 1.0;
+        err[c] = ne;
+        lam[c] = std::max(P.lambda_lower_bound, lam[c] / P.lambda_factor);
+        cr.iterations++;
+        outer_done = true;
+      } else if (!stop) {
+        lam[c] *= P.lambda_factor;
+        if (lam[c] >= P.lambda_upper_bound) outer_done = true;
+      } else {
+        outer_done = true;
+      }
+      if (outer_done) {                                // NonlinearOptimizer::defaultOptimize's convergence test
+        bool done = cr.iterations >= P.max_iterations || !std::isfinite(cur_err[c]) || err[c] <= P.error_tol;
+        const double absdec = cur_err[c] - err[c], reldec = absdec / cur_err[c];
+        if ((P.relative_error_tol != 0.0 && reldec <= P.relative_error_tol) || absdec <= P.absolute_error_tol) done = true;
+        cur_err[c] = err[c];
+        if (done) { active[c] = 0; --n_active; }
+      }
+    }
+    if (solved) {
+      rt::h2d(h->acc_c.p, accept.data(), nc * sizeof(double), st);
+      BCommitArgs a; a.node_comp = h->node_comp.p; a.accept = h->acc_c.p; a.nx = h->nvar[0]; a.nv = h->nvar[1]; a.nb = h->nvar[2];
+      const int cu = h->cur, tr = 1 - h->cur;
+      a.pose = h->val[cu][0].p; a.pose_t = h->val[tr][0].p; a.vel = h->val[cu][1].p; a.vel_t = h->val[tr][1].p;
+      a.bias = h->val[cu][2].p; a.bias_t = h->val[tr][2].p;
+      ClassGuard kc_guard(KC_RETRACT);
+      L_elem<BCommitBody>(a.nx + a.nv + a.nb, st, a);
+      rt::sync(st);                                    // accept[] is reused by the next round
+    }
+    if (P.verbose) std::fprintf(stderr, "round %d: %d components active\n", R.inner_iterations, n_active);
+  }
+  rt::sync(st);
+  int max_it = 0;
+  for (int c = 0; c < nc; ++c) {
+    h->comp_res[c].final_error = err[c];
+    h->comp_res[c].final_lambda = lam[c];
+    R.final_error += err[c];
+    max_it = std::max(max_it, (int)h->comp_res[c].iterations);
+  }
+  R.iterations = max_it;
+  R.final_lambda = lam[0];
   R.ms_total = now_ms() - t_begin;
   R.kernel_launches = g_launches - launches0;
   g_prof.collect();
@@ -1316,6 +1689,24 @@ int vus_set_comm(vus_handle* h, vus_comm_fn fn, void* ctx) {
   return VUS_OK;
 }
 
+int vus_set_components(vus_handle* h, int64_t ncomp, const int64_t* node_start) {
+  if (!h || ncomp < 1 || !node_start) return VUS_ERR_INVALID;
+  if (node_start[0] != 0) return fail(h, VUS_ERR_INVALID, "vus_set_components: node_start[0] must be 0");
+  for (int64_t c = 0; c < ncomp; ++c)
+    if (node_start[c + 1] <= node_start[c]) return fail(h, VUS_ERR_INVALID, "vus_set_components: node ranges must be ascending and non-empty");
+  h->ncomp = (int)ncomp;
+  h->comp_start.assign(node_start, node_start + ncomp + 1);
+  h->analyzed = false;
+  return VUS_OK;
+}
+
+int vus_get_component_results(vus_handle* h, vus_component_result* out) {
+  if (!h || !out) return VUS_ERR_INVALID;
+  if (h->ncomp <= 1 || (int)h->comp_res.size() != h->ncomp) return fail(h, VUS_ERR_STATE, "vus_get_component_results: no batched optimize() has run");
+  std::copy(h->comp_res.begin(), h->comp_res.end(), out);
+  return VUS_OK;
+}
+
 int vus_analyze(vus_handle* h) {
   if (!h) return VUS_ERR_INVALID;
   VUS_TRY(h)
@@ -1343,7 +1734,8 @@ int vus_optimize(vus_handle* h, void* stream, vus_lm_result* result) {
   if (!h) return VUS_ERR_INVALID;
   if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_optimize: call vus_analyze first");
   VUS_TRY(h)
-  const int rc = optimize(h, stream ? (rt::stream_t)stream : h->own_stream);
+  rt::stream_t st_ = stream ? (rt::stream_t)stream : h->own_stream;
+  const int rc = h->ncomp > 1 ? optimize_batched(h, st_) : optimize(h, st_);
   if (result) *result = h->res;
   return rc;
   VUS_CATCH(h)
@@ -1410,6 +1802,7 @@ int vus_solve_step(vus_handle* h, void* stream, double lambda, double* d_pose, d
                    int32_t* pcg_iterations) {
   if (!h) return VUS_ERR_INVALID;
   if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_solve_step: call vus_analyze first");
+  if (h->ncomp > 1) return fail(h, VUS_ERR_UNSUPPORTED, "vus_solve_step: not available on a batched graph (vus_set_components)");
   VUS_TRY(h)
   rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
   run_factors(h, h->cur, true, st);
@@ -1437,6 +1830,7 @@ int vus_solve_step(vus_handle* h, void* stream, double lambda, double* d_pose, d
 int vus_marginal_covariance(vus_handle* h, void* stream, int64_t nq, const int32_t* kinds, const int32_t* idx, double* cov_out) {
   if (!h || nq <= 0 || !kinds || !idx || !cov_out) return VUS_ERR_INVALID;
   if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_marginal_covariance: call vus_analyze first");
+  if (h->ncomp > 1) return fail(h, VUS_ERR_UNSUPPORTED, "vus_marginal_covariance: not available on a batched graph (vus_set_components)");
   if (h->n_owned >= 0) return fail(h, VUS_ERR_UNSUPPORTED, "vus_marginal_covariance: not available on a partitioned graph");
   VUS_TRY(h)
   return marginal_covariance(h, stream ? (rt::stream_t)stream : h->own_stream, nq, kinds, idx, cov_out);
@@ -1446,6 +1840,7 @@ int vus_marginal_covariance(vus_handle* h, void* stream, int64_t nq, const int32
 int vus_debug_band_solve(vus_handle* h, void* stream, double lambda, double* SD_out, double* SU_out, double* x_inout, int nrhs) {
   if (!h) return VUS_ERR_INVALID;
   if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_debug_band_solve: call vus_analyze first");
+  if (h->ncomp > 1) return fail(h, VUS_ERR_UNSUPPORTED, "vus_debug_band_solve: not available on a batched graph (vus_set_components)");
   VUS_TRY(h)
   rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
   const long BB = (long)h->B * h->B, BBP = bcr_bbp(h->B);

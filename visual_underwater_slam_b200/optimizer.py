@@ -106,7 +106,7 @@ def _rows(a, dim):
 class Session:
     """One vus_handle: uploads a packed problem (graph.to_problem), analyses it, exposes the C-ABI calls."""
 
-    def __init__(self, prob, params=None, lib=None, device=0, device_tensors=False, partition=None, comm=None):
+    def __init__(self, prob, params=None, lib=None, device=0, device_tensors=False, partition=None, comm=None, components=None):
         self.lib = lib if lib is not None else _native.load()
         self.prob = prob
         self._h = C.c_void_p()
@@ -126,6 +126,11 @@ class Session:
             if comm is not None:                        # a _native.COMM_FN instance (kept alive by the caller and here)
                 self._comm = comm
                 self._check(self.lib.vus_set_comm(self._h, C.cast(comm, C.c_void_p), None))
+            self.n_components = 1
+            if components is not None:                  # node_start [ncomp + 1]: independent trajectories (parallel.solve_batched)
+                ns = np.ascontiguousarray(components, dtype=np.int64)
+                self.n_components = len(ns) - 1
+                self._check(self.lib.vus_set_components(self._h, self.n_components, ns.ctypes.data_as(_native.c_i64_p)))
             self._check(self.lib.vus_analyze(self._h))
         except Exception:
             self.close()
@@ -256,6 +261,12 @@ class Session:
         res = LmResult()
         self._check(self.lib.vus_optimize(self._h, stream, C.byref(res)))
         return res.as_dict()
+
+    def component_results(self):
+        """Per-trajectory summary of the last batched optimize(): list of dicts (vus_component_result)."""
+        arr = (_native.ComponentResult * self.n_components)()
+        self._check(self.lib.vus_get_component_results(self._h, arr))
+        return [{n: getattr(r, n) for n, _ in _native.ComponentResult._fields_} for r in arr]
 
     def save_values(self):
         self._check(self.lib.vus_save_values(self._h))

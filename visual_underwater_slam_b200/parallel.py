@@ -62,6 +62,91 @@ def solve_local(problems, params=None, lib=None, device=0, threads=4, keep_value
         return list(pool.map(work, items))
 
 
+def concat_problems(problems):
+    """Concatenate independent packed problems (same variable kinds, no landmarks) into ONE packed problem whose
+    components are the inputs: pose / velocity rows of problem t follow those of problem t-1, its bias (if any) becomes
+    bias t, factor indices are shifted accordingly and insertion indices continue across problems.
+    -> (problem, node_start [n + 1]).  Keys are re-issued as X(i) / V(i) / B(t) over the concatenated index."""
+    from .symbol import X, V, B
+    if not problems:
+        raise ValueError("concat_problems: empty batch")
+    n_nodes = [len(p["pose_keys"]) for p in problems]
+    node_start = np.concatenate([[0], np.cumsum(n_nodes)]).astype(np.int64)
+    for p in problems:
+        if len(p["lm_keys"]) or len(p["stereo"]["orig"]):
+            raise NotImplementedError("concat_problems: stereo landmarks are not supported in a batch")
+        if len(p["vel_keys"]) not in (0, len(p["pose_keys"])) or len(p["bias_keys"]) > 1:
+            raise ValueError("concat_problems: every problem needs V(i) for every X(i) (or none) and at most one bias")
+    has_vel = len(problems[0]["vel_keys"]) > 0
+    has_bias = len(problems[0]["bias_keys"]) > 0
+    if any((len(p["vel_keys"]) > 0) != has_vel or (len(p["bias_keys"]) > 0) != has_bias for p in problems):
+        raise ValueError("concat_problems: the problems of a batch must hold the same variable kinds")
+    n = int(node_start[-1])
+    out = {"pose_keys": np.array([X(i) for i in range(n)], dtype=np.uint64),
+           "poses": np.concatenate([p["poses"] for p in problems], 0),
+           "vel_keys": np.array([V(i) for i in range(n)] if has_vel else [], dtype=np.uint64),
+           "vels": np.concatenate([p["vels"] for p in problems], 0) if has_vel else np.zeros((0, 3)),
+           "bias_keys": np.array([B(t) for t in range(len(problems))] if has_bias else [], dtype=np.uint64),
+           "biases": np.concatenate([p["biases"] for p in problems], 0) if has_bias else np.zeros((0, 6)),
+           "lm_keys": np.zeros(0, dtype=np.uint64), "lms": np.zeros((0, 3)),
+           "calib": problems[0]["calib"], "gravity": problems[0]["gravity"]}
+    node_slots = ("x", "x1", "x2", "xi", "xj", "v", "vi", "vj")
+    f0 = 0
+    tables = {}
+    for t, p in enumerate(problems):
+        if not np.array_equal(p["gravity"], out["gravity"]):
+            raise NotImplementedError("concat_problems: all problems must share one n_gravity")
+        for name in ("prior_pose", "prior_vel", "between", "dvl", "stereo", "imu"):
+            f = p[name]
+            cols = tables.setdefault(name, {})
+            for k, v in f.items():
+                v = np.asarray(v)
+                if k in node_slots:
+                    v = v.astype(np.int32) + np.int32(node_start[t])
+                elif k == "b":
+                    v = np.full(len(v), t, dtype=np.int32)
+                elif k == "orig":
+                    v = v.astype(np.int64) + f0
+                cols.setdefault(k, []).append(v)
+        f0 += int(p["n_factors"])
+    for name, cols in tables.items():
+        out[name] = {k: np.concatenate(v, 0) for k, v in cols.items()}
+    out["n_factors"] = f0
+    return out, node_start
+
+
+def split_values(tables, node_start, has_bias=True):
+    """Inverse of concat_problems for the value tables of a batched session: -> list of per-trajectory tables."""
+    out = []
+    for t in range(len(node_start) - 1):
+        a, b = int(node_start[t]), int(node_start[t + 1])
+        out.append(dict(poses=tables["poses"][a:b], vels=tables["vels"][a:b] if len(tables["vels"]) else tables["vels"],
+                        biases=tables["biases"][t:t + 1] if has_bias and len(tables["biases"]) else tables["biases"][:0],
+                        lms=tables["lms"][:0]))
+    return out
+
+
+def solve_batched(problems, params=None, lib=None, device=0, keep_values=True):
+    """Solve a list of independent packed problems as ONE block-diagonal system on this rank's GPU (vus_set_components):
+    every trajectory keeps its own lambda / accept-reject / convergence path, as separate optimizers would.
+    -> list of dict(summary fields..., values=tables or None), in input order (same shape as solve_local's result)."""
+    prob, node_start = concat_problems(problems)
+    s = Session(prob, params or LevenbergMarquardtParams(), lib=lib, device=device, components=node_start)
+    try:
+        total = s.optimize()
+        per = s.component_results()
+        vals = split_values(s.values(), node_start, has_bias=len(prob["bias_keys"]) > 0) if keep_values else [None] * len(per)
+        out = []
+        for r, v in zip(per, vals):
+            d = {k: r[k] for k in SUMMARY_FIELDS}
+            d["values"] = v
+            out.append(d)
+        solve_batched.last_stats = total
+        return out
+    finally:
+        s.close()
+
+
 def solve_sharded(make_problem, n_trajectories, params=None, lib=None, device=0, threads=4, group=None, keep_values=False):
     """Every rank builds and solves trajectories shard_range(n, rank, world) (make_problem(t) -> packed problem), then
     all ranks gather the [n, len(SUMMARY_FIELDS)] summary table.  -> (summary [n, F] float64, local results, (first, last))."""
