@@ -809,6 +809,90 @@ struct SmallBwdBody {      // per eliminated node j = s (2 m + 1):  x_j = Dinv_j
     }
   }
 };
+// factorization, per eliminated node j = s (2 m + 1): Dinv_j = D_j^-1 (unpivoted Gauss-Jordan in shared memory, the nodes of
+// a CTA advance pivot by pivot in lock step), Gl_j = U_{j-s} Dinv_j, Gr_j = U_j^T Dinv_j.   smem: G * (B * B + 1) doubles
+struct SmallElimBody {
+  static VUS_DEV void run(const BcrArgs& A, int blk, int tid, int nthr, double* sm) {
+    const int B = A.B, LD = bcr_ld(B), BB = B * B;
+    const long BBP = bcr_bbp(B);
+    const long nel = ((A.Ns + A.s - 1) / A.s) / 2;
+    double* piv = sm + VUS_SMALLB_G * BB;
+    for (int e = tid; e < VUS_SMALLB_G * BB; e += nthr) {
+      const int g = e / BB, r = (e % BB) / B, c = e % B;
+      const long m = (long)blk * VUS_SMALLB_G + g;
+      sm[e] = m < nel ? A.Dsrc[A.s * (2L * m + 1) * A.d_stride + (long)r * A.d_ld + c] : (r == c ? 1.0 : 0.0);
+    }
+    VUS_SYNC();
+    for (int p = 0; p < B; ++p) {
+      for (int g = tid; g < VUS_SMALLB_G; g += nthr) {
+        const double v = sm[g * BB + p * B + p];
+        if (!(v > 0.0)) *A.fail = 1;
+        piv[g] = 1.0 / v;
+      }
+      VUS_SYNC();
+      for (int e = tid; e < VUS_SMALLB_G * B; e += nthr) {       // pivot row
+        const int g = e / B, c = e % B;
+        double* row = sm + g * BB + p * B;
+        row[c] = (c == p) ? piv[g] : row[c] * piv[g];
+      }
+      VUS_SYNC();
+      for (int e = tid; e < VUS_SMALLB_G * B; e += nthr) {       // the other rows
+        const int g = e / B, r = e % B;
+        if (r == p) continue;
+        double* M = sm + g * BB;
+        const double f = M[r * B + p];
+        for (int c = 0; c < B; ++c) M[r * B + c] = (c == p) ? -f * M[p * B + p] : M[r * B + c] - f * M[p * B + c];
+      }
+      VUS_SYNC();
+    }
+    for (int e = tid; e < VUS_SMALLB_G * BB; e += nthr) {
+      const int g = e / BB, r = (e % BB) / B, c = e % B;
+      const long m = (long)blk * VUS_SMALLB_G + g;
+      if (m >= nel) continue;
+      const long j = A.s * (2L * m + 1);
+      const double* Di = sm + g * BB;
+      A.Dinv[j * BBP + (long)r * LD + c] = Di[r * B + c];
+      const double* Ul = A.Ucur + (j - A.s) * A.u_stride + (long)r * A.u_ld;
+      double gl = 0.0;
+      for (int k = 0; k < B; ++k) gl += Ul[k] * Di[k * B + c];
+      A.Gl[j * BBP + (long)r * LD + c] = gl;
+      if (j + A.s < A.Ns) {
+        const double* Uj = A.Ucur + j * A.u_stride + r;
+        double gr = 0.0;
+        for (int k = 0; k < B; ++k) gr += Uj[(long)k * A.u_ld] * Di[k * B + c];
+        A.Gr[j * BBP + (long)r * LD + c] = gr;
+      }
+    }
+  }
+};
+// per surviving node c = 2 m s, work item (m, r, col):  Dw_c = D_c - Gr_{c-s} U_{c-s} - Gl_{c+s} U_c^T ;  Unext_c = -Gl_{c+s} U_{c+s}
+struct SmallUpdateBody {
+  static VUS_DEV void run(const BcrArgs& A, long w) {
+    const int B = A.B, LD = bcr_ld(B);
+    const long BBP = bcr_bbp(B);
+    const int col = (int)(w % B), r = (int)((w / B) % B);
+    const long c = 2L * (w / ((long)B * B)) * A.s;
+    double acc = A.Dsrc[c * A.d_stride + (long)r * A.d_ld + col];
+    if (c - A.s >= 0) {
+      const double* G = A.Gr + (c - A.s) * BBP + (long)r * LD;
+      const double* U = A.Ucur + (c - A.s) * A.u_stride + col;
+      for (int k = 0; k < B; ++k) acc -= G[k] * U[(long)k * A.u_ld];
+    }
+    if (c + A.s < A.Ns) {
+      const long j = c + A.s;
+      const double* G = A.Gl + j * BBP + (long)r * LD;
+      const double* U = A.Ucur + c * A.u_stride + (long)col * A.u_ld;
+      for (int k = 0; k < B; ++k) acc -= G[k] * U[k];
+      if (j + A.s < A.Ns) {
+        const double* U2 = A.Ucur + j * A.u_stride + col;
+        double un = 0.0;
+        for (int k = 0; k < B; ++k) un -= G[k] * U2[(long)k * A.u_ld];
+        A.Unext[c * BBP + (long)r * LD + col] = un;
+      }
+    }
+    A.Dw[c * BBP + (long)r * LD + col] = acc;
+  }
+};
 struct SmallMatvecBody {   // work item (v, I, r):  y_I[r] = SD_I[r,:] x_I + SU_I[r,:] x_{I+1} + SU_{I-1}[:,r] x_{I-1}
   static VUS_DEV void run(const MatvecArgs& A, long w) {
     const int B = A.B, LD = bcr_ld(B);

@@ -822,8 +822,13 @@ void bcr_factor_launches(vus_handle* h, rt::stream_t st) {
     const long nact = (h->Ns + s - 1) / s;
     const int nel = (int)(nact / 2), nsv = (int)((nact + 1) / 2);
     a.s = s; a.Unext = bufs[w];
-    L_coop<BcrElimBody>(nel, 256, bcr_smem(h->B), st, a);
-    L_coop<BcrUpdateBody>(nsv, 256, bcr_smem(h->B), st, a);
+    if (h->B <= VUS_SMALLB_MAX) {
+      L_coop<SmallElimBody>((nel + VUS_SMALLB_G - 1) / VUS_SMALLB_G, 256, (size_t)VUS_SMALLB_G * (h->B * h->B + 1) * sizeof(double), st, a);
+      L_elem<SmallUpdateBody>((long)nsv * h->B * h->B, st, a);
+    } else {
+      L_coop<BcrElimBody>(nel, 256, bcr_smem(h->B), st, a);
+      L_coop<BcrUpdateBody>(nsv, 256, bcr_smem(h->B), st, a);
+    }
     a.Dsrc = h->Dw.p; a.d_ld = LD; a.d_stride = BBP;
     a.Ucur = bufs[w]; a.u_ld = LD; a.u_stride = BBP;
     w ^= 1;
@@ -1225,12 +1230,12 @@ void form_system_b(vus_handle* h, rt::stream_t st) {       // damping from h->la
 }
 void bdot(vus_handle* h, const double* a, const double* b, int slot, int op, rt::stream_t st) {
   BDotArgs r; r.C = bctx(h); r.a = a; r.b = b; r.scal = h->scal_b.p; r.slot = slot; r.op = op; r.tol = h->prm.pcg_rel_tol;
-  L_coop<BDotBody>(h->ncomp, 128, 128 * sizeof(double), st, r);
+  L_coop<BDotBody>(h->ncomp, 256, 256 * sizeof(double), st, r);
 }
 void bborder_dot(vus_handle* h, const double* Y, long ystride, int nv, double* out, rt::stream_t st) {
   ClassGuard kc_guard(KC_BORDER);
   BBorderDotArgs a; a.C = bctx(h); a.F = h->F.p; a.Y = Y; a.ystride = ystride; a.nv = nv; a.out = out;
-  L_coop<BBorderDotBody>(h->ncomp, 128, 6 * 128 * sizeof(double), st, a);
+  L_coop<BBorderDotBody>(h->ncomp, 256, 6 * 256 * sizeof(double), st, a);
 }
 void precond_setup_b(vus_handle* h, rt::stream_t st) {
   bcr_factor(h, st);
