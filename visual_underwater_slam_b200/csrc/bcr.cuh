@@ -43,6 +43,7 @@ VUS_HD long bcr_smem_doubles(int B) {
 // The assembled system (SD, SU) uses the same tile layout, so level 1 and the band operator stream it the same way.
 struct BcrArgs {
   long Ns; int B; long s;          // level stride
+  int small_g;                     // small-block kernels: supernodes per CTA
   long root_stride;                // the nodes left after the last level are the multiples of root_stride (>= Ns: node 0 only)
   const double* Dsrc; int d_ld; long d_stride;    // diagonal blocks read at this level (level 1: SD, plain; else Dw, padded)
   double* Dw;                      // working diagonal blocks [Ns], padded
@@ -752,58 +753,65 @@ struct BandMatvecBody {
 // global memory.  Same recurrences as the streaming bodies above; single source for the device and the emulation.
 #define VUS_SMALLB_MAX 16
 #define VUS_SMALLB_G 16
+template <int BT>           // BT: compile-time block size (0: A.B) so the k loops unroll and their loads overlap
 struct SmallFwdBody {      // per surviving node c = 2 m s:  b_c -= Gr_{c-s} b_{c-s} + Gl_{c+s} b_{c+s}
   static VUS_DEV void run(const BcrArgs& A, int blk, int tid, int nthr, double*) {
-    const int B = A.B, nv = A.nrhs, LD = bcr_ld(B);
+    const int B = BT ? BT : A.B, nv = A.nrhs, LD = bcr_ld(B), GN = A.small_g;
     const long BBP = bcr_bbp(B);
     const long nsv = ((A.Ns + A.s - 1) / A.s + 1) / 2;
-    for (int e = tid; e < VUS_SMALLB_G * B * nv; e += nthr) {
-      const int r = e % B, g = (e / B) % VUS_SMALLB_G, v = e / (B * VUS_SMALLB_G);
-      const long m = (long)blk * VUS_SMALLB_G + g;
+    for (int e = tid; e < GN * B * nv; e += nthr) {
+      const int r = e % B, g = (e / B) % GN, v = e / (B * GN);
+      const long m = (long)blk * GN + g;
       if (m >= nsv) continue;
       const long c = 2L * m * A.s, jl = c - A.s, jh = c + A.s;
       const double* X = A.X + (long)v * A.xstride;
       double acc = 0.0;
       if (jl >= 0) {
         const double* G = A.Gr + jl * BBP + (long)r * LD;
+#pragma unroll
         for (int k = 0; k < B; ++k) acc += G[k] * X[jl * B + k];
       }
       if (jh < A.Ns) {
         const double* G = A.Gl + jh * BBP + (long)r * LD;
+#pragma unroll
         for (int k = 0; k < B; ++k) acc += G[k] * X[jh * B + k];
       }
       A.X[(long)v * A.xstride + c * B + r] -= acc;
     }
   }
 };
+template <int BT>
 struct SmallBwdBody {      // per eliminated node j = s (2 m + 1):  x_j = Dinv_j b_j - Gl_j^T x_{j-s} - Gr_j^T x_{j+s};  s = 0: the root
   static VUS_DEV void run(const BcrArgs& A, int blk, int tid, int nthr, double* sm) {
-    const int B = A.B, nv = A.nrhs, LD = bcr_ld(B);
+    const int B = BT ? BT : A.B, nv = A.nrhs, LD = bcr_ld(B), GN = A.small_g;
     const long BBP = bcr_bbp(B);
     const long nel = A.s > 0 ? ((A.Ns + A.s - 1) / A.s) / 2 : (A.Ns + A.root_stride - 1) / A.root_stride;
-    for (int e = tid; e < VUS_SMALLB_G * B * nv; e += nthr) {
-      const int r = e % B, g = (e / B) % VUS_SMALLB_G, v = e / (B * VUS_SMALLB_G);
-      const long m = (long)blk * VUS_SMALLB_G + g;
+    for (int e = tid; e < GN * B * nv; e += nthr) {
+      const int r = e % B, g = (e / B) % GN, v = e / (B * GN);
+      const long m = (long)blk * GN + g;
       if (m >= nel) continue;
       const long j = A.s > 0 ? A.s * (2L * m + 1) : m * A.root_stride, jl = j - A.s, jh = j + A.s;
       const double* X = A.X + (long)v * A.xstride;
       const double* Dj = A.Dinv + j * BBP + (long)r * LD;
       double acc = 0.0;
+#pragma unroll
       for (int k = 0; k < B; ++k) acc += Dj[k] * X[j * B + k];
       if (A.s > 0 && jl >= 0) {
         const double* G = A.Gl + j * BBP + r;
+#pragma unroll
         for (int k = 0; k < B; ++k) acc -= G[(long)k * LD] * X[jl * B + k];
       }
       if (A.s > 0 && jh < A.Ns) {
         const double* G = A.Gr + j * BBP + r;
+#pragma unroll
         for (int k = 0; k < B; ++k) acc -= G[(long)k * LD] * X[jh * B + k];
       }
       sm[e] = acc;
     }
     VUS_SYNC();                                           // x_j overwrites b_j: every row of the node is computed first
-    for (int e = tid; e < VUS_SMALLB_G * B * nv; e += nthr) {
-      const int r = e % B, g = (e / B) % VUS_SMALLB_G, v = e / (B * VUS_SMALLB_G);
-      const long m = (long)blk * VUS_SMALLB_G + g;
+    for (int e = tid; e < GN * B * nv; e += nthr) {
+      const int r = e % B, g = (e / B) % GN, v = e / (B * GN);
+      const long m = (long)blk * GN + g;
       if (m >= nel) continue;
       A.X[(long)v * A.xstride + (A.s > 0 ? A.s * (2L * m + 1) : m * A.root_stride) * B + r] = sm[e];
     }
@@ -893,9 +901,10 @@ struct SmallUpdateBody {
     A.Dw[c * BBP + (long)r * LD + col] = acc;
   }
 };
+template <int BT>
 struct SmallMatvecBody {   // work item (v, I, r):  y_I[r] = SD_I[r,:] x_I + SU_I[r,:] x_{I+1} + SU_{I-1}[:,r] x_{I-1}
   static VUS_DEV void run(const MatvecArgs& A, long w) {
-    const int B = A.B, LD = bcr_ld(B);
+    const int B = BT ? BT : A.B, LD = bcr_ld(B);
     const long BBP = bcr_bbp(B);
     const int r = (int)(w % B);
     const long I = (w / B) % A.Ns;
@@ -903,13 +912,16 @@ struct SmallMatvecBody {   // work item (v, I, r):  y_I[r] = SD_I[r,:] x_I + SU_
     const double* x = A.x + (long)v * A.xstride;
     const double* d = A.SD + I * BBP + (long)r * LD;
     double acc = 0.0;
+#pragma unroll
     for (int k = 0; k < B; ++k) acc += d[k] * x[I * B + k];
     if (I + 1 < A.Ns) {
       const double* u = A.SU + I * BBP + (long)r * LD;
+#pragma unroll
       for (int k = 0; k < B; ++k) acc += u[k] * x[(I + 1) * B + k];
     }
     if (I > 0) {
       const double* u = A.SU + (I - 1) * BBP + r;
+#pragma unroll
       for (int k = 0; k < B; ++k) acc += u[(long)k * LD] * x[(I - 1) * B + k];
     }
     A.y[(long)v * A.ystride + I * B + r] = acc;
