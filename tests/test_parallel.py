@@ -23,7 +23,7 @@ n = int(sys.argv[2])
 def make(t):
     d = synthetic.make_trajectory_graph(40, seed=4 + t, n_loops=2, loop_min_gap=10)
     return d["graph"].to_problem(d["initial"])
-table, local, (first, last) = parallel.solve_sharded(make, n, lib=lib, threads=2, keep_values=True)
+table, local, (first, last) = parallel.solve_sharded(make, n, lib=lib, threads=2, keep_values=True, batched=len(sys.argv) > 4)
 if rank == 0:
     np.save(sys.argv[3], table)
 np.save(sys.argv[3] + ".rank%d.npy" % rank, np.stack([r["values"]["poses"] for r in local]) if local else np.zeros((0,)))
@@ -45,7 +45,7 @@ def test_shard_range_covers_everything():
                 assert spans[r][0] <= t < spans[r][1]
 
 
-def _run(world, n, out, tmp_path):
+def _run(world, n, out, tmp_path, extra=()):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     procs = []
@@ -53,7 +53,7 @@ def _run(world, n, out, tmp_path):
     for rank in range(world):
         env = dict(os.environ, WORLD_SIZE=str(world), RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
                    OMP_NUM_THREADS="1")
-        procs.append(subprocess.Popen([sys.executable, str(script), ROOT, str(n), str(out)], env=env,
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT, str(n), str(out), *extra], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     for p in procs:
         o, _ = p.communicate(timeout=600)
@@ -73,6 +73,26 @@ def test_two_rank_gloo_equals_one_rank(tmp_path):
     p1 = np.load(str(one) + ".rank0.npy")
     p2 = np.concatenate([np.load(str(two) + ".rank%d.npy" % r) for r in range(2)], 0)
     assert np.array_equal(p1, p2)
+
+
+def test_two_rank_gloo_batched_shards_match_one_handle_per_trajectory(tmp_path):
+    """Every rank solves its shard as ONE block-diagonal system (vus_set_components); per trajectory the LM path and the
+    result equal the one-handle-per-trajectory run (not bit for bit: a component may receive one more refinement pass
+    when another component of its batch needs it)."""
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "visual_underwater_slam_b200", "csrc"), "emu"], check=True)
+    n = 5
+    one, two = tmp_path / "one.npy", tmp_path / "two.npy"
+    _run(1, n, one, tmp_path)
+    _run(2, n, two, tmp_path, extra=("batched",))
+    t1, t2 = np.load(one), np.load(two)
+    names = parallel.SUMMARY_FIELDS
+    for f in ("iterations", "inner_iterations", "final_lambda"):
+        assert np.array_equal(t1[:, names.index(f)], t2[:, names.index(f)]), f
+    fe = names.index("final_error")
+    assert np.all(np.abs(t1[:, fe] - t2[:, fe]) <= 1e-9 * t1[:, fe])
+    p1 = np.load(str(one) + ".rank0.npy")
+    p2 = np.concatenate([np.load(str(two) + ".rank%d.npy" % r) for r in range(2)], 0)
+    assert np.abs(p1 - p2).max() < 1e-7
 
 
 PART_WORKER = r'''

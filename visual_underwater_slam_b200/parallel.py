@@ -147,9 +147,11 @@ def solve_batched(problems, params=None, lib=None, device=0, keep_values=True):
         s.close()
 
 
-def solve_sharded(make_problem, n_trajectories, params=None, lib=None, device=0, threads=4, group=None, keep_values=False):
+def solve_sharded(make_problem, n_trajectories, params=None, lib=None, device=0, threads=4, group=None, keep_values=False,
+                  batched=False):
     """Every rank builds and solves trajectories shard_range(n, rank, world) (make_problem(t) -> packed problem), then
-    all ranks gather the [n, len(SUMMARY_FIELDS)] summary table.  -> (summary [n, F] float64, local results, (first, last))."""
+    all ranks gather the [n, len(SUMMARY_FIELDS)] summary table.  -> (summary [n, F] float64, local results, (first, last)).
+    batched=True solves a rank's shard as ONE block-diagonal system (solve_batched) instead of one handle per trajectory."""
     import torch
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
@@ -157,7 +159,11 @@ def solve_sharded(make_problem, n_trajectories, params=None, lib=None, device=0,
     else:
         rank, world = 0, 1
     first, last = shard_range(n_trajectories, rank, world)
-    local = solve_local([make_problem(t) for t in range(first, last)], params, lib, device, threads, keep_values=keep_values)
+    shard = [make_problem(t) for t in range(first, last)]
+    if batched and shard:
+        local = solve_batched(shard, params, lib, device, keep_values=keep_values)
+    else:
+        local = solve_local(shard, params, lib, device, threads, keep_values=keep_values)
     table = np.array([[r[k] for k in SUMMARY_FIELDS] for r in local], dtype=np.float64).reshape(last - first, len(SUMMARY_FIELDS))
     if world == 1:
         return table, local, (first, last)
