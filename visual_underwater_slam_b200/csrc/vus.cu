@@ -182,6 +182,7 @@ struct vus_handle {
   long nlong = 0;
   DBuf<double> ulong;
   double cur_lambda = 0.0;
+  bool z0_valid = false;         // column 6 of Z holds M^-1 gs (band part of the first preconditioner application)
   DBuf<double> C, gl, Cinv, E, Pp, Pl;
   // BCR
   DBuf<double> Dw, U1, U2, Dinv, Gl, Gr, Z, Zr, SbInv;
@@ -657,7 +658,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
     const size_t nb = (size_t)h->Ns * bcr_bbp(h->B);
     for (DBuf<double>* b : {&h->Dw, &h->U1, &h->U2, &h->Dinv, &h->Gl, &h->Gr}) { b->alloc(nb); b->zero(st); }
   }
-  h->Z.alloc(6 * h->Lc); h->Zr.alloc(6 * h->Lc); h->SbInv.alloc(36 * std::max<long>(NB, 1));
+  h->Z.alloc(7 * h->Lc); h->Zr.alloc(6 * h->Lc); h->SbInv.alloc(36 * std::max<long>(NB, 1));
   if (h->n_owned >= 0) {
     if (h->has_bias || FS.n || NV) return fail(h, VUS_ERR_UNSUPPORTED, "pose-range partition supports pose graphs (PriorFactorPose3 / BetweenFactorPose3) only");
     if (h->n_owned > NX) return fail(h, VUS_ERR_INVALID, "vus_set_partition: more owned nodes than nodes");
@@ -930,12 +931,21 @@ void apply_band(vus_handle* h, double* Y, long ystride, const double* X, long xs
 }
 
 // preconditioner set-up for the current damped system: BCR of the band, Z = M^-1 F, Sb^-1
-void precond_setup(vus_handle* h, rt::stream_t st) {
+// with_rhs: the band solve of the right-hand side gs rides along as a seventh vector (the DMMA panel is 8 wide, so it
+// costs nothing): the first preconditioner application of the PCG that follows takes it from there.
+void precond_setup(vus_handle* h, rt::stream_t st, bool with_rhs = false) {
   bcr_factor(h, st);
+  h->z0_valid = false;
   if (h->has_bias) {
     BorderColsArgs c; c.F = h->F.p; c.Z = h->Z.p; c.len = h->Lc; c.zstride = h->Lc; c.R = h->Zr.p;
     L_elem<BorderColsBody>(h->Lc * 6, st, c);
-    bcr_solve(h, h->Z.p, h->Lc, 6, st);
+    if (with_rhs) {
+      rt::d2d(h->Z.p + 6 * h->Lc, h->gs.p, h->Lc * sizeof(double), st);
+      bcr_solve(h, h->Z.p, h->Lc, 7, st);
+      h->z0_valid = true;
+    } else {
+      bcr_solve(h, h->Z.p, h->Lc, 6, st);
+    }
     // The bias Schur complement Hbb - F^T M^-1 F cancels to ~1e-8 of its terms on short trajectories (the bias is barely
     // observable), far below the raw ~1e-7 accuracy of the band solve.  With the residual R = F - M Z of the computed
     // Z,  F^T M^-1 F = F^T Z + Z^T R + O(|dZ|^2): one 6-vector band product and a 6x6 dot product restore the
@@ -956,8 +966,14 @@ void precond_setup(vus_handle* h, rt::stream_t st) {
 
 // z = P^-1 r  (z and r are full vectors of length L)
 void precond_apply(vus_handle* h, double* z, const double* r, rt::stream_t st) {
-  rt::d2d(z, r, h->L * sizeof(double), st);
-  bcr_solve(h, z, h->Lc, 1, st);
+  if (h->z0_valid) {                                   // r is gs: its band solve was done with the border columns
+    h->z0_valid = false;
+    rt::d2d(z, h->Z.p + 6 * h->Lc, h->Lc * sizeof(double), st);
+    rt::d2d(z + h->Lc, r + h->Lc, (h->L - h->Lc) * sizeof(double), st);
+  } else {
+    rt::d2d(z, r, h->L * sizeof(double), st);
+    bcr_solve(h, z, h->Lc, 1, st);
+  }
   if (h->has_bias) {
     border_dot(h, z, h->Lc, 1, st);
     BorderSolveArgs b; b.SbInv = h->SbInv.p; b.rb = r + h->Lc; b.partials = h->bpart.p; b.grid = h->red_grid; b.xb = z + h->Lc;
@@ -1025,7 +1041,7 @@ int pcg(vus_handle* h, rt::stream_t st, bool* converged) {
   reduce(h, h->r.p, h->r.p, h->Lr, S_RR, RED_STORE, st);
   const double rr0 = read_scalar(h, S_RR, st);
   *converged = true;
-  if (!(rr0 > 0.0)) return 0;
+  if (!(rr0 > 0.0)) { h->z0_valid = false; return 0; }
   const double tol2 = h->prm.pcg_rel_tol * h->prm.pcg_rel_tol * rr0;
   *converged = false;
   int it = 0;
@@ -1098,7 +1114,7 @@ bool solve_damped(vus_handle* h, double lambda, rt::stream_t st, int* iters, boo
   double t0 = timing ? now_ms() : 0;
   form_system(h, lambda, st);
   if (timing) { rt::sync(st); double t1 = now_ms(); h->res.ms_schur += t1 - t0; t0 = t1; }
-  precond_setup(h, st);
+  precond_setup(h, st, h->n_owned < 0);
   if (timing) { rt::sync(st); double t1 = now_ms(); h->res.ms_factor += t1 - t0; t0 = t1; }
   if (read_fail(h, st)) { *iters = 0; return false; }
   bool conv = false;
@@ -1260,10 +1276,13 @@ void bborder_dot(vus_handle* h, const double* Y, long ystride, int nv, double* o
 }
 void precond_setup_b(vus_handle* h, rt::stream_t st) {
   bcr_factor(h, st);
+  h->z0_valid = false;
   if (!h->has_bias) return;
   BorderColsArgs c; c.F = h->F.p; c.Z = h->Z.p; c.len = h->Lc; c.zstride = h->Lc; c.R = h->Zr.p;
   L_elem<BorderColsBody>(h->Lc * 6, st, c);
-  bcr_solve(h, h->Z.p, h->Lc, 6, st);
+  rt::d2d(h->Z.p + 6 * h->Lc, h->gs.p, h->Lc * sizeof(double), st);      // the right-hand side rides along (precond_setup)
+  bcr_solve(h, h->Z.p, h->Lc, 7, st);
+  h->z0_valid = true;
   apply_band(h, h->Zr.p, h->Lc, h->Z.p, h->Lc, 6, st);     // second-order correction of every component's complement
   L_elem<BorderResidBody>(h->Lc * 6, st, c);
   bborder_dot(h, h->Z.p, h->Lc, 6, h->cdots.p, st);
@@ -1274,8 +1293,14 @@ void precond_setup_b(vus_handle* h, rt::stream_t st) {
   L_elem<BBorderSchurBody>(h->ncomp, st, sa);
 }
 void precond_apply_b(vus_handle* h, double* z, const double* r, rt::stream_t st) {
-  rt::d2d(z, r, h->L * sizeof(double), st);
-  bcr_solve(h, z, h->Lc, 1, st);
+  if (h->z0_valid) {
+    h->z0_valid = false;
+    rt::d2d(z, h->Z.p + 6 * h->Lc, h->Lc * sizeof(double), st);
+    rt::d2d(z + h->Lc, r + h->Lc, (h->L - h->Lc) * sizeof(double), st);
+  } else {
+    rt::d2d(z, r, h->L * sizeof(double), st);
+    bcr_solve(h, z, h->Lc, 1, st);
+  }
   if (!h->has_bias) return;
   bborder_dot(h, z, h->Lc, 1, h->cdots.p, st);
   ClassGuard kc_b(KC_BORDER);
@@ -1331,7 +1356,7 @@ int pcg_b(vus_handle* h, rt::stream_t st, bool* converged) {
   bool bad = false;
   double worst = worst_ratio(h, sb, st, &bad);
   *converged = !bad && worst <= 1.0;
-  if (*converged || bad) return 0;
+  if (*converged || bad) { h->z0_valid = false; return 0; }
   int it = 0;
   double worst_outer = worst;
   for (int outer = 0; outer < 6 && !*converged; ++outer) {
