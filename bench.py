@@ -203,6 +203,32 @@ def roofline(res, lay, nf, ms_class, launches, hbm_peak, steps):
     return out
 
 
+def ncu_traffic(name, lay, t):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of a kernel class over the timed region, from the committed
+    `ncu --set full` captures of its level-1 launches (profiles/r1_ncu_summary.json: 20 000-pose graph, same 81 x 81
+    supernodes): measured bytes per CTA x the CTAs the class ran here.  None when no capture covers the class."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")) as fh:
+            cap = json.load(fh)
+    except Exception:
+        return None
+    per_cta = lambda k: (cap[k]["dram_read_MB"] + cap[k]["dram_write_MB"]) * 1e6 / cap[k]["grid"]
+    Ns = lay["Ns"]
+    levels = max(1, int(np.ceil(np.log2(max(Ns, 2)))))
+    try:
+        if name == "bcr_factor":            # launches = (elim + update per level + root) per factorization
+            facts = t["launches"] / (2 * levels + 1)
+            return facts * ((Ns - 1) * per_cta("elim") + Ns * per_cta("update"))
+        if name == "bcr_solve":
+            applies = t["launches"] / (2 * levels + 1)
+            return applies * (Ns * per_cta("fwd") + (Ns - 1) * per_cta("bwd"))
+        if name == "matvec":
+            return t["launches"] * Ns * per_cta("matvec")
+    except KeyError:
+        return None
+    return None
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -343,7 +369,8 @@ def main():
             t = rf_table[name]
             src = peak_src if t["bound"] == "hbm" else "FP64 DMMA issue-rate microbenchmark, this pool (profiles/r1_dmma_microbench.txt); no FP64 figure in MEASURED_PEAKS.json"
             return {"bound": t["bound"], "kernel": name, "achieved": t["achieved"], "peak": t["peak"], "unit": t["unit"], "frac": t["frac"],
-                    "traffic": None, "peak_source": src, "device_ms": t["ms"], "launches": t["launches"]}
+                    "traffic": ncu_traffic(name, lay, t), "traffic_unit": "bytes over the timed region (algorithmic work over the same region: 'work')",
+                    "work": t["work"], "peak_source": src, "device_ms": t["ms"], "launches": t["launches"]}
         top = max(rf_table, key=lambda k: rf_table[k]["ms"])               # dominant kernel class by device time
         rf = line(top)
         hb = {k: v for k, v in rf_table.items() if v["bound"] == "hbm"}

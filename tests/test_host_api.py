@@ -204,3 +204,53 @@ def test_marginals_facade_keys_and_errors(emu):
     assert np.array_equal(jm.at(V(4), B(0)), jm.at(B(0), V(4)).T)
     with pytest.raises(KeyError):
         m.marginalCovariance(X(999))
+
+
+def test_marginals_and_batched_error_paths(emu):
+    """Error behaviour of the rows added after the path: bad queries, unsupported combinations, malformed batches."""
+    from visual_underwater_slam_b200 import parallel
+    d = synthetic.make_pose_graph(30, seed=2, n_loops=2)
+    prob = d["graph"].to_problem(d["initial"])
+    s = Session(prob, lib=emu)
+    with pytest.raises(RuntimeError, match="out of range"):
+        s.marginal_covariance([("pose", 30)])
+    with pytest.raises(RuntimeError, match="out of range"):
+        s.marginal_covariance([("bias", 0)])                      # a pure pose graph has no bias variable
+    with pytest.raises(RuntimeError, match="no batched optimize"):
+        s.component_results()
+    s.close()
+    with pytest.raises(RuntimeError, match="node_start"):
+        Session(prob, lib=emu, components=[1, 30])                # must start at 0
+    with pytest.raises(RuntimeError, match="cover every pose"):
+        Session(prob, lib=emu, components=[0, 10, 20])            # 30 poses
+    two, node_start = parallel.concat_problems([prob, prob])
+    sb = Session(two, lib=emu, components=node_start)
+    with pytest.raises(RuntimeError, match="batched graph"):
+        sb.marginal_covariance([("pose", 0)])
+    with pytest.raises(RuntimeError, match="batched graph"):
+        sb.solve_step(1e-3)
+    sb.close()
+    ds = synthetic.make_trajectory_graph(20, seed=3, n_landmarks=10, pixel_noise=1.0)
+    with pytest.raises(NotImplementedError, match="stereo"):
+        parallel.concat_problems([ds["graph"].to_problem(ds["initial"])] * 2)
+    with pytest.raises(ValueError):
+        parallel.concat_problems([])
+
+
+def test_graph_and_values_merge_for_incremental_updates():
+    """NonlinearFactorGraph.push_back(graph) keeps insertion order across graphs; Values.insert(Values) refuses duplicates."""
+    d = synthetic.make_trajectory_graph(12, seed=1, pixel_noise=1.0)
+    g = gtsam.NonlinearFactorGraph()
+    g.push_back(d["graph"])
+    g.push_back(d["graph"])
+    n = d["graph"].size()
+    assert g.size() == 2 * n
+    orig = np.sort(np.concatenate([g.table(t)["orig"] for t in ("prior_pose", "prior_vel", "between", "dvl", "stereo", "imu")]))
+    assert np.array_equal(orig, np.arange(2 * n))
+    v = gtsam.Values()
+    v.insert(d["initial"])
+    assert v.size() == d["initial"].size()
+    with pytest.raises(RuntimeError, match="already exists"):
+        v.insert(d["initial"])
+    g.resize(0)
+    assert g.size() == 0
