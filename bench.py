@@ -187,6 +187,16 @@ def roofline(res, lay, nf, ms_class, launches, hbm_peak, steps):
     err_bytes = sum((ALG_BYTES[k] - {"prior_pose": 336, "prior_vel": 96, "between": 624, "dvl": 240, "stereo": 240, "imu": 1800}[k] + 8) * nf[k]
                     for k in nf)
     add("error", "hbm", err_bytes * (tries + steps), 1e6, hbm_peak, "GB/s")
+    # assembly (SURVEY.md 8d "fused linearize+assemble" accounting): whitened J and r of the chain factors read once + one write
+    # of each distinct Hessian / gradient entry they touch; stereo: the fused per-observation products (Pp 224 B + Pl 96 B)
+    # read once + the pose / landmark blocks written once.  The chain part is bound by FP64 atomics, not by bytes.
+    jr = {"prior_pose": 336, "prior_vel": 96, "between": 624, "dvl": 240, "imu": 1800}
+    hess = {"prior_pose": 36 + 6, "prior_vel": 9 + 3, "between": 144 + 12, "dvl": 81 + 9, "imu": 297}
+    chain_bytes = sum((jr[k] + 8 * hess[k]) * nf.get(k, 0) for k in jr)
+    add("assemble", "hbm", chain_bytes * lin, 1e6, hbm_peak, "GB/s")
+    nst = nf.get("stereo", 0)
+    n_obs_poses = min(nf.get("dvl", 0) + 1, nst) if nst else 0
+    add("stereo_assemble", "hbm", (nst * 320 + n_obs_poses * (36 + 6) * 8 + lay.get("n_landmarks", 0) * 12 * 8) * lin, 1e6, hbm_peak, "GB/s")
     # BCR solve: one application streams Gr, Gl (forward) and Dinv, Gl, Gr (backward) of every eliminated node once
     per_apply_launches = 2 * levels + 1
     applies = launches.get("bcr_solve", 0) / per_apply_launches
