@@ -235,6 +235,148 @@ struct BRemBorderBody {
   }
 };
 
+// =====================================================================================  loop closures by capacitance
+// A trajectory of config 4 has a handful of loop closures.  Their off-band blocks W = U S U^T (U selects the 2 x 6 pose
+// dofs of every closure, S = [[0, H_pq], [H_qp, 0]] per closure) are a rank-12 update per closure of the exactly
+// factored part P (band + bias border), and plain PCG needs ~rank iterations per solve -- ~100 for the slowest of 512
+// components.  With R = 12 * (max closures per component) <= 96 columns the update is inverted exactly instead
+// (Woodbury):  A^-1 = P^-1 - Y (I + S K)^-1 S U^T P^-1,  Y = P^-1 U,  K = U^T Y.  The R columns of Y are R / 6
+// six-vector applications of P^-1 for the WHOLE batch (column j of every component rides in the same vector), the
+// R x R capacitance matrix of a component is inverted by one CTA, and PCG on top needs 2-3 iterations of refinement.
+struct BWbCtx {
+  const int* node;      // [ncomp][2 * lmax]  end nodes (p, q) of closure l of the component, -1: unused slot
+  const long* blk;      // [ncomp][lmax]      offset of the REM block (p, q) in Hval
+  int lmax, R;
+};
+// unit right-hand sides: work item (c, v) sets column j0 + v of component c
+struct BWbUnitArgs { BCtx C; BWbCtx W; double* Y; long L; int j0; };
+struct BWbUnitBody {
+  static VUS_DEV void run(const BWbUnitArgs& A, long w) {
+    const int v = (int)(w % 6);
+    const long c = w / 6;
+    const int col = A.j0 + v, l = col / 12, side = (col % 12) / 6, a = col % 6;
+    const int node = A.W.node[(c * A.W.lmax + l) * 2 + side];
+    if (node >= 0) A.Y[(long)v * A.L + (long)node * A.C.D + a] = 1.0;
+  }
+};
+// multi-vector border part of P^-1 for right-hand sides with a ZERO bias part:  xb[c][v] = -SbInv_c (F_c^T y_v)
+struct BBorderMultiArgs { BCtx C; const double* SbInv; const double* dots; double* Y; long L; int nv; const double* Z; long zstride; };
+struct BBorderSolveMultiBody {      // work item (c, v, r)
+  static VUS_DEV void run(const BBorderMultiArgs& A, long w) {
+    const int r = (int)(w % 6), v = (int)((w / 6) % A.nv);
+    const long c = w / (6 * A.nv);
+    double s = 0.0;
+    for (int k = 0; k < 6; ++k) s -= A.SbInv[c * 36 + r * 6 + k] * A.dots[c * (A.nv * 6) + v * 6 + k];
+    A.Y[(long)v * A.L + A.C.Lc + 6 * c + r] = s;
+  }
+};
+struct BSubZxbMultiBody {           // work item (v, i):  y_v[i] -= sum_k Z_k[i] xb[comp(i)][v][k]
+  static VUS_DEV void run(const BBorderMultiArgs& A, long w) {
+    const long i = w % A.C.Lc;
+    const int v = (int)(w / A.C.Lc);
+    const double* xb = A.Y + (long)v * A.L + A.C.Lc + 6 * (long)A.C.node_comp[i / A.C.D];
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s += A.Z[(long)k * A.zstride + i] * xb[k];
+    A.Y[(long)v * A.L + i] -= s;
+  }
+};
+// dof (in the camera vector) of capacitance row m of component c, -1 for an unused slot
+VUS_DEV long wb_dof(const BWbCtx& W, int D, long c, int m) {
+  const int l = m / 12, side = (m % 12) / 6, a = m % 6;
+  const int node = W.node[(c * W.lmax + l) * 2 + side];
+  return node < 0 ? -1 : (long)node * D + a;
+}
+// (S t)[i] for row i = (l, side, a): side p -> sum_b H_pq[a][b] t[(l, q, b)] ; side q -> sum_b H_pq[b][a] t[(l, p, b)]
+VUS_DEV double wb_S_row(const BWbCtx& W, int D, const double* Hval, long c, int i, const double* t, int tstride) {
+  const int l = i / 12, side = (i % 12) / 6, a = i % 6;
+  if (W.node[(c * W.lmax + l) * 2] < 0) return 0.0;
+  const double* H = Hval + W.blk[c * W.lmax + l];
+  double s = 0.0;
+  for (int b = 0; b < 6; ++b)
+    s += (side == 0 ? H[a * D + b] * t[(long)(l * 12 + 6 + b) * tstride] : H[b * D + a] * t[(long)(l * 12 + b) * tstride]);
+  return s;
+}
+// capacitance matrix of every component, inverted in shared memory: CapInv_c = (I + S_c K_c)^-1, K_c[m][j] = Y_j[dof(c, m)].
+// Gauss-Jordan with partial pivoting on the augmented [Cap | I] (R x 2R doubles of shared memory + R for K gathering is
+// avoided by building Cap row by row from global Y).  One CTA per component.
+struct BWbCapArgs { BCtx C; BWbCtx W; const double* Y; long L; const double* Hval; double* CapInv; int* fail; };
+struct BWbCapBody {
+  static VUS_DEV void run(const BWbCapArgs& A, int c, int tid, int nthr, double* sm) {
+    const int R = A.W.R, R2 = 2 * R, D = A.C.D;
+    double* M = sm;                   // [R][2R]
+    double* aux = sm + (long)R * R2;  // [R] multipliers | [1] pivot row
+    // K into the right half first (as scratch), then Cap = I + S K into the left half
+    for (int e = tid; e < R * R; e += nthr) {
+      const int m = e / R, j = e % R;
+      const long d = wb_dof(A.W, D, c, m);
+      M[m * R2 + R + j] = d < 0 ? 0.0 : A.Y[(long)j * A.L + d];
+    }
+    VUS_SYNC();
+    for (int e = tid; e < R * R; e += nthr) {
+      const int i = e / R, j = e % R;
+      M[i * R2 + j] = (i == j ? 1.0 : 0.0) + wb_S_row(A.W, D, A.Hval, c, i, M + R + j, R2);
+    }
+    VUS_SYNC();
+    for (int e = tid; e < R * R; e += nthr) { const int i = e / R, j = e % R; M[i * R2 + R + j] = i == j ? 1.0 : 0.0; }
+    VUS_SYNC();
+    for (int p = 0; p < R; ++p) {
+      if (tid == 0) {                                   // partial pivoting: largest |entry| of column p at or below the diagonal
+        int best = p;
+        double bv = fabs(M[p * R2 + p]);
+        for (int i = p + 1; i < R; ++i) { const double v = fabs(M[i * R2 + p]); if (v > bv) { bv = v; best = i; } }
+        if (!(bv > 0.0)) *A.fail = 1;
+        aux[R] = (double)best;
+      }
+      VUS_SYNC();
+      const int best = (int)aux[R];
+      if (best != p)
+        for (int j = tid; j < R2; j += nthr) { const double v = M[p * R2 + j]; M[p * R2 + j] = M[best * R2 + j]; M[best * R2 + j] = v; }
+      VUS_SYNC();
+      for (int i = tid; i < R; i += nthr) aux[i] = M[i * R2 + p];
+      VUS_SYNC();
+      const double d = 1.0 / aux[p];
+      for (int j = tid; j < R2; j += nthr) M[p * R2 + j] *= d;
+      VUS_SYNC();
+      for (int e = tid; e < R * R2; e += nthr) {
+        const int i = e / R2, j = e % R2;
+        if (i != p) M[i * R2 + j] -= aux[i] * M[p * R2 + j];
+      }
+      VUS_SYNC();
+    }
+    for (int e = tid; e < R * R; e += nthr) { const int i = e / R, j = e % R; A.CapInv[((long)c * R + i) * R + j] = M[i * R2 + R + j]; }
+  }
+};
+// w_c = CapInv_c S_c U^T z   (one CTA per component; 2R doubles of shared memory)
+struct BWbSmallArgs { BCtx C; BWbCtx W; const double* z; const double* Hval; const double* CapInv; double* wout; };
+struct BWbSmallBody {
+  static VUS_DEV void run(const BWbSmallArgs& A, int c, int tid, int nthr, double* sm) {
+    const int R = A.W.R, D = A.C.D;
+    double* t = sm;
+    double* st = sm + R;
+    for (int m = tid; m < R; m += nthr) { const long d = wb_dof(A.W, D, c, m); t[m] = d < 0 ? 0.0 : A.z[d]; }
+    VUS_SYNC();
+    for (int i = tid; i < R; i += nthr) st[i] = wb_S_row(A.W, D, A.Hval, c, i, t, 1);
+    VUS_SYNC();
+    for (int j = tid; j < R; j += nthr) {
+      const double* row = A.CapInv + ((long)c * R + j) * R;
+      double s = 0.0;
+      for (int i = 0; i < R; ++i) s += row[i] * st[i];
+      A.wout[(long)c * R + j] = s;
+    }
+  }
+};
+// z[i] -= sum_j Y_j[i] w[comp(i)][j]     (all dofs, camera and bias)
+struct BWbSubArgs { BCtx C; const double* Y; long L; const double* w; int R; double* z; };
+struct BWbSubBody {
+  static VUS_DEV void run(const BWbSubArgs& A, long i) {
+    const double* w = A.w + (long)comp_of_dof(A.C, i) * A.R;
+    double s = 0.0;
+    for (int j = 0; j < A.R; ++j) s += A.Y[(long)j * A.L + i] * w[j];
+    A.z[i] -= s;
+  }
+};
+
 // ---- per-component sums of per-factor values (graph error, linearised error): out[c] = sum_{q in c} e[list[q]]
 struct BErrSumArgs { const double* e; const int* ptr; const int* list; double* out; };
 struct BErrSumBody {

@@ -205,6 +205,11 @@ struct vus_handle {
   DBuf<long> seg;
   DBuf<double> scal_b, lam_c, acc_c, cdots, cdots2, err_c;
   std::vector<vus_component_result> comp_res;
+  // loop closures of a batched graph by capacitance (batch.cuh): R = 12 * (max closures per component) columns, 0 = off
+  int wb_R = 0, wb_lmax = 0;
+  DBuf<int> wb_node;
+  DBuf<long> wb_blk;
+  DBuf<double> wbY, wbCapInv, wbW;
   // CUDA graphs of the fixed launch sequences + the stream used when the caller passes NULL (capture needs a real stream)
   GraphCache g_factor;
   std::map<std::tuple<const double*, long, int>, GraphCache> g_solve;
@@ -364,7 +369,7 @@ PairDst band_dst(const vus_handle* h, long p, long q, const std::map<std::pair<l
 }
 
 // batched mode: component of every node, dof segments, per-component factor lists (errors) and IMU lists (bias blocks)
-int analyze_components(vus_handle* h, rt::stream_t st) {
+int analyze_components(vus_handle* h, rt::stream_t st, const std::map<std::pair<long, long>, long>& rem_index) {
   const int nc = h->ncomp;
   const long NX = h->nvar[0];
   std::vector<int> node_comp(h->Npad, nc - 1);
@@ -406,6 +411,29 @@ int analyze_components(vus_handle* h, rt::stream_t st) {
   h->node_comp.upload(node_comp, st); h->seg.upload(seg, st);
   h->cf_ptr.upload(cf_ptr, st); h->cf_list.upload(cf_list, st);
   h->ci_ptr.upload(ci_ptr, st); h->ci_list.upload(ci_list, st);
+  // closures per component (unique off-band node pairs p < q); capacitance solve when every component has at most 8
+  h->wb_R = 0; h->wb_lmax = 0;
+  if (!rem_index.empty()) {
+    std::vector<int> cnt(nc, 0);
+    for (const auto& kv : rem_index)
+      if (kv.first.first < kv.first.second) cnt[node_comp[kv.first.first]]++;
+    const int lmax = *std::max_element(cnt.begin(), cnt.end());
+    if (lmax >= 1 && lmax <= 8) {
+      std::vector<int> wnode((size_t)nc * lmax * 2, -1);
+      std::vector<long> wblk((size_t)nc * lmax, 0);
+      std::fill(cnt.begin(), cnt.end(), 0);
+      for (const auto& kv : rem_index) {
+        const long p = kv.first.first, q = kv.first.second;
+        if (p >= q) continue;
+        const int c = node_comp[p], l = cnt[c]++;
+        wnode[((size_t)c * lmax + l) * 2] = (int)p; wnode[((size_t)c * lmax + l) * 2 + 1] = (int)q;
+        wblk[(size_t)c * lmax + l] = h->rem_off + kv.second * h->D * h->D;
+      }
+      h->wb_lmax = lmax; h->wb_R = 12 * lmax;
+      h->wb_node.upload(wnode, st); h->wb_blk.upload(wblk, st);
+      h->wbY.alloc((size_t)h->wb_R * h->L); h->wbCapInv.alloc((size_t)nc * h->wb_R * h->wb_R); h->wbW.alloc((size_t)nc * h->wb_R);
+    }
+  }
   h->scal_b.alloc((size_t)nc * SB_STRIDE); h->scal_b.zero(st);
   h->lam_c.alloc(nc); h->acc_c.alloc(nc); h->cdots.alloc((size_t)nc * 36); h->cdots2.alloc((size_t)nc * 36); h->err_c.alloc(nc);
   rt::sync(st);
@@ -691,7 +719,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
   }
   h->e_all.alloc(eoff); h->le_all.alloc(eoff);
   if (h->ncomp > 1) {
-    const int rc = analyze_components(h, st);
+    const int rc = analyze_components(h, st, rem_index);
     if (rc != VUS_OK) return rc;
   }
   for (int kind = 0; kind < 4; ++kind) h->val[1 - h->cur][kind].alloc((size_t)kVarDim[kind] * h->nvar[kind]);
@@ -1331,6 +1359,45 @@ void bxpby(vus_handle* h, double* y, const double* x, int slot, rt::stream_t st)
   BVecArgs v; v.C = bctx(h); v.y = y; v.x = x; v.scal = h->scal_b.p; v.slot = slot; v.Z = nullptr; v.xb = nullptr; v.zstride = 0;
   L_elem<BXpbyBody>(h->L, st, v);
 }
+BWbCtx wbctx(vus_handle* h) {
+  BWbCtx w; w.node = h->wb_node.p; w.blk = h->wb_blk.p; w.lmax = h->wb_lmax; w.R = h->wb_R;
+  return w;
+}
+// capacitance set-up for the current damped system (after precond_setup_b): Y = P^-1 U six columns at a time, CapInv per component
+void wb_setup(vus_handle* h, rt::stream_t st) {
+  const int R = h->wb_R;
+  const long L = h->L;
+  h->wbY.zero(st);
+  for (int j0 = 0; j0 < R; j0 += 6) {
+    double* Yb = h->wbY.p + (long)j0 * L;
+    BWbUnitArgs u; u.C = bctx(h); u.W = wbctx(h); u.Y = Yb; u.L = L; u.j0 = j0;
+    L_elem<BWbUnitBody>(6L * h->ncomp, st, u);
+    bcr_solve(h, Yb, L, 6, st);
+    if (h->has_bias) {
+      bborder_dot(h, Yb, L, 6, h->cdots.p, st);
+      ClassGuard kc_b(KC_BORDER);
+      BBorderMultiArgs b; b.C = bctx(h); b.SbInv = h->SbInv.p; b.dots = h->cdots.p; b.Y = Yb; b.L = L; b.nv = 6; b.Z = h->Z.p; b.zstride = h->Lc;
+      L_elem<BBorderSolveMultiBody>(36L * h->ncomp, st, b);
+      L_elem<BSubZxbMultiBody>(6 * h->Lc, st, b);
+    }
+  }
+  ClassGuard kc_b(KC_BORDER);
+  BWbCapArgs c; c.C = bctx(h); c.W = wbctx(h); c.Y = h->wbY.p; c.L = L; c.Hval = h->H.p; c.CapInv = h->wbCapInv.p; c.fail = h->fail.p;
+  L_coop<BWbCapBody>(h->ncomp, 256, ((size_t)R * 2 * R + R + 2) * sizeof(double), st, c);
+}
+// z -= Y (I + S K)^-1 S U^T z   on top of z = P^-1 r
+void wb_apply(vus_handle* h, double* z, rt::stream_t st) {
+  ClassGuard kc_b(KC_BORDER);
+  BWbSmallArgs a; a.C = bctx(h); a.W = wbctx(h); a.z = z; a.Hval = h->H.p; a.CapInv = h->wbCapInv.p; a.wout = h->wbW.p;
+  L_coop<BWbSmallBody>(h->ncomp, 128, (size_t)2 * h->wb_R * sizeof(double), st, a);
+  BWbSubArgs b; b.C = bctx(h); b.Y = h->wbY.p; b.L = h->L; b.w = h->wbW.p; b.R = h->wb_R; b.z = z;
+  L_elem<BWbSubBody>(h->L, st, b);
+}
+// the full preconditioner of batched mode: band + border exactly, loop closures by capacitance when set up
+void precond_full_b(vus_handle* h, double* z, const double* r, rt::stream_t st) {
+  precond_apply_b(h, z, r, st);
+  if (h->wb_R) wb_apply(h, z, st);
+}
 // worst ratio rr_c / tol2_c over the components (<= 1: every component met its tolerance); NaN-safe
 double worst_ratio(vus_handle* h, std::vector<double>& sb, rt::stream_t st, bool* bad) {
   rt::d2h(sb.data(), h->scal_b.p, sb.size() * sizeof(double), st);
@@ -1361,7 +1428,7 @@ int pcg_b(vus_handle* h, rt::stream_t st, bool* converged) {
   double worst_outer = worst;
   for (int outer = 0; outer < 6 && !*converged; ++outer) {
     h->d.zero(st);
-    precond_apply_b(h, h->z.p, h->r.p, st);
+    precond_full_b(h, h->z.p, h->r.p, st);
     rt::d2d(h->p.p, h->z.p, L * sizeof(double), st);
     bdot(h, h->r.p, h->z.p, S_RZ, BOP_RZ0, st);
     int since_best = 0;
@@ -1378,7 +1445,7 @@ int pcg_b(vus_handle* h, rt::stream_t st, bool* converged) {
       if (bad || worst <= 1.0) break;
       if (worst < best) { best = worst; since_best = 0; }
       else if (++since_best >= 40) break;
-      precond_apply_b(h, h->z.p, h->r.p, st);
+      precond_full_b(h, h->z.p, h->r.p, st);
       bdot(h, h->r.p, h->z.p, S_RZ, BOP_RZ, st);
       bxpby(h, h->p.p, h->z.p, S_BETA, st);
     }
@@ -1438,6 +1505,7 @@ int optimize_batched(vus_handle* h, rt::stream_t st) {
     rt::h2d(h->lam_c.p, lam.data(), nc * sizeof(double), st);
     form_system_b(h, st);
     precond_setup_b(h, st);
+    if (h->wb_R) wb_setup(h, st);
     const bool solved = !read_fail(h, st);
     if (solved) {
       bool conv = false;
