@@ -753,30 +753,41 @@ struct BandMatvecBody {
 // global memory.  Same recurrences as the streaming bodies above; single source for the device and the emulation.
 #define VUS_SMALLB_MAX 16
 #define VUS_SMALLB_G 16
+#define VUS_SMALLB_MAXV 8
 template <int BT>           // BT: compile-time block size (0: A.B) so the k loops unroll and their loads overlap
 struct SmallFwdBody {      // per surviving node c = 2 m s:  b_c -= Gr_{c-s} b_{c-s} + Gl_{c+s} b_{c+s}
   static VUS_DEV void run(const BcrArgs& A, int blk, int tid, int nthr, double*) {
     const int B = BT ? BT : A.B, nv = A.nrhs, LD = bcr_ld(B), GN = A.small_g;
     const long BBP = bcr_bbp(B);
     const long nsv = ((A.Ns + A.s - 1) / A.s + 1) / 2;
-    for (int e = tid; e < GN * B * nv; e += nthr) {
-      const int r = e % B, g = (e / B) % GN, v = e / (B * GN);
+    for (int e = tid; e < GN * B; e += nthr) {           // item = (node, row): the tile row is read once for all vectors
+      const int r = e % B, g = e / B;
       const long m = (long)blk * GN + g;
       if (m >= nsv) continue;
       const long c = 2L * m * A.s, jl = c - A.s, jh = c + A.s;
-      const double* X = A.X + (long)v * A.xstride;
-      double acc = 0.0;
+      double acc[VUS_SMALLB_MAXV];
+#pragma unroll
+      for (int v = 0; v < VUS_SMALLB_MAXV; ++v) acc[v] = 0.0;
       if (jl >= 0) {
         const double* G = A.Gr + jl * BBP + (long)r * LD;
 #pragma unroll
-        for (int k = 0; k < B; ++k) acc += G[k] * X[jl * B + k];
+        for (int k = 0; k < B; ++k) {
+          const double gk = G[k];
+#pragma unroll
+          for (int v = 0; v < VUS_SMALLB_MAXV; ++v) if (v < nv) acc[v] += gk * A.X[(long)v * A.xstride + jl * B + k];
+        }
       }
       if (jh < A.Ns) {
         const double* G = A.Gl + jh * BBP + (long)r * LD;
 #pragma unroll
-        for (int k = 0; k < B; ++k) acc += G[k] * X[jh * B + k];
+        for (int k = 0; k < B; ++k) {
+          const double gk = G[k];
+#pragma unroll
+          for (int v = 0; v < VUS_SMALLB_MAXV; ++v) if (v < nv) acc[v] += gk * A.X[(long)v * A.xstride + jh * B + k];
+        }
       }
-      A.X[(long)v * A.xstride + c * B + r] -= acc;
+#pragma unroll
+      for (int v = 0; v < VUS_SMALLB_MAXV; ++v) if (v < nv) A.X[(long)v * A.xstride + c * B + r] -= acc[v];
     }
   }
 };
@@ -786,27 +797,41 @@ struct SmallBwdBody {      // per eliminated node j = s (2 m + 1):  x_j = Dinv_j
     const int B = BT ? BT : A.B, nv = A.nrhs, LD = bcr_ld(B), GN = A.small_g;
     const long BBP = bcr_bbp(B);
     const long nel = A.s > 0 ? ((A.Ns + A.s - 1) / A.s) / 2 : (A.Ns + A.root_stride - 1) / A.root_stride;
-    for (int e = tid; e < GN * B * nv; e += nthr) {
-      const int r = e % B, g = (e / B) % GN, v = e / (B * GN);
+    for (int e = tid; e < GN * B; e += nthr) {
+      const int r = e % B, g = e / B;
       const long m = (long)blk * GN + g;
       if (m >= nel) continue;
       const long j = A.s > 0 ? A.s * (2L * m + 1) : m * A.root_stride, jl = j - A.s, jh = j + A.s;
-      const double* X = A.X + (long)v * A.xstride;
       const double* Dj = A.Dinv + j * BBP + (long)r * LD;
-      double acc = 0.0;
+      double acc[VUS_SMALLB_MAXV];
 #pragma unroll
-      for (int k = 0; k < B; ++k) acc += Dj[k] * X[j * B + k];
+      for (int v = 0; v < VUS_SMALLB_MAXV; ++v) acc[v] = 0.0;
+#pragma unroll
+      for (int k = 0; k < B; ++k) {
+        const double dk = Dj[k];
+#pragma unroll
+        for (int v = 0; v < VUS_SMALLB_MAXV; ++v) if (v < nv) acc[v] += dk * A.X[(long)v * A.xstride + j * B + k];
+      }
       if (A.s > 0 && jl >= 0) {
         const double* G = A.Gl + j * BBP + r;
 #pragma unroll
-        for (int k = 0; k < B; ++k) acc -= G[(long)k * LD] * X[jl * B + k];
+        for (int k = 0; k < B; ++k) {
+          const double gk = G[(long)k * LD];
+#pragma unroll
+          for (int v = 0; v < VUS_SMALLB_MAXV; ++v) if (v < nv) acc[v] -= gk * A.X[(long)v * A.xstride + jl * B + k];
+        }
       }
       if (A.s > 0 && jh < A.Ns) {
         const double* G = A.Gr + j * BBP + r;
 #pragma unroll
-        for (int k = 0; k < B; ++k) acc -= G[(long)k * LD] * X[jh * B + k];
+        for (int k = 0; k < B; ++k) {
+          const double gk = G[(long)k * LD];
+#pragma unroll
+          for (int v = 0; v < VUS_SMALLB_MAXV; ++v) if (v < nv) acc[v] -= gk * A.X[(long)v * A.xstride + jh * B + k];
+        }
       }
-      sm[e] = acc;
+#pragma unroll
+      for (int v = 0; v < VUS_SMALLB_MAXV; ++v) if (v < nv) sm[v * GN * B + e] = acc[v];
     }
     VUS_SYNC();                                           // x_j overwrites b_j: every row of the node is computed first
     for (int e = tid; e < GN * B * nv; e += nthr) {

@@ -886,7 +886,7 @@ void bcr_solve_launches(vus_handle* h, double* X, long xstride, int nrhs, rt::st
   const int nroot = (int)((h->Ns + s_root - 1) / s_root);
   for (long s = 1; s < s_root; s <<= 1) levels.push_back(s);
   if (h->B <= VUS_SMALLB_MAX) {                          // tiny supernodes: thread per (node, row), VUS_SMALLB_G nodes per CTA
-    const int GN = std::max(1, std::min(64, nthr / (h->B * std::min(nrhs, 2))));     // ~one item per thread (one vector), a few (six)
+    const int GN = std::max(1, std::min(64, nthr / h->B));     // one (node, row) item per thread, all vectors of the item in registers
     a.small_g = GN;
     const size_t sm_small = (size_t)GN * h->B * nrhs * sizeof(double);
     auto grid_of = [GN](long n) { return (int)((n + GN - 1) / GN); };
