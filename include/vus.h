@@ -140,7 +140,8 @@ int vus_set_comm(vus_handle* h, vus_comm_fn fn, void* ctx);
  * index range [node_start[c], node_start[c+1]) and, if the graphs have one, the bias with index c -- and the library
  * runs gtsam's LM loop for every component at once: each component keeps its own lambda, error, accept / reject /
  * convergence decisions and PCG scalars, exactly as ncomp separate optimizers would.  No factor may connect two
- * components; stereo factors are not supported in this mode.  Call before vus_analyze; vus_optimize then fills the
+ * components; stereo factors are not supported in this mode.  Off-band factors (loop closures) of a component are
+ * inverted exactly by a capacitance (Woodbury) solve on top of the factored band when no component has more than 8.  Call before vus_analyze; vus_optimize then fills the
  * summed errors / the largest iteration count into vus_lm_result and vus_get_component_results the per-trajectory ones. */
 typedef struct vus_component_result {
   int32_t iterations;            /* accepted LM steps of this trajectory */

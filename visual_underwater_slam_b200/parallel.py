@@ -82,11 +82,12 @@ def concat_problems(problems):
     if any((len(p["vel_keys"]) > 0) != has_vel or (len(p["bias_keys"]) > 0) != has_bias for p in problems):
         raise ValueError("concat_problems: the problems of a batch must hold the same variable kinds")
     n = int(node_start[-1])
-    out = {"pose_keys": np.array([X(i) for i in range(n)], dtype=np.uint64),
+    ar = np.arange(n, dtype=np.uint64)
+    out = {"pose_keys": np.uint64(X(0)) + ar,
            "poses": np.concatenate([p["poses"] for p in problems], 0),
-           "vel_keys": np.array([V(i) for i in range(n)] if has_vel else [], dtype=np.uint64),
+           "vel_keys": np.uint64(V(0)) + ar if has_vel else np.zeros(0, dtype=np.uint64),
            "vels": np.concatenate([p["vels"] for p in problems], 0) if has_vel else np.zeros((0, 3)),
-           "bias_keys": np.array([B(t) for t in range(len(problems))] if has_bias else [], dtype=np.uint64),
+           "bias_keys": np.uint64(B(0)) + np.arange(len(problems), dtype=np.uint64) if has_bias else np.zeros(0, dtype=np.uint64),
            "biases": np.concatenate([p["biases"] for p in problems], 0) if has_bias else np.zeros((0, 6)),
            "lm_keys": np.zeros(0, dtype=np.uint64), "lms": np.zeros((0, 3)),
            "calib": problems[0]["calib"], "gravity": problems[0]["gravity"]}
