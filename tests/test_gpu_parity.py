@@ -301,3 +301,30 @@ def test_batched_matches_one_handle_per_trajectory(lib):
     for b, o in zip(bat, one):
         assert b["iterations"] == o["iterations"] and b["inner_iterations"] == o["inner_iterations"]
         assert abs(b["final_error"] - o["final_error"]) <= 1e-9 * o["final_error"]
+
+
+def test_config4_batch_full_trajectory_size_properties(lib):
+    """BASELINE config 4 at its per-trajectory size (500 poses, 5 loop closures, own bias), a block of 64 trajectories in one
+    handle: every trajectory converges (error decreases, gtsam's iteration cap not hit), the per-trajectory LM paths differ
+    (so the per-component controller is exercised), a subset equals one handle per trajectory, and re-solving from the
+    solution is a fixed point for every component (idempotence)."""
+    from visual_underwater_slam_b200 import parallel, synthetic
+    probs = []
+    for t in range(64):
+        d = synthetic.make_trajectory_graph(500, seed=4 + t, n_loops=5, loop_min_gap=100)
+        probs.append(d["graph"].to_problem(d["initial"]))
+    bat = parallel.solve_batched(probs, lib=lib, keep_values=True)
+    assert all(b["final_error"] < b["initial_error"] and 1 <= b["iterations"] < 100 for b in bat)
+    assert len({b["inner_iterations"] for b in bat}) > 1
+    one = parallel.solve_local(probs[:6], lib=lib, threads=3, keep_values=False)
+    for b, o in zip(bat, one):
+        assert b["iterations"] == o["iterations"] and b["inner_iterations"] == o["inner_iterations"]
+        assert abs(b["final_error"] - o["final_error"]) <= 1e-9 * o["final_error"]
+    again = []
+    for p, b in zip(probs, bat):
+        q = dict(p)
+        q["poses"], q["vels"], q["biases"] = b["values"]["poses"], b["values"]["vels"], b["values"]["biases"]
+        again.append(q)
+    re = parallel.solve_batched(again, lib=lib, keep_values=False)
+    for b, r in zip(bat, re):
+        assert r["iterations"] <= 2 and abs(r["final_error"] - b["final_error"]) <= 1e-4 * b["final_error"]   # gtsam's 1e-5 stop
