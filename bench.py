@@ -72,7 +72,8 @@ def cpu_oracle_run(a, steps=1, warmup=0):
     from oracle import lm
     n = a.cpu_poses
     ratio = a.landmarks / max(a.poses, 1)
-    d = synthetic.make_trajectory_graph(n, seed=a.seed, n_landmarks=int(round(ratio * n)), n_loops=0, pixel_noise=1.0,
+    loops = int(round(a.loops * n / max(a.poses, 1)))
+    d = synthetic.make_trajectory_graph(n, seed=a.seed, n_landmarks=int(round(ratio * n)), n_loops=loops, pixel_noise=1.0,
                                         drift_scale=a.drift_scale)
     prob = d["graph"].to_problem(d["initial"])
     times, info = [], None
@@ -85,7 +86,7 @@ def cpu_oracle_run(a, steps=1, warmup=0):
     lin = max(lin, len(info["trace"]["errors"]) - 1)
     nf = d["meta"]["n_factors"]
     t = float(np.mean(times))
-    sample = (f"{n}-pose / {int(round(ratio * n))}-landmark graph from the same generator ({nf} factors), full LM to "
+    sample = (f"{n}-pose / {int(round(ratio * n))}-landmark / {loops}-loop-closure graph from the same generator ({nf} factors), full LM to "
               f"convergence: {info['iterations']} iterations in {t:.2f} s (CPU restatement of gtsam LM, not gtsam)")
     return dict(value=nf * lin / t, unit=UNIT, cores=1, kind="port", sample=sample, seconds=t, iterations=info["iterations"],
                 final_error=info["error"]), t
