@@ -161,3 +161,12 @@ def test_batched_rejects_cross_component_factor(emu):
         prob["imu"][slot][0] = 25
     with pytest.raises(RuntimeError, match="connects two components"):
         Session(prob, lib=emu, components=node_start)
+
+
+def test_batched_mixed_closure_counts_and_fallback(emu):
+    """Capacitance solve of the loop closures: components with no / one / several closures in one batch (unused capacitance
+    slots are identity rows), and the plain-PCG fallback when a component has more than 8 closures."""
+    probs = [pc.make(60, n_loops=nl, loop_min_gap=12, seed=70 + t)[1] for t, nl in enumerate((0, 3, 1, 5))]
+    pc.check_batched_parity(emu, probs)
+    probs = [pc.make(90, n_loops=nl, loop_min_gap=10, seed=80 + t)[1] for t, nl in enumerate((10, 2))]
+    pc.check_batched_parity(emu, probs)
