@@ -133,6 +133,10 @@ enum vus_comm_op { VUS_COMM_ALLREDUCE_SUM = 0, VUS_COMM_HALO = 1 };
 typedef int (*vus_comm_fn)(void* ctx, int op, void* buf, int64_t count);
 int vus_set_partition(vus_handle* h, int64_t n_owned_nodes, const int64_t n_owned_factors[6]);
 int vus_set_comm(vus_handle* h, vus_comm_fn fn, void* ctx);
+/* stream_ordered = 1: the callback enqueues its collective ON THE STREAM passed to vus_optimize (NCCL through torch.distributed
+ * with that stream current) and returns without waiting; the library then neither synchronises before the call nor expects
+ * the result on the host -- the stream orders everything.  0 (default): host-synchronous callbacks (gloo, the CPU tests). */
+int vus_set_comm_mode(vus_handle* h, int stream_ordered);
 
 /* ---- a batch of INDEPENDENT trajectories in one handle (BASELINE.json config 4: 4096 x 500-pose graphs, a block per GPU)
  * The reference runs one gtsam.LevenbergMarquardtOptimizer per graph (batch.py:337); a 500-pose solve cannot fill a B200,

@@ -29,7 +29,7 @@ if rank == 0:
     print(json.dumps(dict(world=world, n=n, seconds=dt, iterations=res["iterations"], tries=res["inner_iterations"], pcg=res["pcg_iterations"],
                           initial_error=res["initial_error"], final_error=res["final_error"], comm=ps.comm_calls,
                           factors_per_s=prob["n_factors"] * res["linearizations"] / dt)), flush=True)
-    if world == 1: np.save("gpurun_out/part_ref_%d.npy" % n, poses)
+    if world == 1 and n <= 500000: np.save("gpurun_out/part_ref_%d.npy" % n, poses)      # reference for the next (multi-rank) run
     elif os.path.exists("gpurun_out/part_ref_%d.npy" % n):
         ref = np.load("gpurun_out/part_ref_%d.npy" % n)
         print("max pose diff vs 1 rank: t %.3e R %.3e" % (np.abs(ref[:, 9:] - poses[:, 9:]).max(), np.abs(ref[:, :9] - poses[:, :9]).max()))

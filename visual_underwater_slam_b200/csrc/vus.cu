@@ -197,6 +197,7 @@ struct vus_handle {
   DBuf<double> e_mask;           // 1 for factors this rank owns, 0 for duplicates of a neighbour's factor
   vus_comm_fn comm = nullptr;
   void* comm_ctx = nullptr;
+  bool comm_stream_ordered = false;   // the callback enqueues its collective on the stream the library runs on: no host sync around it
   // batched mode: independent components (trajectories) in one block-diagonal system (batch.cuh)
   int ncomp = 1;
   long bcr_stop = 1L << 62;      // cyclic reduction needs no stride beyond the longest component (in supernodes)
@@ -279,7 +280,7 @@ void run_factors(vus_handle* h, int which, bool with_J, rt::stream_t st) {
 
 // deterministic sum / dot -> scal[slot] with post-op
 void comm_call(vus_handle* h, int op, void* buf, long count, rt::stream_t st) {
-  rt::sync(st);                                        // the collective runs on the caller's (torch) stream
+  if (!h->comm_stream_ordered) rt::sync(st);           // host-synchronous callbacks: the collective runs on the caller's own stream
   if (h->comm(h->comm_ctx, op, buf, (int64_t)count) != 0) throw std::runtime_error("communication callback failed");
 }
 void reduce(vus_handle* h, const double* a, const double* b, long n, int slot, int op, rt::stream_t st) {
@@ -1823,6 +1824,12 @@ int vus_get_component_results(vus_handle* h, vus_component_result* out) {
   if (!h || !out) return VUS_ERR_INVALID;
   if (h->ncomp <= 1 || (int)h->comp_res.size() != h->ncomp) return fail(h, VUS_ERR_STATE, "vus_get_component_results: no batched optimize() has run");
   std::copy(h->comp_res.begin(), h->comp_res.end(), out);
+  return VUS_OK;
+}
+
+int vus_set_comm_mode(vus_handle* h, int stream_ordered) {
+  if (!h) return VUS_ERR_INVALID;
+  h->comm_stream_ordered = stream_ordered != 0;
   return VUS_OK;
 }
 

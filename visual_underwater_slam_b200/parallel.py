@@ -251,7 +251,7 @@ class PartitionedSolver:
     """One rank of a pose graph split by pose range.  `part` is this rank's entry of partition_pose_graph(); the process
     group must already exist (nccl on GPUs, gloo for the CPU tests)."""
 
-    def __init__(self, part, params=None, lib=None, device=0, group=None):
+    def __init__(self, part, params=None, lib=None, device=0, group=None, stream_ordered=True):
         import torch
         import torch.distributed as dist
         from . import _native
@@ -267,11 +267,24 @@ class PartitionedSolver:
         self._send_idx = {p: torch.as_tensor(ix, device=self.device) for p, ix in part["send"].items()}
         self.comm_calls = {"allreduce": 0, "halo": 0}
         self._cb = _native.COMM_FN(self._comm)
+        self._views = {}
+        # NCCL: the library runs on a torch stream of ours and every collective is enqueued on that same stream, so neither
+        # side waits on the host (vus_set_comm_mode); gloo (CPU tests): host-synchronous callbacks
+        self.stream = torch.cuda.Stream(self.device) if (self.cuda and self.world > 1 and stream_ordered) else None
         self.session = Session(part["prob"], params, lib=lib, device=device, partition=(self.n_owned, part["nf_owned"]),
                                comm=self._cb if self.world > 1 else None)
+        if self.stream is not None:
+            self.session._check(self.session.lib.vus_set_comm_mode(self.session._h, 1))
 
     # ---- device memory handed over by the library as a torch tensor (no copy)
     def _view(self, ptr, count):
+        key = (int(ptr), int(count))
+        v = self._views.get(key)
+        if v is None:
+            v = self._views[key] = self._make_view(ptr, count)
+        return v
+
+    def _make_view(self, ptr, count):
         torch = self.torch
         if self.cuda:
             class _Arr:
@@ -282,6 +295,22 @@ class PartitionedSolver:
 
     def _comm(self, ctx, op, buf, count):
         try:
+            if self.stream is not None:
+                with self.torch.cuda.stream(self.stream):
+                    self._collective(op, buf, count)
+            else:
+                self._collective(op, buf, count)
+                if self.cuda:
+                    self.torch.cuda.synchronize(self.device)
+            return 0
+        except Exception as exc:                        # never let an exception cross the C boundary
+            import traceback
+            traceback.print_exc()
+            self.error = exc
+            return 1
+
+    def _collective(self, op, buf, count):
+        if True:
             from . import _native
             dist, torch = self.dist, self.torch
             if op == _native.COMM_ALLREDUCE_SUM:
@@ -300,18 +329,10 @@ class PartitionedSolver:
                     ops.append(dist.P2POp(dist.irecv, vec[self.n_owned + off:self.n_owned + off + cnt], peer, group=self.group))
                 if ops:
                     for w in dist.batch_isend_irecv(ops):
-                        w.wait()
-            if self.cuda:
-                torch.cuda.synchronize(self.device)
-            return 0
-        except Exception as exc:                        # never let an exception cross the C boundary
-            import traceback
-            traceback.print_exc()
-            self.error = exc
-            return 1
+                        w.wait()                        # NCCL: makes the current stream wait, not the host
 
     def optimize(self):
-        return self.session.optimize()
+        return self.session.optimize(stream=self.stream.cuda_stream if self.stream is not None else None)
 
     def owned_poses(self):
         return self.session.values()["poses"][:self.n_owned]
