@@ -893,11 +893,13 @@ void bcr_solve_launches(vus_handle* h, double* X, long xstride, int nrhs, rt::st
     auto grid_of = [GN](long n) { return (int)((n + GN - 1) / GN); };
     auto fwd = [&](int grid) {
       if (h->B == 9) L_coop<SmallFwdBody<9>>(grid, nthr, 0, st, a);
+      else if (h->B == 12) L_coop<SmallFwdBody<12>>(grid, nthr, 0, st, a);
       else if (h->B == 6) L_coop<SmallFwdBody<6>>(grid, nthr, 0, st, a);
       else L_coop<SmallFwdBody<0>>(grid, nthr, 0, st, a);
     };
     auto bwd = [&](int grid) {
       if (h->B == 9) L_coop<SmallBwdBody<9>>(grid, nthr, sm_small, st, a);
+      else if (h->B == 12) L_coop<SmallBwdBody<12>>(grid, nthr, sm_small, st, a);
       else if (h->B == 6) L_coop<SmallBwdBody<6>>(grid, nthr, sm_small, st, a);
       else L_coop<SmallBwdBody<0>>(grid, nthr, sm_small, st, a);
     };
@@ -943,6 +945,7 @@ void border_dot(vus_handle* h, const double* Y, long ystride, int nv, rt::stream
 
 void small_matvec(vus_handle* h, long items, const MatvecArgs& a, rt::stream_t st) {
   if (h->B == 9) L_elem<SmallMatvecBody<9>>(items, st, a);
+  else if (h->B == 12) L_elem<SmallMatvecBody<12>>(items, st, a);     // pose graphs with skip factors (config 5): k = 2, D = 6
   else if (h->B == 6) L_elem<SmallMatvecBody<6>>(items, st, a);
   else L_elem<SmallMatvecBody<0>>(items, st, a);
 }
