@@ -170,3 +170,25 @@ def test_batched_mixed_closure_counts_and_fallback(emu):
     pc.check_batched_parity(emu, probs)
     probs = [pc.make(90, n_loops=nl, loop_min_gap=10, seed=80 + t)[1] for t, nl in enumerate((10, 2))]
     pc.check_batched_parity(emu, probs)
+
+
+def test_golden_rows_on_the_emulation(emu):
+    """The frozen fixtures of the rows around the path (marginals, batched trajectories) through the host emulation."""
+    import json
+    from visual_underwater_slam_b200 import parallel
+    from visual_underwater_slam_b200.optimizer import Session
+    golden = os.path.join(ROOT, "tests", "golden")
+    g = np.load(os.path.join(golden, "rows_marginals.npz"))
+    meta = json.loads(str(g["meta"]))
+    _, prob = pc.make(**meta["make"])
+    s = Session(prob, lib=emu)
+    cov = s.marginal_covariance([tuple(q) for q in meta["queries"]])
+    s.close()
+    scale = np.sqrt(np.outer(np.diag(g["cov"]), np.diag(g["cov"])))
+    assert np.abs((cov - g["cov"]) / scale).max() <= 1e-4
+    g = np.load(os.path.join(golden, "rows_batched.npz"))
+    meta = json.loads(str(g["meta"]))
+    res = parallel.solve_batched([pc.make(**mk)[1] for mk in meta["batch"]], lib=emu)
+    for r, row in zip(res, g["summary"]):
+        assert r["iterations"] == int(row[0]) and r["inner_iterations"] == int(row[1])
+        assert abs(r["final_error"] - row[2]) <= 1e-6 * row[2]

@@ -328,3 +328,26 @@ def test_config4_batch_full_trajectory_size_properties(lib):
     re = parallel.solve_batched(again, lib=lib, keep_values=False)
     for b, r in zip(bat, re):
         assert r["iterations"] <= 2 and abs(r["final_error"] - b["final_error"]) <= 1e-4 * b["final_error"]   # gtsam's 1e-5 stop
+
+
+def test_golden_rows_marginals_and_batched(lib):
+    """Frozen oracle answers for the rows around the path (tests/golden/make_golden_rows.py)."""
+    from visual_underwater_slam_b200 import parallel
+    from visual_underwater_slam_b200.optimizer import Session
+    g = np.load(os.path.join(GOLDEN, "rows_marginals.npz"))
+    meta = json.loads(str(g["meta"]))
+    _, prob = pc.make(**meta["make"])
+    s = Session(prob, lib=lib)
+    cov = s.marginal_covariance([tuple(q) for q in meta["queries"]])
+    s.close()
+    scale = np.sqrt(np.outer(np.diag(g["cov"]), np.diag(g["cov"])))
+    assert np.abs(cov - g["cov"]).max() <= 1e-6 * scale.max() and np.abs((cov - g["cov"]) / scale).max() <= 1e-4
+    g = np.load(os.path.join(GOLDEN, "rows_batched.npz"))
+    meta = json.loads(str(g["meta"]))
+    probs = [pc.make(**mk)[1] for mk in meta["batch"]]
+    res = parallel.solve_batched(probs, lib=lib)
+    for r, row in zip(res, g["summary"]):
+        assert r["iterations"] == int(row[0]) and r["inner_iterations"] == int(row[1])
+        assert abs(r["final_error"] - row[2]) <= 1e-6 * row[2] and abs(r["final_lambda"] - row[3]) <= 1e-12 * row[3]
+    poses = np.concatenate([r["values"]["poses"] for r in res], 0)
+    assert np.sqrt(((poses[:, 9:] - g["poses"][:, 9:]) ** 2).sum(1).mean()) < 1e-6 and np.abs(poses[:, :9] - g["poses"][:, :9]).max() < 1e-6
