@@ -254,3 +254,21 @@ def test_graph_and_values_merge_for_incremental_updates():
         v.insert(d["initial"])
     g.resize(0)
     assert g.size() == 0
+
+
+def test_optimize_many_is_n_separate_optimizers(emu):
+    """gtsam-named entry for BASELINE config 4: N graphs + N initial Values in, N Values out, each equal to what its own
+    LevenbergMarquardtOptimizer returns (keys of every trajectory are its own X(i) / V(i) / B(0))."""
+    ds = [synthetic.make_trajectory_graph(40 + 8 * t, seed=50 + t, n_loops=2, loop_min_gap=12) for t in range(3)]
+    vals, info = gtsam.optimize_many([d["graph"] for d in ds], [d["initial"] for d in ds], lib=emu)
+    assert len(vals) == 3
+    for d, v, s in zip(ds, vals, info):
+        opt = gtsam.LevenbergMarquardtOptimizer(d["graph"], d["initial"], gtsam.LevenbergMarquardtParams(), lib=emu)
+        ref = opt.optimize()
+        assert s["iterations"] == opt.iterations() and abs(s["error"] - opt.error()) <= 1e-9 * opt.error()
+        n = d["meta"]["n_poses"]
+        assert v.exists(X(n - 1)) and not v.exists(X(n)) and v.exists(B(0))
+        a, b = v.atPose3(X(n - 1)), ref.atPose3(X(n - 1))
+        assert abs(a.x() - b.x()) + abs(a.y() - b.y()) + abs(a.z() - b.z()) < 1e-7
+    with pytest.raises(ValueError):
+        gtsam.optimize_many([], [])

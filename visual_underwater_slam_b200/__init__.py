@@ -15,7 +15,7 @@ from .factors import (PriorFactorPose3, PriorFactorVector, BetweenFactorPose3, D
                       GenericStereoFactor3D, ImuFactor, CustomFactor)
 from .values import Values
 from .graph import NonlinearFactorGraph
-from .optimizer import LevenbergMarquardtParams, LevenbergMarquardtOptimizer, Marginals, JointMarginal
+from .optimizer import LevenbergMarquardtParams, LevenbergMarquardtOptimizer, Marginals, JointMarginal, optimize_many
 from .incremental import ISAM2, ISAM2Result
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -344,6 +344,26 @@ class LevenbergMarquardtOptimizer:
         return dict(self._result or {})
 
 
+def optimize_many(graphs, initial_values, params=None, lib=None, device=0):
+    """N independent `LevenbergMarquardtOptimizer(graph_t, initial_t, params).optimize()` calls (batch.py:337 once per
+    trajectory; BASELINE config 4) as ONE batched solve on the device: -> (list of Values, list of per-trajectory summaries
+    with gtsam's iterations() / error() / lambda_()).  Every trajectory keeps its own LM path (include/vus.h,
+    vus_set_components)."""
+    from . import parallel
+    graphs, initial_values = list(graphs), list(initial_values)
+    if len(graphs) != len(initial_values) or not graphs:
+        raise ValueError("optimize_many: one initial Values per graph, at least one graph")
+    probs = [g.to_problem(v) for g, v in zip(graphs, initial_values)]
+    res = parallel.solve_batched(probs, params or LevenbergMarquardtParams(), lib=lib, device=device, keep_values=True)
+    out = []
+    for p, r in zip(probs, res):
+        out.append(_values_from(p, dict(poses=r["values"]["poses"], vels=r["values"]["vels"], biases=r["values"]["biases"],
+                                        lms=r["values"]["lms"])))
+    summaries = [dict(iterations=r["iterations"], error=r["final_error"], lambda_=r["final_lambda"],
+                      inner_iterations=r["inner_iterations"], initial_error=r["initial_error"]) for r in res]
+    return out, summaries
+
+
 class JointMarginal:
     """gtsam.JointMarginal: the joint covariance (or information) of several variables, blocks in the order asked."""
 
