@@ -87,7 +87,8 @@ def cpu_oracle_run(a, steps=1, warmup=0):
     nf = d["meta"]["n_factors"]
     t = float(np.mean(times))
     sample = (f"{n}-pose / {int(round(ratio * n))}-landmark / {loops}-loop-closure graph from the same generator ({nf} factors), full LM to "
-              f"convergence: {info['iterations']} iterations in {t:.2f} s (CPU restatement of gtsam LM, not gtsam)")
+              f"convergence: {info['iterations']} iterations in {t:.2f} s (CPU restatement of gtsam LM, not gtsam; one graph = one "
+              f"thread, as gtsam's own LM without TBB: of {os.cpu_count()} host cores it can use 1)")
     return dict(value=nf * lin / t, unit=UNIT, cores=1, kind="port", sample=sample, seconds=t, iterations=info["iterations"],
                 final_error=info["error"]), t
 
