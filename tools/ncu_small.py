@@ -13,5 +13,6 @@ probs = []
 for t in range(T):
     d = synthetic.make_trajectory_graph(n, seed=4 + t, n_loops=5, loop_min_gap=100 if n >= 300 else n // 3)
     probs.append(d["graph"].to_problem(d["initial"]))
-res = parallel.solve_batched(probs, keep_values=False)
-print("solved", len(res), "trajectories; rounds", parallel.solve_batched.last_stats["inner_iterations"])
+stats = {}
+res = parallel.solve_batched(probs, keep_values=False, stats=stats)
+print("solved", len(res), "trajectories; rounds", stats["inner_iterations"])

@@ -127,10 +127,11 @@ def split_values(tables, node_start, has_bias=True):
     return out
 
 
-def solve_batched(problems, params=None, lib=None, device=0, keep_values=True):
+def solve_batched(problems, params=None, lib=None, device=0, keep_values=True, stats=None):
     """Solve a list of independent packed problems as ONE block-diagonal system on this rank's GPU (vus_set_components):
     every trajectory keeps its own lambda / accept-reject / convergence path, as separate optimizers would.
-    -> list of dict(summary fields..., values=tables or None), in input order (same shape as solve_local's result)."""
+    -> list of dict(summary fields..., values=tables or None), in input order (same shape as solve_local's result).
+    `stats`: optional dict that receives the whole-batch vus_lm_result (rounds, PCG iterations, launches, per-class times)."""
     prob, node_start = concat_problems(problems)
     s = Session(prob, params or LevenbergMarquardtParams(), lib=lib, device=device, components=node_start)
     try:
@@ -142,7 +143,8 @@ def solve_batched(problems, params=None, lib=None, device=0, keep_values=True):
             d = {k: r[k] for k in SUMMARY_FIELDS}
             d["values"] = v
             out.append(d)
-        solve_batched.last_stats = total
+        if stats is not None:
+            stats.update(total)
         return out
     finally:
         s.close()
