@@ -465,6 +465,97 @@ struct SchurArgs {
   // implicit Schur term of the long-track landmarks (operator only)
   long nlong; const int* long_ids; double* ulong;     // ulong [3][nlong]
   const double* xin; double* yout;
+  // SchurBlockBody: partner[t * ndj + dj] = row of the observation of the same landmark from pose i + dj (-1: none), t over
+  // the pose-major observation list; ndj = longest short-track span + 1
+  int* partner; int ndj;
+};
+// analysis time, work item (t, dj): the partner of observation pose_obs[t] at pose offset dj.  Tracks are pose-sorted and
+// hold every pose at most once (a landmark seen twice from one pose is handled by the implicit path, like a long track).
+struct SchurPartnerBody {
+  static VUS_DEV void run(const SchurArgs& A, long w) {
+    const int dj = (int)(w % A.ndj);
+    const long t = w / A.ndj;
+    const int o = A.pose_obs[t];
+    const int l = A.idx[A.n + o];
+    int q = -1;
+    if (!A.lm_long[l]) {
+      const int target = A.idx[o] + dj;
+      for (int c = o; c < A.lm_ptr[l + 1]; ++c) {
+        const int pc = A.idx[c];
+        if (pc == target) { q = c; break; }
+        if (pc > target) break;
+      }
+    }
+    A.partner[w] = q;
+  }
+};
+// per lambda, work item (pose slot pi, dj, half): rows 3 half .. 3 half + 2 of the 6 x 6 block  S(i, i + dj) -= sum_o W_o E_q^T
+// (W_o = E_o Cinv_l, q the partner of o at pose i + dj) accumulated in registers: 18 outputs per 12 loaded values per
+// observation pair, no shared memory, exactly one thread writes an entry, and the two halves of a block sit in neighbouring
+// lanes so their E_q loads hit the same sectors.  The kernel it replaces (one thread per block ENTRY, partial blocks in
+// shared memory) was bound by L1 sector throughput: 516 M sectors per launch at C3 (profiles/r1_ncu_schur_c3.txt).
+// The dj = 0 items also reduce the gradient  gs_i -= sum_o W_o gl_l.
+struct SchurBlockBody {
+  static VUS_DEV void run(const SchurArgs& A, long w) {
+    const int r0 = 3 * (int)(w & 1);
+    const int dj = (int)((w >> 1) % A.ndj);
+    const long pi = (w >> 1) / A.ndj;
+    const long i = A.pose_ids[pi];
+    double acc[18], gacc[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int e = 0; e < 18; ++e) acc[e] = 0.0;
+    bool any = false;
+    for (int t = A.pose_ptr[pi]; t < A.pose_ptr[pi + 1]; ++t) {
+      const int q = A.partner[(long)t * A.ndj + dj];
+      if (q < 0 && dj != 0) continue;
+      const long o = A.pose_obs[t];
+      const long l = A.idx[A.n + o];
+      double W[9];
+      {
+        double ci[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) ci[e] = A.Cinv[e * A.nl + l];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const double* er = A.E + o * 18 + (r0 + r) * 3;
+          const double e0 = er[0], e1 = er[1], e2 = er[2];
+          W[r * 3] = e0 * ci[0] + e1 * ci[3] + e2 * ci[6];
+          W[r * 3 + 1] = e0 * ci[1] + e1 * ci[4] + e2 * ci[7];
+          W[r * 3 + 2] = e0 * ci[2] + e1 * ci[5] + e2 * ci[8];
+        }
+      }
+      if (dj == 0) {
+        const double g0 = A.gl[l], g1 = A.gl[A.nl + l], g2 = A.gl[2 * A.nl + l];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) gacc[r] += W[r * 3] * g0 + W[r * 3 + 1] * g1 + W[r * 3 + 2] * g2;
+        if (q < 0) continue;                           // long track: only the gradient is reduced here (LongSchur*Body)
+      }
+      any = true;
+      const double* eq = A.E + (long)q * 18;
+#pragma unroll
+      for (int sc = 0; sc < 6; ++sc) {
+        const double v0 = eq[sc * 3], v1 = eq[sc * 3 + 1], v2 = eq[sc * 3 + 2];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) acc[r * 6 + sc] += W[r * 3] * v0 + W[r * 3 + 1] * v1 + W[r * 3 + 2] * v2;
+      }
+    }
+    const int D = A.D, k = A.k, B = A.ld;
+    if (dj == 0) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) A.gs[i * D + r0 + r] -= gacc[r];
+    }
+    if (!any) return;
+    const long I = i / k, j = i + dj, J = j / k;
+    const int ri = (int)(i - I * k), rj = (int)(j - J * k);
+    double* blk = (J == I ? A.SD : A.SU) + I * A.bs;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int sc = 0; sc < 6; ++sc) {
+        blk[(long)(ri * D + r0 + r) * B + rj * D + sc] -= acc[r * 6 + sc];
+        if (J == I && dj) blk[(long)(rj * D + sc) * B + ri * D + r0 + r] -= acc[r * 6 + sc];
+      }
+  }
 };
 struct LmInvertBody {    // per landmark
   static VUS_DEV void run(const SchurArgs& A, long l) {

@@ -182,6 +182,8 @@ struct vus_handle {
   long nlong = 0;
   DBuf<double> ulong;
   double cur_lambda = 0.0;
+  int schur_ndj = 1;
+  DBuf<int> partner;
   bool z0_valid = false;         // column 6 of Z holds M^-1 gs (band part of the first preconditioner application)
   DBuf<double> C, gl, Cinv, E, Pp, Pl;
   // BCR
@@ -368,6 +370,8 @@ PairDst band_dst(const vus_handle* h, long p, long q, const std::map<std::pair<l
   }
   return d;
 }
+
+SchurArgs schur_args(vus_handle* h, double lambda);
 
 // batched mode: component of every node, dof segments, per-component factor lists (errors) and IMU lists (bias blocks)
 int analyze_components(vus_handle* h, rt::stream_t st, const std::map<std::pair<long, long>, long>& rem_index) {
@@ -640,12 +644,16 @@ int analyze(vus_handle* h, rt::stream_t st) {
   for (long f = 0; f < FI.n; ++f) add_rem(FI.h_idx[f], FI.h_idx[2 * FI.n + f]);
   // landmarks whose track does not fit inside the band keep their Schur term implicit (LongSchur*Body)
   std::vector<int> lm_long(NL, 0), long_ids;
+  long track_span = 0;                                  // longest pose span of a track that is folded into the band
   for (long l = 0; l < NL; ++l) {
     const long pf = FS.h_idx[lm_ptr[l]], pl = FS.h_idx[lm_ptr[l + 1] - 1];   // observations are pose-sorted
-    if (pl / k - pf / k <= 1) continue;                 // whole track inside the band
+    bool twice = false;                                 // seen twice from one pose: SchurBlockBody expects one partner per pose
+    for (int q = lm_ptr[l] + 1; q < lm_ptr[l + 1] && !twice; ++q) twice = FS.h_idx[q] == FS.h_idx[q - 1];
+    if (pl / k - pf / k <= 1 && !twice) { track_span = std::max(track_span, pl - pf); continue; }   // whole track inside the band
     long_ids.push_back((int)l);
     lm_long[l] = (int)long_ids.size();                  // 1 + position in long_ids
   }
+  h->schur_ndj = (int)track_span + 1;
   h->nlong = (long)long_ids.size();
   h->lm_long.upload(lm_long, st);
   if (h->nlong) { h->long_ids.upload(long_ids, st); h->ulong.alloc((size_t)3 * h->nlong); }
@@ -724,6 +732,11 @@ int analyze(vus_handle* h, rt::stream_t st) {
     if (rc != VUS_OK) return rc;
   }
   for (int kind = 0; kind < 4; ++kind) h->val[1 - h->cur][kind].alloc((size_t)kVarDim[kind] * h->nvar[kind]);
+  if (FS.n) {                                           // partner table of the per-lambda Schur kernel
+    h->partner.alloc((size_t)FS.n * h->schur_ndj);
+    SchurArgs pa = schur_args(h, 0.0);
+    L_elem<SchurPartnerBody>(FS.n * h->schur_ndj, st, pa);
+  }
   rt::sync(st);
   tick("uploads + allocations");
   h->analyzed = true;
@@ -796,6 +809,7 @@ SchurArgs schur_args(vus_handle* h, double lambda) {
   a.lm_ptr = h->lm_ptr.p; a.lm_long = h->lm_long.p;
   a.fail = h->fail.p; a.xc = h->x.p; a.xl = h->xl.p;
   a.nlong = h->nlong; a.long_ids = h->long_ids.p; a.ulong = h->ulong.p; a.xin = nullptr; a.yout = nullptr;
+  a.partner = h->partner.p; a.ndj = h->schur_ndj;
   return a;
 }
 
@@ -812,7 +826,7 @@ void form_system(vus_handle* h, double lambda, rt::stream_t st) {
   if (h->nobs) {
     SchurArgs a = schur_args(h, lambda);
     L_elem<LmInvertBody>(a.nl, st, a);
-    L_coop<SchurPoseBody>((int)h->nposes_obs, schur_pose_threads(), (size_t)schur_pose_smem_doubles(h->k) * sizeof(double), st, a);
+    L_elem<SchurBlockBody>(2 * h->nposes_obs * h->schur_ndj, st, a);
   }
 }
 
