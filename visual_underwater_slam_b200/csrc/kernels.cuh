@@ -575,95 +575,6 @@ struct LmInvertBody {    // per landmark
     for (int e = 0; e < 9; ++e) A.Cinv[e * A.nl + l] = inv[e];
   }
 };
-#define VUS_SCHUR_GROUPS 4
-// Thread (grp, rs): entry rs = (r, s) of every block S(i, j >= i), over the observations t = grp (mod ngrp) of pose i --
-// the groups shorten each thread's chain of dependent loads; their partial blocks are summed in a fixed order.
-struct SchurPoseBody {
-  static VUS_DEV void run(const SchurArgs& A, int pi, int tid, int nthr, double* sm) {
-    const long i = A.pose_ids[pi];
-    const int D = A.D, k = A.k, B = A.ld;      // B: row stride of the tiles
-    const long BB = A.bs;
-    const int ndj = 2 * k;
-    int ngrp = nthr / 36;
-    if (ngrp > VUS_SCHUR_GROUPS) ngrp = VUS_SCHUR_GROUPS;
-    if (ngrp < 1) ngrp = 1;
-    const int gstride = ndj * 37;       // per group: acc [ndj][36] | touched [ndj]
-    for (int e = tid; e < ngrp * gstride; e += nthr) sm[e] = 0.0;
-    VUS_SYNC();
-    const long I = i / k;
-    const int ri = (int)(i - I * k);
-    for (int w = tid; w < ngrp * 36; w += nthr) {
-      const int grp = w / 36, rs = w - grp * 36;
-      const int r = rs / 6, s = rs - r * 6;
-      double* acc = sm + grp * gstride;
-      double* touched = acc + ndj * 36;
-      double gacc = 0.0;
-      for (int t = A.pose_ptr[pi] + grp; t < A.pose_ptr[pi + 1]; t += ngrp) {
-        const long o = A.pose_obs[t];
-        const long l = A.idx[A.n + o];
-        const double e0 = A.E[o * 18 + r * 3], e1 = A.E[o * 18 + r * 3 + 1], e2 = A.E[o * 18 + r * 3 + 2];
-        const double w0 = e0 * A.Cinv[l] + e1 * A.Cinv[3 * A.nl + l] + e2 * A.Cinv[6 * A.nl + l];
-        const double w1 = e0 * A.Cinv[A.nl + l] + e1 * A.Cinv[4 * A.nl + l] + e2 * A.Cinv[7 * A.nl + l];
-        const double w2 = e0 * A.Cinv[2 * A.nl + l] + e1 * A.Cinv[5 * A.nl + l] + e2 * A.Cinv[8 * A.nl + l];
-        if (s == 0) gacc += w0 * A.gl[l] + w1 * A.gl[A.nl + l] + w2 * A.gl[2 * A.nl + l];
-        if (A.lm_long[l]) continue;                  // long track: only the gradient is reduced here (LongSchur*Body)
-        // observations are stored landmark-major and pose-sorted: the partners with j >= i start at o itself
-        // (or at an earlier observation of the same pose, if the landmark was seen twice from pose i)
-        int q0 = (int)o;
-        const int qbeg = A.lm_ptr[l], qend = A.lm_ptr[l + 1];
-        while (q0 > qbeg && A.idx[q0 - 1] == i) --q0;
-        for (int qb = q0; qb < qend; qb += 4) {           // partners in batches of 4: all loads of a batch are independent
-          long jj[4];
-          double ev[4][3];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int q = qb + u < qend ? qb + u : qend - 1;
-            jj[u] = qb + u < qend ? (long)A.idx[q] : -1;
-            ev[u][0] = A.E[(long)q * 18 + s * 3]; ev[u][1] = A.E[(long)q * 18 + s * 3 + 1]; ev[u][2] = A.E[(long)q * 18 + s * 3 + 2];
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const long j = jj[u];
-            if (j < 0) continue;
-            const double v = w0 * ev[u][0] + w1 * ev[u][1] + w2 * ev[u][2];
-            const int dj = (int)(j - i);             // every partner of a short track is in-band by construction: dj < 2k
-            acc[dj * 36 + rs] += v;
-            if (rs == 0) touched[dj] = 1.0;
-          }
-        }
-      }
-      if (s == 0) sm[ngrp * gstride + grp * 6 + r] = gacc;
-    }
-    VUS_SYNC();
-    for (int e = tid; e < 6; e += nthr) {
-      double gsum = 0.0;
-      for (int grp = 0; grp < ngrp; ++grp) gsum += sm[ngrp * gstride + grp * 6 + e];
-      A.gs[i * D + e] -= gsum;
-    }
-    for (int e = tid; e < ndj * 36; e += nthr) {
-      const int dj = e / 36, rs = e - dj * 36;
-      double v = 0.0, any = 0.0;
-      for (int grp = 0; grp < ngrp; ++grp) { v += sm[grp * gstride + e]; any += sm[grp * gstride + ndj * 36 + dj]; }
-      if (any == 0.0) continue;
-      const int r = rs / 6, s = rs - r * 6;
-      const long j = i + dj;
-      const long J = j / k;
-      const int rj = (int)(j - J * k);
-      if (J == I) {
-        A.SD[I * BB + (long)(ri * D + r) * B + rj * D + s] -= v;
-        if (dj) A.SD[I * BB + (long)(rj * D + s) * B + ri * D + r] -= v;
-      } else {
-        A.SU[I * BB + (long)(ri * D + r) * B + rj * D + s] -= v;
-      }
-    }
-  }
-};
-#ifdef VUS_EMU
-VUS_HD int schur_pose_threads() { return 64; }
-#else
-VUS_HD int schur_pose_threads() { return 160; }      // 4 observation groups x 36 entries (+ padding to a warp multiple)
-#endif
-VUS_HD long schur_pose_smem_doubles(int k) { return (long)VUS_SCHUR_GROUPS * (2 * k * 37 + 6); }
 // Landmarks whose track is longer than the band cannot be folded into the block-tridiagonal matrix without making it
 // indefinite (the Schur complement subtracts from every block it touches).  They are still eliminated EXACTLY, but
 // their term  - E_l (C_l + lambda I)^-1 E_l^T  is applied implicitly inside the operator and left out of the band
