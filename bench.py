@@ -94,6 +94,8 @@ def cpu_oracle_run(a, steps=1, warmup=0):
 
 
 class ClockSampler:
+    """SM clock / throttle reasons DURING the timed region.  NVML in-process (a sample every 10 ms from a thread, so even a
+    0.3 s timed region gets dozens of samples); `nvidia-smi -lms` as the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -101,10 +103,36 @@ class ClockSampler:
         self.index = index
         self.rows = []
         self.proc = None
+        self.nvml = None
+        self.samples = []          # (sm_mhz, sm_max_mhz, reason bitmask)
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _nvml_loop(self, pynvml, handle):
+        smax = pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.samples.append((pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM), smax, int(get_reasons(handle))))
+            except Exception:
+                pass
+            self._stop.wait(0.01)
 
     def start(self):
         if os.environ.get("VUS_BENCH_NO_SMI"):
             return
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else self.index
+            handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self._thread = threading.Thread(target=self._nvml_loop, args=(pynvml, handle), daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -117,6 +145,20 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+            n = self.nvml
+            names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", 0x8), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", 0x20), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", 0x4))
+            if self.samples:
+                reasons = set()
+                for _, _, mask in self.samples:
+                    for name, attr, default in names:
+                        if mask & int(getattr(n, attr, default)):
+                            reasons.add(name)
+                return dict(sm_mhz=float(np.median([x[0] for x in self.samples])), sm_max_mhz=float(self.samples[0][1]),
+                            reasons=sorted(reasons), samples=len(self.samples), source="nvml")
         if self.proc:
             self.proc.terminate()
         sm, smax, reasons = [], [], set()
@@ -131,7 +173,7 @@ class ClockSampler:
                 pass
         if not sm:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
-        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(smax)), reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(smax)), reasons=sorted(reasons), samples=len(sm), source="nvidia-smi")
 
 
 def peaks():
