@@ -272,3 +272,25 @@ def test_optimize_many_is_n_separate_optimizers(emu):
         assert abs(a.x() - b.x()) + abs(a.y() - b.y()) + abs(a.z() - b.z()) < 1e-7
     with pytest.raises(ValueError):
         gtsam.optimize_many([], [])
+
+
+def test_batch_py_import_list_resolves():
+    """Every name batch.py imports from gtsam (batch.py:19-27) exists in the package, so its import block works with the
+    module swapped; the ones it never uses on the path raise when constructed."""
+    import importlib
+    src = open("/root/reference/batch.py").read() if os.path.exists("/root/reference/batch.py") else None
+    names = ["ISAM2", "BetweenFactorConstantBias", "Cal3_S2", "ConstantTwistScenario", "ImuFactor", "NonlinearFactorGraph",
+             "PinholeCameraCal3_S2", "Point3", "Pose3", "PriorFactorConstantBias", "PriorFactorPose3", "PriorFactorVector", "Rot3",
+             "Values", "PriorFactorPoint3", "NavState", "Cal3_S2Stereo", "StereoPoint2", "GenericStereoFactor3D"]
+    if src is not None:                                   # the list above is batch.py's own (checked where the reference exists)
+        m = re.search(r"from gtsam import \((.*?)\)", src, re.S)
+        assert sorted(n.strip() for n in m.group(1).replace("\n", " ").split(",") if n.strip()) == sorted(names)
+    for n in names:
+        assert hasattr(gtsam, n), n
+    sh = importlib.import_module("visual_underwater_slam_b200.symbol_shorthand") if False else gtsam.symbol_shorthand
+    assert all(hasattr(sh, k) for k in "BVXL")
+    plot = importlib.import_module("visual_underwater_slam_b200.utils").plot
+    with pytest.raises(NotImplementedError):
+        plot.plot_trajectory(1, None)
+    with pytest.raises(NotImplementedError):
+        gtsam.NavState()

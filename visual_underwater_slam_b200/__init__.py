@@ -6,7 +6,8 @@ LevenbergMarquardtOptimizer(graph, initial, LevenbergMarquardtParams()).optimize
 All arithmetic runs in hand-written sm_100a CUDA kernels behind the C-ABI in include/vus.h;
 there is no CPU fallback.
 """
-from .symbol import Symbol, symbol, symbolChr, symbolIndex, symbol_shorthand
+from .symbol import Symbol, symbol, symbolChr, symbolIndex
+from . import symbol_shorthand
 from .geometry import Point3, Rot3, Pose3, StereoPoint2, Cal3_S2Stereo
 from .noise import noiseModel
 from .navigation import (PreintegrationParams, PreintegratedImuMeasurements, imuBias, ConstantBias,
@@ -17,5 +18,8 @@ from .values import Values
 from .graph import NonlinearFactorGraph
 from .optimizer import LevenbergMarquardtParams, LevenbergMarquardtOptimizer, Marginals, JointMarginal, optimize_many
 from .incremental import ISAM2, ISAM2Result
+from .unused import (BetweenFactorConstantBias, Cal3_S2, ConstantTwistScenario, PinholeCameraCal3_S2,
+                     PriorFactorConstantBias, PriorFactorPoint3, NavState)
+from . import utils
 
 __all__ = [n for n in dir() if not n.startswith("_")]
