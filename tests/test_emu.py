@@ -192,3 +192,22 @@ def test_golden_rows_on_the_emulation(emu):
     for r, row in zip(res, g["summary"]):
         assert r["iterations"] == int(row[0]) and r["inner_iterations"] == int(row[1])
         assert abs(r["final_error"] - row[2]) <= 1e-6 * row[2]
+
+
+def test_landmark_seen_twice_from_one_pose_stays_exact(emu):
+    """A landmark observed twice from the same pose (two stereo factors on one (X, L) pair): the register-blocked Schur kernel
+    expects one partner per pose, so such a landmark takes the implicit path of the long tracks -- still eliminated exactly."""
+    _, prob = pc.make(40, n_lm=60, seed=21)
+    st = {k: np.asarray(v).copy() for k, v in prob["stereo"].items()}
+    dup = np.array([3, 4, 50, 51, 200])                              # duplicate a few observations (same pose, same landmark)
+    for k in st:
+        st[k] = np.concatenate([st[k], st[k][dup]], 0)
+    st["meas"][-len(dup):] += 0.3                                     # a second, slightly different measurement
+    st["orig"][-len(dup):] = prob["n_factors"] + np.arange(len(dup))
+    prob = dict(prob)
+    prob["stereo"] = st
+    prob["n_factors"] = prob["n_factors"] + len(dup)
+    pc.check_factor_parity(emu, prob)
+    its = pc.check_solve_parity(emu, prob, 1e-2, 1e-6)
+    assert its < 60
+    pc.check_lm_parity(emu, prob)
