@@ -211,3 +211,32 @@ def test_landmark_seen_twice_from_one_pose_stays_exact(emu):
     its = pc.check_solve_parity(emu, prob, 1e-2, 1e-6)
     assert its < 60
     pc.check_lm_parity(emu, prob)
+
+
+def test_tracks_with_gaps_keep_parity(emu):
+    """Ragged landmark tracks (poses missing inside a track, tracks of different lengths): the partner table of the Schur
+    kernel must skip the gaps -- factor, solve and LM parity on a graph with 30 % of the observations removed."""
+    _, prob = pc.make(50, n_lm=80, seed=31)
+    st = {k: np.asarray(v) for k, v in prob["stereo"].items()}
+    rng = np.random.default_rng(5)
+    keep = rng.random(len(st["orig"])) > 0.3
+    for l in range(len(prob["lm_keys"])):                           # every landmark keeps at least two observations
+        rows = np.nonzero(st["l"] == l)[0]
+        if keep[rows].sum() < 2:
+            keep[rows[:2]] = True
+    st = {k: v[keep].copy() for k, v in st.items()}
+    removed = int((~keep).sum())
+    prob = dict(prob)
+    # insertion indices stay a permutation of 0 .. n_factors-1: renumber everything after dropping the removed factors
+    order = np.sort(np.concatenate([np.asarray(prob[t]["orig"]) for t in ("prior_pose", "prior_vel", "between", "dvl", "imu")] + [st["orig"]]))
+    remap = {int(o): i for i, o in enumerate(order)}
+    for t in ("prior_pose", "prior_vel", "between", "dvl", "imu"):
+        f = dict(prob[t])
+        f["orig"] = np.array([remap[int(o)] for o in f["orig"]], dtype=np.int64)
+        prob[t] = f
+    st["orig"] = np.array([remap[int(o)] for o in st["orig"]], dtype=np.int64)
+    prob["stereo"] = st
+    prob["n_factors"] = prob["n_factors"] - removed
+    pc.check_factor_parity(emu, prob)
+    pc.check_solve_parity(emu, prob, 1e-2, 1e-6)
+    pc.check_lm_parity(emu, prob)
