@@ -164,6 +164,15 @@ int vus_get_layout(vus_handle* h, int64_t out[8]);
  * (a cudaStream_t, may be NULL); the call returns after the convergence decision. Values are updated in place. */
 int vus_optimize(vus_handle* h, void* stream, vus_lm_result* result);
 
+/* Try-by-try history of the last single-graph vus_optimize -- gtsam's LM with verbosityLM = TRYLAMBDA prints the same
+ * sequence: the lambda tried, whether the damped system could be solved, the error at the trial point (inf when the step
+ * was rejected before evaluation) and whether the step was accepted.  Writes min(count, capacity) entries. */
+typedef struct vus_lm_try {
+  double lambda, new_error;
+  int32_t solved, accepted, pcg_iterations, reserved;
+} vus_lm_try;
+int vus_get_trace(vus_handle* h, int32_t capacity, vus_lm_try* out, int32_t* count);
+
 /* NonlinearFactorGraph::error(values) = sum 1/2 ||whitened r||^2 at the current values */
 int vus_error(vus_handle* h, void* stream, double* out);
 /* per-factor 1/2 ||r||^2 in ORIGINAL insertion order (length = total factor count) */

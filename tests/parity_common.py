@@ -75,6 +75,16 @@ def check_lm_parity(lib, prob, params=None):
         vals, info = lm.lm_optimize(prob)
         assert res["iterations"] == info["iterations"], (res["iterations"], info["iterations"])
         assert res["inner_iterations"] == len(info["trace"]["tries"])
+        # the same LM trajectory, try by try: lambda history, accept / reject decisions, trial errors
+        tr = s.trace()
+        assert len(tr) == len(info["trace"]["tries"])
+        for mine, ref in zip(tr, info["trace"]["tries"]):
+            assert abs(mine["lam"] - ref["lam"]) <= 1e-12 * ref["lam"]
+            assert mine["solved"] == ref["solved"] and mine["success"] == ref["success"]
+            if np.isfinite(ref["new_err"]):
+                assert abs(mine["new_err"] - ref["new_err"]) <= 1e-6 * ref["new_err"]
+            else:
+                assert not np.isfinite(mine["new_err"])
         assert abs(res["final_error"] - info["error"]) <= 1e-6 * info["error"]          # tolerance from north_star
         assert abs(res["final_lambda"] - info["lam"]) <= 1e-12 * info["lam"]
         v = s.values()

@@ -40,6 +40,11 @@ class LmResult(C.Structure):
         return d
 
 
+class LmTry(C.Structure):                               # vus_lm_try
+    _fields_ = [("lambda_", C.c_double), ("new_error", C.c_double), ("solved", C.c_int32), ("accepted", C.c_int32),
+                ("pcg_iterations", C.c_int32), ("reserved", C.c_int32)]
+
+
 class ComponentResult(C.Structure):                     # vus_component_result
     _fields_ = [("iterations", C.c_int32), ("inner_iterations", C.c_int32), ("initial_error", C.c_double),
                 ("final_error", C.c_double), ("final_lambda", C.c_double)]
@@ -69,6 +74,7 @@ EXPORTS = {
     "vus_analyze": (C.c_int, [C.c_void_p]),
     "vus_get_layout": (C.c_int, [C.c_void_p, c_i64_p]),
     "vus_optimize": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(LmResult)]),
+    "vus_get_trace": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(LmTry), c_i32_p]),
     "vus_error": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p]),
     "vus_factor_errors": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p]),
     "vus_linearize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_double_p, c_double_p]),

@@ -226,6 +226,7 @@ struct vus_handle {
   }
   // stats
   vus_lm_result res;
+  std::vector<vus_lm_try> trace;   // one entry per lambda try of the last single-graph optimize()
 };
 
 namespace {
@@ -1213,6 +1214,7 @@ void retract(vus_handle* h, rt::stream_t st) {
 int optimize(vus_handle* h, rt::stream_t st) {
   vus_lm_result& R = h->res;
   R = vus_lm_result();
+  h->trace.clear();
   const vus_lm_params& P = h->prm;
   const long launches0 = g_launches;
   g_prof.reset();
@@ -1261,6 +1263,7 @@ int optimize(vus_handle* h, rt::stream_t st) {
         }
         R.ms_update += now_ms() - t2;
         if (P.verbose) std::fprintf(stderr, "  try lam=%.3e solved=%d pcg=%d new_err=%.9e success=%d\n", lambda, (int)solved, its, new_err, (int)success);
+        { vus_lm_try tr; tr.lambda = lambda; tr.new_error = new_err; tr.solved = solved; tr.accepted = success; tr.pcg_iterations = its; tr.reserved = 0; h->trace.push_back(tr); }
         if (success) {
           h->cur = 1 - h->cur;
           err = new_err;
@@ -1882,6 +1885,13 @@ int vus_optimize(vus_handle* h, void* stream, vus_lm_result* result) {
   if (result) *result = h->res;
   return rc;
   VUS_CATCH(h)
+}
+
+int vus_get_trace(vus_handle* h, int32_t capacity, vus_lm_try* out, int32_t* count) {
+  if (!h || !count) return VUS_ERR_INVALID;
+  *count = (int32_t)h->trace.size();
+  if (out) std::copy(h->trace.begin(), h->trace.begin() + std::min<size_t>(h->trace.size(), capacity > 0 ? capacity : 0), out);
+  return VUS_OK;
 }
 
 int vus_error(vus_handle* h, void* stream, double* out) {

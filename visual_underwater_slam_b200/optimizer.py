@@ -262,6 +262,15 @@ class Session:
         self._check(self.lib.vus_optimize(self._h, stream, C.byref(res)))
         return res.as_dict()
 
+    def trace(self):
+        """Try-by-try history of the last optimize(): list of dict(lam, solved, success, new_err, pcg_iterations)."""
+        n = C.c_int32()
+        self._check(self.lib.vus_get_trace(self._h, 0, None, C.byref(n)))
+        arr = (_native.LmTry * max(n.value, 1))()
+        self._check(self.lib.vus_get_trace(self._h, n.value, arr, C.byref(n)))
+        return [dict(lam=t.lambda_, solved=bool(t.solved), success=bool(t.accepted), new_err=t.new_error,
+                     pcg_iterations=t.pcg_iterations) for t in arr[:n.value]]
+
     def component_results(self):
         """Per-trajectory summary of the last batched optimize(): list of dicts (vus_component_result)."""
         arr = (_native.ComponentResult * self.n_components)()
@@ -340,8 +349,11 @@ class LevenbergMarquardtOptimizer:
         return self._params.lambdaInitial if self._result is None else self._result["final_lambda"]
 
     def stats(self):
-        """Per-phase timings, PCG iterations, kernel launches of the last optimize()."""
-        return dict(self._result or {})
+        """Per-phase timings, PCG iterations, kernel launches and the try-by-try lambda / error history of the last optimize()."""
+        d = dict(self._result or {})
+        if self._result is not None:
+            d["trace"] = self._session.trace()
+        return d
 
 
 def optimize_many(graphs, initial_values, params=None, lib=None, device=0):
