@@ -240,3 +240,8 @@ def test_tracks_with_gaps_keep_parity(emu):
     pc.check_factor_parity(emu, prob)
     pc.check_solve_parity(emu, prob, 1e-2, 1e-6)
     pc.check_lm_parity(emu, prob)
+
+
+def test_batch_of_one_is_the_single_graph_path(emu):
+    probs = [pc.make(45, n_loops=2, loop_min_gap=12, seed=5)[1]]
+    pc.check_batched_parity(emu, probs)

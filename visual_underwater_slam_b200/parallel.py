@@ -132,6 +132,11 @@ def solve_batched(problems, params=None, lib=None, device=0, keep_values=True, s
     every trajectory keeps its own lambda / accept-reject / convergence path, as separate optimizers would.
     -> list of dict(summary fields..., values=tables or None), in input order (same shape as solve_local's result).
     `stats`: optional dict that receives the whole-batch vus_lm_result (rounds, PCG iterations, launches, per-class times)."""
+    if len(problems) == 1:                               # a batch of one is the single-graph path (batch.py:337 as it stands)
+        out = solve_local(problems, params, lib=lib, device=device, threads=1, keep_values=keep_values)
+        if stats is not None:
+            stats.update(inner_iterations=out[0]["inner_iterations"], iterations=out[0]["iterations"])
+        return out
     prob, node_start = concat_problems(problems)
     s = Session(prob, params or LevenbergMarquardtParams(), lib=lib, device=device, components=node_start)
     try:
