@@ -245,3 +245,21 @@ def test_tracks_with_gaps_keep_parity(emu):
 def test_batch_of_one_is_the_single_graph_path(emu):
     probs = [pc.make(45, n_loops=2, loop_min_gap=12, seed=5)[1]]
     pc.check_batched_parity(emu, probs)
+
+
+def test_marginals_never_return_an_unconverged_column(emu):
+    """Tracks longer than the band leave most of the stereo information to PCG; the undamped unit-vector solves of
+    gtsam.Marginals can then fail to converge.  The library must either return the oracle's covariance or refuse
+    (VUS_ERR_STATE, 'did not converge') -- never hand back the unconverged column (found by tools/fuzz_single.py)."""
+    from visual_underwater_slam_b200 import synthetic
+    d = synthetic.make_trajectory_graph(68, seed=5892, n_landmarks=89, obs_per_landmark=13, n_loops=3, loop_min_gap=17, pixel_noise=1.0)
+    prob = d["graph"].to_problem(d["initial"])
+    pc.check_marginals(emu, prob, [("pose", 10), ("vel", 30), ("bias", 0), ("lm", 5)], rtol=1e-5)     # these converge
+    refused = 0
+    for q in ([("pose", 0)], [("pose", 8)], [("lm", 0)]):
+        try:
+            pc.check_marginals(emu, prob, q, rtol=1e-5)
+        except RuntimeError as e:
+            assert "did not converge" in str(e)
+            refused += 1
+    assert refused >= 1

@@ -184,6 +184,7 @@ struct vus_handle {
   double cur_lambda = 0.0;
   int schur_ndj = 1;
   DBuf<int> partner;
+  double last_rel_res = 0.0;     // true relative residual ||rhs - A x|| / ||rhs|| at the end of the last pcg()
   bool z0_valid = false;         // column 6 of Z holds M^-1 gs (band part of the first preconditioner application)
   DBuf<double> C, gl, Cinv, E, Pp, Pl;
   // BCR
@@ -1088,7 +1089,9 @@ int pcg(vus_handle* h, rt::stream_t st, bool* converged) {
   reduce(h, h->r.p, h->r.p, h->Lr, S_RR, RED_STORE, st);
   const double rr0 = read_scalar(h, S_RR, st);
   *converged = true;
+  h->last_rel_res = 0.0;
   if (!(rr0 > 0.0)) { h->z0_valid = false; return 0; }
+  h->last_rel_res = INFINITY;
   const double tol2 = h->prm.pcg_rel_tol * h->prm.pcg_rel_tol * rr0;
   *converged = false;
   int it = 0;
@@ -1133,6 +1136,7 @@ int pcg(vus_handle* h, rt::stream_t st, bool* converged) {
     reduce(h, h->r.p, h->r.p, h->Lr, S_RR, RED_STORE, st);
     const double rr_true = read_scalar(h, S_RR, st);
     if (h->prm.verbose > 1) std::fprintf(stderr, "    pcg outer %d true rel_res %.3e\n", outer, std::sqrt(rr_true / rr0));
+    h->last_rel_res = std::sqrt(rr_true / rr0);
     if (rr_true <= tol2) { *converged = true; break; }
     if (!(rr_true < 0.25 * rr_outer) || it >= h->prm.pcg_max_iterations) break;   // no further progress possible
     rr_outer = rr_true;
@@ -1664,6 +1668,15 @@ int marginal_covariance(vus_handle* h, rt::stream_t st, long nq, const int32_t* 
       L_elem<UnitRhsBody>(1, st, u);
       bool conv = false;
       pcg(h, st, &conv);
+      // The undamped system can be far harder than the damped ones of the LM loop (no lambda, unit right-hand sides that excite
+      // the weakest directions; graphs whose tracks exceed the band leave most of the stereo information to PCG): refuse to
+      // hand back a covariance column whose solve did not reach a small true residual.
+      if (!conv && !(h->last_rel_res <= 1e-7)) {
+        char msg[200];
+        std::snprintf(msg, sizeof msg, "vus_marginal_covariance: the undamped solve of column %d of query %ld did not converge "
+                      "(true relative residual %.2e)", j, q, h->last_rel_res);
+        return fail(h, VUS_ERR_STATE, msg);
+      }
       if (any_lm) {
         SchurArgs a = schur_args(h, 0.0);
         L_elem<LmBacksubBody>(a.nl, st, a);
