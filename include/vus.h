@@ -51,7 +51,9 @@ enum vus_var_kind { VUS_VAR_POSE = 0, VUS_VAR_VEL = 1, VUS_VAR_BIAS = 2, VUS_VAR
  *                 batch.py:196-233, :241-250
  *   STEREO        gtsam.GenericStereoFactor3D batch.py:300-305 x, l                    3 (uL, uR, v)         3
  *   IMU           gtsam.ImuFactor          batch.py:238        xi, vi, xj, vj, b       67 (packed PIM)       45 (upper-tri R, R^T R = Sigma^-1)
- * Packed PIM: dR 9 | dP 3 | dV 3 | dt 1 | bias_hat 6 | dR/dbg 9 | dP/dba 9 | dP/dbg 9 | dV/dba 9 | dV/dbg 9.
+ * Packed PIM: dR 9 | dP 3 | dV 3 | dt 1 | bias_hat 6 | dR/dbg 9 | dP/dba 9 | dP/dbg 9 | dV/dba 9 | dV/dbg 9   (manifold build)
+ *             theta 3, 6 unused | p 3 | v 3 | dt 1 | bias_hat 6 | dtheta/dbg 9 | dp/dba 9 | dp/dbg 9 | dv/dba 9 | dv/dbg 9   (tangent build,
+ *             vus_set_gtsam_build; every IMU factor of a handle is of the handle's build).
  * Whitened Jacobian layouts returned by vus_linearize (node order, element (row,col) at J[(row*cols+col)*n+f]):
  *   PRIOR_POSE 6x6 | PRIOR_VEL 3x3 | BETWEEN 6x12 [H1|H2] | DVL 3x9 [Hx|Hv] | STEREO 3x9 [Hpose|Hlm]
  *   IMU 9x24 [Hxi Hvi | Hxj Hvj | Hbias]                                                              */
@@ -82,8 +84,8 @@ typedef struct vus_lm_result {
   int32_t inner_iterations;      /* lambda tries */
   int32_t linearizations;
   int32_t pcg_iterations;        /* total */
-  int32_t solve_failures;
-  int32_t reserved;
+  int32_t solve_failures;        /* lambda tries whose damped system could not be solved (non-positive pivot, or the PCG below) */
+  int32_t pcg_not_converged;     /* of those: PCG ended on a NaN or stalled with a true relative residual above 1e-6 */
   double initial_error, final_error, final_lambda;
   double ms_total, ms_linearize, ms_assemble, ms_schur, ms_factor, ms_pcg, ms_update;
   int64_t kernel_launches;
@@ -93,6 +95,7 @@ typedef struct vus_lm_result {
    * 7 BCR solve | 8 matvec | 9 border | 10 vector/reduce | 11 retract */
   double ms_class[16];
   int64_t launches_class[16];
+  double worst_pcg_rel_residual; /* largest TRUE relative residual ||rhs - A x|| / ||rhs|| any damped solve ended with */
 } vus_lm_result;
 
 void vus_default_lm_params(vus_lm_params* p);
@@ -116,6 +119,14 @@ int vus_add_factors(vus_handle* h, int type, int64_t n, const int32_t* var_idx, 
 int vus_set_calibration(vus_handle* h, const double K[6]);       /* Cal3_S2Stereo fx fy s u0 v0 b (batch.py:115) */
 int vus_set_gravity(vus_handle* h, const double g[3]);           /* PreintegrationParams n_gravity (batch.py:181) */
 int vus_set_lm_params(vus_handle* h, const vus_lm_params* p);
+/* The two CMake switches of gtsam that change this path's arithmetic (the reference pins no gtsam version, README.md:18):
+ *   tangent_preintegration          GTSAM_TANGENT_PREINTEGRATION (ON in the gtsam 4.0 - 4.2 wheels): ImuFactor::evaluateError
+ *                                   corrects the preintegrated 9-vector linearly for the bias and retracts it
+ *                                   (TangentPreintegration.cpp); 0 = ManifoldPreintegration.cpp
+ *   slow_but_correct_betweenfactor  GTSAM_SLOW_BUT_CORRECT_BETWEENFACTOR (OFF in the wheels): BetweenFactor::evaluateError
+ *                                   multiplies its Jacobians by the derivative of Local(); 0 = H1 = -Ad(hx^-1), H2 = I
+ * Defaults: 1, 0 (the pip wheel build).  Also selects the variant vus_preintegrate_imu computes. */
+int vus_set_gtsam_build(vus_handle* h, int tangent_preintegration, int slow_but_correct_betweenfactor);
 
 /* ---- one graph split across GPUs by contiguous pose range (BASELINE.json config 5) -------------------
  * Each rank holds a LOCAL graph: its owned poses first, then the halo poses (owned by other ranks) that its factors
@@ -197,7 +208,7 @@ int vus_marginal_covariance(vus_handle* h, void* stream, int64_t nq, const int32
  * gtsam.PreintegratedImuMeasurements.integrateMeasurement x k + resetIntegration per keyframe interval
  * (batch.py:289-293; covariances of batch.py:183-185): acc, gyro [n][k][3], constant dt (batch.py:290 passes 0.005).
  * Emits what vus_add_factors(VUS_FACTOR_IMU) takes: pim_out [n][67] (packed PIM), sqrt_info_out [n][45] (upper R,
- * R^T R = preintMeasCov^-1).  Manifold preintegration. */
+ * R^T R = preintMeasCov^-1), in the preintegration variant of vus_set_gtsam_build. */
 int vus_preintegrate_imu(vus_handle* h, void* stream, int64_t n, int32_t k, const double* acc, const double* gyro, double dt,
                          const double bias_hat[6], const double acc_cov[9], const double gyro_cov[9], const double int_cov[9],
                          double* pim_out, double* sqrt_info_out, int mem);

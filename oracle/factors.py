@@ -49,12 +49,19 @@ def prior_vec(v, vm, sqrt_info):
 
 
 # ---------------------------------------------------------------- BetweenFactor<Pose3>
-def between(R1, t1, R2, t2, Rm, tm, sqrt_info):
-    """hx = T1^-1 T2 ; e = Log(m^-1 hx); H2 = dLog(e); H1 = -dLog(e) Ad(hx^-1)."""
+def between(R1, t1, R2, t2, Rm, tm, sqrt_info, exact_jacobian=False):
+    """hx = T1^-1 T2 ; e = Local(measured, hx) = Log(m^-1 hx).
+
+    BetweenFactor.h::evaluateError has two builds:
+      default (gtsam 4.1 / 4.2 wheels)            H1 = -Ad(hx^-1), H2 = I   -- the Jacobians of Between() only; the
+                                                  derivative of Local() is left out (exact only at e = 0);
+      GTSAM_SLOW_BUT_CORRECT_BETWEENFACTOR=ON     H1 = -dLog(e) Ad(hx^-1), H2 = dLog(e)   (exact_jacobian=True).
+    """
     Rh, th = lie.pose_between(R1, t1, R2, t2)
     Re, te = lie.pose_between(Rm, tm, Rh, th)
     e = lie.pose_log(Re, te)
-    D = lie.pose_dlog_xi(e)
+    n = R1.shape[0]
+    D = lie.pose_dlog_xi(e) if exact_jacobian else np.broadcast_to(np.eye(6), (n, 6, 6))
     Rhi, thi = lie.pose_inverse(Rh, th)
     H1 = -D @ lie.pose_adjoint(Rhi, thi)
     H2 = D
@@ -132,8 +139,14 @@ def unpack_triu(tri, d=9):
     return M
 
 
-def imu(Ri, ti, vi, Rj, tj, vj, bias, pim, sqrt_info_triu, gravity):
-    """ImuFactor, keys (X_i, V_i, X_j, V_j, B) (batch.py:238), ManifoldPreintegration.
+def imu(Ri, ti, vi, Rj, tj, vj, bias, pim, sqrt_info_triu, gravity, tangent=False):
+    """ImuFactor, keys (X_i, V_i, X_j, V_j, B) (batch.py:238).
+
+    tangent=False: ManifoldPreintegration::biasCorrectedDelta -- dR_c = dR Exp(JRg dbg);
+    tangent=True : TangentPreintegration::biasCorrectedDelta  -- the preintegrated 9-vector is corrected LINEARLY,
+                   theta_c = theta + (d theta / d bg) dbg, and PreintegrationBase::predict retracts it: dR_c = Exp(theta_c)
+                   (pim columns 0:3 = theta, 22:31 = d theta / d bg; preint.preintegrate_tangent).
+    Everything after the bias-corrected deltas is shared (PreintegrationBase::computeError / NavState).
 
     error = NavState_j.localCoordinates(predict(state_i, bias)) =
       [Log(Rj^T Ri Exp(th_c)); Rj^T(p_i + v_i dt + g dt^2/2 + Ri p_c - p_j); Rj^T(v_i + g dt + Ri v_c - v_j)]
@@ -147,8 +160,12 @@ def imu(Ri, ti, vi, Rj, tj, vj, bias, pim, sqrt_info_triu, gravity):
     dba = bias[:, 0:3] - P['bhat'][:, 0:3]
     dbg = bias[:, 3:6] - P['bhat'][:, 3:6]
     # bias-corrected deltas (ManifoldPreintegration::biasCorrectedDelta)
-    corr = _mv(P['JRg'], dbg)
-    dRc = P['dR'] @ lie.so3_exp(corr)
+    if tangent:
+        corr = pim[:, 0:3] + _mv(P['JRg'], dbg)        # theta_c
+        dRc = lie.so3_exp(corr)
+    else:
+        corr = _mv(P['JRg'], dbg)
+        dRc = P['dR'] @ lie.so3_exp(corr)
     pc = P['dP'] + _mv(P['JPa'], dba) + _mv(P['JPg'], dbg)
     vc = P['dV'] + _mv(P['JVa'], dba) + _mv(P['JVg'], dbg)
     RjT = _T(Rj)

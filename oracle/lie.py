@@ -117,6 +117,43 @@ def so3_dlog(w):
     return J
 
 
+def so3_apply_dexp_deriv(w, c):
+    """d/dw [ Jr(w) c ] at fixed c  (SO3.cpp DexpFunctor::applyDexp, H1), batched [n,3,3].
+
+    Jr(w) c = c - A (w x c) + B (w x (w x c)),  A = (1 - cos th)/th^2,  B = (th - sin th)/th^3;  th^2 <= eps -> [c]x / 2.
+    """
+    w = np.atleast_2d(np.asarray(w, dtype=np.float64))
+    c = np.atleast_2d(np.asarray(c, dtype=np.float64))
+    n = w.shape[0]
+    th2 = np.einsum('ni,ni->n', w, w)
+    near = th2 <= EPS
+    th2s = np.where(near, 1.0, th2)
+    th = np.sqrt(th2s)
+    s, co = np.sin(th), np.cos(th)
+    omc = 2.0 * np.sin(0.5 * th) ** 2
+    A = omc / th2s
+    B = (th - s) / (th2s * th)
+    dA = (th * s - 2.0 * omc) / (th2s * th)              # dA/dth
+    dB = (omc * th - 3.0 * (th - s)) / (th2s * th2s)     # dB/dth
+    wxc = np.cross(w, c)
+    wwc = np.cross(w, wxc)
+    wc = np.einsum('ni,ni->n', w, c)
+    outer = lambda a, b: a[:, :, None] * b[:, None, :]
+    D = (-(dA / th)[:, None, None] * outer(wxc, w) + A[:, None, None] * skew(c)
+         + (dB / th)[:, None, None] * outer(wwc, w)
+         + B[:, None, None] * (wc[:, None, None] * _eye(n) + outer(w, c) - 2.0 * outer(c, w)))
+    D[near] = (0.5 * skew(c))[near]
+    return D
+
+
+def so3_apply_inv_dexp(w, v):
+    """DexpFunctor::applyInvDexp: c = Jr(w)^-1 v, H_w = -Jr^-1 d/dw[Jr(w) c], H_v = Jr^-1.  -> (c, H_w, H_v)"""
+    Jr = so3_dexp(w)
+    inv = np.linalg.inv(Jr)
+    c = np.einsum('nij,nj->ni', inv, np.atleast_2d(v))
+    return c, -inv @ so3_apply_dexp_deriv(w, c), inv
+
+
 def pose_compose(Ra, ta, Rb, tb):
     return Ra @ Rb, ta + np.einsum('nij,nj->ni', Ra, tb)
 

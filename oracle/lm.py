@@ -69,6 +69,15 @@ def values_of(prob):
                 biases=prob['biases'].copy(), lms=prob['lms'].copy())
 
 
+def build_options(prob):
+    """The two compile-time switches of gtsam that change this path's arithmetic (prob['options'], written by
+    graph.to_problem): GTSAM_TANGENT_PREINTEGRATION and GTSAM_SLOW_BUT_CORRECT_BETWEENFACTOR.  A problem without the
+    entry is read as the gtsam 4.2 wheel build: tangent preintegration ON, slow-but-correct BetweenFactor OFF."""
+    o = dict(tangent_preintegration=True, slow_but_correct_betweenfactor=False)
+    o.update(prob.get('options') or {})
+    return o
+
+
 def eval_factors(prob, vals, ftype):
     """-> (r_whitened [n,m], [J_k], [(kind, idx)_k]) for one factor type at `vals`."""
     f = prob.get(ftype)
@@ -84,7 +93,8 @@ def eval_factors(prob, vals, ftype):
         return r, J, [('v', f['v'])]
     if ftype == 'between':
         Rm, tm = split_pose(f['meas'])
-        r, J = F.between(R[f['x1']], t[f['x1']], R[f['x2']], t[f['x2']], Rm, tm, f['sqrt_info'])
+        r, J = F.between(R[f['x1']], t[f['x1']], R[f['x2']], t[f['x2']], Rm, tm, f['sqrt_info'],
+                         exact_jacobian=bool(build_options(prob)['slow_but_correct_betweenfactor']))
         return r, J, [('x', f['x1']), ('x', f['x2'])]
     if ftype == 'dvl':
         r, J = F.dvl(vals['vels'][f['v']], R[f['x']], f['meas'], f['sqrt_info'])
@@ -94,7 +104,8 @@ def eval_factors(prob, vals, ftype):
         return r, J, [('x', f['x']), ('l', f['l'])]
     if ftype == 'imu':
         r, J = F.imu(R[f['xi']], t[f['xi']], vals['vels'][f['vi']], R[f['xj']], t[f['xj']], vals['vels'][f['vj']],
-                     vals['biases'][f['b']], f['pim'], f['sqrt_info'], prob['gravity'])
+                     vals['biases'][f['b']], f['pim'], f['sqrt_info'], prob['gravity'],
+                     tangent=bool(build_options(prob)['tangent_preintegration']))
         return r, J, [('x', f['xi']), ('v', f['vi']), ('x', f['xj']), ('v', f['vj']), ('b', f['b'])]
     raise KeyError(ftype)
 
@@ -158,13 +169,75 @@ def _splu_sym(A):
     return spla.splu(A.tocsc(), permc_spec='MMD_AT_PLUS_A', diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
 
 
-def solve_damped(J, b, lam, lay, schur=True):
-    """Exact solve of (J^T J + lam I) d = J^T b.  schur=True eliminates landmarks first (same system)."""
+def _solve_banded_bordered(S, gc, lay, max_halfband=400):
+    """Exact solve of the reduced camera system S dc = gc for a CHAIN graph by LAPACK's banded Cholesky (dpbtrf / dpbtrs
+    through scipy.linalg): the unknowns are re-ordered node-major ([x_i (6), v_i (3)] per keyframe), which makes S banded
+    with half-bandwidth (track length) x 9, plus the dense 6-wide border of the shared bias, eliminated by block
+    elimination (6 extra right-hand sides).  This is the elimination order a fill-reducing ordering finds for a chain; it
+    is what lets the CPU arm solve the 100 000-pose graph at all (SuperLU runs out of memory there).  Returns None when the
+    graph is not a chain (loop closures put entries outside the band) -- the caller falls back to the general sparse solve.
+    Column order of S / gc: the oracle's camera order [b | v | x]."""
+    import scipy.linalg as sla
+    nb, nv, nx = lay.nb, lay.nv, lay.nx
+    if nb > 1 or nv not in (0, nx):
+        return None
+    D = 9 if nv else 6
+    ncam = D * nx
+    # position of oracle camera column c in the node-major order (bias last)
+    perm = np.empty(6 * nb + 3 * nv + 6 * nx, dtype=np.int64)
+    perm[:6 * nb] = ncam + np.arange(6 * nb)
+    if nv:
+        perm[6 * nb:6 * nb + 3 * nv] = (D * np.arange(nv)[:, None] + 6 + np.arange(3)[None, :]).ravel()
+    perm[6 * nb + 3 * nv:] = (D * np.arange(nx)[:, None] + np.arange(6)[None, :]).ravel()
+    C = S.tocoo()
+    r, c = perm[C.row], perm[C.col]
+    cam = (r < ncam) & (c < ncam)
+    low = cam & (r >= c)
+    hb = int((r[low] - c[low]).max()) if np.any(low) else 0
+    if hb > max_halfband:
+        return None
+    ab = np.zeros((hb + 1, ncam))
+    np.add.at(ab, (r[low] - c[low], c[low]), C.data[low])
+    rhs = np.zeros((ncam, 1 + 6 * nb))
+    g2 = np.empty(ncam + 6 * nb)
+    g2[perm] = gc
+    rhs[:, 0] = g2[:ncam]
+    Hbb = np.zeros((6 * nb, 6 * nb))
+    if nb:
+        bor = (r < ncam) & (c >= ncam)
+        np.add.at(rhs, (r[bor], 1 + c[bor] - ncam), C.data[bor])
+        bb = (r >= ncam) & (c >= ncam)
+        np.add.at(Hbb, (r[bb] - ncam, c[bb] - ncam), C.data[bb])
+    cb = sla.cholesky_banded(ab, lower=True, overwrite_ab=True, check_finite=False)
+    Z = sla.cho_solve_banded((cb, True), rhs, overwrite_b=True, check_finite=False)
+    d2 = np.empty(ncam + 6 * nb)
+    if nb:
+        F = np.zeros((ncam, 6 * nb))
+        np.add.at(F, (r[bor], c[bor] - ncam), C.data[bor])
+        Sb = Hbb - F.T @ Z[:, 1:]
+        db = np.linalg.solve(Sb, g2[ncam:] - F.T @ Z[:, 0])
+        d2[:ncam] = Z[:, 0] - Z[:, 1:] @ db
+        d2[ncam:] = db
+    else:
+        d2[:ncam] = Z[:, 0]
+    return d2[perm]
+
+
+def solve_damped(J, b, lam, lay, schur=True, banded=None):
+    """Exact solve of (J^T J + lam I) d = J^T b.  schur=True eliminates landmarks first (same system).
+    banded: solve the reduced camera system by banded Cholesky (_solve_banded_bordered) -- None = when it has more than
+    200 000 unknowns (where SuperLU stops fitting); the parity tests check both routes against each other."""
     H = (J.T @ J).tocsc()
     g = J.T @ b
     n = lay.n
     H = H + lam * sp.identity(n, format='csc')
+    if banded is None:
+        banded = (n - 3 * lay.nl) > 200000
     if not schur or lay.nl == 0:
+        if banded:
+            d = _solve_banded_bordered(H, g, lay)
+            if d is not None:
+                return d
         return _splu_sym(H).solve(g)
     l0, l1 = lay.ol, lay.ov
     cam = np.concatenate([np.arange(0, l0), np.arange(l1, n)])
@@ -184,7 +257,9 @@ def solve_damped(J, b, lam, lay, schur=True):
     ECi = (E @ Cinv).tocsc()
     S = (Hc - ECi @ E.T).tocsc()
     gc = g[cam] - ECi @ g[lm]
-    dc = _splu_sym(S).solve(gc)
+    dc = _solve_banded_bordered(S, gc, lay) if banded else None
+    if dc is None:
+        dc = _splu_sym(S).solve(gc)
     dl = Cinv @ (g[lm] - E.T @ dc)
     d = np.empty(n)
     d[cam] = dc

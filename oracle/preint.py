@@ -6,9 +6,12 @@ un-vendored) for the call sites /root/reference/batch.py:91 (construction), :290
 (integrateMeasurement(acc, gyro, 0.005)) and :293 (resetIntegration), with the
 parameters of batch.py:181-187 (MakeSharedU(9.81), no Coriolis, no body_P_sensor).
 
-PARITY UNPINNED (no GTSAM here).  Variant: MANIFOLD preintegration.
+PARITY UNPINNED (no GTSAM here).  Both build variants of gtsam are restated:
+`preintegrate` = ManifoldPreintegration (GTSAM_TANGENT_PREINTEGRATION=OFF), `preintegrate_tangent` =
+TangentPreintegration.cpp::UpdatePreintegrated / ::update (the default of the gtsam 4.0-4.2 builds).
 Pinned in tests by (i) exactness on constant-rate motion, (ii) finite differences of the
-bias Jacobians, (iii) Monte-Carlo covariance.
+bias Jacobians, (iii) Monte-Carlo covariance, (iv) an independent autodiff derivation
+(tests/independent_ref.py).
 
 Batched over n factors, sequential over k samples (as the reference loop at batch.py:289).
 """
@@ -83,6 +86,68 @@ def preintegrate(acc, gyro, dt, bhat, acc_cov, gyro_cov, int_cov):
         T = T + h
     pim = np.concatenate([dR.reshape(n, 9), dP, dV, T[:, None], bhat, JRg.reshape(n, 9), JPa.reshape(n, 9),
                           JPg.reshape(n, 9), JVa.reshape(n, 9), JVg.reshape(n, 9)], axis=1)
+    return pim, cov
+
+
+def preintegrate_tangent(acc, gyro, dt, bhat, acc_cov, gyro_cov, int_cov):
+    """TangentPreintegration: the preintegrated state is the 9-vector [theta, p, v] in the tangent space at the
+    start of the interval.  Per sample (a = acc - bhat_a, w = gyro - bhat_g, R = Exp(theta)):
+        theta += Jr(theta)^-1 w dt ;  p += v dt + R a dt^2/2 ;  v += R a dt
+    with A = d new / d old (9x9), B = d new / d a (9x3), C = d new / d w (9x3):
+        H_biasAcc <- A H_biasAcc - B ;  H_biasOmega <- A H_biasOmega - C
+        cov <- A cov A^T + B (aCov/dt) B^T + C (wCov/dt) C^T ;  cov[3:6,3:6] += iCov dt
+    Returns (pim [n,67], cov [n,9,9]); pim columns 0:3 hold theta (3:9 are zero), 22:31 hold d theta / d b_gyro,
+    the p / v tables are as in the manifold layout (factors.PIM_COLS).
+    """
+    acc = np.asarray(acc, dtype=np.float64)
+    gyro = np.asarray(gyro, dtype=np.float64)
+    n, k, _ = acc.shape
+    dts = np.broadcast_to(np.asarray(dt, dtype=np.float64), (n, k))
+    bhat = np.broadcast_to(np.asarray(bhat, dtype=np.float64), (n, 6))
+    x = np.zeros((n, 9))
+    T = np.zeros(n)
+    Ha = np.zeros((n, 9, 3))
+    Hg = np.zeros((n, 9, 3))
+    cov = np.zeros((n, 9, 9))
+    aC = np.asarray(acc_cov, dtype=np.float64)
+    wC = np.asarray(gyro_cov, dtype=np.float64)
+    iC = np.asarray(int_cov, dtype=np.float64)
+    I9 = np.broadcast_to(np.eye(9), (n, 9, 9))
+    for s in range(k):
+        h = dts[:, s]
+        h1 = h[:, None]
+        h2 = h[:, None, None]
+        dt22 = (0.5 * h * h)
+        a = acc[:, s] - bhat[:, 0:3]
+        w = gyro[:, s] - bhat[:, 3:6]
+        theta = x[:, 0:3]
+        w_tan, w_tan_H_theta, invH = lie.so3_apply_inv_dexp(theta, w)
+        R = lie.so3_exp(theta)
+        a_nav = np.einsum('nij,nj->ni', R, a)
+        a_nav_H_theta = R @ lie.skew(-a) @ lie.so3_dexp(theta)
+        A = I9.copy()
+        A[:, 0:3, 0:3] += w_tan_H_theta * h2
+        A[:, 3:6, 0:3] = a_nav_H_theta * dt22[:, None, None]
+        A[:, 3:6, 6:9] = np.eye(3)[None] * h2
+        A[:, 6:9, 0:3] = a_nav_H_theta * h2
+        B = np.zeros((n, 9, 3))
+        B[:, 3:6] = R * dt22[:, None, None]
+        B[:, 6:9] = R * h2
+        C = np.zeros((n, 9, 3))
+        C[:, 0:3] = invH * h2
+        xn = np.concatenate([theta + w_tan * h1, x[:, 3:6] + x[:, 6:9] * h1 + a_nav * dt22[:, None],
+                             x[:, 6:9] + a_nav * h1], axis=1)
+        x = xn
+        T = T + h
+        Ha = A @ Ha - B
+        Hg = A @ Hg - C
+        cov = A @ cov @ np.swapaxes(A, 1, 2)
+        cov = cov + B @ (aC[None] / h2) @ np.swapaxes(B, 1, 2)
+        cov = cov + C @ (wC[None] / h2) @ np.swapaxes(C, 1, 2)
+        cov[:, 3:6, 3:6] += iC[None] * h2
+    pim = np.concatenate([x[:, 0:3], np.zeros((n, 6)), x[:, 3:6], x[:, 6:9], T[:, None], bhat,
+                          Hg[:, 0:3].reshape(n, 9), Ha[:, 3:6].reshape(n, 9), Hg[:, 3:6].reshape(n, 9),
+                          Ha[:, 6:9].reshape(n, 9), Hg[:, 6:9].reshape(n, 9)], axis=1)
     return pim, cov
 
 

@@ -18,7 +18,7 @@ vals0 = lm.values_of(prob)
 fe0 = lm.factor_errors(prob, vals0)
 vals, info = lm.lm_optimize(prob)
 meta = dict(make=make, iterations=info["iterations"], final_error=info["error"], final_lambda=info["lam"],
-            errors=info["trace"]["errors"], preintegration="manifold")
+            errors=info["trace"]["errors"], options=prob["options"])
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "lm_small.npz"), factor_errors_initial=fe0,
                     poses=vals["poses"], vels=vals["vels"], biases=vals["biases"], lms=vals["lms"], meta=json.dumps(meta))
 print(meta)

@@ -161,7 +161,7 @@ def split_for_incremental(d, cuts):
               "between": lambda G, k, m, i: G.add_between_factors(k[:, 0], k[:, 1], m, i),
               "dvl": lambda G, k, m, i: G.add_dvl_factors(k[:, 0], k[:, 1], m, i),
               "stereo": lambda G, k, m, i: G.add_stereo_factors(k[:, 0], k[:, 1], m, i, g.calib),
-              "imu": lambda G, k, m, i: G.add_imu_factors(k[:, 0], k[:, 1], k[:, 2], k[:, 3], k[:, 4], m, i, g.gravity)}
+              "imu": lambda G, k, m, i: G.add_imu_factors(k[:, 0], k[:, 1], k[:, 2], k[:, 3], k[:, 4], m, i, g.gravity, tangent=g.imu_tangent)}
     seen = set()
     out = []
     lo = 0
@@ -211,4 +211,41 @@ def check_batched_parity(lib, problems):
             assert np.abs(v["vels"] - vals["vels"]).max() < 1e-6
         if len(vals["biases"]):
             assert np.abs(v["biases"] - vals["biases"]).max() < 1e-6
+    return res
+
+
+def check_golden_config(lib, path, max_poses=None):
+    """One frozen BASELINE config (tests/golden/make_golden_configs.py) against the library behind the C-ABI."""
+    import json
+    import os
+    import pytest
+    if not os.path.exists(path):
+        pytest.skip("golden fixture not generated: " + os.path.basename(path))
+    g = np.load(path)
+    meta = json.loads(str(g["meta"]))
+    if max_poses is not None and meta["make"]["n_poses"] > max_poses:
+        pytest.skip("too large for the host emulation")
+    d = synthetic.make_trajectory_graph(**meta["make"])
+    assert d["meta"]["n_factors"] == meta["n_factors"]
+    prob = d["graph"].to_problem(d["initial"])
+    assert prob["options"] == meta["options"]
+    s = Session(prob, LevenbergMarquardtParams(), lib=lib)
+    try:
+        res = s.optimize()
+        v = s.values()
+        tr = s.trace()
+    finally:
+        s.close()
+    assert res["iterations"] == meta["iterations"] and res["inner_iterations"] == len(meta["tries"])
+    for mine, (lam, success, solved, new_err) in zip(tr, meta["tries"]):
+        assert abs(mine["lam"] - lam) <= 1e-12 * lam and mine["success"] == success and mine["solved"] == solved
+        if np.isfinite(new_err):
+            assert abs(mine["new_err"] - new_err) <= 1e-4 * new_err      # intermediate iterates: conditioning-limited on both sides
+    assert abs(res["final_error"] - meta["final_error"]) <= 1e-6 * meta["final_error"]      # north_star tolerance
+    assert abs(res["final_lambda"] - meta["final_lambda"]) <= 1e-12 * meta["final_lambda"]
+    st = meta.get("pose_stride", 1)
+    assert np.sqrt(((v["poses"][::st, 9:] - g["poses"][:, 9:]) ** 2).sum(1).mean()) < 1e-6      # metres
+    assert np.abs(v["poses"][::st, :9] - g["poses"][:, :9]).max() < 1e-6                        # ~radians
+    assert np.abs(v["vels"][::st] - g["vels"]).max() < 1e-6
+    assert np.abs(v["biases"] - g["biases"]).max() < 1e-6
     return res

@@ -1,5 +1,5 @@
 """device IMU preintegration and stereo back-projection against the host restatements
-(navigation.preintegrate_batch follows gtsam's ManifoldPreintegration; the back-projection follows StereoCamera)."""
+(navigation.preintegrate_batch follows gtsam's Tangent- / ManifoldPreintegration; the back-projection follows StereoCamera)."""
 import os
 import subprocess
 import numpy as np
@@ -21,10 +21,11 @@ def _imu(n, k, seed=0):
 
 def _check_preint(lib):
     params = synthetic.reference_imu_params()
-    for k, bias in ((40, None), (7, np.array([0.02, -0.01, 0.015, 0.002, -0.001, 0.0015]))):
+    for k, bias, tangent in ((40, None, True), (7, np.array([0.02, -0.01, 0.015, 0.002, -0.001, 0.0015]), True),
+                             (40, None, False), (7, np.array([0.02, -0.01, 0.015, 0.002, -0.001, 0.0015]), False)):
         acc, gyro = _imu(33, k, seed=k)
-        pim_h, info_h, cov_h = preintegrate_batch(acc, gyro, synthetic.IMU_DT, params, bias)
-        pim_d, info_d = preintegrate_imu(acc, gyro, synthetic.IMU_DT, params, bias, lib=lib)
+        pim_h, info_h, cov_h = preintegrate_batch(acc, gyro, synthetic.IMU_DT, params, bias, tangent=tangent)
+        pim_d, info_d = preintegrate_imu(acc, gyro, synthetic.IMU_DT, params, bias, lib=lib, tangent=tangent)
         assert np.abs(pim_d - pim_h).max() <= 1e-12 * max(1.0, np.abs(pim_h).max())
         iu = np.triu_indices(9)
         Rh = np.zeros((33, 9, 9)); Rh[:, iu[0], iu[1]] = info_h

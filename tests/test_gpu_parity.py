@@ -166,28 +166,12 @@ def test_concurrent_handles_match_sequential(lib):
         assert np.abs(a["values"]["poses"] - b["values"]["poses"]).max() < 1e-6
 
 
-@pytest.mark.parametrize("name", ["lm_c1", "lm_c2s"])
+@pytest.mark.parametrize("name", ["lm_c1", "lm_c2s", "lm_c2", "lm_c3"])
 def test_golden_configs(lib, name):
-    """BASELINE.json config 1 at full size / config 2 reduced: the whole LM path (error after every accepted step,
-    accepted / rejected lambda tries) and the final poses against the frozen oracle run."""
-    from visual_underwater_slam_b200 import synthetic
-    from visual_underwater_slam_b200.optimizer import Session, LevenbergMarquardtParams
-    g = np.load(os.path.join(GOLDEN, name + ".npz"))
-    meta = json.loads(str(g["meta"]))
-    d = synthetic.make_trajectory_graph(**meta["make"])
-    assert d["meta"]["n_factors"] == meta["n_factors"]
-    prob = d["graph"].to_problem(d["initial"])
-    s = Session(prob, LevenbergMarquardtParams(), lib=lib)
-    res = s.optimize()
-    v = s.values()
-    s.close()
-    assert res["iterations"] == meta["iterations"] and res["inner_iterations"] == len(meta["tries"])
-    assert abs(res["final_error"] - meta["final_error"]) <= 1e-6 * meta["final_error"]      # north_star tolerance
-    assert abs(res["final_lambda"] - meta["final_lambda"]) <= 1e-12 * meta["final_lambda"]
-    assert np.sqrt(((v["poses"][:, 9:] - g["poses"][:, 9:]) ** 2).sum(1).mean()) < 1e-6      # metres
-    assert np.abs(v["poses"][:, :9] - g["poses"][:, :9]).max() < 1e-6                        # ~radians
-    assert np.abs(v["vels"] - g["vels"]).max() < 1e-6
-    assert np.abs(v["biases"] - g["biases"]).max() < 1e-6
+    """BASELINE.json configs 1, 2 and 3 AT FULL SIZE (and the reduced config 2 of round 1): the whole LM path -- every lambda
+    try with its accept / reject decision and trial error, the error after every accepted step -- and a strided subsample of
+    the final values against the frozen oracle run (tests/golden/make_golden_configs.py)."""
+    pc.check_golden_config(lib, os.path.join(GOLDEN, name + ".npz"))
 
 
 def test_config2_full_size_properties(lib):
@@ -351,3 +335,21 @@ def test_golden_rows_marginals_and_batched(lib):
         assert abs(r["final_error"] - row[2]) <= 1e-6 * row[2] and abs(r["final_lambda"] - row[3]) <= 1e-12 * row[3]
     poses = np.concatenate([r["values"]["poses"] for r in res], 0)
     assert np.sqrt(((poses[:, 9:] - g["poses"][:, 9:]) ** 2).sum(1).mean()) < 1e-6 and np.abs(poses[:, :9] - g["poses"][:, :9]).max() < 1e-6
+
+
+def test_bad_pivot_stays_in_its_component(lib):
+    import test_emu
+    test_emu.check_bad_pivot_stays_in_its_component(lib)
+
+
+def test_lm_parity_manifold_build_with_exact_between(lib):
+    """The other gtsam build (GTSAM_TANGENT_PREINTEGRATION=OFF, GTSAM_SLOW_BUT_CORRECT_BETWEENFACTOR=ON) on the CUDA path."""
+    import visual_underwater_slam_b200 as gtsam
+    prev = gtsam.gtsam_build()
+    gtsam.set_gtsam_build(tangent_preintegration=False, slow_but_correct_betweenfactor=True)
+    try:
+        _, prob = pc.make(300, n_lm=400, n_loops=4, loop_min_gap=60)
+    finally:
+        gtsam.set_gtsam_build(**prev)
+    pc.check_factor_parity(lib, prob)
+    pc.check_lm_parity(lib, prob)

@@ -39,11 +39,20 @@ def test_between_jacobians():
     dR, dt = rand_pose(n, 0.2, 0.3)
     Rm, tm = lie.pose_compose(Rm, tm, dR, dt)
     s = np.abs(rng.standard_normal((n, 6))) + 0.5
-    r, (H1, H2) = F.between(R1, t1, R2, t2, Rm, tm, s)
+    # GTSAM_SLOW_BUT_CORRECT_BETWEENFACTOR build: the exact Jacobians
+    r, (H1, H2) = F.between(R1, t1, R2, t2, Rm, tm, s, exact_jacobian=True)
     n1 = fd_pose(lambda R, t: F.between(R, t, R2, t2, Rm, tm, s)[0], R1, t1)
     n2 = fd_pose(lambda R, t: F.between(R1, t1, R, t, Rm, tm, s)[0], R2, t2)
     assert np.allclose(H1, n1, atol=5e-8, rtol=1e-7)
     assert np.allclose(H2, n2, atol=5e-8, rtol=1e-7)
+    # default build (gtsam 4.1 / 4.2 wheels): the Jacobians of Between() only -- exact where the residual is zero
+    r0, (G1, G2) = F.between(R1, t1, R2, t2, Rm, tm, s)
+    assert np.array_equal(r0, r) and not np.allclose(G2, n2, atol=1e-3)
+    assert np.allclose(G2, s[:, :, None] * np.eye(6)[None])
+    Rz, tz = lie.pose_between(R1, t1, R2, t2)
+    _, (Z1, Z2) = F.between(R1, t1, R2, t2, Rz, tz, s)
+    z1 = fd_pose(lambda R, t: F.between(R, t, R2, t2, Rz, tz, s)[0], R1, t1)
+    assert np.allclose(Z1, z1, atol=5e-8, rtol=1e-7)
 
 
 def test_prior_pose_matches_gtsam_identity_jacobian():
@@ -193,10 +202,16 @@ def test_product_preintegration_matches_oracle():
     acc, gyr, bhat, pim, cov = _imu_case(n)
     p = PreintegrationParams.MakeSharedU(9.81)
     p.setAccelerometerCovariance(np.eye(3) * 9e-8); p.setGyroscopeCovariance(np.eye(3) * 1.2e-7); p.setIntegrationCovariance(np.eye(3) * 1e-7)
-    pim2, info2, cov2 = preintegrate_batch(acc, gyr, 0.005, p, bhat)
+    pim2, info2, cov2 = preintegrate_batch(acc, gyr, 0.005, p, bhat, tangent=False)
     assert np.allclose(pim2, pim, atol=1e-13)
     assert np.allclose(cov2, cov, rtol=1e-10, atol=1e-20)
     assert np.allclose(info2, preint.sqrt_info_upper(cov), rtol=1e-8)
+    # the tangent build (the default, config.py)
+    pim_t, cov_t = preint.preintegrate_tangent(acc, gyr, 0.005, bhat, np.eye(3) * 9e-8, np.eye(3) * 1.2e-7, np.eye(3) * 1e-7)
+    pim3, info3, cov3 = preintegrate_batch(acc, gyr, 0.005, p, bhat)
+    assert np.allclose(pim3, pim_t, atol=1e-13)
+    assert np.allclose(cov3, cov_t, rtol=1e-10, atol=1e-20)
+    assert np.allclose(info3, preint.sqrt_info_upper(cov_t), rtol=1e-8)
 
 
 def test_oracle_reproduces_golden_small():

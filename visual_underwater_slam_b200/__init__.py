@@ -6,6 +6,7 @@ LevenbergMarquardtOptimizer(graph, initial, LevenbergMarquardtParams()).optimize
 All arithmetic runs in hand-written sm_100a CUDA kernels behind the C-ABI in include/vus.h;
 there is no CPU fallback.
 """
+from .config import gtsam_build, set_gtsam_build
 from .symbol import Symbol, symbol, symbolChr, symbolIndex
 from . import symbol_shorthand
 from .geometry import Point3, Rot3, Pose3, StereoPoint2, Cal3_S2Stereo

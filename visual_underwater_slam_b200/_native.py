@@ -26,12 +26,12 @@ class LmParams(C.Structure):
 
 class LmResult(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("inner_iterations", C.c_int32), ("linearizations", C.c_int32),
-                ("pcg_iterations", C.c_int32), ("solve_failures", C.c_int32), ("reserved", C.c_int32),
+                ("pcg_iterations", C.c_int32), ("solve_failures", C.c_int32), ("pcg_not_converged", C.c_int32),
                 ("initial_error", C.c_double), ("final_error", C.c_double), ("final_lambda", C.c_double),
                 ("ms_total", C.c_double), ("ms_linearize", C.c_double), ("ms_assemble", C.c_double),
                 ("ms_schur", C.c_double), ("ms_factor", C.c_double), ("ms_pcg", C.c_double), ("ms_update", C.c_double),
                 ("kernel_launches", C.c_int64), ("factors_linearized", C.c_int64),
-                ("ms_class", C.c_double * 16), ("launches_class", C.c_int64 * 16)]
+                ("ms_class", C.c_double * 16), ("launches_class", C.c_int64 * 16), ("worst_pcg_rel_residual", C.c_double)]
 
     def as_dict(self):
         d = {n: getattr(self, n) for n, _ in self._fields_ if n not in ("reserved", "ms_class", "launches_class")}
@@ -66,6 +66,7 @@ EXPORTS = {
     "vus_set_calibration": (C.c_int, [C.c_void_p, c_double_p]),
     "vus_set_gravity": (C.c_int, [C.c_void_p, c_double_p]),
     "vus_set_lm_params": (C.c_int, [C.c_void_p, C.POINTER(LmParams)]),
+    "vus_set_gtsam_build": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "vus_set_partition": (C.c_int, [C.c_void_p, C.c_int64, c_i64_p]),
     "vus_set_comm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vus_set_comm_mode": (C.c_int, [C.c_void_p, C.c_int]),

@@ -73,6 +73,13 @@ struct BSubZxbBody {
   }
 };
 
+// zero the entries of the components whose factorization failed (mask[c] != 0): with a zero right-hand side their PCG
+// recursion never starts (rr0 = 0), so a bad pivot in one trajectory leaves every other trajectory's solve untouched
+struct BZeroCompArgs { BCtx C; const int* mask; double* v; };
+struct BZeroCompBody {
+  static VUS_DEV void run(const BZeroCompArgs& A, long i) { if (A.mask[comp_of_dof(A.C, i)]) A.v[i] = 0.0; }
+};
+
 // ---- damping: lambda of the dof's component on the real dofs, identity on the padding, lambda on every bias diagonal
 struct BDampArgs { BCtx C; double* SD; double* Hbb; long nreal; int B; const double* lam; int ld; long bs; };
 struct BDampBody {
@@ -164,6 +171,7 @@ struct BBorderSchurArgs { int ncomp; const double* Hbb; const double* ftz; const
 struct BBorderSchurBody {
   static VUS_DEV void run(const BBorderSchurArgs& A, long c) {
     double S[36];
+    bool failed = false;                                 // a failed complement is returned as zero: the component is frozen anyway
     for (int e = 0; e < 36; ++e) S[e] = A.Hbb[c * 36 + e];
     for (int v = 0; v < 6; ++v)
       for (int k = 0; k < 6; ++k) S[k * 6 + v] -= A.ftz[c * 36 + v * 6 + k];
@@ -173,8 +181,8 @@ struct BBorderSchurBody {
       S[k * 6 + a] -= 0.5 * A.ztr[c * 36 + e];
     }
     for (int p = 0; p < 6; ++p) {
-      const double piv = S[p * 6 + p];
-      if (!(piv > 0.0)) *A.fail = 1;
+      double piv = S[p * 6 + p];
+      if (!(piv > 0.0)) { A.fail[c] = 1; failed = true; piv = 1.0; }
       const double d = 1.0 / piv;
       double rowp[6], colp[6];
       for (int i = 0; i < 6; ++i) { rowp[i] = S[p * 6 + i]; colp[i] = S[i * 6 + p]; }
@@ -187,7 +195,7 @@ struct BBorderSchurBody {
           S[i * 6 + j] = v;
         }
     }
-    for (int e = 0; e < 36; ++e) A.SbInv[c * 36 + e] = S[e];
+    for (int e = 0; e < 36; ++e) A.SbInv[c * 36 + e] = failed ? 0.0 : S[e];
   }
 };
 // work item (c, r):  xb[c][r] = sum_k SbInv_c[r][k] (rb[c][k] - fty[c][k])
@@ -325,7 +333,7 @@ struct BWbCapBody {
         int best = p;
         double bv = fabs(M[p * R2 + p]);
         for (int i = p + 1; i < R; ++i) { const double v = fabs(M[i * R2 + p]); if (v > bv) { bv = v; best = i; } }
-        if (!(bv > 0.0)) *A.fail = 1;
+        if (!(bv > 0.0)) { A.fail[c] = 1; M[best * R2 + p] = 1.0; }
         aux[R] = (double)best;
       }
       VUS_SYNC();

@@ -50,11 +50,14 @@ struct BcrArgs {
   const double* Ucur; int u_ld; long u_stride;    // couplings at this level (level 1: SU, plain; else padded)
   double* Unext;                   // couplings of the next level, padded
   double* Dinv; double* Gl; double* Gr;   // per eliminated node, padded
-  int* fail;
+  int* fail;                       // [ncomp] non-positive pivot seen in a block of this component (single graph: one entry)
+  const int* node_comp; int knodes; // batched mode: component of every node, nodes per supernode (null: everything is component 0)
   // solve
   double* X; long xstride; int nrhs;
 };
 VUS_HD long bcr_bbp(int B) { return bcr_buf_doubles(B); }          // doubles per padded block
+// where supernode j reports a failed pivot: the flag of the component its first node belongs to
+VUS_HD int* bcr_fail_of(const BcrArgs& A, long j) { return A.node_comp ? A.fail + A.node_comp[j * A.knodes] : A.fail; }
 
 #ifndef VUS_EMU
 // =====================================================================================  sm_100a: DMMA tile engine
@@ -191,9 +194,13 @@ VUS_DEV void acc_load_global(Acc& c, const double* src, int ld, const Tiles& G) 
 //   step p:  P = M[p][p]^-1 ;  M[i][j] += (-M[i][p] P) M[p][j]  (i, j != p) ;  M[p][j] = P M[p][j] ;  M[i][p] = -M[i][p] P ;  M[p][p] = P
 // The rank-8 updates are DMMAs on the resident accumulators; only the pivot row / column panels go through shared
 // memory (double buffered: two barriers per step).  `sm` needs VUS_GJ_DOUBLES doubles.
+// A non-positive pivot raises *fail and the block's inverse is returned as ZERO: the node then passes nothing on to its
+// neighbours (Gl = Gr = 0), so a bad block cannot leak Inf / NaN into the other components of a batched system.
 VUS_DEV void mma_gj_inverse(Acc& c, double* sm, const Tiles& G, int* fail) {
   const int LDP = VUS_GJ_LDP, LDQ = VUS_GJ_LDQ;
   const int g = G.g, t = G.t;
+  __shared__ int bad_block_;
+  if (G.warp == 0 && G.lane == 0) bad_block_ = 0;      // published by the first barrier of step 0
   for (int p = 0; p < G.T; ++p) {
     double* Rraw = sm + (p & 1) * VUS_GJ_SET;
     double* Rnew = Rraw + 8 * LDP;
@@ -228,8 +235,8 @@ VUS_DEV void mma_gj_inverse(Acc& c, double* sm, const Tiles& G, int* fail) {
         double prow[8];
 #pragma unroll
         for (int q2 = 0; q2 < 8; ++q2) prow[q2] = __shfl_sync(0xffffffffu, row[q2], q);
-        const double piv = prow[q];
-        if (G.lane == 0 && !(piv > 0.0)) *fail = 1;
+        double piv = prow[q];
+        if (!(piv > 0.0)) { if (G.lane == 0) { *fail = 1; bad_block_ = 1; } piv = 1.0; }   // keep the sweep finite; the flag decides
         // reciprocal by hardware seed + two Newton steps (full FP64 accuracy for normal pivots): the IEEE division's
         // slow-path checks sit on the serial chain of every sweep
         double d;
@@ -297,6 +304,7 @@ VUS_DEV void mma_gj_inverse(Acc& c, double* sm, const Tiles& G, int* fail) {
     __syncwarp();
   }
   __syncthreads();
+  if (bad_block_) acc_zero(c);
 }
 
 // one operand of a factor kernel: padded blocks arrive by one bulk copy, the plain level-1 inputs by 8-byte cp.async
@@ -328,7 +336,7 @@ struct BcrElimBody {
     mb.init(&bar_, tid);
     Acc c;
     acc_load_global(c, A.Dsrc + j * A.d_stride, A.d_ld, G);
-    mma_gj_inverse(c, sm, G, A.fail);                    // ends with a barrier (also publishes the mbarrier init)
+    mma_gj_inverse(c, sm, G, bcr_fail_of(A, j));         // ends with a barrier (also publishes the mbarrier init)
     acc_store_global<false>(A.Dinv + j * BBP, G.LD, c, 1.0, G);
     acc_store_smem(buf1, c, G);
     Staged st = stage_any(buf0, A.Ucur + (j - A.s) * A.u_stride, A.u_ld, G, mb, tid);
@@ -416,7 +424,7 @@ struct BcrRootBody {
     const long j = (long)m * A.root_stride;
     Acc c;
     acc_load_global(c, A.Dsrc + j * A.d_stride, A.d_ld, G);
-    mma_gj_inverse(c, sm, G, A.fail);
+    mma_gj_inverse(c, sm, G, bcr_fail_of(A, j));
     acc_store_global<false>(A.Dinv + j * bcr_bbp(A.B), G.LD, c, 1.0, G);
   }
 };
@@ -432,12 +440,13 @@ template <> struct CoopBounds<BcrRootBody> { static constexpr int kMaxThreads = 
 // =====================================================================================  host emulation (tests only)
 inline void emu_spd_inverse(const double* M, int ldm, double* out, int ldo, int B, int* fail) {
   std::vector<double> w((size_t)B * B), rowp(B), colp(B);
+  bool failed = false;                                   // a failed block is returned as zero (see mma_gj_inverse)
   for (int i = 0; i < B; ++i)
     for (int j = 0; j < B; ++j) w[(size_t)i * B + j] = M[(long)i * ldm + j];
   for (int p = 0; p < B; ++p) {
     for (int i = 0; i < B; ++i) { colp[i] = w[(size_t)i * B + p]; rowp[i] = w[(size_t)p * B + i]; }
-    const double piv = rowp[p];
-    if (!(piv > 0.0)) *fail = 1;
+    double piv = rowp[p];
+    if (!(piv > 0.0)) { *fail = 1; failed = true; piv = 1.0; }
     const double d = 1.0 / piv;
     for (int i = 0; i < B; ++i) {
       double* row = w.data() + (size_t)i * B;
@@ -445,8 +454,10 @@ inline void emu_spd_inverse(const double* M, int ldm, double* out, int ldo, int 
       else { const double ci = colp[i] * d; for (int j = 0; j < B; ++j) row[j] = (j == p) ? -ci : row[j] - ci * rowp[j]; }
     }
   }
+  bool bad = false;
+  for (int p = 0; p < B && !bad; ++p) bad = !(w[(size_t)p * B + p] == w[(size_t)p * B + p]);
   for (int i = 0; i < B; ++i)
-    for (int j = 0; j < B; ++j) out[(long)i * ldo + j] = w[(size_t)i * B + j];
+    for (int j = 0; j < B; ++j) out[(long)i * ldo + j] = (failed || bad) ? 0.0 : w[(size_t)i * B + j];
 }
 // C = Cin + alpha * op(A) op(B)   (Cin may be null); every operand is a B x B block with its own row stride
 inline void emu_gemm(double* C, int ldc, const double* Cin, int ldi, const double* A, int lda, bool ta, const double* Bm, int ldb, bool tb,
@@ -466,7 +477,7 @@ struct BcrElimBody {
     const int B = A.B, LD = bcr_ld(B);
     const long BBP = bcr_bbp(B);
     const long j = A.s * (2L * m + 1);
-    emu_spd_inverse(A.Dsrc + j * A.d_stride, A.d_ld, A.Dinv + j * BBP, LD, B, A.fail);
+    emu_spd_inverse(A.Dsrc + j * A.d_stride, A.d_ld, A.Dinv + j * BBP, LD, B, bcr_fail_of(A, j));
     emu_gemm(A.Gl + j * BBP, LD, nullptr, 0, A.Ucur + (j - A.s) * A.u_stride, A.u_ld, false, A.Dinv + j * BBP, LD, false, B, 1.0);
     if (j + A.s < A.Ns) emu_gemm(A.Gr + j * BBP, LD, nullptr, 0, A.Ucur + j * A.u_stride, A.u_ld, true, A.Dinv + j * BBP, LD, false, B, 1.0);
   }
@@ -497,7 +508,7 @@ struct BcrUpdateBody {
 struct BcrRootBody {
   static VUS_DEV void run(const BcrArgs& A, int m, int, int, double*) {
     const long j = (long)m * A.root_stride;
-    emu_spd_inverse(A.Dsrc + j * A.d_stride, A.d_ld, A.Dinv + j * bcr_bbp(A.B), bcr_ld(A.B), A.B, A.fail);
+    emu_spd_inverse(A.Dsrc + j * A.d_stride, A.d_ld, A.Dinv + j * bcr_bbp(A.B), bcr_ld(A.B), A.B, bcr_fail_of(A, j));
   }
 };
 #endif
@@ -850,6 +861,8 @@ struct SmallElimBody {
     const long BBP = bcr_bbp(B);
     const long nel = ((A.Ns + A.s - 1) / A.s) / 2;
     double* piv = sm + VUS_SMALLB_G * BB;
+    VUS_SHARED int bad_node_[VUS_SMALLB_G];              // a node with a non-positive pivot gets a ZERO inverse (see mma_gj_inverse)
+    for (int g = tid; g < VUS_SMALLB_G; g += nthr) bad_node_[g] = 0;
     for (int e = tid; e < VUS_SMALLB_G * BB; e += nthr) {
       const int g = e / BB, r = (e % BB) / B, c = e % B;
       const long m = (long)blk * VUS_SMALLB_G + g;
@@ -858,8 +871,9 @@ struct SmallElimBody {
     VUS_SYNC();
     for (int p = 0; p < B; ++p) {
       for (int g = tid; g < VUS_SMALLB_G; g += nthr) {
-        const double v = sm[g * BB + p * B + p];
-        if (!(v > 0.0)) *A.fail = 1;
+        double v = sm[g * BB + p * B + p];
+        const long mg = (long)blk * VUS_SMALLB_G + g;
+        if (!(v > 0.0)) { if (mg < nel) { *bcr_fail_of(A, A.s * (2L * mg + 1)) = 1; bad_node_[g] = 1; } v = 1.0; }
         piv[g] = 1.0 / v;
       }
       VUS_SYNC();
@@ -878,6 +892,8 @@ struct SmallElimBody {
       }
       VUS_SYNC();
     }
+    for (int e = tid; e < VUS_SMALLB_G * BB; e += nthr) if (bad_node_[e / BB]) sm[e] = 0.0;
+    VUS_SYNC();
     for (int e = tid; e < VUS_SMALLB_G * BB; e += nthr) {
       const int g = e / BB, r = (e % BB) / B, c = e % B;
       const long m = (long)blk * VUS_SMALLB_G + g;

@@ -108,8 +108,10 @@ VUS_HD void f_prior_vel(const ValuesView& V, const FactorView& F, const LinOut& 
 }
 
 // ------------------------------------------------------------------ BetweenFactor<Pose3>
+// slow_but_correct = gtsam's GTSAM_SLOW_BUT_CORRECT_BETWEENFACTOR build: H1 = -dLog(e) Ad(hx^-1), H2 = dLog(e).  The default
+// gtsam build (4.1 / 4.2 wheels) leaves the derivative of Local() out: H1 = -Ad(hx^-1), H2 = I (BetweenFactor.h).
 template <bool WJ>
-VUS_HD void f_between(const ValuesView& V, const FactorView& F, const LinOut& O, long f) {
+VUS_HD void f_between(const ValuesView& V, const FactorView& F, const LinOut& O, long f, bool slow_but_correct) {
   const long n = F.n;
   double R1[9], t1[3], R2[9], t2[3], Rm[9], tm[3];
   load_pose(V.pose, V.nx, F.idx[f], R1, t1);
@@ -134,7 +136,12 @@ VUS_HD void f_between(const ValuesView& V, const FactorView& F, const LinOut& O,
   if (O.e2) O.e2[f] = 0.5 * acc;
   if (WJ) {
     double Jw[9], Q2[9];
-    pose_dlog(xi, Jw, Q2);
+    if (slow_but_correct) {
+      pose_dlog(xi, Jw, Q2);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) { Jw[c] = (c % 4 == 0) ? 1.0 : 0.0; Q2[c] = 0.0; }
+    }
     // hx^-1 = (Rh^T, -Rh^T th);  Ad = [[Ri,0],[[ti]x Ri, Ri]]
     double ti[3], JwRi[9], Q2Ri[9], Tx[9], TxRi[9], JwTxRi[9];
     m3_Tvec(Rh, th, ti);
@@ -292,8 +299,8 @@ VUS_HD void f_stereo(const ValuesView& V, const FactorView& F, const LinOut& O, 
   }
 }
 
-// ------------------------------------------------------------------ ImuFactor (manifold preintegration)
-// packed PIM row: dR 9 | dP 3 | dV 3 | dt 1 | bhat 6 | JRg 9 | JPa 9 | JPg 9 | JVa 9 | JVg 9
+// ------------------------------------------------------------------ ImuFactor (both gtsam preintegration builds)
+// packed PIM row: dR 9 (tangent: theta 3, then 6 unused) | dP 3 | dV 3 | dt 1 | bhat 6 | JRg 9 | JPa 9 | JPg 9 | JVa 9 | JVg 9
 VUS_HD void imu_whiten9(const double* W, const double* e, double* y) {   // y = W e, W upper-tri packed row-major
   int p = 0;
 #pragma unroll
@@ -317,8 +324,10 @@ VUS_HD void imu_emit(double* J, long n, long f, int col0, const double* W, const
   }
 }
 
+// tangent = gtsam's GTSAM_TANGENT_PREINTEGRATION build (TangentPreintegration::biasCorrectedDelta): the packed row holds
+// theta (columns 0..2) and d theta / d bg (22..30); theta_c = theta + (d theta / d bg) dbg and dR_c = Exp(theta_c).
 template <bool WJ>
-VUS_HD void f_imu(const ValuesView& V, const FactorView& F, const LinOut& O, long f, const double* g) {
+VUS_HD void f_imu(const ValuesView& V, const FactorView& F, const LinOut& O, long f, const double* g, bool tangent) {
   const long n = F.n;
   double Ri[9], ti[3], vi[3], Rj[9], tj[3], vj[3], bias[6];
   load_pose(V.pose, V.nx, F.idx[f], Ri, ti);
@@ -344,8 +353,14 @@ VUS_HD void f_imu(const ValuesView& V, const FactorView& F, const LinOut& O, lon
   // bias-corrected deltas
   double corr[3], Ec[9], dRc[9], pc[3], vc[3];
   m3_vec(JRg, dbg, corr);
-  so3_exp(corr, Ec);
-  m3_mul(dR, Ec, dRc);
+  if (tangent) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) corr[c] += dR[c];      // theta_c
+    so3_exp(corr, dRc);
+  } else {
+    so3_exp(corr, Ec);
+    m3_mul(dR, Ec, dRc);
+  }
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     double ap = dP[r], av = dV[r];
@@ -430,7 +445,7 @@ VUS_HD void f_imu(const ValuesView& V, const FactorView& F, const LinOut& O, lon
     for (int k = 0; k < 9; ++k) Jm[k] = PIM(49 + k);
     m3_mul(A, Jm, blk + 18);
     imu_emit(O.J, n, f, 18, W, blk);
-    // --- bias gyro: [dlog Jr(corr) JRg ; A JPg ; A JVg]
+    // --- bias gyro: [dlog Jr(corr) JRg ; A JPg ; A JVg]   (tangent: corr = theta_c, JRg = d theta / d bg)
     double Jr[9];
     so3_dexp(corr, Jr);
     m3_mul(dlog, Jr, T);

@@ -2,8 +2,9 @@
 // builds, moved to the device so raw 200 Hz IMU streams and stereo feature tracks can be ingested without a host pass.
 //
 //   PreintBody   gtsam.PreintegratedImuMeasurements.integrateMeasurement x k + resetIntegration (batch.py:289-293):
-//                one thread per ImuFactor runs the k samples of its keyframe interval -- manifold preintegration
-//                (Forster et al.), bias Jacobians, first-order 9x9 covariance -- and emits the packed
+//                one thread per ImuFactor runs the k samples of its keyframe interval -- tangent (gtsam
+//                TangentPreintegration.cpp, the 4.0-4.2 wheel default) or manifold (Forster et al.) preintegration
+//                (vus_set_gtsam_build), bias Jacobians, first-order 9x9 covariance -- and emits the packed
 //                PIM row (67) and the upper sqrt-information (45) the ImuFactor table of include/vus.h takes.
 //   BackprojBody the disparity back-projection of get_landmarks (batch.py:144-176) in gtsam's StereoCamera convention
 //                (uR = fx (x - b) / z): landmark = T_i * backproject(uL, uR, v).
@@ -21,6 +22,7 @@ struct PreintArgs {
   double* pim;                               // [67][n] component-major
   double* sinfo;                             // [45][n]
   int* fail;
+  bool tangent;                              // TangentPreintegration (state = 9-vector [theta, p, v]) instead of ManifoldPreintegration
 };
 
 VUS_HD void m9_mul(const double* A, const double* B, double* C, bool tb) {   // C = A B  or  A B^T   (9x9)
@@ -32,6 +34,98 @@ VUS_HD void m9_mul(const double* A, const double* B, double* C, bool tb) {   // 
     }
 }
 
+// d/dw [ Jr(w) c ] at fixed c  (gtsam so3::DexpFunctor::applyDexp, H1):
+//   Jr(w) c = c - A (w x c) + B (w x (w x c)),  A = (1 - cos th) / th^2,  B = (th - sin th) / th^3
+VUS_HD void so3_apply_dexp_deriv(const double* w, const double* c, double* D) {
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  double Cx[9];
+  skew(c, Cx);
+  if (th2 <= VUS_EPS) {
+    for (int e = 0; e < 9; ++e) D[e] = 0.5 * Cx[e];
+    return;
+  }
+  const double th = sqrt(th2), sn = sin(th), s2 = sin(0.5 * th), omc = 2.0 * s2 * s2;
+  const double A = omc / th2, B = (th - sn) / (th2 * th);
+  const double dA = (th * sn - 2.0 * omc) / (th2 * th) / th;            // (dA/dth) / th
+  const double dB = (omc * th - 3.0 * (th - sn)) / (th2 * th2) / th;
+  const double wxc[3] = {w[1] * c[2] - w[2] * c[1], w[2] * c[0] - w[0] * c[2], w[0] * c[1] - w[1] * c[0]};
+  const double wwc[3] = {w[1] * wxc[2] - w[2] * wxc[1], w[2] * wxc[0] - w[0] * wxc[2], w[0] * wxc[1] - w[1] * wxc[0]};
+  const double wc = w[0] * c[0] + w[1] * c[1] + w[2] * c[2];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      D[3 * i + j] = -dA * wxc[i] * w[j] + A * Cx[3 * i + j] + dB * wwc[i] * w[j]
+                     + B * ((i == j ? wc : 0.0) + w[i] * c[j] - 2.0 * c[i] * w[j]);
+}
+
+// One sample of TangentPreintegration::update (+ the covariance line of PreintegratedImuMeasurements::integrateMeasurement):
+//   theta += Jr(theta)^-1 w h ;  p += v h + Exp(theta) a h^2 / 2 ;  v += Exp(theta) a h
+//   H_biasAcc <- A H_biasAcc - B ;  H_biasOmega <- A H_biasOmega - C ;  cov <- A cov A^T + B (aC/h) B^T + C (wC/h) C^T, cov[3:6,3:6] += iC h
+// x[9] state, Ha / Hg [9][3] row-major, cov [81]; A9 / tmp: 81-double scratch.
+VUS_HD void preint_tangent_step(double* x, double* Ha, double* Hg, double* cov, const double* a, const double* w, double h,
+                                const double* aC, const double* wC, const double* iC, double* A9, double* tmp) {
+  const double q = 0.5 * h * h;
+  double R[9], Jr[9], inv[9], c[3], D[9], wH[9], ax[9], Rax[9], aH[9];
+  so3_exp(x, R);
+  so3_dexp(x, Jr);
+  so3_dlog(x, inv);                                  // Jr^-1
+  m3_vec(inv, w, c);
+  so3_apply_dexp_deriv(x, c, D);
+  m3_mul(inv, D, wH);                                // -(d c / d theta)
+  skew(a, ax);
+  m3_mul(R, ax, Rax);
+  m3_mul(Rax, Jr, aH);                               // -(d (R a) / d theta)
+  for (int e = 0; e < 81; ++e) A9[e] = 0.0;
+  for (int i = 0; i < 9; ++i) A9[10 * i] = 1.0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      A9[9 * i + j] -= wH[3 * i + j] * h;
+      A9[9 * (3 + i) + j] = -aH[3 * i + j] * q;
+      A9[9 * (6 + i) + j] = -aH[3 * i + j] * h;
+    }
+  for (int i = 0; i < 3; ++i) A9[9 * (3 + i) + 6 + i] = h;
+  // bias Jacobians: H <- A H - [B | C]   (B = [0; R q; R h], C = [Jr^-1 h; 0; 0])
+  double nHa[27], nHg[27];
+  for (int i = 0; i < 9; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double sa = 0.0, sg = 0.0;
+      for (int l = 0; l < 9; ++l) { sa += A9[9 * i + l] * Ha[3 * l + j]; sg += A9[9 * i + l] * Hg[3 * l + j]; }
+      if (i < 3) sg -= inv[3 * i + j] * h;
+      else if (i < 6) sa -= R[3 * (i - 3) + j] * q;
+      else sa -= R[3 * (i - 6) + j] * h;
+      nHa[3 * i + j] = sa; nHg[3 * i + j] = sg;
+    }
+  for (int e = 0; e < 27; ++e) { Ha[e] = nHa[e]; Hg[e] = nHg[e]; }
+  // covariance
+  m9_mul(A9, cov, tmp, false);
+  m9_mul(tmp, A9, cov, true);
+  {
+    double Bm[18], t1[18];                           // rows 3..8 of B
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) { Bm[3 * i + j] = R[3 * i + j] * q; Bm[3 * (3 + i) + j] = R[3 * i + j] * h; }
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 3; ++j) t1[3 * i + j] = (Bm[3 * i] * aC[j] + Bm[3 * i + 1] * aC[3 + j] + Bm[3 * i + 2] * aC[6 + j]) / h;
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) cov[9 * (3 + i) + 3 + j] += t1[3 * i] * Bm[3 * j] + t1[3 * i + 1] * Bm[3 * j + 1] + t1[3 * i + 2] * Bm[3 * j + 2];
+    double Cm[9], t2[9];
+    for (int e = 0; e < 9; ++e) Cm[e] = inv[e] * h;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) t2[3 * i + j] = (Cm[3 * i] * wC[j] + Cm[3 * i + 1] * wC[3 + j] + Cm[3 * i + 2] * wC[6 + j]) / h;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        cov[9 * i + j] += t2[3 * i] * Cm[3 * j] + t2[3 * i + 1] * Cm[3 * j + 1] + t2[3 * i + 2] * Cm[3 * j + 2];
+        cov[9 * (3 + i) + 3 + j] += iC[3 * i + j] * h;
+      }
+  }
+  // state
+  double Ra[3];
+  m3_vec(R, a, Ra);
+  for (int k = 0; k < 3; ++k) {
+    x[3 + k] += x[6 + k] * h + Ra[k] * q;
+    x[6 + k] += Ra[k] * h;
+    x[k] += c[k] * h;
+  }
+}
+
 struct PreintBody {
   static VUS_DEV void run(const PreintArgs& P, long f) {
     double dR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, dP[3] = {0, 0, 0}, dV[3] = {0, 0, 0}, T = 0.0;
@@ -39,7 +133,21 @@ struct PreintBody {
     double cov[81], A[81], tmp[81];
     for (int e = 0; e < 81; ++e) cov[e] = 0.0;
     const double h = P.dt, q = 0.5 * h * h;
-    for (int s = 0; s < P.k; ++s) {
+    if (P.tangent) {
+      double x[9] = {0}, Ha[27] = {0}, Hg[27] = {0};
+      for (int s = 0; s < P.k; ++s) {
+        const double* am = P.acc + ((long)f * P.k + s) * 3;
+        const double* wm = P.gyro + ((long)f * P.k + s) * 3;
+        const double a[3] = {am[0] - P.bhat[0], am[1] - P.bhat[1], am[2] - P.bhat[2]};
+        const double w[3] = {wm[0] - P.bhat[3], wm[1] - P.bhat[4], wm[2] - P.bhat[5]};
+        preint_tangent_step(x, Ha, Hg, cov, a, w, h, P.aC, P.wC, P.iC, A, tmp);
+        T += h;
+      }
+      for (int e = 0; e < 9; ++e) dR[e] = e < 3 ? x[e] : 0.0;        // packed row: theta in the first three slots
+      for (int c = 0; c < 3; ++c) { dP[c] = x[3 + c]; dV[c] = x[6 + c]; }
+      for (int e = 0; e < 9; ++e) { JRg[e] = Hg[e]; JPa[e] = Ha[9 + e]; JPg[e] = Hg[9 + e]; JVa[e] = Ha[18 + e]; JVg[e] = Hg[18 + e]; }
+    }
+    for (int s = 0; s < (P.tangent ? 0 : P.k); ++s) {
       const double* am = P.acc + ((long)f * P.k + s) * 3;
       const double* wm = P.gyro + ((long)f * P.k + s) * 3;
       const double a[3] = {am[0] - P.bhat[0], am[1] - P.bhat[1], am[2] - P.bhat[2]};

@@ -30,17 +30,19 @@ struct LinArgs {
   double K[6];
   double g[3];
   int type;
+  int opts;        // VUS_OPT_* bits: the gtsam build switches that change the arithmetic (vus_set_gtsam_build)
 };
+enum { VUS_OPT_TANGENT = 1, VUS_OPT_SLOW_BETWEEN = 2 };
 
 template <int TYPE, bool WJ>
 struct LinBody {
   static VUS_DEV void run(const LinArgs& a, long f) {
     if (TYPE == VUS_F_PRIOR_POSE) f_prior_pose<WJ>(a.V, a.F, a.O, f);
     else if (TYPE == VUS_F_PRIOR_VEL) f_prior_vel<WJ>(a.V, a.F, a.O, f);
-    else if (TYPE == VUS_F_BETWEEN) f_between<WJ>(a.V, a.F, a.O, f);
+    else if (TYPE == VUS_F_BETWEEN) f_between<WJ>(a.V, a.F, a.O, f, (a.opts & VUS_OPT_SLOW_BETWEEN) != 0);
     else if (TYPE == VUS_F_DVL) f_dvl<WJ>(a.V, a.F, a.O, f);
     else if (TYPE == VUS_F_STEREO) f_stereo<WJ>(a.V, a.F, a.O, f, a.K);
-    else f_imu<WJ>(a.V, a.F, a.O, f, a.g);
+    else f_imu<WJ>(a.V, a.F, a.O, f, a.g, (a.opts & VUS_OPT_TANGENT) != 0);
   }
 };
 

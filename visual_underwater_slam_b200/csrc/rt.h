@@ -24,6 +24,8 @@ inline void d2d(void* d, const void* s, size_t n, stream_t) { std::memmove(d, s,
 inline void dzero(void* d, size_t n, stream_t) { std::memset(d, 0, n); }
 inline void sync(stream_t) {}
 inline int sm_count() { return 4; }
+inline int& tl_device() { static thread_local int d = 0; return d; }
+inline stream_t& tl_stream() { static thread_local stream_t s = nullptr; return s; }
 
 template <class Body, class Args>
 inline void launch_elem(long n, stream_t, const Args& a) {
@@ -50,22 +52,31 @@ inline void pool_setup(int device) {
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
 }
+// The C-ABI entry points run under a DeviceGuard (vus.cu) that makes the handle's device current on the calling thread and
+// records it -- and the stream the handle works on -- here: per-device caches below are keyed by it, and memory is allocated
+// and freed in the order of the handle's stream, never on the legacy default stream (which a non-blocking compute stream
+// does not wait for).
+inline int& tl_device() { static thread_local int d = 0; return d; }
+inline stream_t& tl_stream() { static thread_local stream_t s = nullptr; return s; }
 inline void* dalloc(size_t bytes) {
   void* p = nullptr;
-  check(cudaMallocAsync(&p, bytes ? bytes : 8, 0), "cudaMallocAsync");
-  check(cudaStreamSynchronize(0), "alloc sync");
+  check(cudaMallocAsync(&p, bytes ? bytes : 8, tl_stream()), "cudaMallocAsync");
+  check(cudaStreamSynchronize(tl_stream()), "alloc sync");       // usable from any stream once the call returns
   return p;
 }
-inline void dfree(void* p) { if (p) cudaFreeAsync(p, 0); }
+inline void dfree(void* p) { if (p) cudaFreeAsync(p, tl_stream()); }
 inline void h2d(void* d, const void* s, size_t n, stream_t st) { if (n) check(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st), "h2d"); }
 inline void d2h(void* d, const void* s, size_t n, stream_t st) { if (n) check(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st), "d2h"); }
 inline void d2d(void* d, const void* s, size_t n, stream_t st) { if (n) check(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st), "d2d"); }
 inline void dzero(void* d, size_t n, stream_t st) { if (n) check(cudaMemsetAsync(d, 0, n, st), "memset"); }
 inline void sync(stream_t st) { check(cudaStreamSynchronize(st), "stream sync"); }
+constexpr int kMaxDevices = 64;
 inline int sm_count() {
-  static int n = 0;
-  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
-  return n;
+  static std::atomic<int> n[kMaxDevices];
+  const int dev = tl_device() & (kMaxDevices - 1);
+  int v = n[dev].load();
+  if (!v) { cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, tl_device()); if (v <= 0) v = 148; n[dev].store(v); }
+  return v;
 }
 
 template <class Body, class Args>
@@ -94,10 +105,11 @@ template <class Body, class Args>
 inline void launch_coop(int grid, int block, size_t smem_bytes, stream_t st, const Args& a) {
   if (grid <= 0) return;
   if (smem_bytes > 48 * 1024) {
-    static std::atomic<size_t> configured{0};   // per (Body,Args) instantiation
-    if (smem_bytes > configured.load()) {
+    static std::atomic<size_t> configured[kMaxDevices];   // per (Body, Args) instantiation AND per device (the attribute is per device)
+    std::atomic<size_t>& c = configured[tl_device() & (kMaxDevices - 1)];
+    if (smem_bytes > c.load()) {
       check(cudaFuncSetAttribute(k_coop<Body, Args>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes), "smem attr");
-      configured.store(smem_bytes);
+      c.store(smem_bytes);
     }
   }
   k_coop<Body, Args><<<grid, block, smem_bytes, st>>>(a);

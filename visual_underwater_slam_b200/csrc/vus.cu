@@ -158,6 +158,7 @@ struct vus_handle {
   vus_lm_params prm;
   double K[6] = {1, 1, 0, 0, 0, 1};
   double grav[3] = {0, 0, -9.81};
+  int opts = VUS_OPT_TANGENT;    // gtsam build switches (vus_set_gtsam_build): tangent preintegration on, slow BetweenFactor off
   // variables
   long nvar[4] = {0, 0, 0, 0};
   std::vector<uint64_t> keys[4];
@@ -208,6 +209,7 @@ struct vus_handle {
   DBuf<int> node_comp, cf_ptr, cf_list, ci_ptr, ci_list;
   DBuf<long> seg;
   DBuf<double> scal_b, lam_c, acc_c, cdots, cdots2, err_c;
+  DBuf<int> fail_mask;           // [ncomp] components whose factorization failed in the current round
   std::vector<vus_component_result> comp_res;
   // loop closures of a batched graph by capacitance (batch.cuh): R = 12 * (max closures per component) columns, 0 = off
   int wb_R = 0, wb_lmax = 0;
@@ -219,11 +221,8 @@ struct vus_handle {
   std::map<std::tuple<const double*, long, int>, GraphCache> g_solve;
   rt::stream_t own_stream = 0;
   void drop_graphs() { g_factor.reset(); for (auto& kv : g_solve) kv.second.reset(); g_solve.clear(); }
-  ~vus_handle() {
+  ~vus_handle() {      // vus_destroy holds the DeviceGuard; members (device buffers) are freed after this body, on own_stream's order
     drop_graphs();
-#ifndef VUS_EMU
-    if (own_stream) cudaStreamDestroy(own_stream);
-#endif
   }
   // stats
   vus_lm_result res;
@@ -276,6 +275,7 @@ void run_factors(vus_handle* h, int which, bool with_J, rt::stream_t st) {
     for (int i = 0; i < 6; ++i) a.K[i] = h->K[i];
     for (int i = 0; i < 3; ++i) a.g[i] = h->grav[i];
     a.type = t;
+    a.opts = h->opts;
     if (fused) L_coop<LinStereoTileBody>((int)((T.n + VUS_LIN_TILE - 1) / VUS_LIN_TILE), VUS_LIN_TILE, (size_t)VUS_LIN_TILE * VUS_LIN_ROW * sizeof(double), st, a);
     else if (with_J) launch_lin_type<true>(h, t, a, st);
     else launch_lin_type<false>(h, t, a, st);
@@ -442,7 +442,7 @@ int analyze_components(vus_handle* h, rt::stream_t st, const std::map<std::pair<
     }
   }
   h->scal_b.alloc((size_t)nc * SB_STRIDE); h->scal_b.zero(st);
-  h->lam_c.alloc(nc); h->acc_c.alloc(nc); h->cdots.alloc((size_t)nc * 36); h->cdots2.alloc((size_t)nc * 36); h->err_c.alloc(nc);
+  h->fail_mask.alloc(nc); h->lam_c.alloc(nc); h->acc_c.alloc(nc); h->cdots.alloc((size_t)nc * 36); h->cdots2.alloc((size_t)nc * 36); h->err_c.alloc(nc);
   rt::sync(st);
   return VUS_OK;
 }
@@ -720,7 +720,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
   h->partials.alloc(h->red_grid);
   h->bpart.alloc((size_t)h->red_grid * 42);
   h->bpart2.alloc((size_t)h->red_grid * 36);
-  h->fail.alloc(1); h->fail.zero(st);
+  h->fail.alloc(std::max(h->ncomp, 1)); h->fail.zero(st);     // one flag per component (batched mode), else one
   long eoff = 0;
   for (int t = 0; t < VUS_F_NTYPES; ++t) {
     FactorTable& T = h->ft[t];
@@ -849,6 +849,7 @@ BcrArgs bcr_args(vus_handle* h) {
   a.Dsrc = nullptr; a.d_ld = 0; a.d_stride = 0; a.Dw = h->Dw.p;
   a.Ucur = nullptr; a.u_ld = 0; a.u_stride = 0; a.Unext = nullptr;
   a.Dinv = h->Dinv.p; a.Gl = h->Gl.p; a.Gr = h->Gr.p; a.fail = h->fail.p;
+  a.node_comp = h->ncomp > 1 ? h->node_comp.p : nullptr; a.knodes = h->k;
   a.X = nullptr; a.xstride = 0; a.nrhs = 1;
   return a;
 }
@@ -1080,7 +1081,7 @@ struct AddBody {
 // PCG on the reduced system with residual replacement: the inner recursion solves A d = r for a correction,
 // the outer loop recomputes the TRUE residual r = rhs - A x (the recursive residual drifts on these badly scaled
 // systems: IMU information ~1e10 next to lambda ~1e-5).  Returns inner iterations; solution in h->x.
-int pcg(vus_handle* h, rt::stream_t st, bool* converged) {
+int pcg(vus_handle* h, rt::stream_t st, bool* converged, bool* bad_out = nullptr) {
   const long L = h->L;
   VecArgs v; v.z = nullptr; v.scal = h->scal.p; v.slot = 0; v.n = L; v.Z = nullptr; v.xb = nullptr; v.zstride = 0;
   h->x.zero(st);
@@ -1089,7 +1090,9 @@ int pcg(vus_handle* h, rt::stream_t st, bool* converged) {
   reduce(h, h->r.p, h->r.p, h->Lr, S_RR, RED_STORE, st);
   const double rr0 = read_scalar(h, S_RR, st);
   *converged = true;
+  if (bad_out) *bad_out = false;
   h->last_rel_res = 0.0;
+  if (!(rr0 == rr0)) { if (bad_out) *bad_out = true; *converged = false; h->last_rel_res = INFINITY; h->z0_valid = false; return 0; }
   if (!(rr0 > 0.0)) { h->z0_valid = false; return 0; }
   h->last_rel_res = INFINITY;
   const double tol2 = h->prm.pcg_rel_tol * h->prm.pcg_rel_tol * rr0;
@@ -1124,7 +1127,7 @@ int pcg(vus_handle* h, rt::stream_t st, bool* converged) {
       reduce(h, h->r.p, h->z.p, h->Lr, S_RZ, RED_RZ, st);
       xpby(h, h->p.p, h->z.p, S_BETA, st);
     }
-    if (bad) break;
+    if (bad) { if (bad_out) *bad_out = true; break; }
     // ---- x += d ; true residual
     v.y = h->x.p; v.x = h->d.p;
     L_elem<AddBody>(L, st, v);
@@ -1144,11 +1147,26 @@ int pcg(vus_handle* h, rt::stream_t st, bool* converged) {
   return it;
 }
 
+// per-component flags of the last factorization (batched mode); clears them.  Returns whether any was set.
+bool read_fail_vec(vus_handle* h, rt::stream_t st, std::vector<int>& out) {
+  out.assign(std::max(h->ncomp, 1), 0);
+  rt::d2h(out.data(), h->fail.p, out.size() * sizeof(int), st);
+  rt::sync(st);
+  bool any = false;
+  for (int v : out) any |= v != 0;
+  if (any) h->fail.zero(st);
+  return any;
+}
 int read_fail(vus_handle* h, rt::stream_t st) {
   int f = 0;
-  rt::d2h(&f, h->fail.p, sizeof(int), st);
-  rt::sync(st);
-  if (f) h->fail.zero(st);
+  if (h->ncomp > 1) {
+    std::vector<int> v;
+    f = read_fail_vec(h, st, v) ? 1 : 0;
+  } else {
+    rt::d2h(&f, h->fail.p, sizeof(int), st);
+    rt::sync(st);
+    if (f) h->fail.zero(st);
+  }
   if (h->comm) {                                       // every rank must take the same decision
     double v = f ? 1.0 : 0.0;
     rt::h2d(h->scal.p + S_COMM, &v, sizeof(double), st);
@@ -1160,6 +1178,8 @@ int read_fail(vus_handle* h, rt::stream_t st) {
   return f;
 }
 
+// a PCG run that stopped short of pcg_rel_tol still counts as a solve when its TRUE relative residual is below this
+const double kPcgAcceptRelRes = 1e-6;
 // solve the damped system at the current linearization; delta in h->x (camera+bias) and h->xl
 bool solve_damped(vus_handle* h, double lambda, rt::stream_t st, int* iters, bool timing) {
   double t0 = timing ? now_ms() : 0;
@@ -1168,8 +1188,16 @@ bool solve_damped(vus_handle* h, double lambda, rt::stream_t st, int* iters, boo
   precond_setup(h, st, h->n_owned < 0);
   if (timing) { rt::sync(st); double t1 = now_ms(); h->res.ms_factor += t1 - t0; t0 = t1; }
   if (read_fail(h, st)) { *iters = 0; return false; }
-  bool conv = false;
-  *iters = pcg(h, st, &conv);
+  bool conv = false, bad = false;
+  *iters = pcg(h, st, &conv, &bad);
+  h->res.worst_pcg_rel_residual = std::max(h->res.worst_pcg_rel_residual, bad ? (double)INFINITY : h->last_rel_res);
+  // gtsam's elimination either solves the damped system or throws (-> "increase lambda"); an iterative solve that ended on a
+  // NaN or stalled far from the solution is the same event, not a step: the try fails and lambda is raised.
+  if (bad || (!conv && !(h->last_rel_res <= kPcgAcceptRelRes))) {
+    h->res.pcg_not_converged++;
+    if (timing) { rt::sync(st); double t1 = now_ms(); h->res.ms_pcg += t1 - t0; t0 = t1; }
+    return false;
+  }
   halo(h, h->x.p, st);                                 // the step of the halo poses comes from their owners
   if (h->nobs) {
     SchurArgs a = schur_args(h, lambda);
@@ -1438,7 +1466,7 @@ double worst_ratio(vus_handle* h, std::vector<double>& sb, rt::stream_t st, bool
 }
 // PCG with per-component scalars: the block-diagonal system is solved as ncomp independent CG recursions advanced in
 // lock step (one set of kernels for all of them); a component whose residual met the tolerance stops moving.
-int pcg_b(vus_handle* h, rt::stream_t st, bool* converged) {
+int pcg_b(vus_handle* h, rt::stream_t st, bool* converged, bool* bad_out = nullptr) {
   const long L = h->L;
   VecArgs v; v.z = nullptr; v.scal = nullptr; v.slot = 0; v.n = L; v.Z = nullptr; v.xb = nullptr; v.zstride = 0;
   std::vector<double> sb((size_t)h->ncomp * SB_STRIDE);
@@ -1448,6 +1476,7 @@ int pcg_b(vus_handle* h, rt::stream_t st, bool* converged) {
   bool bad = false;
   double worst = worst_ratio(h, sb, st, &bad);
   *converged = !bad && worst <= 1.0;
+  if (bad_out) *bad_out = bad;
   if (*converged || bad) { h->z0_valid = false; return 0; }
   int it = 0;
   double worst_outer = worst;
@@ -1474,7 +1503,7 @@ int pcg_b(vus_handle* h, rt::stream_t st, bool* converged) {
       bdot(h, h->r.p, h->z.p, S_RZ, BOP_RZ, st);
       bxpby(h, h->p.p, h->z.p, S_BETA, st);
     }
-    if (bad) break;
+    if (bad) { if (bad_out) *bad_out = true; break; }
     v.y = h->x.p; v.x = h->d.p;
     L_elem<AddBody>(L, st, v);
     apply_A_b(h, h->r.p, h->x.p, st);
@@ -1483,7 +1512,7 @@ int pcg_b(vus_handle* h, rt::stream_t st, bool* converged) {
     bdot(h, h->r.p, h->r.p, S_RR, BOP_STORE, st);
     const double worst_true = worst_ratio(h, sb, st, &bad);
     if (h->prm.verbose > 1) std::fprintf(stderr, "    pcg_b outer %d true worst rr/tol2 %.3e\n", outer, worst_true);
-    if (bad) break;
+    if (bad) { if (bad_out) *bad_out = true; break; }
     if (worst_true <= 1.0) { *converged = true; break; }
     if (!(worst_true < 0.25 * worst_outer) || it >= h->prm.pcg_max_iterations) break;
     worst_outer = worst_true;
@@ -1531,17 +1560,30 @@ int optimize_batched(vus_handle* h, rt::stream_t st) {
     form_system_b(h, st);
     precond_setup_b(h, st);
     if (h->wb_R) wb_setup(h, st);
-    const bool solved = !read_fail(h, st);
-    if (solved) {
+    // a non-positive pivot fails the try of THE COMPONENT it belongs to (as one optimizer per trajectory would see it): its
+    // right-hand side is zeroed so its PCG recursion never starts, every other component is solved as usual
+    std::vector<int> failc;
+    const bool any_fail = read_fail_vec(h, st, failc);
+    if (any_fail) {
+      rt::h2d(h->fail_mask.p, failc.data(), nc * sizeof(int), st);
+      BZeroCompArgs z; z.C = bctx(h); z.mask = h->fail_mask.p; z.v = h->gs.p;
+      L_elem<BZeroCompBody>(h->L, st, z);
+      z.v = h->Z.p + 6 * h->Lc;                          // the right-hand side that rode along the border solve
+      if (h->z0_valid) L_elem<BZeroCompBody>(h->Lc, st, z);
+      for (int c = 0; c < nc; ++c) if (failc[c] && active[c]) R.solve_failures++;
+    }
+    bool pcg_bad = false;
+    {
       bool conv = false;
-      R.pcg_iterations += pcg_b(h, st, &conv);
+      R.pcg_iterations += pcg_b(h, st, &conv, &pcg_bad);
+      if (pcg_bad) { R.solve_failures++; R.pcg_not_converged++; }
+    }
+    if (!pcg_bad) {
       linear_error_launches(h, st);
       comp_sums(h, h->le_all.p, new_lin, st);
       retract(h, st);
       run_factors(h, 1 - h->cur, false, st);
       comp_sums(h, h->e_all.p, new_err, st);
-    } else {
-      R.solve_failures++;
     }
     R.inner_iterations++;
     for (int c = 0; c < nc; ++c) {
@@ -1551,6 +1593,7 @@ int optimize_batched(vus_handle* h, rt::stream_t st) {
       cr.inner_iterations++;
       bool success = false, stop = false;
       double ne = INFINITY;
+      const bool solved = !pcg_bad && !failc[c];
       if (solved) {
         const double old_lin = err[c];
         const double lin_change = old_lin - new_lin[c];
@@ -1583,7 +1626,7 @@ int optimize_batched(vus_handle* h, rt::stream_t st) {
         if (done) { active[c] = 0; --n_active; }
       }
     }
-    if (solved) {
+    if (!pcg_bad) {
       rt::h2d(h->acc_c.p, accept.data(), nc * sizeof(double), st);
       BCommitArgs a; a.node_comp = h->node_comp.p; a.accept = h->acc_c.p; a.nx = h->nvar[0]; a.nv = h->nvar[1]; a.nb = h->nvar[2];
       const int cu = h->cur, tr = 1 - h->cur;
@@ -1705,7 +1748,36 @@ int marginal_covariance(vus_handle* h, rt::stream_t st, long nq, const int32_t* 
 // =====================================================================================
 // C-ABI
 // =====================================================================================
-#define VUS_TRY(h) try {
+// Every entry point that touches the device runs with the handle's device current on the CALLING thread (a handle may be
+// created on one thread and driven from another, and one process may hold handles on several GPUs) and restores the
+// caller's device on the way out.
+struct DeviceGuard {
+  int prev = -1, dev;
+  rt::stream_t prev_stream;
+  int prev_tl;
+  explicit DeviceGuard(const vus_handle* h) : dev(h ? h->device : 0), prev_stream(rt::tl_stream()), prev_tl(rt::tl_device()) {
+#ifndef VUS_EMU
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+#endif
+    rt::tl_device() = dev;
+    rt::tl_stream() = h ? h->own_stream : 0;
+  }
+  ~DeviceGuard() {
+#ifndef VUS_EMU
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+#endif
+    rt::tl_device() = prev_tl;
+    rt::tl_stream() = prev_stream;
+  }
+};
+// the stream an entry point works on (the caller's, or the handle's own); temporaries are freed in its order
+inline rt::stream_t use_stream(vus_handle* h, void* stream) {
+  rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
+  rt::tl_stream() = st;
+  return st;
+}
+#define VUS_TRY(h) try { DeviceGuard vus_device_guard_(h);
 #define VUS_CATCH(h)                                                         \
   } catch (const std::exception& e) { return fail(h, VUS_ERR_CUDA, e.what()); } \
   catch (...) { return fail(h, VUS_ERR_CUDA, "unknown error"); }
@@ -1724,6 +1796,8 @@ int vus_create(int device, vus_handle** out) {
 #ifndef VUS_EMU
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return VUS_ERR_CUDA;
+  int prev_device = -1;
+  cudaGetDevice(&prev_device);
   if (cudaSetDevice(device) != cudaSuccess) return VUS_ERR_CUDA;
 #endif
   rt::pool_setup(device);
@@ -1731,13 +1805,23 @@ int vus_create(int device, vus_handle** out) {
   h->device = device;
 #ifndef VUS_EMU
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) h->own_stream = 0;
+  if (prev_device >= 0 && prev_device != device) cudaSetDevice(prev_device);      // the caller's current device is left as it was
 #endif
   vus_default_lm_params(&h->prm);
   *out = h;
   return VUS_OK;
 }
 
-void vus_destroy(vus_handle* h) { delete h; }
+void vus_destroy(vus_handle* h) {
+  if (!h) return;
+  DeviceGuard guard(h);
+  rt::stream_t st = h->own_stream;
+  try { rt::sync(st); } catch (...) {}
+  delete h;                                  // device buffers are released in the order of `st` (rt::dfree)
+#ifndef VUS_EMU
+  if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+#endif
+}
 
 const char* vus_last_error(const vus_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
@@ -1750,8 +1834,8 @@ int vus_set_variables(vus_handle* h, int kind, int64_t n, const uint64_t* keys, 
   h->nvar[kind] = n;
   DBuf<double>& b = h->val[h->cur][kind];
   b.alloc((size_t)kVarDim[kind] * n);
-  import_table(b.p, data, n, kVarDim[kind], mem, 0);
-  rt::sync(0);
+  import_table(b.p, data, n, kVarDim[kind], mem, h->own_stream);
+  rt::sync(h->own_stream);
   h->analyzed = false;
   return VUS_OK;
   VUS_CATCH(h)
@@ -1760,8 +1844,8 @@ int vus_set_variables(vus_handle* h, int kind, int64_t n, const uint64_t* keys, 
 int vus_get_variables(vus_handle* h, int kind, double* out, int mem) {
   if (!h || kind < 0 || kind >= 4) return fail(h, VUS_ERR_INVALID, "vus_get_variables: bad arguments");
   VUS_TRY(h)
-  export_table(out, h->val[h->cur][kind].p, h->nvar[kind], kVarDim[kind], mem, 0);
-  rt::sync(0);
+  export_table(out, h->val[h->cur][kind].p, h->nvar[kind], kVarDim[kind], mem, h->own_stream);
+  rt::sync(h->own_stream);
   return VUS_OK;
   VUS_CATCH(h)
 }
@@ -1772,9 +1856,9 @@ int vus_save_values(vus_handle* h) {
   for (int kind = 0; kind < 4; ++kind) {
     const size_t n = (size_t)kVarDim[kind] * h->nvar[kind];
     h->saved[kind].alloc(n);
-    rt::d2d(h->saved[kind].p, h->val[h->cur][kind].p, n * sizeof(double), 0);
+    rt::d2d(h->saved[kind].p, h->val[h->cur][kind].p, n * sizeof(double), h->own_stream);
   }
-  rt::sync(0);
+  rt::sync(h->own_stream);
   h->has_saved = true;
   return VUS_OK;
   VUS_CATCH(h)
@@ -1785,8 +1869,8 @@ int vus_restore_values(vus_handle* h) {
   if (!h->has_saved) return fail(h, VUS_ERR_STATE, "vus_restore_values: nothing saved");
   VUS_TRY(h)
   for (int kind = 0; kind < 4; ++kind)
-    rt::d2d(h->val[h->cur][kind].p, h->saved[kind].p, (size_t)kVarDim[kind] * h->nvar[kind] * sizeof(double), 0);
-  rt::sync(0);
+    rt::d2d(h->val[h->cur][kind].p, h->saved[kind].p, (size_t)kVarDim[kind] * h->nvar[kind] * sizeof(double), h->own_stream);
+  rt::sync(h->own_stream);
   return VUS_OK;
   VUS_CATCH(h)
 }
@@ -1800,12 +1884,12 @@ int vus_add_factors(vus_handle* h, int type, int64_t n, const int32_t* var_idx, 
   T.n = n;
   T.h_idx.assign(var_idx, var_idx + (size_t)kFactorSlots[type] * n);
   T.orig.assign(orig_index, orig_index + n);
-  T.idx.upload(T.h_idx, 0);
+  T.idx.upload(T.h_idx, h->own_stream);
   T.meas.alloc((size_t)kFactorMeas[type] * n);
   T.sinfo.alloc((size_t)kFactorInfo[type] * n);
-  import_table(T.meas.p, meas, n, kFactorMeas[type], mem, 0);
-  import_table(T.sinfo.p, sqrt_info, n, kFactorInfo[type], mem, 0);
-  rt::sync(0);
+  import_table(T.meas.p, meas, n, kFactorMeas[type], mem, h->own_stream);
+  import_table(T.sinfo.p, sqrt_info, n, kFactorInfo[type], mem, h->own_stream);
+  rt::sync(h->own_stream);
   h->nfactors += n;
   h->analyzed = false;
   return VUS_OK;
@@ -1820,6 +1904,11 @@ int vus_set_calibration(vus_handle* h, const double K[6]) {
 int vus_set_gravity(vus_handle* h, const double g[3]) {
   if (!h || !g) return VUS_ERR_INVALID;
   for (int i = 0; i < 3; ++i) h->grav[i] = g[i];
+  return VUS_OK;
+}
+int vus_set_gtsam_build(vus_handle* h, int tangent_preintegration, int slow_but_correct_betweenfactor) {
+  if (!h) return VUS_ERR_INVALID;
+  h->opts = (tangent_preintegration ? VUS_OPT_TANGENT : 0) | (slow_but_correct_betweenfactor ? VUS_OPT_SLOW_BETWEEN : 0);
   return VUS_OK;
 }
 int vus_set_lm_params(vus_handle* h, const vus_lm_params* p) {
@@ -1879,7 +1968,7 @@ int vus_analyze(vus_handle* h) {
         if (v < 0 || v >= h->nvar[slot_kind[t][s]]) return fail(h, VUS_ERR_INVALID, "vus_analyze: factor references a variable index out of range");
       }
   }
-  return analyze(h, 0);
+  return analyze(h, h->own_stream);
   VUS_CATCH(h)
 }
 
@@ -1893,7 +1982,7 @@ int vus_optimize(vus_handle* h, void* stream, vus_lm_result* result) {
   if (!h) return VUS_ERR_INVALID;
   if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_optimize: call vus_analyze first");
   VUS_TRY(h)
-  rt::stream_t st_ = stream ? (rt::stream_t)stream : h->own_stream;
+  rt::stream_t st_ = use_stream(h, stream);
   const int rc = h->ncomp > 1 ? optimize_batched(h, st_) : optimize(h, st_);
   if (result) *result = h->res;
   return rc;
@@ -1911,7 +2000,7 @@ int vus_error(vus_handle* h, void* stream, double* out) {
   if (!h || !out) return VUS_ERR_INVALID;
   if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_error: call vus_analyze first");
   VUS_TRY(h)
-  *out = graph_error(h, h->cur, stream ? (rt::stream_t)stream : h->own_stream);
+  *out = graph_error(h, h->cur, use_stream(h, stream));
   return VUS_OK;
   VUS_CATCH(h)
 }
@@ -1920,7 +2009,7 @@ int vus_factor_errors(vus_handle* h, void* stream, double* out) {
   if (!h || !out) return VUS_ERR_INVALID;
   if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_factor_errors: call vus_analyze first");
   VUS_TRY(h)
-  rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
+  rt::stream_t st = use_stream(h, stream);
   run_factors(h, h->cur, false, st);
   finish_order(h->ft[VUS_F_STEREO], st);
   std::vector<double> tmp(h->nfactors);
@@ -1941,7 +2030,7 @@ int vus_linearize(vus_handle* h, void* stream, int type, double* r_out, double* 
   if (!h || type < 0 || type >= VUS_F_NTYPES) return VUS_ERR_INVALID;
   if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_linearize: call vus_analyze first");
   VUS_TRY(h)
-  rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
+  rt::stream_t st = use_stream(h, stream);
   run_factors(h, h->cur, true, st);
   FactorTable& T = h->ft[type];
   finish_order(T, st);
@@ -1970,7 +2059,7 @@ int vus_solve_step(vus_handle* h, void* stream, double lambda, double* d_pose, d
   if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_solve_step: call vus_analyze first");
   if (h->ncomp > 1) return fail(h, VUS_ERR_UNSUPPORTED, "vus_solve_step: not available on a batched graph (vus_set_components)");
   VUS_TRY(h)
-  rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
+  rt::stream_t st = use_stream(h, stream);
   run_factors(h, h->cur, true, st);
   assemble_base(h, st);
   int its = 0;
@@ -1999,7 +2088,7 @@ int vus_marginal_covariance(vus_handle* h, void* stream, int64_t nq, const int32
   if (h->ncomp > 1) return fail(h, VUS_ERR_UNSUPPORTED, "vus_marginal_covariance: not available on a batched graph (vus_set_components)");
   if (h->n_owned >= 0) return fail(h, VUS_ERR_UNSUPPORTED, "vus_marginal_covariance: not available on a partitioned graph");
   VUS_TRY(h)
-  return marginal_covariance(h, stream ? (rt::stream_t)stream : h->own_stream, nq, kinds, idx, cov_out);
+  return marginal_covariance(h, use_stream(h, stream), nq, kinds, idx, cov_out);
   VUS_CATCH(h)
 }
 
@@ -2008,7 +2097,7 @@ int vus_debug_band_solve(vus_handle* h, void* stream, double lambda, double* SD_
   if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_debug_band_solve: call vus_analyze first");
   if (h->ncomp > 1) return fail(h, VUS_ERR_UNSUPPORTED, "vus_debug_band_solve: not available on a batched graph (vus_set_components)");
   VUS_TRY(h)
-  rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
+  rt::stream_t st = use_stream(h, stream);
   const long BB = (long)h->B * h->B, BBP = bcr_bbp(h->B);
   const int LD = bcr_ld(h->B);
   run_factors(h, h->cur, true, st);
@@ -2044,7 +2133,7 @@ int vus_preintegrate_imu(vus_handle* h, void* stream, int64_t n, int32_t k, cons
   if (!h || n < 0 || k <= 0 || !(dt > 0.0) || !acc || !gyro || !pim_out || !sqrt_info_out || (mem != VUS_MEM_HOST_ROWS && mem != VUS_MEM_DEVICE_ROWS))
     return fail(h, VUS_ERR_INVALID, "vus_preintegrate_imu: bad arguments (tables are row-major: mem = VUS_MEM_HOST_ROWS or VUS_MEM_DEVICE_ROWS)");
   VUS_TRY(h)
-  rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
+  rt::stream_t st = use_stream(h, stream);
   if (n == 0) return VUS_OK;
   const size_t in_bytes = (size_t)n * k * 3 * sizeof(double);
   DBuf<double> dacc, dgyr, pim, sinfo;
@@ -2059,6 +2148,7 @@ int vus_preintegrate_imu(vus_handle* h, void* stream, int64_t n, int32_t k, cons
   for (int i = 0; i < 9; ++i) { P.aC[i] = acc_cov[i]; P.wC[i] = gyro_cov[i]; P.iC[i] = int_cov[i]; }
   pim.alloc((size_t)67 * n); sinfo.alloc((size_t)45 * n);
   P.pim = pim.p; P.sinfo = sinfo.p;
+  P.tangent = (h->opts & VUS_OPT_TANGENT) != 0;
   if (!h->fail.p) { h->fail.alloc(1); h->fail.zero(st); }
   P.fail = h->fail.p;
   L_elem<PreintBody>(n, st, P);
@@ -2075,7 +2165,7 @@ int vus_backproject_stereo(vus_handle* h, void* stream, int64_t n, const int32_t
     return fail(h, VUS_ERR_INVALID, "vus_backproject_stereo: bad arguments (tables are row-major)");
   if (!h->nvar[0]) return fail(h, VUS_ERR_STATE, "vus_backproject_stereo: set the pose variables first");
   VUS_TRY(h)
-  rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
+  rt::stream_t st = use_stream(h, stream);
   if (n == 0) return VUS_OK;
   for (int64_t o = 0; o < n; ++o)
     if (pose_idx[o] < 0 || pose_idx[o] >= h->nvar[0]) return fail(h, VUS_ERR_INVALID, "vus_backproject_stereo: pose index out of range");
@@ -2100,7 +2190,7 @@ int vus_time_linearize(vus_handle* h, void* stream, int reps, double* ms_per_rep
   if (!h || !ms_per_rep || reps <= 0) return VUS_ERR_INVALID;
   if (!h->analyzed) return fail(h, VUS_ERR_STATE, "vus_time_linearize: call vus_analyze first");
   VUS_TRY(h)
-  rt::stream_t st = stream ? (rt::stream_t)stream : h->own_stream;
+  rt::stream_t st = use_stream(h, stream);
   run_factors(h, h->cur, true, st);
   rt::sync(st);
 #ifndef VUS_EMU

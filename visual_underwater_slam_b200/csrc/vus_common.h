@@ -22,12 +22,14 @@
   #define VUS_DEV inline
   #define VUS_SYNC() ((void)0)
   #define VUS_RESTRICT
+  #define VUS_SHARED
 #else
   #include <cuda_runtime.h>
   #define VUS_HD __host__ __device__ __forceinline__
   #define VUS_DEV __device__ __forceinline__
   #define VUS_SYNC() __syncthreads()
   #define VUS_RESTRICT __restrict__
+  #define VUS_SHARED __shared__
 #endif
 
 #define VUS_EPS 2.220446049250313e-16

@@ -106,6 +106,7 @@ class ImuFactor(_Factor):
         iu = np.triu_indices(9)
         self.sqrt_info = Rm[iu[0], iu[1]]
         self.gravity = pim.params().n_gravity.copy()
+        self.tangent = pim.tangent()
 
 
 class CustomFactor(_Factor):

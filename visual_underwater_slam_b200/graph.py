@@ -11,6 +11,7 @@ marshaller (optimizer.py) and the test oracle consume.  The bulk `add_*_factors`
 the vectorised construction API that bypasses the per-factor Python loop.
 """
 import numpy as np
+from . import config
 from . import factors as F
 from .values import Values
 from .symbol import symbolChr, symbolIndex
@@ -32,6 +33,7 @@ class NonlinearFactorGraph:
         self._custom = []
         self.calib = None
         self.gravity = None
+        self.imu_tangent = None      # preintegration variant of the ImuFactors in this graph (all alike; config.py)
 
     # ------------------------------------------------------------------ gtsam API
     def add(self, factor):
@@ -52,6 +54,7 @@ class NonlinearFactorGraph:
             self._set_once("calib", factor.K, "Cal3_S2Stereo")
         if t == "imu":
             self._set_once("gravity", factor.gravity, "n_gravity")
+            self._set_variant(factor.tangent)
         meas = factor.pim if t == "imu" else factor.meas
         self._pending[t].append((factor.keys(), meas, factor.sqrt_info, self._n))
         self._n += 1
@@ -67,6 +70,8 @@ class NonlinearFactorGraph:
             self._set_once("calib", other.calib, "Cal3_S2Stereo")
         if other.gravity is not None:
             self._set_once("gravity", other.gravity, "n_gravity")
+        if other.imu_tangent is not None:
+            self._set_variant(other.imu_tangent)
         for t in FACTOR_TYPES:
             tab = other.table(t)
             if len(tab["orig"]) == 0:
@@ -96,6 +101,13 @@ class NonlinearFactorGraph:
         elif not np.array_equal(cur, value):
             raise NotImplementedError(f"all factors must share one {what} on the B200 path")
 
+    def _set_variant(self, tangent):
+        if self.imu_tangent is None:
+            self.imu_tangent = bool(tangent)
+        elif self.imu_tangent != bool(tangent):
+            raise NotImplementedError("all ImuFactors of a graph must come from the same preintegration variant "
+                                      "(tangent / manifold; a gtsam build has only one)")
+
     # ------------------------------------------------------------------ bulk construction API
     def _add_bulk(self, t, keys, meas, sqrt_info):
         keys = np.asarray(keys, dtype=np.uint64).reshape(-1, len(_SLOTS[t]))
@@ -123,8 +135,11 @@ class NonlinearFactorGraph:
         self._set_once("calib", np.asarray(K.vector() if hasattr(K, "vector") else K), "Cal3_S2Stereo")
         self._add_bulk("stereo", np.stack([xkeys, lkeys], 1), meas, sqrt_info)
 
-    def add_imu_factors(self, xi, vi, xj, vj, b, pim, sqrt_info_triu, n_gravity):
+    def add_imu_factors(self, xi, vi, xj, vj, b, pim, sqrt_info_triu, n_gravity, tangent=None):
+        """pim rows in the layout of navigation.py; tangent: the variant they were preintegrated with
+        (None = config.gtsam_build()["tangent_preintegration"], what preintegrate_batch uses by default)."""
         self._set_once("gravity", n_gravity, "n_gravity")
+        self._set_variant(config.gtsam_build()["tangent_preintegration"] if tangent is None else tangent)
         self._add_bulk("imu", np.stack([xi, vi, xj, vj, b], 1), pim, sqrt_info_triu)
 
     def set_insertion_order(self, ftype, orig):
@@ -192,6 +207,10 @@ class NonlinearFactorGraph:
                 out[slot] = pos.astype(np.int32)
             prob[t] = out
         prob["n_factors"] = self._n
+        build = config.gtsam_build()
+        prob["options"] = dict(
+            tangent_preintegration=build["tangent_preintegration"] if self.imu_tangent is None else self.imu_tangent,
+            slow_but_correct_betweenfactor=build["slow_but_correct_betweenfactor"])
         return prob
 
     # ------------------------------------------------------------------ evaluation (CUDA path)

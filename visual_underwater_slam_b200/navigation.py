@@ -6,13 +6,16 @@ gtsam.PreintegratedImuMeasurements (batch.py:91, :290, :293), gtsam.imuBias.Cons
 O(#samples); it runs on the host, vectorised ACROSS factors (`preintegrate_batch`) so that
 100k factors x 40 samples take ~1 s of numpy.  The factor residual/Jacobians run on the GPU.
 
-Variant: MANIFOLD preintegration (Forster et al.; gtsam ManifoldPreintegration.cpp) -- stated in
-every result file because gtsam 4.0-4.2 wheels default to the Tangent variant.
+Both build variants of gtsam are implemented (config.py): TANGENT preintegration
+(gtsam TangentPreintegration.cpp, the default of the 4.0-4.2 wheels and the default here) and MANIFOLD
+preintegration (Forster et al.; ManifoldPreintegration.cpp).  The variant is stated in every result file.
 
 Packed PIM row (67 doubles, the layout include/vus.h documents for VUS_FACTOR_IMU):
-  dR 9 | dP 3 | dV 3 | dt 1 | bias_hat(acc,gyro) 6 | dR/dbg 9 | dP/dba 9 | dP/dbg 9 | dV/dba 9 | dV/dbg 9
+  manifold: dR 9         | dP 3 | dV 3 | dt 1 | bias_hat(acc,gyro) 6 | dR/dbg 9     | dP/dba 9 | dP/dbg 9 | dV/dba 9 | dV/dbg 9
+  tangent : theta 3, 0*6 | p 3  | v 3  | dt 1 | bias_hat(acc,gyro) 6 | dtheta/dbg 9 | dp/dba 9 | dp/dbg 9 | dv/dba 9 | dv/dbg 9
 """
 import numpy as np
+from . import config
 from .noise import upper_sqrt_information
 
 PIM_COLS = 67
@@ -48,11 +51,40 @@ def _exp_and_jr(phi):
     return E, Jr
 
 
+def _inv_dexp_and_derivative(theta, w):
+    """c = Jr(theta)^-1 w with d c / d theta and Jr^-1 (gtsam so3::DexpFunctor::applyInvDexp), batched."""
+    n = theta.shape[0]
+    _, Jr = _exp_and_jr(theta)
+    inv = np.linalg.inv(Jr)
+    c = np.einsum('nij,nj->ni', inv, w)
+    th2 = np.sum(theta * theta, axis=1)
+    small = th2 <= _EPS
+    t2 = np.where(small, 1.0, th2)
+    th = np.sqrt(t2)
+    sn = np.sin(th)
+    omc = 2.0 * np.sin(0.5 * th) ** 2
+    A = omc / t2
+    B = (th - sn) / (t2 * th)
+    dA = (th * sn - 2.0 * omc) / (t2 * th) / th            # (dA/dth) / th
+    dB = (omc * th - 3.0 * (th - sn)) / (t2 * t2) / th
+    txc = np.cross(theta, c)
+    ttc = np.cross(theta, txc)
+    tc = np.sum(theta * c, axis=1)
+    I = np.broadcast_to(np.eye(3), (n, 3, 3))
+    D = (-dA[:, None, None] * txc[:, :, None] * theta[:, None, :] + A[:, None, None] * _hat_b(c)
+         + dB[:, None, None] * ttc[:, :, None] * theta[:, None, :]
+         + B[:, None, None] * (tc[:, None, None] * I + theta[:, :, None] * c[:, None, :] - 2.0 * c[:, :, None] * theta[:, None, :]))
+    if np.any(small):
+        D[small] = (0.5 * _hat_b(c))[small]
+    return c, -inv @ D, inv
+
+
 class _PimState:
     """Batched running preintegration state (n factors advance in lock step)."""
 
-    def __init__(self, n, bhat):
+    def __init__(self, n, bhat, tangent=None):
         self.n = n
+        self.tangent = config.gtsam_build()["tangent_preintegration"] if tangent is None else bool(tangent)
         self.bhat = np.broadcast_to(np.asarray(bhat, dtype=np.float64), (n, 6)).copy()
         self.reset()
 
@@ -68,12 +100,49 @@ class _PimState:
         self.JVa = np.zeros((n, 3, 3))
         self.JVg = np.zeros((n, 3, 3))
         self.cov = np.zeros((n, 9, 9))
+        self.theta = np.zeros((n, 3))            # tangent variant: dR = Exp(theta) is kept in step with it
+
+    def _step_tangent(self, a, w, h, aC, wC, iC):
+        """TangentPreintegration::UpdatePreintegrated + ::update + the covariance line of integrateMeasurement."""
+        n = self.n
+        hh = h[:, None, None]
+        q = (0.5 * h * h)[:, None, None]
+        wt, wt_H_theta, invH = _inv_dexp_and_derivative(self.theta, w)
+        R, Jr = _exp_and_jr(self.theta)
+        a_nav = np.einsum('nij,nj->ni', R, a)
+        aH = -(R @ _hat_b(a)) @ Jr                        # d (R a) / d theta
+        A = np.broadcast_to(np.eye(9), (n, 9, 9)).copy()
+        A[:, 0:3, 0:3] += wt_H_theta * hh
+        A[:, 3:6, 0:3] = aH * q
+        A[:, 3:6, 6:9] = np.eye(3)[None] * hh
+        A[:, 6:9, 0:3] = aH * hh
+        Bm = np.concatenate([np.zeros((n, 3, 3)), R * q, R * hh], axis=1)
+        Cm = np.concatenate([invH * hh, np.zeros((n, 6, 3))], axis=1)
+        Ha = np.concatenate([np.zeros((n, 3, 3)), self.JPa, self.JVa], axis=1)
+        Hg = np.concatenate([self.JRg, self.JPg, self.JVg], axis=1)
+        Ha = A @ Ha - Bm
+        Hg = A @ Hg - Cm
+        self.JPa, self.JVa = Ha[:, 3:6], Ha[:, 6:9]
+        self.JRg, self.JPg, self.JVg = Hg[:, 0:3], Hg[:, 3:6], Hg[:, 6:9]
+        cov = A @ self.cov @ np.swapaxes(A, 1, 2)
+        cov += Bm @ (aC[None] / hh) @ np.swapaxes(Bm, 1, 2)
+        cov += Cm @ (wC[None] / hh) @ np.swapaxes(Cm, 1, 2)
+        cov[:, 3:6, 3:6] += iC[None] * hh
+        self.cov = cov
+        self.dP = self.dP + self.dV * h[:, None] + a_nav * (0.5 * h * h)[:, None]
+        self.dV = self.dV + a_nav * h[:, None]
+        self.theta = self.theta + wt * h[:, None]
+        self.dR, _ = _exp_and_jr(self.theta)
+        self.T = self.T + h
 
     def step(self, acc, gyro, dt, aC, wC, iC):
         n = self.n
         h = np.broadcast_to(np.asarray(dt, dtype=np.float64), (n,))
         a = acc - self.bhat[:, :3]
         w = gyro - self.bhat[:, 3:]
+        if self.tangent:
+            self._step_tangent(a, w, h, aC, wC, iC)
+            return
         inc, Jr = _exp_and_jr(w * h[:, None])
         incT = np.swapaxes(inc, 1, 2)
         ax = _hat_b(a)
@@ -111,7 +180,8 @@ class _PimState:
 
     def pack(self):
         n = self.n
-        return np.concatenate([self.dR.reshape(n, 9), self.dP, self.dV, self.T[:, None], self.bhat,
+        head = np.concatenate([self.theta, np.zeros((n, 6))], axis=1) if self.tangent else self.dR.reshape(n, 9)
+        return np.concatenate([head, self.dP, self.dV, self.T[:, None], self.bhat,
                                self.JRg.reshape(n, 9), self.JPa.reshape(n, 9), self.JPg.reshape(n, 9),
                                self.JVa.reshape(n, 9), self.JVg.reshape(n, 9)], axis=1)
 
@@ -188,7 +258,10 @@ class PreintegratedImuMeasurements:
     def __init__(self, params, bias=None):
         self._p = params
         bhat = (bias or ConstantBias()).vector()
-        self._s = _PimState(1, bhat[None])
+        self._s = _PimState(1, bhat[None])        # variant: config.gtsam_build() at construction, like the gtsam build
+
+    def tangent(self):
+        return self._s.tangent
 
     def integrateMeasurement(self, measuredAcc, measuredOmega, dt):
         """batch.py:290."""
@@ -227,13 +300,14 @@ class PreintegratedImuMeasurements:
         return self._s.pack()[0], self._s.cov[0].copy()
 
 
-def preintegrate_batch(acc, gyro, dt, params, bias_hat=None):
-    """Bulk API: acc, gyro [n,k,3]; dt scalar or [n,k]. -> (pim [n,67], sqrt_info_triu [n,45], cov [n,9,9])."""
+def preintegrate_batch(acc, gyro, dt, params, bias_hat=None, tangent=None):
+    """Bulk API: acc, gyro [n,k,3]; dt scalar or [n,k]. -> (pim [n,67], sqrt_info_triu [n,45], cov [n,9,9]).
+    tangent: None = config.gtsam_build()["tangent_preintegration"]."""
     acc = np.asarray(acc, dtype=np.float64)
     gyro = np.asarray(gyro, dtype=np.float64)
     n, k, _ = acc.shape
     dts = np.broadcast_to(np.asarray(dt, dtype=np.float64), (n, k))
-    st = _PimState(n, np.zeros(6) if bias_hat is None else bias_hat)
+    st = _PimState(n, np.zeros(6) if bias_hat is None else bias_hat, tangent)
     for s in range(k):
         st.step(acc[:, s], gyro[:, s], dts[:, s], params.accelerometerCovariance,
                 params.gyroscopeCovariance, params.integrationCovariance)

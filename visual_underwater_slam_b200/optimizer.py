@@ -8,7 +8,7 @@ reads results back; PyTorch tensors are accepted as device-buffer carriers (`Ses
 """
 import ctypes as C
 import numpy as np
-from . import _native
+from . import _native, config
 from ._native import LmParams, LmResult
 from .values import Values
 
@@ -175,6 +175,10 @@ class Session:
         g = np.ascontiguousarray(prob["gravity"], dtype=np.float64)
         self._check(lib.vus_set_calibration(self._h, K.ctypes.data_as(_native.c_double_p)))
         self._check(lib.vus_set_gravity(self._h, g.ctypes.data_as(_native.c_double_p)))
+        opt = dict(config.gtsam_build())
+        opt.update(prob.get("options") or {})
+        self.options = opt
+        self._check(lib.vus_set_gtsam_build(self._h, int(opt["tangent_preintegration"]), int(opt["slow_but_correct_betweenfactor"])))
         self.nf = {}
         for t, name in enumerate(FACTOR_TYPES):
             f = prob[name]
@@ -428,9 +432,10 @@ class Marginals:
 
 
 # ---------------------------------------------------------------------------------------------- front-end rows
-def preintegrate_imu(acc, gyro, dt, params, bias_hat=None, lib=None, device=0, stream=None):
+def preintegrate_imu(acc, gyro, dt, params, bias_hat=None, lib=None, device=0, stream=None, tangent=None):
     """Device version of navigation.preintegrate_batch (the integrateMeasurement loop of batch.py:289-293):
-    acc, gyro [n, k, 3], constant dt -> (pim [n, 67], sqrt_info_triu [n, 45]) ready for graph.add_imu_factors."""
+    acc, gyro [n, k, 3], constant dt -> (pim [n, 67], sqrt_info_triu [n, 45]) ready for graph.add_imu_factors.
+    tangent: preintegration variant (None = config.gtsam_build())."""
     lib = lib if lib is not None else _native.load()
     acc = np.ascontiguousarray(acc, dtype=np.float64)
     gyro = np.ascontiguousarray(gyro, dtype=np.float64)
@@ -441,6 +446,8 @@ def preintegrate_imu(acc, gyro, dt, params, bias_hat=None, lib=None, device=0, s
     if lib.vus_create(int(device), C.byref(h)) != 0:
         raise RuntimeError("vus_create failed: no usable CUDA device; this path has no CPU fallback")
     try:
+        tan = config.gtsam_build()["tangent_preintegration"] if tangent is None else bool(tangent)
+        lib.vus_set_gtsam_build(h, int(tan), 0)
         pim = np.empty((n, 67))
         info = np.empty((n, 45))
         P = _native.c_double_p

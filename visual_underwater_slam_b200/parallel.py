@@ -90,13 +90,15 @@ def concat_problems(problems):
            "bias_keys": np.uint64(B(0)) + np.arange(len(problems), dtype=np.uint64) if has_bias else np.zeros(0, dtype=np.uint64),
            "biases": np.concatenate([p["biases"] for p in problems], 0) if has_bias else np.zeros((0, 6)),
            "lm_keys": np.zeros(0, dtype=np.uint64), "lms": np.zeros((0, 3)),
-           "calib": problems[0]["calib"], "gravity": problems[0]["gravity"]}
+           "calib": problems[0]["calib"], "gravity": problems[0]["gravity"], "options": problems[0].get("options")}
     node_slots = ("x", "x1", "x2", "xi", "xj", "v", "vi", "vj")
     f0 = 0
     tables = {}
     for t, p in enumerate(problems):
         if not np.array_equal(p["gravity"], out["gravity"]):
             raise NotImplementedError("concat_problems: all problems must share one n_gravity")
+        if p.get("options") != out["options"]:
+            raise NotImplementedError("concat_problems: all problems must come from the same gtsam build options (config.py)")
         for name in ("prior_pose", "prior_vel", "between", "dvl", "stereo", "imu"):
             f = p[name]
             cols = tables.setdefault(name, {})
