@@ -3,16 +3,17 @@
 
 One "step" = one full `optimize()` (LM to convergence, gtsam defaults) of the BASELINE.json workload
 "100k-pose underwater trajectory graph with IMU preintegration and 2M stereo factors" (config C3; synthetic,
-generator in visual_underwater_slam_b200/synthetic.py).  At N > 1 every rank solves its own independent
+generator settings synthetic.CONFIGS["C3"]: stereo noise 10 px, drift scale 1.0 -- SURVEY.md 8d).  At N > 1 every rank solves its own independent
 instance of that graph (the path shards by trajectory with no data-path collective): weak scaling.
 
   value        Sum over ranks of (factors x LM linearizations) / time-to-converge, inputs resident in HBM
   e2e          same metric through the public C-ABI session with HOST tables: host->device copy of every table,
                symbolic analysis, optimize(), device->host read of all optimised values inside the timed region
   roofline     dominant kernel class, algorithmic bytes / CUDA-event device time vs MEASURED_PEAKS.json
-  cpu_baseline the CPU oracle (numpy/scipy restatement of gtsam LM, NOT gtsam) on a bounded sample
+  cpu_baseline the CPU oracle (numpy/scipy restatement of gtsam LM, NOT gtsam) on the SAME graph: its first LM iteration(s)
 
-`--impl reference` times that CPU oracle arm alone (rank 0 only).
+`--impl reference` times that CPU oracle arm alone (rank 0 only): the same graph, one LM iteration per step, as many
+steps as fit in --ref-budget-s (the counts in the JSON line are the ones actually timed).
 """
 import argparse
 import json
@@ -38,59 +39,97 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--poses", type=int, default=100000)
-    ap.add_argument("--landmarks", type=int, default=200000)
-    ap.add_argument("--loops", type=int, default=0)
-    ap.add_argument("--seed", type=int, default=3)
-    ap.add_argument("--drift-scale", type=float, default=0.1, help="initial odometry drift: per-step sigma = scale x (0.002 rad, 0.01 m)")
-    ap.add_argument("--cpu-poses", type=int, default=2500, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--config", default="C3", help="workload: a key of synthetic.CONFIGS (C1, C2, C3 = BASELINE.json configs 1-3 at the "
+                    "noise of SURVEY.md 8d; C?-soft = the round-1 settings: 1 px stereo noise, drift scale 0.1)")
+    ap.add_argument("--poses", type=int, default=None, help="override the number of poses of the config")
+    ap.add_argument("--landmarks", type=int, default=None)
+    ap.add_argument("--loops", type=int, default=None)
+    ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--max-supernode", type=int, default=0, help="cap on poses per supernode (0 = from the graph)")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="CPU reference arm: stop starting new LM iterations after this many seconds")
+    ap.add_argument("--cpu-budget-s", type=float, default=30.0, help="cpu_baseline leg of the GPU arm: same, default one LM iteration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="do not time individual kernels with CUDA events")
     return ap.parse_args()
 
 
-def workload_name(a):
-    return (f"C3-style synthetic DVL/IMU/stereo trajectory graph: {a.poses} poses, {a.landmarks} landmarks x 10 obs, "
-            f"{a.loops} loop closures, seed {a.seed}, manifold preintegration, stereo pixel noise 1 px, "
-            f"initial drift scale {a.drift_scale}")
+def generator_settings(a):
+    from visual_underwater_slam_b200 import synthetic
+    kw = dict(synthetic.CONFIGS[a.config])
+    if a.poses is not None:
+        ratio = kw.get("n_landmarks", 0) / kw["n_poses"]
+        lratio = kw.get("n_loops", 0) / kw["n_poses"]
+        kw["n_poses"] = a.poses
+        if "n_landmarks" in kw:
+            kw["n_landmarks"] = int(round(ratio * a.poses))
+        if "n_loops" in kw:
+            kw["n_loops"] = int(round(lratio * a.poses))
+    if a.landmarks is not None:
+        kw["n_landmarks"] = a.landmarks
+    if a.loops is not None:
+        kw["n_loops"] = a.loops
+    if a.seed is not None:
+        kw["seed"] = a.seed
+    return kw
 
 
-def make_problem(a, rank):
+def make_problem(a):
     from visual_underwater_slam_b200 import synthetic
     # every rank solves its own instance of the SAME synthetic graph (identical work per GPU: clean weak scaling)
-    d = synthetic.make_trajectory_graph(a.poses, seed=a.seed, n_landmarks=a.landmarks, n_loops=a.loops, pixel_noise=1.0,
-                                        drift_scale=a.drift_scale)
+    d = synthetic.make_trajectory_graph(**generator_settings(a))
     return d, d["graph"].to_problem(d["initial"])
 
 
+def bench_config(a, d, prob):
+    """The `config` object of the JSON line -- built the same way by both arms from the generated graph, so that the two
+    lines can be compared key by key."""
+    kw = generator_settings(a)
+    nf = {k: int(len(prob[k]["orig"])) for k in ("prior_pose", "prior_vel", "between", "dvl", "stereo", "imu")}
+    px = kw.get("pixel_noise")
+    workload = (f"{a.config}: synthetic DVL/IMU/stereo trajectory graph (batch.py:270-305), {kw['n_poses']} poses, "
+                f"{kw.get('n_landmarks', 0)} landmarks x 10 observations, {kw.get('n_loops', 0)} loop closures, seed {kw['seed']}; "
+                f"stereo measurement noise {10.0 if px is None else px} px (noise model sigma 10 px, batch.py:118), initial drift "
+                f"{kw.get('drift_scale', 1.0)} x (0.002 rad, 0.01 m) per step [{kw.get('drift_model', 'random_walk')}], landmark "
+                f"initialisation {kw.get('landmark_init', 'first_obs')}")
+    return {"workload": workload, "generator": {k: (list(v) if isinstance(v, tuple) else v) for k, v in sorted(kw.items())},
+            "n_factors_per_gpu": int(sum(nf.values())), "factor_mix": nf,
+            "gtsam_build": {k: bool(v) for k, v in sorted(prob["options"].items())},
+            "preintegration": "tangent" if prob["options"]["tangent_preintegration"] else "manifold",
+            "lm_params": "gtsam defaults (batch.py:337)",
+            "l2_policy": "inputs larger than L2 (factor tables + Jacobians + band system > 1 GB per solve)"}
+
+
 # ---------------------------------------------------------------------------------------------- CPU arm
-def cpu_oracle_run(a, steps=1, warmup=0):
-    """CPU restatement of gtsam LM (oracle/, NOT gtsam) on a bounded sample of the same generator."""
-    from visual_underwater_slam_b200 import synthetic
+def cpu_oracle_run(a, d, prob, max_steps, budget_s):
+    """The CPU arm: gtsam's LM restated in numpy / scipy (oracle/, NOT gtsam: none is installable here) on the SAME graph as the
+    GPU arm, from the same initial estimate.  One step = one LM iteration (linearize, damped exact solves until a step is
+    accepted, error evaluations), continuing the same solve; the run stops at convergence, after `max_steps` iterations, or
+    when `budget_s` seconds are used up (a 100 000-pose iteration costs ~45 s of one core; the whole solve ~13 min).
+    -> (cpu_baseline dict, seconds per step, steps timed)"""
     from oracle import lm
-    n = a.cpu_poses
-    ratio = a.landmarks / max(a.poses, 1)
-    loops = int(round(a.loops * n / max(a.poses, 1)))
-    d = synthetic.make_trajectory_graph(n, seed=a.seed, n_landmarks=int(round(ratio * n)), n_loops=loops, pixel_noise=1.0,
-                                        drift_scale=a.drift_scale)
-    prob = d["graph"].to_problem(d["initial"])
-    times, info = [], None
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        _, info = lm.lm_optimize(prob)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    lin = info["iterations"] + (1 if len(info["trace"]["tries"]) > info["iterations"] else 0)
-    lin = max(lin, len(info["trace"]["errors"]) - 1)
+    vals = lm.values_of(prob)
+    lam = lm.LM_DEFAULTS["lambdaInitial"]
     nf = d["meta"]["n_factors"]
-    t = float(np.mean(times))
-    sample = (f"{n}-pose / {int(round(ratio * n))}-landmark / {loops}-loop-closure graph from the same generator ({nf} factors), full LM to "
-              f"convergence: {info['iterations']} iterations in {t:.2f} s (CPU restatement of gtsam LM, not gtsam; one graph = one "
-              f"thread, as gtsam's own LM without TBB: of {os.cpu_count()} host cores it can use 1)")
-    return dict(value=nf * lin / t, unit=UNIT, cores=1, kind="port", sample=sample, seconds=t, iterations=info["iterations"],
-                final_error=info["error"]), t
+    times, lin, tries, err, converged = [], 0, 0, None, False
+    t_begin = time.perf_counter()
+    while len(times) < max_steps and not converged and (not times or time.perf_counter() - t_begin + np.mean(times) <= budget_s):
+        p = dict(prob)
+        p.update(poses=vals["poses"], vels=vals["vels"], biases=vals["biases"], lms=vals["lms"])
+        t0 = time.perf_counter()
+        vals, info = lm.lm_optimize(p, params=dict(maxIterations=1, lambdaInitial=lam))
+        times.append(time.perf_counter() - t0)
+        converged = info["iterations"] == 0 or (err is not None and (err - info["error"] <= 1e-5 * err or err - info["error"] <= 1e-5))
+        lam, err = info["lam"], info["error"]
+        lin += 1
+        tries += len(info["trace"]["tries"])
+    t = float(np.sum(times))
+    sample = (f"the first {len(times)} LM iteration(s) ({tries} lambda tries) of the SAME {nf}-factor graph the GPU arm solves, from the same "
+              f"initial estimate: {t:.1f} s, error {err:.6e}{' (converged)' if converged else ''}.  CPU restatement of gtsam's LM in numpy / scipy "
+              f"(oracle/lm.py: vectorised linearization, exact solve by LAPACK banded Cholesky or SuperLU), NOT gtsam; one graph is one "
+              f"thread, as in gtsam's own LM without TBB, so of the {os.cpu_count()} host cores it uses 1")
+    return dict(value=nf * lin / t, unit=UNIT, cores=1, kind="port", sample=sample, seconds=t, iterations=lin,
+                final_error=err), t / len(times), len(times)
 
 
 class ClockSampler:
@@ -292,10 +331,14 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        cb, t = cpu_oracle_run(a, steps=max(1, a.steps), warmup=min(a.warmup, 1))
-        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-                "warmup": a.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(a), "reference_arm": cb["sample"]},
+        d, prob = make_problem(a)
+        cb, t_step, n_steps = cpu_oracle_run(a, d, prob, max_steps=max(1, a.steps), budget_s=a.ref_budget_s)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": n_steps,
+                "warmup": 0, "steps_requested": a.steps, "warmup_requested": a.warmup,
+                "step_definition": "one LM iteration of the same solve (a CPU run needs no warm-up; fewer steps than requested are timed "
+                                   "when the time budget --ref-budget-s ends first, and the counts say so)",
+                "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": bench_config(a, d, prob),
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -312,7 +355,7 @@ def main():
 
     from visual_underwater_slam_b200.optimizer import Session, LevenbergMarquardtParams
 
-    d, prob = make_problem(a, rank)
+    d, prob = make_problem(a)
     nf = {k: len(prob[k]["orig"]) for k in ("prior_pose", "prior_vel", "between", "dvl", "stereo", "imu")}
     n_factors = sum(nf.values())
     params = LevenbergMarquardtParams()
@@ -432,15 +475,13 @@ def main():
             rf_hbm = line(max(hb, key=lambda k: hb[k]["ms"]))              # dominant HBM-bound class
     cpu = None
     if not a.no_cpu_baseline:
-        cpu, _ = cpu_oracle_run(a)
+        cpu, _, _ = cpu_oracle_run(a, d, prob, max_steps=max(1, a.steps), budget_s=a.cpu_budget_s)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(a), "n_factors_per_gpu": n_factors, "factor_mix": nf, "layout": lay,
-                   "l2_policy": "inputs larger than L2 (factor tables + Jacobians + band system > 1 GB per solve)",
-                   "preintegration": "manifold", "lm_params": "gtsam defaults (batch.py:337)"},
+        "config": bench_config(a, d, prob), "layout": lay,
         "time_to_converge_ms": ms / a.steps, "lm_iterations": res["iterations"], "lm_tries": res["inner_iterations"],
         "pcg_iterations": res["pcg_iterations"], "final_error": res["final_error"], "setup_s_upload_plus_analyze": setup_s,
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": rf, "roofline_hbm": rf_hbm, "cpu_baseline": cpu,

@@ -139,7 +139,8 @@ def test_larger_properties(lib):
     """Size-independent properties at a size the oracle is too slow for in a unit test: error decreases
     monotonically over accepted steps, re-optimising a converged solution is a fixed point (idempotence)."""
     from visual_underwater_slam_b200.optimizer import Session
-    d, prob = pc.make(5000, n_lm=10000, seed=2)
+    from visual_underwater_slam_b200 import synthetic
+    d, prob = pc.make(5000, n_lm=10000, seed=2, **synthetic._SPEC)      # the generator settings of BASELINE configs 2 / 3
     s = Session(prob, lib=lib)
     e0 = s.error()
     res = s.optimize()
@@ -213,7 +214,7 @@ def test_config3_full_size_properties(lib):
     assert fe.shape == (n,) and abs(fe.sum() - e0) <= 1e-10 * e0
     assert fe[0] == 0.0                                   # factor 0 is the pose prior at its own mean (batch.py:281)
     res = s.optimize()
-    assert res["solve_failures"] == 0 and res["final_error"] < 1e-4 * e0 and res["final_error"] < 0.5 * n
+    assert res["solve_failures"] == 0 and res["final_error"] < 1e-4 * e0 and res["final_error"] < 1.5 * n     # chi-square per factor ~2.6 of 3 residuals at the noise level (stereo sigma = 10 px)
     v1 = s.values()["poses"]
     res2 = s.optimize()
     assert res2["iterations"] <= 2 and abs(res2["final_error"] - res["final_error"]) <= 1e-4 * res["final_error"]
