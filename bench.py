@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--loops", type=int, default=None)
     ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--max-supernode", type=int, default=0, help="cap on poses per supernode (0 = from the graph)")
+    ap.add_argument("--band-chunks", type=int, default=0, help="band factorization: 0 auto (chunked block Cholesky), n chunks, -1 plain cyclic reduction")
     ap.add_argument("--ref-budget-s", type=float, default=240.0, help="CPU reference arm: stop starting new LM iterations after this many seconds")
     ap.add_argument("--cpu-budget-s", type=float, default=30.0, help="cpu_baseline leg of the GPU arm: same, default one LM iteration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -361,6 +362,7 @@ def main():
     params = LevenbergMarquardtParams()
     params.profileKernels = not a.no_profile
     params.maxSupernode = a.max_supernode
+    params.bandChunks = a.band_chunks
 
     t0 = time.perf_counter()
     sess = Session(prob, params, device=local_rank)
@@ -375,6 +377,7 @@ def main():
 
     from visual_underwater_slam_b200.optimizer import LevenbergMarquardtParams as _P
     plain = _P()
+    plain.bandChunks = a.band_chunks
     plain.maxSupernode = a.max_supernode                   # timed region: no per-kernel events, fixed sequences replay as CUDA graphs
     sess.set_params(plain)
     res = None
@@ -433,6 +436,7 @@ def main():
             f["sqrt_info"] = pin(f["sqrt_info"])
             pinned[k] = f
         p2 = LevenbergMarquardtParams()
+        p2.bandChunks = a.band_chunks
         times = []
         for i in range(2):
             barrier()

@@ -77,6 +77,8 @@ typedef struct vus_lm_params {
   int32_t max_supernode;         /* 0 = auto (band width from the graph, capped so k*D <= 96) */
   int32_t verbose;
   int32_t profile_kernels;       /* 1: time every kernel launch with CUDA events, per kernel class (ms_class) */
+  int32_t band_chunks;           /* band factorization of stereo-scale supernodes: 0 = auto (block Cholesky inside one chunk per SM,
+                                    cyclic reduction across the separators), n > 0 = n chunks, < 0 = cyclic reduction of the whole chain */
 } vus_lm_params;
 
 typedef struct vus_lm_result {

@@ -21,7 +21,7 @@ class LmParams(C.Structure):
                 ("error_tol", C.c_double), ("lambda_initial", C.c_double), ("lambda_factor", C.c_double),
                 ("lambda_upper_bound", C.c_double), ("lambda_lower_bound", C.c_double), ("min_model_fidelity", C.c_double),
                 ("pcg_max_iterations", C.c_int32), ("pcg_rel_tol", C.c_double), ("max_supernode", C.c_int32),
-                ("verbose", C.c_int32), ("profile_kernels", C.c_int32)]
+                ("verbose", C.c_int32), ("profile_kernels", C.c_int32), ("band_chunks", C.c_int32)]
 
 
 class LmResult(C.Structure):

@@ -6,6 +6,7 @@
 #include "../../include/vus.h"
 #include "rt.h"
 #include "kernels.cuh"
+#include "chunk.cuh"
 #include "frontend.cuh"
 #include <algorithm>
 #include <chrono>
@@ -190,6 +191,11 @@ struct vus_handle {
   DBuf<double> C, gl, Cinv, E, Pp, Pl;
   // BCR
   DBuf<double> Dw, U1, U2, Dinv, Gl, Gr, Z, Zr, SbInv;
+  // chunked band factorization (chunk.cuh): P chunks + the separator system, which is the one the cyclic reduction then factors.
+  // Dinv / Gl / Gr hold Linv / X / W of the chunk interiors.
+  int chunk_P = 0;               // 0: plain cyclic reduction of the whole chain
+  ChunkGeom cgeom;
+  DBuf<double> SepL, SepR, SepU, Dsep, Usep, sDw, sU1, sU2, sDinv, sGl, sGr, tL, tR, xsep;
   // PCG
   DBuf<double> x, r, z, p, Ap, d, xl, scal, partials, bpart, bpart2, e_all, le_all;
   DBuf<int> fail;
@@ -694,8 +700,25 @@ int analyze(vus_handle* h, rt::stream_t st) {
   h->F.alloc(h->Lc * 6); h->Hbb0.alloc(36 * std::max<long>(NB, 1)); h->Hbb.alloc(36 * std::max<long>(NB, 1)); h->gb.alloc(6 * std::max<long>(NB, 1));
   h->C.alloc(9 * NL); h->gl.alloc(3 * NL); h->Cinv.alloc(9 * NL); h->E.alloc(18 * FS.n); h->Pp.alloc(28 * FS.n); h->Pl.alloc(12 * FS.n);
   {   // the reduction's own blocks are padded [KP][LD] tiles; the padding must be (and stays) zero
+    // Stereo-scale supernodes on one long chain: block Cholesky inside P chunks (one per SM), cyclic reduction across the
+    // P - 1 separators only (chunk.cuh).  Tiny supernodes (chain graphs), batched and partitioned graphs keep the plain reduction.
+    h->chunk_P = 0;
+    if (h->ncomp <= 1 && h->n_owned < 0 && h->B > VUS_SMALLB_MAX && h->prm.band_chunks >= 0) {
+      long P = h->prm.band_chunks > 0 ? h->prm.band_chunks : std::min<long>(rt::sm_count(), h->Ns / 6);
+      P = std::min<long>(P, (h->Ns + 1) / 2);            // every chunk needs at least one interior supernode
+      if (P >= 2) { h->chunk_P = (int)P; h->cgeom = chunk_geom(h->Ns, (int)P); }
+    }
     const size_t nb = (size_t)h->Ns * bcr_bbp(h->B);
-    for (DBuf<double>* b : {&h->Dw, &h->U1, &h->U2, &h->Dinv, &h->Gl, &h->Gr}) { b->alloc(nb); b->zero(st); }
+    for (DBuf<double>* b : {&h->Dinv, &h->Gl, &h->Gr}) { b->alloc(nb); b->zero(st); }
+    if (!h->chunk_P) {
+      for (DBuf<double>* b : {&h->Dw, &h->U1, &h->U2}) { b->alloc(nb); b->zero(st); }
+    } else {
+      const size_t np = (size_t)h->chunk_P * bcr_bbp(h->B);
+      for (DBuf<double>* b : {&h->SepL, &h->SepR, &h->SepU, &h->Dsep, &h->Usep, &h->sDw, &h->sU1, &h->sU2, &h->sDinv, &h->sGl, &h->sGr}) { b->alloc(np); b->zero(st); }
+      h->tL.alloc((size_t)h->chunk_P * VUS_CHUNK_MAXV * h->B); h->tL.zero(st);
+      h->tR.alloc((size_t)h->chunk_P * VUS_CHUNK_MAXV * h->B); h->tR.zero(st);
+      h->xsep.alloc((size_t)VUS_CHUNK_MAXV * h->chunk_P * h->B); h->xsep.zero(st);
+    }
   }
   h->Z.alloc(7 * h->Lc); h->Zr.alloc(6 * h->Lc); h->SbInv.alloc(36 * std::max<long>(NB, 1));
   if (h->n_owned >= 0) {
@@ -836,22 +859,51 @@ void form_system(vus_handle* h, double lambda, rt::stream_t st) {
 // The reduction stops at the first stride that no coupling can span: the whole chain for one graph; the longest component
 // for a batch of independent trajectories (their couplings across component boundaries are zero), where the nodes left
 // -- the multiples of that stride, one or none per component -- are all roots and are inverted / solved in one launch.
-long bcr_root_stride(const vus_handle* h) {
+// A block-tridiagonal system the cyclic reduction works on: the whole supernode chain, or -- in chunk mode -- the separators.
+struct BandSys {
+  long Ns;
+  const double* D; const double* U;                  // input blocks (padded tiles)
+  double* Dw; double* U1; double* U2;                // working blocks
+  double* Dinv; double* Gl; double* Gr;              // factors
+};
+BandSys band_sys(vus_handle* h) {
+  BandSys y;
+  if (h->chunk_P) {
+    y.Ns = h->chunk_P - 1; y.D = h->Dsep.p; y.U = h->Usep.p;
+    y.Dw = h->sDw.p; y.U1 = h->sU1.p; y.U2 = h->sU2.p; y.Dinv = h->sDinv.p; y.Gl = h->sGl.p; y.Gr = h->sGr.p;
+  } else {
+    y.Ns = h->Ns; y.D = h->H.p + h->sd_off; y.U = h->H.p + h->su_off;
+    y.Dw = h->Dw.p; y.U1 = h->U1.p; y.U2 = h->U2.p; y.Dinv = h->Dinv.p; y.Gl = h->Gl.p; y.Gr = h->Gr.p;
+  }
+  return y;
+}
+long bcr_root_stride(const vus_handle* h, long Ns) {
   long s = 1;
-  while (s < h->Ns && s < h->bcr_stop) s <<= 1;
+  while (s < Ns && s < h->bcr_stop) s <<= 1;
   return s;
 }
 size_t bcr_smem(int B) { return (size_t)bcr_smem_doubles(B) * sizeof(double); }
 
-BcrArgs bcr_args(vus_handle* h) {
+BcrArgs bcr_args(vus_handle* h, const BandSys& y) {
   BcrArgs a;
-  a.Ns = h->Ns; a.B = h->B; a.s = 1; a.root_stride = bcr_root_stride(h); a.small_g = VUS_SMALLB_G;
-  a.Dsrc = nullptr; a.d_ld = 0; a.d_stride = 0; a.Dw = h->Dw.p;
+  a.Ns = y.Ns; a.B = h->B; a.s = 1; a.root_stride = bcr_root_stride(h, y.Ns); a.small_g = VUS_SMALLB_G;
+  a.Dsrc = nullptr; a.d_ld = 0; a.d_stride = 0; a.Dw = y.Dw;
   a.Ucur = nullptr; a.u_ld = 0; a.u_stride = 0; a.Unext = nullptr;
-  a.Dinv = h->Dinv.p; a.Gl = h->Gl.p; a.Gr = h->Gr.p; a.fail = h->fail.p;
+  a.Dinv = y.Dinv; a.Gl = y.Gl; a.Gr = y.Gr; a.fail = h->fail.p;
   a.node_comp = h->ncomp > 1 ? h->node_comp.p : nullptr; a.knodes = h->k;
   a.X = nullptr; a.xstride = 0; a.nrhs = 1;
   return a;
+}
+ChunkArgs chunk_args(vus_handle* h) {
+  ChunkArgs c;
+  c.G = h->cgeom; c.B = h->B; c.D = h->D;
+  c.SD = h->H.p + h->sd_off; c.SU = h->H.p + h->su_off;
+  c.Linv = h->Dinv.p; c.X = h->Gl.p; c.W = h->Gr.p;
+  c.SepL = h->SepL.p; c.SepR = h->SepR.p; c.SepU = h->SepU.p; c.Dsep = h->Dsep.p; c.Usep = h->Usep.p;
+  c.fail = h->fail.p;
+  c.Xv = nullptr; c.xstride = 0; c.nrhs = 1;
+  c.tL = h->tL.p; c.tR = h->tR.p; c.xsep = h->xsep.p; c.sepstride = (long)(h->chunk_P - 1) * h->B;
+  return c;
 }
 
 void bcr_factor_launches(vus_handle* h, rt::stream_t st);
@@ -862,15 +914,21 @@ void bcr_factor_launches(vus_handle* h, rt::stream_t st) {
   ClassGuard kc_guard(KC_BCR_FACTOR);
   const long BBP = bcr_bbp(h->B);
   const int LD = bcr_ld(h->B);
-  BcrArgs a = bcr_args(h);
+  if (h->chunk_P) {                                    // chunk interiors first: they produce the separator system
+    ChunkArgs c = chunk_args(h);
+    L_coop<ChunkFactorBody>(h->chunk_P, VUS_CH_THREADS, chunk_factor_smem(h->B), st, c);
+    L_elem<SepAssembleBody>((long)(h->chunk_P - 1) * BBP, st, c);
+  }
+  const BandSys y = band_sys(h);
+  BcrArgs a = bcr_args(h, y);
   // level 1 reads the assembled system in place; deeper levels read the working arrays (all padded tiles)
-  a.Dsrc = h->H.p + h->sd_off; a.d_ld = LD; a.d_stride = BBP;
-  a.Ucur = h->H.p + h->su_off; a.u_ld = LD; a.u_stride = BBP;
-  double* bufs[2] = {h->U1.p, h->U2.p};
+  a.Dsrc = y.D; a.d_ld = LD; a.d_stride = BBP;
+  a.Ucur = y.U; a.u_ld = LD; a.u_stride = BBP;
+  double* bufs[2] = {y.U1, y.U2};
   int w = 0;
-  const long s_root = bcr_root_stride(h);
+  const long s_root = bcr_root_stride(h, y.Ns);
   for (long s = 1; s < s_root; s <<= 1) {
-    const long nact = (h->Ns + s - 1) / s;
+    const long nact = (y.Ns + s - 1) / s;
     const int nel = (int)(nact / 2), nsv = (int)((nact + 1) / 2);
     a.s = s; a.Unext = bufs[w];
     if (h->B <= VUS_SMALLB_MAX) {
@@ -880,11 +938,11 @@ void bcr_factor_launches(vus_handle* h, rt::stream_t st) {
       L_coop<BcrElimBody>(nel, 256, bcr_smem(h->B), st, a);
       L_coop<BcrUpdateBody>(nsv, 256, bcr_smem(h->B), st, a);
     }
-    a.Dsrc = h->Dw.p; a.d_ld = LD; a.d_stride = BBP;
+    a.Dsrc = y.Dw; a.d_ld = LD; a.d_stride = BBP;
     a.Ucur = bufs[w]; a.u_ld = LD; a.u_stride = BBP;
     w ^= 1;
   }
-  L_coop<BcrRootBody>((int)((h->Ns + s_root - 1) / s_root), 256, bcr_smem(h->B), st, a);
+  L_coop<BcrRootBody>((int)((y.Ns + s_root - 1) / s_root), 256, bcr_smem(h->B), st, a);
 }
 
 // in-place solve of the band system for nrhs vectors X[v*xstride + ...]
@@ -894,14 +952,27 @@ void bcr_solve(vus_handle* h, double* X, long xstride, int nrhs, rt::stream_t st
   GraphCache& gc = h->g_solve[std::make_tuple((const double*)X, xstride, nrhs)];
   run_graphed(gc, st, [&] { bcr_solve_launches(h, X, xstride, nrhs, st); });
 }
+void bcr_system_solve_launches(vus_handle* h, const BandSys& y, double* X, long xstride, int nrhs, rt::stream_t st);
 void bcr_solve_launches(vus_handle* h, double* X, long xstride, int nrhs, rt::stream_t st) {
   ClassGuard kc_guard(KC_BCR_SOLVE);
-  BcrArgs a = bcr_args(h);
+  const BandSys y = band_sys(h);
+  if (!h->chunk_P) { bcr_system_solve_launches(h, y, X, xstride, nrhs, st); return; }
+  if (nrhs > VUS_CHUNK_MAXV) throw std::runtime_error("band solve: at most 8 right-hand sides at a time");
+  ChunkArgs c = chunk_args(h);
+  c.Xv = X; c.xstride = xstride; c.nrhs = nrhs;
+  const int P = h->chunk_P;
+  L_coop<ChunkFwdBody>(P, 256, chunk_sweep_smem(h->B), st, c);          // interiors forward, separator right-hand sides
+  L_elem<SepRhsBody>((long)nrhs * (P - 1) * h->B, st, c);
+  bcr_system_solve_launches(h, y, h->xsep.p, c.sepstride, nrhs, st);    // separators by cyclic reduction
+  L_coop<ChunkBwdBody>(P, 256, chunk_sweep_smem(h->B), st, c);          // interiors backward
+}
+void bcr_system_solve_launches(vus_handle* h, const BandSys& y, double* X, long xstride, int nrhs, rt::stream_t st) {
+  BcrArgs a = bcr_args(h, y);
   a.X = X; a.xstride = xstride; a.nrhs = nrhs;
   const int nthr = 256;
   std::vector<long> levels;
-  const long s_root = bcr_root_stride(h);
-  const int nroot = (int)((h->Ns + s_root - 1) / s_root);
+  const long s_root = bcr_root_stride(h, y.Ns);
+  const int nroot = (int)((y.Ns + s_root - 1) / s_root);
   for (long s = 1; s < s_root; s <<= 1) levels.push_back(s);
   if (h->B <= VUS_SMALLB_MAX) {                          // tiny supernodes: thread per (node, row), VUS_SMALLB_G nodes per CTA
     const int GN = std::max(1, std::min(64, nthr / h->B));     // one (node, row) item per thread, all vectors of the item in registers
@@ -922,13 +993,13 @@ void bcr_solve_launches(vus_handle* h, double* X, long xstride, int nrhs, rt::st
     };
     for (long s : levels) {
       a.s = s;
-      fwd(grid_of(((h->Ns + s - 1) / s + 1) / 2));
+      fwd(grid_of(((y.Ns + s - 1) / s + 1) / 2));
     }
     a.s = 0;
     bwd(grid_of(nroot));
     for (auto it = levels.rbegin(); it != levels.rend(); ++it) {
       a.s = *it;
-      bwd(grid_of(((h->Ns + a.s - 1) / a.s) / 2));
+      bwd(grid_of(((y.Ns + a.s - 1) / a.s) / 2));
     }
     return;
   }
@@ -937,7 +1008,7 @@ void bcr_solve_launches(vus_handle* h, double* X, long xstride, int nrhs, rt::st
   const size_t smem_deep = (size_t)3 * blk_slot_doubles(h->B) * sizeof(double);
   const int deep_max = smem_deep <= 220 * 1024 ? rt::sm_count() : 0;
   for (long s : levels) {
-    const long nact = (h->Ns + s - 1) / s;
+    const long nact = (y.Ns + s - 1) / s;
     a.s = s;
     const int grid = (int)((nact + 1) / 2);
     if (grid <= deep_max) L_coop<BcrFwdDeepBody>(grid, nthr, smem_deep, st, a);
@@ -946,7 +1017,7 @@ void bcr_solve_launches(vus_handle* h, double* X, long xstride, int nrhs, rt::st
   L_coop<BcrRootSolveBody>(nroot, nthr, smem, st, a);
   for (auto it = levels.rbegin(); it != levels.rend(); ++it) {
     const long s = *it;
-    const long nact = (h->Ns + s - 1) / s;
+    const long nact = (y.Ns + s - 1) / s;
     a.s = s;
     const int grid = (int)(nact / 2);
     if (grid <= deep_max) L_coop<BcrBwdDeepBody>(grid, nthr, smem_deep, st, a);
@@ -1788,6 +1859,7 @@ void vus_default_lm_params(vus_lm_params* p) {
   p->max_iterations = 100; p->relative_error_tol = 1e-5; p->absolute_error_tol = 1e-5; p->error_tol = 0.0;
   p->lambda_initial = 1e-5; p->lambda_factor = 10.0; p->lambda_upper_bound = 1e5; p->lambda_lower_bound = 0.0;
   p->min_model_fidelity = 1e-3; p->pcg_max_iterations = 500; p->pcg_rel_tol = 1e-12; p->max_supernode = 0; p->verbose = 0; p->profile_kernels = 0;
+  p->band_chunks = 0;
 }
 
 int vus_create(int device, vus_handle** out) {

@@ -56,6 +56,7 @@ class LevenbergMarquardtParams:
         self.pcgRelTol = 1e-12
         self.maxSupernode = 0
         self.profileKernels = False
+        self.bandChunks = 0           # band factorization: 0 auto, n > 0 chunks, < 0 plain cyclic reduction (include/vus.h)
 
     setMaxIterations, getMaxIterations = _set("maxIterations"), _get("maxIterations")
     setRelativeErrorTol, getRelativeErrorTol = _set("relativeErrorTol"), _get("relativeErrorTol")
@@ -92,6 +93,7 @@ class LevenbergMarquardtParams:
         p.pcg_rel_tol = float(self.pcgRelTol)
         p.max_supernode = int(self.maxSupernode)
         p.profile_kernels = int(bool(self.profileKernels))
+        p.band_chunks = int(self.bandChunks)
         p.verbose = {"SILENT": 0, "SUMMARY": 1, "TERMINATION": 1, "LAMBDA": 1, "TRYLAMBDA": 1, "TRYCONFIG": 2,
                      "DAMPED": 2, "TRYDELTA": 2}.get(str(self.verbosityLM).upper(), 0)
         return p
