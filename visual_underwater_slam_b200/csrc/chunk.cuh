@@ -82,12 +82,16 @@ struct SepRhsBody {
 
 #ifndef VUS_EMU
 // =====================================================================================  sm_100a
-// 512 threads = 16 warps.  Lower-triangle tiles (Cholesky, D', E) are owned cyclically: tile idx = ti (ti + 1) / 2 + tj belongs
-// to warp idx % 16, slot idx / 16 (at most 5 slots for T <= 12).  Full products run on a 4 x 4 warp grid of 3 x 3 tile blocks.  Inside a tile lane (g = lane / 4, t = lane % 4) holds (row g, cols 2t, 2t + 1), as in bcr.cuh.
-#define VUS_CH_THREADS 512
+// 512 threads = 16 warps (8 measured slower: 105 vs 86 ms of factorization per config-3 solve).  Lower-triangle tiles (Cholesky, D', E)
+// are owned cyclically: tile idx = ti (ti + 1) / 2 + tj belongs to warp idx % 16, slot idx / 16 (at most 5 slots for T <= 12).  Full
+// products run on a 4 x 4 warp grid of 3 x 3 tile blocks.  Inside a tile lane (g = lane / 4, t = lane % 4) holds (row g, cols 2t, 2t + 1), as in bcr.cuh.
+#ifndef VUS_CH_WARPS
 #define VUS_CH_WARPS 16
-#define VUS_CH_LSLOTS 5
-#define VUS_CH_FSLOTS 9
+#endif
+#define VUS_CH_THREADS (32 * VUS_CH_WARPS)
+#define VUS_CH_LSLOTS ((78 + VUS_CH_WARPS - 1) / VUS_CH_WARPS)
+#define VUS_CH_FBC (VUS_CH_WARPS == 16 ? 3 : 6)      /* tile columns per warp block (rows: 3) */
+#define VUS_CH_FSLOTS (3 * VUS_CH_FBC)
 #define VUS_CH_LDQ 12
 #define VUS_CH_LDP 100
 // scratch of the blocked Cholesky: pivot tile inverse [64] | Craw, Cnew [96][12] | Rraw, Rnew [8][100]
@@ -131,43 +135,41 @@ VUS_DEV void tile_mma(double& c0, double& c1, const double* sA, const double* sB
     dmma884(c0, c1, NEG ? -a : a, b);
   }
 }
-// Full T x T product on 16 warps as a 4 x 4 grid of 3 x 3 tile blocks: slot s = 3 a + b is tile (3 wr + a, 3 wc + b).  Per k step
-// a warp loads three A and three B fragments for nine independent DMMAs.  kb / ke give every TILE its own k range (structural
+// Full T x T product on a 4 x 2 warp grid of 3 x 6 tile blocks (8 warps; 4 x 4 of 3 x 3 with 16): per k step a warp loads three A and
+// six B fragments for eighteen independent DMMAs.  kb / ke give every TILE its own k range (structural
 // zeros of the operands are skipped); a block runs over the union.
 struct KRange { int kb[VUS_CH_FSLOTS], ke[VUS_CH_FSLOTS], kmin, kmax; };
+VUS_DEV int fblock_r(const CT& G) { return VUS_CH_WARPS == 16 ? (G.warp >> 2) : (G.warp >> 1); }
+VUS_DEV int fblock_c(const CT& G) { return VUS_CH_WARPS == 16 ? (((G.warp & 3) - (G.warp >> 2)) & 3) : ((G.warp ^ (G.warp >> 2)) & 1); }
 template <bool TA, bool TB, bool NEG>
 VUS_DEV void block_mma(FAcc& r, const double* sA, const double* sB, const KRange& K, const CT& G) {
-  const int wr = G.warp >> 2, wc = ((G.warp & 3) - wr) & 3, LD = G.LD;
-  int ia[3], jb[3];
+  const int wr = fblock_r(G), wc = fblock_c(G), LD = G.LD;
+  int ia[3], jb[VUS_CH_FBC];
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    int i = (3 * wr + a) * 8 + G.g, j = (3 * wc + a) * 8 + G.g;
-    ia[a] = i < G.B ? i : G.B - 1;                     // padded rows / columns re-read the last real one; their results are never kept
-    jb[a] = j < G.B ? j : G.B - 1;
-  }
+  for (int a = 0; a < 3; ++a) { const int i = (3 * wr + a) * 8 + G.g; ia[a] = i < G.B ? i : G.B - 1; }   // padded rows / columns re-read the
+#pragma unroll
+  for (int b = 0; b < VUS_CH_FBC; ++b) { const int j = (VUS_CH_FBC * wc + b) * 8 + G.g; jb[b] = j < G.B ? j : G.B - 1; }   // last real one
 #pragma unroll
   for (int s = 0; s < VUS_CH_FSLOTS; ++s) r[s][0] = r[s][1] = 0.0;
 #pragma unroll 2
   for (int k0 = K.kmin; k0 < K.kmax; k0 += 4) {
     const int k = k0 + G.t;
-    double af[3], bf[3];
+    double af[3], bf[VUS_CH_FBC];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const double v = TA ? sA[k * LD + ia[a]] : sA[ia[a] * LD + k];
-      af[a] = NEG ? -v : v;
-      bf[a] = TB ? sB[jb[a] * LD + k] : sB[k * LD + jb[a]];
-    }
+    for (int a = 0; a < 3; ++a) { const double v = TA ? sA[k * LD + ia[a]] : sA[ia[a] * LD + k]; af[a] = NEG ? -v : v; }
+#pragma unroll
+    for (int b = 0; b < VUS_CH_FBC; ++b) bf[b] = TB ? sB[jb[b] * LD + k] : sB[k * LD + jb[b]];
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
-      for (int b = 0; b < 3; ++b)
-        if (k0 >= K.kb[3 * a + b] && k0 < K.ke[3 * a + b]) dmma884(r[3 * a + b][0], r[3 * a + b][1], af[a], bf[b]);
+      for (int b = 0; b < VUS_CH_FBC; ++b)
+        if (k0 >= K.kb[VUS_CH_FBC * a + b] && k0 < K.ke[VUS_CH_FBC * a + b]) dmma884(r[VUS_CH_FBC * a + b][0], r[VUS_CH_FBC * a + b][1], af[a], bf[b]);
   }
 }
-// The four warps of one scheduler (warp % 4: each SM sub-partition has its own FP64 tensor unit) get four different row blocks AND
-// four different column blocks, so k ranges that shrink along rows or along columns load the four tensor units evenly.
-VUS_DEV int ftile_i(const CT& G, int s) { return 3 * (G.warp >> 2) + s / 3; }
-VUS_DEV int ftile_j(const CT& G, int s) { return 3 * (((G.warp & 3) - (G.warp >> 2)) & 3) + s % 3; }
+// The warps of one scheduler (warp % 4: each SM sub-partition has its own FP64 tensor unit) get different row blocks AND different
+// column blocks, so k ranges that shrink along rows or along columns load the four tensor units evenly.
+VUS_DEV int ftile_i(const CT& G, int s) { return 3 * fblock_r(G) + s / VUS_CH_FBC; }
+VUS_DEV int ftile_j(const CT& G, int s) { return VUS_CH_FBC * fblock_c(G) + s % VUS_CH_FBC; }
 // symmetric product on the lower tiles a warp owns, all slots interleaved (independent accumulators):
 //   c[s] += sign * sum_{k >= kb[s]} A[ti][k] A[tj][k]
 template <bool NEG>
