@@ -138,9 +138,11 @@ struct LinErrBody {
 // =====================================================================================
 // deterministic two-stage sum reduction with a scalar post-op
 // =====================================================================================
-enum { RED_STORE = 0, RED_PAP = 1, RED_RZ = 2, RED_RZ0 = 3 };
-// scalar slots
-enum { S_RZ = 0, S_PAP = 1, S_ALPHA = 2, S_BETA = 3, S_RR = 4, S_TMP = 5, S_NEG_ALPHA = 6, S_COMM = 8, S_COUNT = 16 };
+enum { RED_STORE = 0, RED_PAP = 1, RED_RZ = 2, RED_RZ0 = 3, RED_RR = 4 };
+// scalar slots.  S_TOL2: the PCG recursion is live while S_RR > S_TOL2 -- once the residual meets the tolerance alpha and beta
+// are forced to zero ON THE DEVICE, so a block of iterations can be replayed without the host looking at every residual;
+// S_NAN counts residual norms that were not finite, S_ITS the iterations that ran live.
+enum { S_RZ = 0, S_PAP = 1, S_ALPHA = 2, S_BETA = 3, S_RR = 4, S_TMP = 5, S_NEG_ALPHA = 6, S_TOL2 = 7, S_COMM = 8, S_NAN = 9, S_ITS = 10, S_COUNT = 16 };
 
 struct RedArgs {
   const double* a; const double* b;   // sum a[i]*b[i] (b null -> sum a[i])
@@ -167,10 +169,12 @@ struct Red1Body {
   }
 };
 VUS_DEV void red_post(double* s, int slot, int op, double v) {
+  const bool live = s[S_RR] > s[S_TOL2];               // (S_TOL2 = -1 outside a PCG recursion: always live)
   if (op == RED_STORE) s[slot] = v;
-  else if (op == RED_PAP) { s[S_PAP] = v; const double al = (v != 0.0) ? s[S_RZ] / v : 0.0; s[S_ALPHA] = al; s[S_NEG_ALPHA] = -al; }
-  else if (op == RED_RZ) { const double old = s[S_RZ]; s[S_BETA] = (old != 0.0) ? v / old : 0.0; s[S_RZ] = v; }
+  else if (op == RED_PAP) { s[S_PAP] = v; const double al = (live && v != 0.0) ? s[S_RZ] / v : 0.0; s[S_ALPHA] = al; s[S_NEG_ALPHA] = -al; }
+  else if (op == RED_RZ) { const double old = s[S_RZ]; s[S_BETA] = (live && old != 0.0) ? v / old : 0.0; s[S_RZ] = v; }
   else if (op == RED_RZ0) { s[S_RZ] = v; s[S_BETA] = 0.0; }
+  else if (op == RED_RR) { if (live) { s[S_RR] = v; s[S_ITS] += 1.0; if (!(v == v)) s[S_NAN] += 1.0; } }   // a frozen recursion keeps the norm it stopped at
 }
 struct Red2Args {
   const double* partials; int grid;

@@ -91,16 +91,19 @@ struct GraphCache {
 #endif
 };
 
+thread_local bool g_capturing = false;       // a fixed sequence is being captured: sequences nested in it are recorded inline
 template <class F>
 void run_graphed(GraphCache& gc, rt::stream_t st, F&& body) {
 #ifndef VUS_EMU
-  if (!g_prof.on && st != 0) {
+  if (!g_prof.on && st != 0 && !g_capturing) {
     if (!gc.exec) {
       if (!gc.warm) { body(); gc.warm = true; return; }       // first use runs eagerly (sets kernel attributes)
       const long l0 = g_launches;
       cudaGraph_t graph = nullptr;
       rt::check(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal), "graph capture begin");
-      body();
+      g_capturing = true;
+      try { body(); } catch (...) { g_capturing = false; cudaStreamEndCapture(st, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+      g_capturing = false;
       rt::check(cudaStreamEndCapture(st, &graph), "graph capture end");
       gc.launches = g_launches - l0;
       g_launches = l0;
@@ -223,10 +226,10 @@ struct vus_handle {
   DBuf<long> wb_blk;
   DBuf<double> wbY, wbCapInv, wbW;
   // CUDA graphs of the fixed launch sequences + the stream used when the caller passes NULL (capture needs a real stream)
-  GraphCache g_factor;
+  GraphCache g_factor, g_pcg_iter;
   std::map<std::tuple<const double*, long, int>, GraphCache> g_solve;
   rt::stream_t own_stream = 0;
-  void drop_graphs() { g_factor.reset(); for (auto& kv : g_solve) kv.second.reset(); g_solve.clear(); }
+  void drop_graphs() { g_factor.reset(); g_pcg_iter.reset(); for (auto& kv : g_solve) kv.second.reset(); g_solve.clear(); }
   ~vus_handle() {      // vus_destroy holds the DeviceGuard; members (device buffers) are freed after this body, on own_stream's order
     drop_graphs();
   }
@@ -1141,6 +1144,11 @@ void xpby(vus_handle* h, double* y, const double* x, int slot, rt::stream_t st) 
   L_elem<XpbyBody>(h->L, st, v);
 }
 
+const int kPcgBlock = 8;     // most PCG iterations replayed per look of the host at the residual norm
+struct SetScalarArgs { double* dst; double v; };
+struct SetScalarBody {
+  static VUS_DEV void run(const SetScalarArgs& A, long) { *A.dst = A.v; }
+};
 // y = x - y   (used for the true residual r = rhs - A x)
 struct RsubBody {
   static VUS_DEV void run(const VecArgs& A, long i) { A.y[i] = A.x[i] - A.y[i]; }
@@ -1152,12 +1160,40 @@ struct AddBody {
 // PCG on the reduced system with residual replacement: the inner recursion solves A d = r for a correction,
 // the outer loop recomputes the TRUE residual r = rhs - A x (the recursive residual drifts on these badly scaled
 // systems: IMU information ~1e10 next to lambda ~1e-5).  Returns inner iterations; solution in h->x.
+// one PCG iteration as a fixed launch sequence (every scalar it needs -- alpha, beta, the freeze once the residual met the
+// tolerance -- lives on the device): replayed as a CUDA graph, several per look of the host at the residual norm
+void pcg_iteration_launches(vus_handle* h, rt::stream_t st) {
+  precond_apply(h, h->z.p, h->r.p, st);
+  reduce(h, h->r.p, h->z.p, h->Lr, S_RZ, RED_RZ, st);   // beta = rz / rz_old (0 on the first iteration: rz_old = 0)
+  xpby(h, h->p.p, h->z.p, S_BETA, st);                  // p = z + beta p
+  halo(h, h->p.p, st);
+  apply_A(h, h->Ap.p, h->p.p, st);
+  zero_halo(h, h->Ap.p, st);
+  reduce(h, h->p.p, h->Ap.p, h->Lr, S_PAP, RED_PAP, st);
+  axpy(h, h->d.p, h->p.p, S_ALPHA, st);
+  axpy(h, h->r.p, h->Ap.p, S_NEG_ALPHA, st);
+  reduce(h, h->r.p, h->r.p, h->Lr, S_RR, RED_RR, st);
+}
+void set_scalar(vus_handle* h, int slot, double v, rt::stream_t st) {
+  SetScalarArgs q; q.dst = h->scal.p + slot; q.v = v;
+  L_elem<SetScalarBody>(1, st, q);
+}
+
+// PCG on the reduced system with residual replacement: the inner recursion solves A d = r for a correction,
+// the outer loop recomputes the TRUE residual r = rhs - A x (the recursive residual drifts on these badly scaled
+// systems: IMU information ~1e10 next to lambda ~1e-5).  Returns inner iterations; solution in h->x.
+// The recursion is device resident: the host replays kPcgBlock iterations at a time and reads the residual norm once per
+// block; a recursion that met its tolerance inside a block freezes itself (alpha = beta = 0), so the extra iterations of the
+// block leave the iterate untouched.
 int pcg(vus_handle* h, rt::stream_t st, bool* converged, bool* bad_out = nullptr) {
   const long L = h->L;
   VecArgs v; v.z = nullptr; v.scal = h->scal.p; v.slot = 0; v.n = L; v.Z = nullptr; v.xb = nullptr; v.zstride = 0;
   h->x.zero(st);
   zero_halo(h, h->gs.p, st);                           // halo rows belong to another rank's system
   rt::d2d(h->r.p, h->gs.p, L * sizeof(double), st);
+  set_scalar(h, S_TOL2, -1.0, st);
+  set_scalar(h, S_NAN, 0.0, st);
+  set_scalar(h, S_ITS, 0.0, st);
   reduce(h, h->r.p, h->r.p, h->Lr, S_RR, RED_STORE, st);
   const double rr0 = read_scalar(h, S_RR, st);
   *converged = true;
@@ -1168,36 +1204,46 @@ int pcg(vus_handle* h, rt::stream_t st, bool* converged, bool* bad_out = nullptr
   h->last_rel_res = INFINITY;
   const double tol2 = h->prm.pcg_rel_tol * h->prm.pcg_rel_tol * rr0;
   *converged = false;
-  int it = 0;
+  // host-side callbacks (partitioned graphs over gloo) cannot be captured: one iteration per look there
+  const int block = (h->comm && !h->comm_stream_ordered) ? 1 : kPcgBlock;
+  int it = 0, live_its = 0;                            // launched / live (not frozen) iterations
   double rr_outer = rr0;
   for (int outer = 0; outer < 6 && !*converged; ++outer) {
     // ---- inner PCG: A d = r, d = 0
     h->d.zero(st);
-    precond_apply(h, h->z.p, h->r.p, st);
-    rt::d2d(h->p.p, h->z.p, L * sizeof(double), st);
-    reduce(h, h->r.p, h->z.p, h->Lr, S_RZ, RED_RZ0, st);
+    h->p.zero(st);
+    set_scalar(h, S_RZ, 0.0, st);                        // first iteration: beta = 0, p = z
+    set_scalar(h, S_RR, rr_outer, st);
+    set_scalar(h, S_TOL2, tol2, st);
     int since_best = 0;
     double best = rr_outer;
     bool bad = false;
+    int looks = 0;
     while (it < h->prm.pcg_max_iterations) {
-      halo(h, h->p.p, st);
-      apply_A(h, h->Ap.p, h->p.p, st);
-      zero_halo(h, h->Ap.p, st);
-      reduce(h, h->p.p, h->Ap.p, h->Lr, S_PAP, RED_PAP, st);
-      axpy(h, h->d.p, h->p.p, S_ALPHA, st);
-      axpy(h, h->r.p, h->Ap.p, S_NEG_ALPHA, st);
-      ++it;
-      reduce(h, h->r.p, h->r.p, h->Lr, S_RR, RED_STORE, st);
-      const double rr = read_scalar(h, S_RR, st);
+      // an exactly factored band converges in one to three iterations: look after every one of the first three, then let the
+      // block grow (closure-dominated graphs run a hundred iterations per solve)
+      const int want = looks < 3 ? 1 : std::min(block, 1 << std::min(looks - 2, 3));
+      const int nb = std::min(want, h->prm.pcg_max_iterations - it);
+      ++looks;
+      for (int b = 0; b < nb; ++b) {
+        // collectives inside, or the first preconditioner application that rode along the border solve: not the captured sequence
+        if (h->comm || h->z0_valid) pcg_iteration_launches(h, st);
+        else run_graphed(h->g_pcg_iter, st, [&] { pcg_iteration_launches(h, st); });
+      }
+      it += nb;
+      double sc[S_COUNT];
+      rt::d2h(sc, h->scal.p, sizeof(sc), st);
+      rt::sync(st);
+      const double rr = sc[S_RR];
+      const double two[2] = {rr, sc[S_NAN]};
+      live_its = (int)sc[S_ITS];
       if (h->prm.verbose > 1) std::fprintf(stderr, "    pcg %d.%d rel_res %.3e\n", outer, it, std::sqrt(rr / rr0));
-      if (!(rr == rr)) { bad = true; break; }
+      if (!(rr == rr) || two[1] > 0.0) { bad = true; break; }
       if (rr <= tol2) break;
       if (rr < best) { best = rr; since_best = 0; }
-      else if (++since_best >= 40) break;              // CG residuals are not monotone: only a long stall ends the recursion
-      precond_apply(h, h->z.p, h->r.p, st);
-      reduce(h, h->r.p, h->z.p, h->Lr, S_RZ, RED_RZ, st);
-      xpby(h, h->p.p, h->z.p, S_BETA, st);
+      else if ((since_best += nb) >= 40) break;          // CG residuals are not monotone: only a long stall ends the recursion
     }
+    set_scalar(h, S_TOL2, -1.0, st);
     if (bad) { if (bad_out) *bad_out = true; break; }
     // ---- x += d ; true residual
     v.y = h->x.p; v.x = h->d.p;
@@ -1215,7 +1261,7 @@ int pcg(vus_handle* h, rt::stream_t st, bool* converged, bool* bad_out = nullptr
     if (!(rr_true < 0.25 * rr_outer) || it >= h->prm.pcg_max_iterations) break;   // no further progress possible
     rr_outer = rr_true;
   }
-  return it;
+  return live_its;
 }
 
 // per-component flags of the last factorization (batched mode); clears them.  Returns whether any was set.
