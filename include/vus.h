@@ -150,6 +150,19 @@ int vus_set_comm(vus_handle* h, vus_comm_fn fn, void* ctx);
  * with that stream current) and returns without waiting; the library then neither synchronises before the call nor expects
  * the result on the host -- the stream orders everything.  0 (default): host-synchronous callbacks (gloo, the CPU tests). */
 int vus_set_comm_mode(vus_handle* h, int stream_ordered);
+/* Collectives issued by the library itself (vus_comm_init(ncclUniqueId, rank, nranks)): NCCL over NVLink on the
+ * stream the solve runs on -- ncclAllReduce for the PCG / LM scalars, grouped ncclSend / ncclRecv for the halo nodes -- so the
+ * collectives sit INSIDE the captured launch sequences (one PCG iteration = one CUDA graph) and no host code runs per
+ * collective.  libnccl.so.2 is loaded at run time (no link-time dependency).  Rank 0 obtains an id with vus_nccl_unique_id
+ * and hands it to every rank by any out-of-band means (128 bytes); vus_set_halo gives the exchange lists:
+ *   peers[q]                       rank exchanged with
+ *   send_idx[send_ptr[q] .. send_ptr[q+1])   LOCAL indices of the owned nodes peer q holds as halo, in the order of its halo
+ *   recv_off[q], recv_cnt[q]       where peer q's nodes sit in this rank's halo (halo nodes are sorted by owner: contiguous)
+ * Overrides vus_set_comm for the handle. */
+int vus_nccl_unique_id(void* out128);
+int vus_comm_init(vus_handle* h, const void* unique_id128, int rank, int nranks);
+int vus_set_halo(vus_handle* h, int32_t npeers, const int32_t* peers, const int64_t* send_ptr, const int32_t* send_idx,
+                 const int64_t* recv_off, const int64_t* recv_cnt);
 
 /* ---- a batch of INDEPENDENT trajectories in one handle (BASELINE.json config 4: 4096 x 500-pose graphs, a block per GPU)
  * The reference runs one gtsam.LevenbergMarquardtOptimizer per graph (batch.py:337); a 500-pose solve cannot fill a B200,

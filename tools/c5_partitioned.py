@@ -33,5 +33,5 @@ if rank == 0:
     elif os.path.exists("gpurun_out/part_ref_%d.npy" % n):
         ref = np.load("gpurun_out/part_ref_%d.npy" % n)
         print("max pose diff vs 1 rank: t %.3e R %.3e" % (np.abs(ref[:, 9:] - poses[:, 9:]).max(), np.abs(ref[:, :9] - poses[:, :9]).max()))
-ps.close()
+ps.session.close()
 dist.destroy_process_group()

@@ -70,6 +70,9 @@ EXPORTS = {
     "vus_set_partition": (C.c_int, [C.c_void_p, C.c_int64, c_i64_p]),
     "vus_set_comm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vus_set_comm_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "vus_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "vus_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "vus_set_halo": (C.c_int, [C.c_void_p, C.c_int32, c_i32_p, c_i64_p, c_i32_p, c_i64_p, c_i64_p]),
     "vus_set_components": (C.c_int, [C.c_void_p, C.c_int64, c_i64_p]),
     "vus_get_component_results": (C.c_int, [C.c_void_p, C.POINTER(ComponentResult)]),
     "vus_analyze": (C.c_int, [C.c_void_p]),

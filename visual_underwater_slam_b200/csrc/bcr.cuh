@@ -948,8 +948,8 @@ struct SmallMatvecBody {   // work item (v, I, r):  y_I[r] = SD_I[r,:] x_I + SU_
     const int B = BT ? BT : A.B, LD = bcr_ld(B);
     const long BBP = bcr_bbp(B);
     const int r = (int)(w % B);
-    const long I = (w / B) % A.Ns;
-    const int v = (int)(w / ((long)B * A.Ns));
+    const long I = (w / B) % A.Nrows;
+    const int v = (int)(w / ((long)B * A.Nrows));
     const double* x = A.x + (long)v * A.xstride;
     const double* d = A.SD + I * BBP + (long)r * LD;
     double acc = 0.0;

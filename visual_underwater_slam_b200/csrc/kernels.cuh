@@ -662,6 +662,7 @@ struct DampBody {
 // MatvecArgs / BandMatvecBody (band operator) live in bcr.cuh with the other streaming block kernels
 struct MatvecArgs {
   const double* SD; const double* SU; long Ns; int B;
+  long Nrows;                        // supernode rows computed (a rank of a partitioned graph only needs the rows of the nodes it owns)
   const double* x; double* y;        // camera parts, length Ns*B (per vector)
   int nv; long xstride, ystride;     // nv vectors: x[v*xstride + i], y[v*ystride + i]
   // remainder

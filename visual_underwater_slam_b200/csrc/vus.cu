@@ -16,6 +16,7 @@
 #include <tuple>
 #ifndef VUS_EMU
 #include <cub/device/device_radix_sort.cuh>
+#include <dlfcn.h>
 #endif
 
 using namespace vus;
@@ -150,6 +151,54 @@ void finish_order(FactorTable& T, rt::stream_t st) {
 }
 
 
+#ifndef VUS_EMU
+// NCCL is loaded at run time (dlopen of the libnccl.so.2 the process already uses -- torch's -- or the system one): the
+// library has no link-time dependency on a communication stack and loads on a box without one.  Only the handful of entry
+// points the pose-range partition needs are bound; the types are NCCL's ABI (nccl.h: 128-byte unique id, ncclDouble = 8,
+// ncclSum = 0).
+struct NcclApi {
+  typedef struct { char internal[128]; } UniqueId;
+  int (*GetUniqueId)(UniqueId*) = nullptr;
+  int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) { api.why = std::string("libnccl.so.2 not found: ") + dlerror(); return api; }
+  auto bind = [&](const char* name) { void* p = dlsym(lib, name); if (!p) api.why = std::string("missing NCCL symbol ") + name; return p; };
+  api.GetUniqueId = (int (*)(NcclApi::UniqueId*))bind("ncclGetUniqueId");
+  api.CommInitRank = (int (*)(void**, int, NcclApi::UniqueId, int))bind("ncclCommInitRank");
+  api.CommDestroy = (int (*)(void*))bind("ncclCommDestroy");
+  api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))bind("ncclAllReduce");
+  api.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))bind("ncclSend");
+  api.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))bind("ncclRecv");
+  api.GroupStart = (int (*)())bind("ncclGroupStart");
+  api.GroupEnd = (int (*)())bind("ncclGroupEnd");
+  api.GetErrorString = (const char* (*)(int))bind("ncclGetErrorString");
+  api.ok = api.why.empty();
+  return api;
+}
+void nccl_check(int rc, const char* what) {
+  if (rc != 0) {
+    NcclApi& n = nccl_api();
+    throw std::runtime_error(std::string(what) + ": " + (n.GetErrorString ? n.GetErrorString(rc) : "NCCL error"));
+  }
+}
+#endif
+
 double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -177,6 +226,7 @@ struct vus_handle {
   // layout
   int D = 6, k = 1, B = 6, has_bias = 0;
   long N = 0, Ns = 0, Npad = 0, Lc = 0, L = 0;   // Lc = Npad*D camera dofs, L = Lc + 6*has_bias
+  long Ns_band = 0;              // supernodes the band preconditioner / operator rows cover: all, or the owned prefix of a partition
   long nrem = 0, sd_off = 0, su_off = 0, rem_off = 0, hlen = 0;
   DBuf<double> H0, H;            // SD | SU | REM   (undamped base / damped + Schur)
   DBuf<int> rem_ptr, rem_col;
@@ -210,6 +260,15 @@ struct vus_handle {
   DBuf<double> e_mask;           // 1 for factors this rank owns, 0 for duplicates of a neighbour's factor
   vus_comm_fn comm = nullptr;
   void* comm_ctx = nullptr;
+  // collectives issued by the library itself (vus_comm_init): NCCL on the stream the solve runs on, inside the captured sequences
+  void* nccl = nullptr;          // ncclComm_t
+  int nccl_rank = 0, nccl_nranks = 1;
+  std::vector<int> halo_peers;                   // ranks this one exchanges halo nodes with
+  std::vector<long> halo_send_ptr;               // [npeers + 1] into halo_send_idx: the owned nodes each peer needs
+  std::vector<long> halo_recv_off, halo_recv_cnt;   // [npeers] where each peer's nodes sit in the halo (contiguous per owner)
+  DBuf<int> halo_send_idx;
+  DBuf<double> halo_sendbuf;
+  long halo_nsend = 0;
   bool comm_stream_ordered = false;   // the callback enqueues its collective on the stream the library runs on: no host sync around it
   // batched mode: independent components (trajectories) in one block-diagonal system (batch.cuh)
   int ncomp = 1;
@@ -292,7 +351,36 @@ void run_factors(vus_handle* h, int which, bool with_J, rt::stream_t st) {
 }
 
 // deterministic sum / dot -> scal[slot] with post-op
+struct HaloPackArgs { const double* vec; double* out; const int* idx; long n; int D; };
+struct HaloPackBody {       // out[e][c] = vec[idx[e]][c]: the owned nodes other ranks hold as halo, packed per peer
+  static VUS_DEV void run(const HaloPackArgs& A, long w) { A.out[w] = A.vec[(long)A.idx[w / A.D] * A.D + w % A.D]; }
+};
+bool has_comm(const vus_handle* h) { return h->comm != nullptr || h->nccl != nullptr; }
 void comm_call(vus_handle* h, int op, void* buf, long count, rt::stream_t st) {
+#ifndef VUS_EMU
+  if (h->nccl) {                                       // stream-ordered, capturable
+    NcclApi& n = nccl_api();
+    if (op == VUS_COMM_ALLREDUCE_SUM) {
+      nccl_check(n.AllReduce(buf, buf, (size_t)count, 8 /* ncclDouble */, 0 /* ncclSum */, h->nccl, st), "ncclAllReduce");
+      return;
+    }
+    const int D = (int)count;
+    double* vec = (double*)buf;
+    if (h->halo_nsend) {
+      HaloPackArgs a; a.vec = vec; a.out = h->halo_sendbuf.p; a.idx = h->halo_send_idx.p; a.n = h->halo_nsend; a.D = D;
+      L_elem<HaloPackBody>(h->halo_nsend * D, st, a);
+    }
+    nccl_check(n.GroupStart(), "ncclGroupStart");
+    for (size_t q = 0; q < h->halo_peers.size(); ++q) {
+      const long ns = h->halo_send_ptr[q + 1] - h->halo_send_ptr[q];
+      if (ns) nccl_check(n.Send(h->halo_sendbuf.p + h->halo_send_ptr[q] * D, (size_t)ns * D, 8, h->halo_peers[q], h->nccl, st), "ncclSend");
+      if (h->halo_recv_cnt[q])
+        nccl_check(n.Recv(vec + (h->n_owned + h->halo_recv_off[q]) * D, (size_t)h->halo_recv_cnt[q] * D, 8, h->halo_peers[q], h->nccl, st), "ncclRecv");
+    }
+    nccl_check(n.GroupEnd(), "ncclGroupEnd");
+    return;
+  }
+#endif
   if (!h->comm_stream_ordered) rt::sync(st);           // host-synchronous callbacks: the collective runs on the caller's own stream
   if (h->comm(h->comm_ctx, op, buf, (int64_t)count) != 0) throw std::runtime_error("communication callback failed");
 }
@@ -300,7 +388,7 @@ void reduce(vus_handle* h, const double* a, const double* b, long n, int slot, i
   RedArgs r1; r1.a = a; r1.b = b; r1.n = n; r1.partials = h->partials.p; r1.grid = h->red_grid;
   L_coop<Red1Body>(h->red_grid, 256, 256 * sizeof(double), st, r1);
   Red2Args r2; r2.partials = h->partials.p; r2.grid = h->red_grid; r2.scal = h->scal.p; r2.slot = slot; r2.op = op;
-  if (!h->comm) {
+  if (!has_comm(h)) {
     L_coop<Red2Body>(1, 256, 256 * sizeof(double), st, r2);
     return;
   }
@@ -311,7 +399,7 @@ void reduce(vus_handle* h, const double* a, const double* b, long n, int slot, i
 }
 // fill the halo entries of a node vector (D doubles per node) from their owners
 void halo(vus_handle* h, double* vec, rt::stream_t st) {
-  if (h->comm && h->n_owned >= 0 && h->n_owned < h->N) comm_call(h, VUS_COMM_HALO, vec, h->D, st);
+  if (has_comm(h) && h->n_owned >= 0 && h->n_owned < h->N) comm_call(h, VUS_COMM_HALO, vec, h->D, st);
 }
 void zero_halo(vus_handle* h, double* vec, rt::stream_t st) {
   if (h->n_owned >= 0 && h->Lc > h->Lr) rt::dzero(vec + h->Lr, (size_t)(h->Lc - h->Lr) * sizeof(double), st);
@@ -639,6 +727,9 @@ int analyze(vus_handle* h, rt::stream_t st) {
   const int k = h->k;
   h->B = k * D;
   h->Ns = (NX + k - 1) / k;
+  // a rank of a partitioned graph factors / multiplies only the supernodes of the nodes it owns: the halo nodes' rows belong
+  // to their owners (with random loop closures the halo is as large as the owned range -- measured: twice the work otherwise)
+  h->Ns_band = h->n_owned >= 0 ? std::max<long>(1, std::min<long>(h->Ns, (h->n_owned + k - 1) / k)) : h->Ns;
   h->Npad = h->Ns * k;
   h->Lc = h->Npad * D;
   h->L = h->Lc + 6 * NB;
@@ -875,7 +966,7 @@ BandSys band_sys(vus_handle* h) {
     y.Ns = h->chunk_P - 1; y.D = h->Dsep.p; y.U = h->Usep.p;
     y.Dw = h->sDw.p; y.U1 = h->sU1.p; y.U2 = h->sU2.p; y.Dinv = h->sDinv.p; y.Gl = h->sGl.p; y.Gr = h->sGr.p;
   } else {
-    y.Ns = h->Ns; y.D = h->H.p + h->sd_off; y.U = h->H.p + h->su_off;
+    y.Ns = h->Ns_band; y.D = h->H.p + h->sd_off; y.U = h->H.p + h->su_off;
     y.Dw = h->Dw.p; y.U1 = h->U1.p; y.U2 = h->U2.p; y.Dinv = h->Dinv.p; y.Gl = h->Gl.p; y.Gr = h->Gr.p;
   }
   return y;
@@ -1045,12 +1136,12 @@ void apply_band(vus_handle* h, double* Y, long ystride, const double* X, long xs
   ClassGuard kc_guard(KC_MATVEC);
   MatvecArgs a;
   a.SD = h->H.p + h->sd_off; a.SU = h->H.p + h->su_off; a.Ns = h->Ns; a.B = h->B; a.x = X; a.y = Y;
-  a.nv = nv; a.xstride = xstride; a.ystride = ystride;
+  a.nv = nv; a.xstride = xstride; a.ystride = ystride; a.Nrows = h->Ns_band;
   a.rem_ptr = nullptr; a.rem_col = nullptr; a.rem_val = nullptr; a.nnodes = h->N; a.D = h->D;
   a.F = nullptr; a.Hbb = nullptr; a.xb = nullptr; a.yb = nullptr; a.has_bias = 0;
-  if (h->B <= VUS_SMALLB_MAX) { small_matvec(h, h->Ns * h->B * nv, a, st); return; }
+  if (h->B <= VUS_SMALLB_MAX) { small_matvec(h, h->Ns_band * h->B * nv, a, st); return; }
   const size_t smem = (size_t)blk_smem_doubles(h->B, nv, 256) * sizeof(double);
-  L_coop<BandMatvecBody>((int)h->Ns, 256, smem, st, a);
+  L_coop<BandMatvecBody>((int)h->Ns_band, 256, smem, st, a);
 }
 
 // preconditioner set-up for the current damped system: BCR of the band, Z = M^-1 F, Sb^-1
@@ -1111,16 +1202,18 @@ void apply_A(vus_handle* h, double* y, const double* x, rt::stream_t st) {
   ClassGuard kc_guard(KC_MATVEC);
   MatvecArgs a;
   a.SD = h->H.p + h->sd_off; a.SU = h->H.p + h->su_off; a.Ns = h->Ns; a.B = h->B; a.x = x; a.y = y;
-  a.nv = 1; a.xstride = 0; a.ystride = 0;
+  a.nv = 1; a.xstride = 0; a.ystride = 0; a.Nrows = h->Ns_band;
   a.rem_ptr = h->nrem ? h->rem_ptr.p : nullptr; a.rem_col = h->rem_col.p; a.rem_val = h->H.p + h->rem_off; a.nnodes = h->N; a.D = h->D;
   a.F = h->F.p; a.Hbb = h->Hbb.p; a.xb = x + h->Lc; a.yb = y + h->Lc; a.has_bias = h->has_bias;
   if (h->B <= VUS_SMALLB_MAX) {
-    small_matvec(h, h->Ns * h->B, a, st);
+    small_matvec(h, h->Ns_band * h->B, a, st);
   } else {
     const size_t smem = (size_t)blk_smem_doubles(h->B, 1, 256) * sizeof(double);
-    L_coop<BandMatvecBody>((int)h->Ns, 256, smem, st, a);
+    L_coop<BandMatvecBody>((int)h->Ns_band, 256, smem, st, a);
   }
-  if (h->nrem || h->has_bias) { ClassGuard kc_b(KC_BORDER); L_elem<RemBorderMatvecBody>(h->N * h->D, st, a); }
+  // off-band blocks and border: only the rows of the nodes this rank owns (the others are zeroed by zero_halo right after)
+  const long nrow_nodes = h->n_owned >= 0 ? std::min<long>(h->N, h->Ns_band * h->k) : h->N;
+  if (h->nrem || h->has_bias) { ClassGuard kc_b(KC_BORDER); L_elem<RemBorderMatvecBody>(nrow_nodes * h->D, st, a); }
   if (h->nlong) {                                      // implicit Schur term of the long-track landmarks
     ClassGuard kc_s(KC_SCHUR);
     SchurArgs sa = schur_args(h, h->cur_lambda);
@@ -1205,7 +1298,7 @@ int pcg(vus_handle* h, rt::stream_t st, bool* converged, bool* bad_out = nullptr
   const double tol2 = h->prm.pcg_rel_tol * h->prm.pcg_rel_tol * rr0;
   *converged = false;
   // host-side callbacks (partitioned graphs over gloo) cannot be captured: one iteration per look there
-  const int block = (h->comm && !h->comm_stream_ordered) ? 1 : kPcgBlock;
+  const int block = (h->comm && !h->nccl && !h->comm_stream_ordered) ? 1 : kPcgBlock;
   int it = 0, live_its = 0;                            // launched / live (not frozen) iterations
   double rr_outer = rr0;
   for (int outer = 0; outer < 6 && !*converged; ++outer) {
@@ -1227,7 +1320,7 @@ int pcg(vus_handle* h, rt::stream_t st, bool* converged, bool* bad_out = nullptr
       ++looks;
       for (int b = 0; b < nb; ++b) {
         // collectives inside, or the first preconditioner application that rode along the border solve: not the captured sequence
-        if (h->comm || h->z0_valid) pcg_iteration_launches(h, st);
+        if ((h->comm && !h->nccl) || h->z0_valid) pcg_iteration_launches(h, st);
         else run_graphed(h->g_pcg_iter, st, [&] { pcg_iteration_launches(h, st); });
       }
       it += nb;
@@ -1284,7 +1377,7 @@ int read_fail(vus_handle* h, rt::stream_t st) {
     rt::sync(st);
     if (f) h->fail.zero(st);
   }
-  if (h->comm) {                                       // every rank must take the same decision
+  if (has_comm(h)) {                                   // every rank must take the same decision
     double v = f ? 1.0 : 0.0;
     rt::h2d(h->scal.p + S_COMM, &v, sizeof(double), st);
     comm_call(h, VUS_COMM_ALLREDUCE_SUM, h->scal.p + S_COMM, 1, st);
@@ -1935,6 +2028,9 @@ void vus_destroy(vus_handle* h) {
   DeviceGuard guard(h);
   rt::stream_t st = h->own_stream;
   try { rt::sync(st); } catch (...) {}
+#ifndef VUS_EMU
+  if (h->nccl) { h->drop_graphs(); nccl_api().CommDestroy(h->nccl); h->nccl = nullptr; }
+#endif
   delete h;                                  // device buffers are released in the order of `st` (rt::dfree)
 #ifndef VUS_EMU
   if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
@@ -2047,6 +2143,62 @@ int vus_set_comm(vus_handle* h, vus_comm_fn fn, void* ctx) {
   if (!h) return VUS_ERR_INVALID;
   h->comm = fn; h->comm_ctx = ctx;
   return VUS_OK;
+}
+
+int vus_nccl_unique_id(void* out128) {
+  if (!out128) return VUS_ERR_INVALID;
+#ifndef VUS_EMU
+  NcclApi& n = nccl_api();
+  if (!n.ok) return VUS_ERR_UNSUPPORTED;
+  NcclApi::UniqueId id;
+  if (n.GetUniqueId(&id) != 0) return VUS_ERR_CUDA;
+  std::memcpy(out128, id.internal, 128);
+  return VUS_OK;
+#else
+  std::memset(out128, 0, 128);
+  return VUS_ERR_UNSUPPORTED;
+#endif
+}
+
+int vus_comm_init(vus_handle* h, const void* unique_id128, int rank, int nranks) {
+  if (!h || !unique_id128 || rank < 0 || nranks < 1 || rank >= nranks) return fail(h, VUS_ERR_INVALID, "vus_comm_init: bad arguments");
+#ifndef VUS_EMU
+  VUS_TRY(h)
+  NcclApi& n = nccl_api();
+  if (!n.ok) return fail(h, VUS_ERR_UNSUPPORTED, "vus_comm_init: " + n.why);
+  if (h->nccl) { n.CommDestroy(h->nccl); h->nccl = nullptr; }
+  NcclApi::UniqueId id;
+  std::memcpy(id.internal, unique_id128, 128);
+  nccl_check(n.CommInitRank(&h->nccl, nranks, id, rank), "ncclCommInitRank");
+  h->nccl_rank = rank; h->nccl_nranks = nranks;
+  h->comm_stream_ordered = true;
+  h->drop_graphs();
+  return VUS_OK;
+  VUS_CATCH(h)
+#else
+  return fail(h, VUS_ERR_UNSUPPORTED, "vus_comm_init: the host emulation has no NCCL (use vus_set_comm with caller-supplied collectives)");
+#endif
+}
+
+int vus_set_halo(vus_handle* h, int32_t npeers, const int32_t* peers, const int64_t* send_ptr, const int32_t* send_idx,
+                 const int64_t* recv_off, const int64_t* recv_cnt) {
+  if (!h || npeers < 0 || (npeers > 0 && (!peers || !send_ptr || !recv_off || !recv_cnt))) return fail(h, VUS_ERR_INVALID, "vus_set_halo: bad arguments");
+  VUS_TRY(h)
+  h->halo_peers.assign(peers, peers + npeers);
+  h->halo_send_ptr.assign(1, 0);
+  if (npeers) h->halo_send_ptr.assign(send_ptr, send_ptr + npeers + 1);
+  h->halo_recv_off.assign(recv_off, recv_off + npeers);
+  h->halo_recv_cnt.assign(recv_cnt, recv_cnt + npeers);
+  h->halo_nsend = h->halo_send_ptr.back();
+  if (h->halo_nsend) {
+    if (!send_idx) return fail(h, VUS_ERR_INVALID, "vus_set_halo: send_idx missing");
+    h->halo_send_idx.upload(send_idx, (size_t)h->halo_nsend, h->own_stream);
+    h->halo_sendbuf.alloc((size_t)h->halo_nsend * 12);
+    rt::sync(h->own_stream);
+  }
+  h->drop_graphs();
+  return VUS_OK;
+  VUS_CATCH(h)
 }
 
 int vus_set_components(vus_handle* h, int64_t ncomp, const int64_t* node_start) {

@@ -199,6 +199,24 @@ class Session:
                                             orig.ctypes.data_as(_native.c_i64_p), mem))
         self.n_factors = sum(self.nf.values())
 
+    def comm_init(self, unique_id, rank, nranks):
+        """Collectives issued by the library itself: NCCL communicator from a 128-byte id every rank received (vus_comm_init)."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self.lib.vus_comm_init(self._h, buf, int(rank), int(nranks)))
+
+    def set_halo(self, peers, send_lists, recv_ranges):
+        """Halo exchange lists of a pose-range partition (vus_set_halo): peers [q], send_lists[q] = local indices of the owned
+        nodes peer q needs, recv_ranges[q] = (offset, count) of peer q's nodes in this rank's halo."""
+        peers = np.ascontiguousarray(peers, dtype=np.int32)
+        ptr = np.zeros(len(peers) + 1, dtype=np.int64)
+        for q, ix in enumerate(send_lists):
+            ptr[q + 1] = ptr[q] + len(ix)
+        idx = np.ascontiguousarray(np.concatenate([np.asarray(ix, dtype=np.int32) for ix in send_lists]) if len(peers) and ptr[-1] else np.zeros(0, np.int32))
+        off = np.ascontiguousarray([r[0] for r in recv_ranges], dtype=np.int64)
+        cnt = np.ascontiguousarray([r[1] for r in recv_ranges], dtype=np.int64)
+        self._check(self.lib.vus_set_halo(self._h, len(peers), peers.ctypes.data_as(_native.c_i32_p), ptr.ctypes.data_as(_native.c_i64_p),
+                                          idx.ctypes.data_as(_native.c_i32_p), off.ctypes.data_as(_native.c_i64_p), cnt.ctypes.data_as(_native.c_i64_p)))
+
     def set_params(self, params):
         p = params.to_c() if hasattr(params, "to_c") else params
         self._check(self.lib.vus_set_lm_params(self._h, C.byref(p)))

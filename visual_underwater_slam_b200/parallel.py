@@ -260,7 +260,7 @@ class PartitionedSolver:
     """One rank of a pose graph split by pose range.  `part` is this rank's entry of partition_pose_graph(); the process
     group must already exist (nccl on GPUs, gloo for the CPU tests)."""
 
-    def __init__(self, part, params=None, lib=None, device=0, group=None, stream_ordered=True):
+    def __init__(self, part, params=None, lib=None, device=0, group=None, stream_ordered=True, nccl_in_library=None):
         import torch
         import torch.distributed as dist
         from . import _native
@@ -279,9 +279,28 @@ class PartitionedSolver:
         self._views = {}
         # NCCL: the library runs on a torch stream of ours and every collective is enqueued on that same stream, so neither
         # side waits on the host (vus_set_comm_mode); gloo (CPU tests): host-synchronous callbacks
-        self.stream = torch.cuda.Stream(self.device) if (self.cuda and self.world > 1 and stream_ordered) else None
+        # On GPUs the library issues the collectives itself (vus_comm_init: NCCL on its own stream, inside its captured launch
+        # sequences); torch.distributed only carries the 128-byte NCCL id to every rank.  Callbacks remain for gloo (CPU tests)
+        # and as a fallback (nccl_in_library=False): there the library runs on a torch stream of ours and every collective is
+        # enqueued on that same stream (vus_set_comm_mode).
+        if nccl_in_library is None:
+            nccl_in_library = self.cuda and self.world > 1 and dist.get_backend(group) == "nccl"
+        self.nccl_in_library = bool(nccl_in_library) and self.world > 1
+        self.stream = torch.cuda.Stream(self.device) if (self.cuda and self.world > 1 and stream_ordered and not self.nccl_in_library) else None
         self.session = Session(part["prob"], params, lib=lib, device=device, partition=(self.n_owned, part["nf_owned"]),
-                               comm=self._cb if self.world > 1 else None)
+                               comm=self._cb if (self.world > 1 and not self.nccl_in_library) else None)
+        if self.nccl_in_library:
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if self.rank == 0:
+                buf = (C.c_char * 128)()
+                self.session._check(self.session.lib.vus_nccl_unique_id(buf))
+                uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+            uid = uid.to(self.device)
+            dist.broadcast(uid, src=0, group=group)
+            self.session.comm_init(uid.cpu().numpy().tobytes(), self.rank, self.world)
+            peers = sorted(set(part["send"].keys()) | set(part["recv"].keys()))
+            self.session.set_halo(peers, [part["send"].get(q, np.zeros(0, np.int64)) for q in peers],
+                                  [part["recv"].get(q, (0, 0)) for q in peers])
         if self.stream is not None:
             self.session._check(self.session.lib.vus_set_comm_mode(self.session._h, 1))
 
