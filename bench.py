@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--band-chunks", type=int, default=0, help="band factorization: 0 auto (chunked block Cholesky), n chunks, -1 plain cyclic reduction")
     ap.add_argument("--ref-budget-s", type=float, default=240.0, help="CPU reference arm: stop starting new LM iterations after this many seconds")
     ap.add_argument("--cpu-budget-s", type=float, default=30.0, help="cpu_baseline leg of the GPU arm: same, default one LM iteration")
+    ap.add_argument("--trajectories", type=int, default=512, help="config C4: trajectories per GPU")
     ap.add_argument("--c5-lm-iterations", type=int, default=2, help="config C5: accepted LM steps per bounded solve")
     ap.add_argument("--c5-pcg-iterations", type=int, default=200, help="config C5: PCG iterations per damped solve")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -251,6 +252,29 @@ def bcr_factor_flops(Ns, B):
     return fl + 2 * b3          # root inverse
 
 
+def chunk_factor_flops(Ns, B, D, P):
+    """Algorithmic flops of one chunked band factorization (chunk.cuh): per interior supernode a Cholesky (B^3/3) and a triangular
+    inverse (B^3/3) plus the five structured products, counted at ELEMENT granularity with the zeros the algorithm knows about
+    skipped (Linv lower triangular, U block-lower-triangular in D x D blocks -> X[a][c] = 0 for c < D blk(a)), symmetric results
+    once; plus the cyclic reduction of the P - 1 separators.  Returns (flops, flops of a plain sequential band Cholesky of the same
+    matrix at its true half-bandwidth -- the lower bound a multifrontal elimination of the chain needs)."""
+    a = np.arange(B)
+    blk = D * (a // D)
+    x_fl = 2.0 * np.maximum(0, a[None, :] - blk[:, None] + 1).sum()                    # X[a][c]: k from D blk(a) to c
+    lo = a[:, None] >= a[None, :]
+    d_fl = 2.0 * ((B - np.maximum(blk[:, None], blk[None, :])) * lo).sum()             # D' lower: k from D blk(max) to B
+    w_fl = 2.0 * B * (a + 1).sum()                                                     # W[r][c]: k <= c
+    e_fl = 2.0 * B * lo.sum()                                                          # E lower, full k
+    s_fl = 2.0 * B * (B - blk).sum()                                                   # S'[r][b]: k >= D blk(b)
+    band = 2.0 * B ** 3 / 3.0 + x_fl + d_fl
+    spike = w_fl + e_fl + s_fl
+    interior = Ns - (P - 1)
+    first_chunk = interior / P                                                          # the first chunk has no left separator: no spike
+    fl = interior * band + (interior - first_chunk) * spike + bcr_factor_flops(max(P - 1, 1), B)
+    hb = (D * (B // D + 1))                                                             # true half-bandwidth in scalars (track span + 1 nodes)
+    return fl, float(Ns) * B * hb * hb
+
+
 def roofline(res, lay, nf, ms_class, launches, hbm_peak, steps):
     """Per kernel class: algorithmic bytes (or flops) / CUDA-event device time summed over the timed region.
     bcr_factor is FP64-tensor bound (DMMA); every other class is HBM bound.  Returns {class: {...}}."""
@@ -283,10 +307,20 @@ def roofline(res, lay, nf, ms_class, launches, hbm_peak, steps):
     nst = nf.get("stereo", 0)
     n_obs_poses = min(nf.get("dvl", 0) + 1, nst) if nst else 0
     add("stereo_assemble", "hbm", (nst * 320 + n_obs_poses * (36 + 6) * 8 + lay.get("n_landmarks", 0) * 12 * 8) * lin, 1e6, hbm_peak, "GB/s")
-    # BCR solve: one application streams Gr, Gl (forward) and Dinv, Gl, Gr (backward) of every eliminated node once
-    per_apply_launches = 2 * levels + 1
-    applies = launches.get("bcr_solve", 0) / per_apply_launches
-    add("bcr_solve", "hbm", applies * (5 * (Ns - 1) * BB8 + BB8 + 4 * L * 8), 1e6, hbm_peak, "GB/s")
+    P = lay.get("band_chunks", 0)
+    if P:
+        # chunked band solve: forward and backward sweep each stream Linv, X (and W, except in the first chunk) of every interior
+        # supernode once; the separators go through a cyclic reduction of P - 1 supernodes
+        seplev = max(1, int(np.ceil(np.log2(max(P - 1, 2)))))
+        per_apply_launches = 3 + 2 * seplev + 1
+        applies = launches.get("bcr_solve", 0) / per_apply_launches
+        interior = Ns - (P - 1)
+        add("bcr_solve", "hbm", applies * (2 * (3 * interior - interior / P) * BB8 + 5 * (P - 1) * BB8 + 4 * L * 8), 1e6, hbm_peak, "GB/s")
+    else:
+        # BCR solve: one application streams Gr, Gl (forward) and Dinv, Gl, Gr (backward) of every eliminated node once
+        per_apply_launches = 2 * levels + 1
+        applies = launches.get("bcr_solve", 0) / per_apply_launches
+        add("bcr_solve", "hbm", applies * (5 * (Ns - 1) * BB8 + BB8 + 4 * L * 8), 1e6, hbm_peak, "GB/s")
     # band operator: SD + SU (used twice: as SU and SU^T) per application.  Accounting basis = full block storage
     # (SURVEY.md 8d): 3Ns-2 blocks; only 2Ns-1 blocks are stored (SU^T is the same tile read again, from L2 when the
     # neighbouring CTA just streamed it), which is why this class can exceed the DRAM roofline.
@@ -295,8 +329,35 @@ def roofline(res, lay, nf, ms_class, launches, hbm_peak, steps):
         out["matvec"]["achieved_stored_bytes_basis"] = out["matvec"]["achieved"] * (2 * Ns - 1) / (3 * Ns - 2)
     # damp + Schur: copy of the base system (read + write), E stream (144 B / observation) read ~once, Cinv
     add("schur", "hbm", tries * (2 * (2 * Ns - 1) * BB8 + nf.get("stereo", 0) * 144 * 2), 1e6, hbm_peak, "GB/s")
-    add("bcr_factor", "tensor", tries * bcr_factor_flops(Ns, B), 1e9, FP64_TENSOR_PEAK_TFLOPS, "TFLOP/s")
+    if P:
+        fl, fl_band = chunk_factor_flops(Ns, B, lay["D"], P)
+        add("bcr_factor", "tensor", tries * fl, 1e9, FP64_TENSOR_PEAK_TFLOPS, "TFLOP/s")
+        if "bcr_factor" in out:      # the same time on the two other flop bases VERDICT r1 asked for
+            t = out["bcr_factor"]
+            t["algorithm"] = f"chunked block Cholesky ({P} chunks) + cyclic reduction of the separators"
+            t["flops_per_factorization"] = fl
+            t["frac_on_cyclic_reduction_flop_basis"] = tries * bcr_factor_flops(Ns, B) / t["ms"] / 1e9 / FP64_TENSOR_PEAK_TFLOPS
+            t["frac_on_sequential_band_cholesky_flop_basis"] = tries * fl_band / t["ms"] / 1e9 / FP64_TENSOR_PEAK_TFLOPS
+            t["flops_cyclic_reduction_of_whole_chain"] = bcr_factor_flops(Ns, B)
+            t["flops_sequential_band_cholesky"] = fl_band
+    else:
+        add("bcr_factor", "tensor", tries * bcr_factor_flops(Ns, B), 1e9, FP64_TENSOR_PEAK_TFLOPS, "TFLOP/s")
     return out
+
+
+def ncu_traffic_r2(name, lay, t, tries):
+    """DRAM bytes of a kernel class over the timed region from the committed round-2 `ncu --set full` captures AT THE C3 SIZE
+    (profiles/r2_ncu_summary.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel of the class x
+    the launches of that kernel in the region).  None when no capture covers the class or the layout differs from the captured one."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_summary.json")) as fh:
+            cap = json.load(fh)
+    except Exception:
+        return None
+    c = cap.get(name)
+    if not c or c.get("Ns") != lay["Ns"] or c.get("band_chunks") != lay.get("band_chunks"):
+        return None
+    return float(c["dram_bytes_per_launch"]) * (tries if c.get("per") == "try" else t["launches"] / max(1, c.get("launches_per_unit", 1)))
 
 
 def ncu_traffic(name, lay, t):
@@ -456,6 +517,138 @@ def run_c5(a, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------- config 4: independent trajectories
+def run_c4(a, rank, world, local_rank):
+    """BASELINE.json config 4: a batch of independent 500-pose trajectories (IMU + DVL chain, 5 loop closures each), 512 per GPU
+    (4 096 over 8), every shard solved as ONE block-diagonal system on its GPU (vus_set_components: each trajectory keeps its
+    own gtsam LM path).  No data-path collective: weak scaling."""
+    import torch
+    import torch.distributed as dist
+    from visual_underwater_slam_b200 import parallel, synthetic
+    from visual_underwater_slam_b200.optimizer import LevenbergMarquardtParams, Session
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    T = a.trajectories
+    n = a.poses if a.poses is not None else 500
+    t0 = time.perf_counter()
+    probs = []
+    for t in range(rank * T, (rank + 1) * T):                 # seeds 4 + t (SURVEY.md 8d)
+        d = synthetic.make_trajectory_graph(n, seed=4 + t, n_loops=5, loop_min_gap=100 if n >= 300 else max(2, n // 3),
+                                            drift_model="depth_attitude_aided")
+        probs.append(d["graph"].to_problem(d["initial"]))
+    prob, node_start = parallel.concat_problems(probs)
+    gen_s = time.perf_counter() - t0
+    n_factors = int(prob["n_factors"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    p = LevenbergMarquardtParams()
+    sess = Session(prob, p, device=local_rank, components=node_start)
+    sess.save_values()
+    res = None
+    for _ in range(a.warmup):
+        sess.restore_values()
+        res = sess.optimize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    launches = 0
+    for _ in range(a.steps):
+        sess.restore_values()
+        res = sess.optimize()
+        launches += res["kernel_launches"]
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    per = sess.component_results()
+    lin_total = float(sum(r["iterations"] + (1 if r["inner_iterations"] > r["iterations"] else 0) for r in per))   # per-trajectory linearizations
+    nf_traj = n_factors / T
+    tmax = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    work = torch.tensor([nf_traj * lin_total * a.steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work)
+    ms = float(tmax.item())
+    value = float(work.item()) / (ms * 1e-3)
+    ms_class, launches_class, rp = {}, {}, None
+    if not a.no_profile:
+        pp = LevenbergMarquardtParams()
+        pp.profileKernels = True
+        sess.set_params(pp)
+        sess.restore_values()
+        rp = sess.optimize()
+        ms_class = {k: v for k, v in rp["ms_class"].items() if v}
+        launches_class = rp["launches_class"]
+    e2e = None
+    if not a.no_e2e:
+        barrier()
+        t0 = time.perf_counter()
+        s2 = Session(prob, p, device=local_rank, components=node_start)
+        r2 = s2.optimize()
+        per2 = s2.component_results()
+        out = s2.values()
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        lin2 = float(sum(r["iterations"] + (1 if r["inner_iterations"] > r["iterations"] else 0) for r in per2))
+        we = torch.tensor([nf_traj * lin2], dtype=torch.float64, device="cuda")
+        hb = torch.tensor([float(s2.h2d_bytes), float(s2.d2h_bytes)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(we)
+            dist.all_reduce(hb)
+        e2e = {"value": float(we.item()) / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(hb[0].item()), "d2h_bytes_per_step": int(hb[1].item()),
+               "seconds": float(te.item()), "includes": "H2D of the concatenated tables of every shard, symbolic analysis, batched LM to convergence, D2H of all values"}
+        s2.close()
+    if rank == 0:
+        peak, peak_src = peaks()
+        lay = sess.layout()
+        rf = None
+        if ms_class:
+            top = max(ms_class, key=ms_class.get)
+            L8 = lay["L"] * 8
+            per_apply = {"bcr_solve": 5 * lay["Ns"] * lay["B"] ** 2 * 8 + 4 * L8, "matvec": (3 * lay["Ns"] - 2) * lay["B"] ** 2 * 8,
+                         "border": 8 * L8, "vector": 3 * L8}
+            levels = max(1, int(np.ceil(np.log2(max(2, n)))))
+            applies = launches_class.get(top, 0) / ((2 * levels + 1) if top == "bcr_solve" else 1)
+            work_b = per_apply.get(top, 0) * applies
+            ach = work_b / ms_class[top] / 1e6 if work_b else None
+            rf = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": None,
+                  "work": work_b, "peak_source": peak_src, "device_ms": ms_class[top], "launches": launches_class.get(top),
+                  "note": "kernel class with the largest device time over one batched solve (event-timed re-run); six-vector band solves count as one application"}
+        its = [r["iterations"] for r in per]
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"C4: {T} independent {n}-pose trajectories per GPU (IMU + DVL chain, 5 loop closures each, seeds 4 + t), "
+                                       f"{T * world} in total, one batched solve per GPU", "n_factors_per_gpu": n_factors,
+                           "gtsam_build": {k: bool(v) for k, v in sorted(prob["options"].items())}, "lm_params": "gtsam defaults (batch.py:337)",
+                           "l2_policy": "inputs larger than L2"},
+                "ms_per_trajectory": ms / a.steps / T, "trajectories_per_s": T * world / (ms * 1e-3 / a.steps), "lm_rounds": res["inner_iterations"],
+                "lm_iterations_min_max": [min(its), max(its)], "pcg_iterations": res["pcg_iterations"], "final_error_sum": res["final_error"],
+                "generate_s": gen_s, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": rf, "layout": lay,
+                "kernel_class_device_ms": ms_class, "cpu_baseline": None}
+        if not a.no_cpu_baseline:
+            from oracle import lm
+            t0 = time.perf_counter()
+            lin = 0
+            m = min(T, 4)
+            for q in range(m):
+                _, info = lm.lm_optimize(probs[q])
+                lin += info["iterations"] + (1 if len(info["trace"]["tries"]) > info["iterations"] else 0)
+            t = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": nf_traj * lin / t, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"the first {m} trajectories of rank 0's shard, each solved to convergence by the CPU restatement of gtsam's LM "
+                                              f"(oracle/lm.py, NOT gtsam) in {t:.1f} s on one core"}
+        print(json.dumps(line))
+    sess.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -463,6 +656,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if a.config == "C5" and a.impl != "reference":
         run_c5(a, rank, world, local_rank)
+        return
+    if a.config == "C4" and a.impl != "reference":
+        run_c4(a, rank, world, local_rank)
         return
 
     if a.impl == "reference":
@@ -605,8 +801,9 @@ def main():
         def line(name):
             t = rf_table[name]
             src = peak_src if t["bound"] == "hbm" else "FP64 DMMA issue-rate microbenchmark, this pool (profiles/r1_dmma_microbench.txt); no FP64 figure in MEASURED_PEAKS.json"
-            return {"bound": t["bound"], "kernel": name, "achieved": t["achieved"], "peak": t["peak"], "unit": t["unit"], "frac": t["frac"],
-                    "traffic": ncu_traffic(name, lay, t), "traffic_unit": "bytes over the timed region (algorithmic work over the same region: 'work')",
+            extra = {k: v for k, v in t.items() if k.startswith("frac_on_") or k.startswith("flops_") or k == "algorithm"}
+            return {**extra, "bound": t["bound"], "kernel": name, "achieved": t["achieved"], "peak": t["peak"], "unit": t["unit"], "frac": t["frac"],
+                    "traffic": ncu_traffic_r2(name, lay, t, res["inner_iterations"] * a.steps) if lay.get("band_chunks") else ncu_traffic(name, lay, t), "traffic_unit": "bytes over the timed region (algorithmic work over the same region: 'work')",
                     "work": t["work"], "peak_source": src, "device_ms": t["ms"], "launches": t["launches"]}
         top = max(rf_table, key=lambda k: rf_table[k]["ms"])               # dominant kernel class by device time
         rf = line(top)

@@ -183,8 +183,10 @@ int vus_get_component_results(vus_handle* h, vus_component_result* out /* [ncomp
 
 /* symbolic phase: node ordering, supernode band layout, off-band blocks, Schur destination lists */
 int vus_analyze(vus_handle* h);
-/* band description after analyze: D (node dof), k (nodes per supernode), Ns, nrem, ndst */
-int vus_get_layout(vus_handle* h, int64_t out[8]);
+/* band description after analyze: D (node dof), k (nodes per supernode), Ns (supernodes), nrem (off-band blocks), stereo observations,
+ * B = k D, L (reduced dofs), factors, chunks of the band factorization (0 = plain cyclic reduction), supernodes the band
+ * preconditioner covers (the owned prefix of a partition), landmarks, reserved */
+int vus_get_layout(vus_handle* h, int64_t out[12]);
 
 /* LevenbergMarquardtOptimizer::optimize()  (batch.py:337). Asynchronous work is issued on `stream`
  * (a cudaStream_t, may be NULL); the call returns after the convergence decision. Values are updated in place. */

@@ -2242,9 +2242,10 @@ int vus_analyze(vus_handle* h) {
   VUS_CATCH(h)
 }
 
-int vus_get_layout(vus_handle* h, int64_t out[8]) {
+int vus_get_layout(vus_handle* h, int64_t out[12]) {
   if (!h || !h->analyzed) return fail(h, VUS_ERR_STATE, "vus_get_layout: call vus_analyze first");
   out[0] = h->D; out[1] = h->k; out[2] = h->Ns; out[3] = h->nrem; out[4] = h->nobs; out[5] = h->B; out[6] = h->L; out[7] = h->nfactors;
+  out[8] = h->chunk_P; out[9] = h->Ns_band; out[10] = h->nvar[3]; out[11] = 0;
   return VUS_OK;
 }
 

@@ -223,9 +223,10 @@ class Session:
 
     # ------------------------------------------------------------------ C-ABI calls
     def layout(self):
-        out = (C.c_int64 * 8)()
+        out = (C.c_int64 * 12)()
         self._check(self.lib.vus_get_layout(self._h, out))
-        return dict(D=out[0], k=out[1], Ns=out[2], nrem=out[3], ndst=out[4], B=out[5], L=out[6], n_factors=out[7])
+        return dict(D=out[0], k=out[1], Ns=out[2], nrem=out[3], ndst=out[4], B=out[5], L=out[6], n_factors=out[7],
+                    band_chunks=out[8], Ns_band=out[9], n_landmarks=out[10])
 
     def error(self, stream=None):
         v = C.c_double()
