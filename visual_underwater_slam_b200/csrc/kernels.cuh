@@ -14,12 +14,6 @@
 
 namespace vus {
 
-#ifdef VUS_EMU
-VUS_DEV void atomic_add(double* p, double v) { *p += v; }
-#else
-VUS_DEV void atomic_add(double* p, double v) { atomicAdd(p, v); }
-#endif
-
 // =====================================================================================
 // Kernel 1: linearize / error
 // =====================================================================================
@@ -200,7 +194,7 @@ struct RedPostBody {
 };
 
 // =====================================================================================
-// Kernel 2: assembly of the non-stereo factors (atomic scatter-add)
+// Kernel 2: assembly of the non-stereo factors (node-major / pair-major gathers: no atomics, fixed summation order)
 // =====================================================================================
 // Block-banded Hessian storage (all FP64, row-major):
 //   SD[Ns][B][B]   diagonal supernode blocks (B = k*D, full symmetric storage)
@@ -215,16 +209,6 @@ struct PairDst {        // where block (p,q) of a two-node factor goes (built by
   int pad;
 };
 
-struct AsmArgs {
-  int type; long n;
-  const int* idx; const double* J; const double* r;
-  int D, k, B;
-  int ld; long bs;      // row / block stride of the padded supernode tiles
-  double* Hval;         // base of SD | SU | REM
-  double* g; double* F; double* Hbb; double* gb;
-  const PairDst* pair;  // [n] for between / imu
-};
-
 // element (la, lb) of the diagonal node block of `node` inside SD; ld / bs = row stride / block stride of the padded
 // supernode tiles ([KP][LD], bcr.cuh)
 VUS_HD long diag_off(long node, int la, int lb, int D, int k, int ld, long bs) {
@@ -233,125 +217,124 @@ VUS_HD long diag_off(long node, int la, int lb, int D, int k, int ld, long bs) {
   return I * bs + (long)(rp * D + la) * ld + rp * D + lb;
 }
 
-template <int TYPE>
-struct AsmBody {
-  // work item = (e, f): e < C*C -> Hessian entry (a,b); e >= C*C -> gradient entry a
-  static VUS_DEV void run(const AsmArgs& A, long w) {
-    constexpr int M = kFactorM[TYPE], C = kFactorCols[TYPE];
-    const long n = A.n;
-    const long f = w % n;
-    const int e = (int)(w / n);
-    const int D = A.D;
-    long p = 0, q = 0;
-    if (TYPE == VUS_F_PRIOR_POSE || TYPE == VUS_F_PRIOR_VEL) p = A.idx[f];
-    else if (TYPE == VUS_F_BETWEEN) { p = A.idx[f]; q = A.idx[n + f]; }
-    else if (TYPE == VUS_F_DVL) p = A.idx[n + f];
-    else { p = A.idx[f]; q = A.idx[2 * n + f]; }
-    // column -> (group, local dof)
-    auto grp = [](int c, int& g, int& l) {
-      if (TYPE == VUS_F_PRIOR_POSE || TYPE == VUS_F_DVL) { g = 0; l = c; }
-      else if (TYPE == VUS_F_PRIOR_VEL) { g = 0; l = 6 + c; }
-      else if (TYPE == VUS_F_BETWEEN) { g = c < 6 ? 0 : 1; l = c < 6 ? c : c - 6; }
-      else { g = c < 9 ? 0 : (c < 18 ? 1 : 2); l = c < 9 ? c : (c < 18 ? c - 9 : c - 18); }
-    };
-    if (e >= C * C) {                              // gradient: g_a -= sum_r J[r][a] r[r]
-      const int a = e - C * C;
-      double s = 0.0;
-#pragma unroll
-      for (int r = 0; r < M; ++r) s += A.J[(r * C + a) * n + f] * A.r[r * n + f];
-      int ga, la;
-      grp(a, ga, la);
-      if (ga == 2) return;                           // bias gradient: ImuBiasBody (block reduction, no atomics)
-      atomic_add(&A.g[(ga == 0 ? p : q) * D + la], -s);
-      return;
+// Every Hessian / gradient entry the chain factors (priors, Between, DVL, IMU) touch has exactly ONE writer, which sums the
+// contributions of the factors incident to it in a fixed order (factor type, then insertion index: the lists vus_analyze
+// builds) and stores the result: the base system is bit-identical from run to run and needs no zero-fill per linearization.
+// (The first version scattered J^T J with FP64 atomicAdd: ~30 M atomics per config-3 linearization, 0.11 of the HBM
+// roofline, and a summation order -- hence low-order bits -- that changed from run to run.)
+//   list entry: code = type * 2 + side  (side 0: the factor's first node p, 1: its second node q), f = row in the type's table
+struct ChainTables {
+  long n[VUS_F_NTYPES];
+  const double* J[VUS_F_NTYPES];
+  const double* r[VUS_F_NTYPES];
+};
+// Jacobian column of local node dof `a` (pose 0..5, velocity 6..8) on `side` of a factor of `type`; -1: the factor does not touch it
+VUS_HD int chain_col(int type, int side, int a) {
+  switch (type) {
+    case VUS_F_PRIOR_POSE: return a < 6 ? a : -1;
+    case VUS_F_PRIOR_VEL: return a >= 6 ? a - 6 : -1;
+    case VUS_F_BETWEEN: return a < 6 ? 6 * side + a : -1;
+    case VUS_F_DVL: return a;                                  // [Hx | Hv], node order
+    case VUS_F_IMU: return 9 * side + a;
+    default: return -1;
+  }
+}
+VUS_HD int chain_rows(int type) { return type == VUS_F_IMU ? 9 : ((type == VUS_F_PRIOR_POSE || type == VUS_F_BETWEEN) ? 6 : 3); }
+VUS_HD int chain_cols(int type) {
+  return type == VUS_F_IMU ? 24 : (type == VUS_F_BETWEEN ? 12 : (type == VUS_F_DVL ? 9 : (type == VUS_F_PRIOR_POSE ? 6 : 3)));
+}
+
+struct NodeAsmArgs {
+  ChainTables T;
+  long nnodes;                 // real nodes
+  int D, k, ld; long bs;       // node dof, nodes per supernode, row / block stride of the padded supernode tiles
+  int has_bias, ne;            // ne = D (D + 1) / 2 + D + (has_bias ? 6 D : 0) outputs per node
+  const int* ptr;              // [nnodes + 1]
+  const int* code; const int* fac;     // [nent]
+  double* SD; double* g; double* F;
+};
+// work item = (tile of 32 consecutive nodes, output e, lane = node): a warp walks the same output of 32 neighbouring nodes,
+// whose incident chain factors are neighbouring rows of the component-major J tables (coalesced).
+//   e < nd = D (D + 1) / 2 : diagonal block entry (a <= b), stored with its mirror image
+//   nd <= e < nd + D       : gradient  g_a = -sum J[:, a] . r
+//   nd + D <= e            : bias border F[a][b] = sum J[:, a] . J[:, 18 + b]   (IMU factors only)
+struct NodeAsmBody {
+  static VUS_DEV void run(const NodeAsmArgs& A, long w) {
+    const long tile = w / (32 * A.ne);
+    const int rem = (int)(w - tile * 32 * A.ne);
+    const int e = rem >> 5;
+    const long node = tile * 32 + (rem & 31);
+    if (node >= A.nnodes) return;
+    const int D = A.D, nd = D * (D + 1) / 2;
+    int kind, a = 0, b = 0;
+    if (e < nd) {
+      int t = e;
+      while (t >= D - a) { t -= D - a; ++a; }
+      b = a + t; kind = 0;
+    } else if (e < nd + D) { a = e - nd; kind = 1; }
+    else { const int t = e - nd - D; a = t / 6; b = t - 6 * a; kind = 2; }
+    double s = 0.0;
+    for (int t = A.ptr[node]; t < A.ptr[node + 1]; ++t) {
+      const int code = A.code[t], type = code >> 1, side = code & 1;
+      if (kind == 2 && type != VUS_F_IMU) continue;
+      const int ca = chain_col(type, side, a);
+      if (ca < 0) continue;
+      const int cb = kind == 0 ? chain_col(type, side, b) : (kind == 2 ? 18 + b : 0);
+      if (cb < 0) continue;
+      const long n = A.T.n[type], f = A.fac[t];
+      const int M = chain_rows(type), C = chain_cols(type);
+      const double* J = A.T.J[type];
+      if (kind == 1) {
+        const double* r = A.T.r[type];
+        for (int q = 0; q < M; ++q) s += J[(long)(q * C + ca) * n + f] * r[(long)q * n + f];
+      } else {
+        for (int q = 0; q < M; ++q) s += J[(long)(q * C + ca) * n + f] * J[(long)(q * C + cb) * n + f];
+      }
     }
-    const int a = e / C, b = e % C;
-    int ga, la, gb, lb;
-    grp(a, ga, la);
-    grp(b, gb, lb);
-    if (ga > gb) return;                           // (q,p), (bias,p), (bias,q): written by the mirrored item
-    if (ga == 2 && gb == 2) return;                // bias-bias block: ImuBiasBody
-    double h = 0.0;
-#pragma unroll
-    for (int r = 0; r < M; ++r) h += A.J[(r * C + a) * n + f] * A.J[(r * C + b) * n + f];
-    if (ga == gb) {
-      if (ga == 2) return;                           // bias-bias block: ImuBiasBody
-      atomic_add(&A.Hval[diag_off(ga == 0 ? p : q, la, lb, D, A.k, A.ld, A.bs)], h);
-    } else if (gb == 2) {                          // (node, bias) border
-      atomic_add(&A.F[((ga == 0 ? p : q) * D + la) * 6 + lb], h);
-    } else {                                       // (p, q) coupling
-      const PairDst d = A.pair[f];
-      if (d.transposed) atomic_add(&A.Hval[d.off + (long)lb * d.ld + la], h);
-      else atomic_add(&A.Hval[d.off + (long)la * d.ld + lb], h);
-      if (d.moff >= 0) atomic_add(&A.Hval[d.moff + (long)lb * d.mld + la], h);
+    if (kind == 0) {
+      A.SD[diag_off(node, a, b, D, A.k, A.ld, A.bs)] = s;
+      if (a != b) A.SD[diag_off(node, b, a, D, A.k, A.ld, A.bs)] = s;
+    } else if (kind == 1) {
+      A.g[node * D + a] = -s;
+    } else {
+      A.F[(node * D + a) * 6 + b] = s;
     }
   }
 };
 
-// ImuFactor assembly, tiled: one CTA stages the whitened Jacobians (9 x 24) and residuals of 32 consecutive factors in
-// shared memory with coalesced loads (J is component-major, so a warp reads 32 factors' component c in one request),
-// then lane = factor, warps stride over the 297 distinct outputs of a factor:
-//   45 H_pp (a <= b, mirrored) | 45 H_qq | 81 H_pq | 54 F_p | 54 F_q | 18 gradient      (bias-bias block: ImuBiasBody)
-// Destinations are those of AsmBody<VUS_F_IMU>; chain neighbours share diagonal blocks, hence the atomics.
-#define VUS_IMU_TILE 32
-struct ImuAsmBody {
-  static VUS_DEV void run(const AsmArgs& A, int tile, int tid, int nthr, double* sm) {
-    const long n = A.n;
-    const long f0 = (long)tile * VUS_IMU_TILE;
-    const int nf = (int)((n - f0 < VUS_IMU_TILE) ? (n - f0) : VUS_IMU_TILE);
-    double* sJ = sm;                              // [216][32]
-    double* sR = sm + 216 * VUS_IMU_TILE;         // [9][32]
-    for (int e = tid; e < 225 * VUS_IMU_TILE; e += nthr) {
-      const int c = e / VUS_IMU_TILE, fl = e - c * VUS_IMU_TILE;
-      double v = 0.0;
-      if (fl < nf) v = c < 216 ? A.J[(long)c * n + f0 + fl] : A.r[(long)(c - 216) * n + f0 + fl];
-      sm[e] = v;
+// coupling blocks: one group per unordered node pair {lo < hi} with at least one two-node factor; entry (a, b) of block
+// (lo, hi) = sum over the group's factors of J[:, col(lo, a)] . J[:, col(hi, b)].   code = type * 2 + flip  (flip: the
+// factor's first node is hi)
+struct PairAsmArgs {
+  ChainTables T;
+  long ngroups; int D;
+  const int* ptr; const int* code; const int* fac;
+  const PairDst* dst;          // [ngroups], oriented lo -> hi
+  double* Hval;                // base of SD | SU | REM
+};
+struct PairAsmBody {
+  static VUS_DEV void run(const PairAsmArgs& A, long w) {
+    const int D = A.D, ne = D * D;
+    const long tile = w / (32 * ne);
+    const int rem = (int)(w - tile * 32 * ne);
+    const int e = rem >> 5;
+    const long grp = tile * 32 + (rem & 31);
+    if (grp >= A.ngroups) return;
+    const int a = e / D, b = e - a * D;
+    double s = 0.0;
+    for (int t = A.ptr[grp]; t < A.ptr[grp + 1]; ++t) {
+      const int code = A.code[t], type = code >> 1, flip = code & 1;
+      const int ca = chain_col(type, flip, a), cb = chain_col(type, 1 - flip, b);
+      if (ca < 0 || cb < 0) continue;
+      const long n = A.T.n[type], f = A.fac[t];
+      const int M = chain_rows(type), C = chain_cols(type);
+      const double* J = A.T.J[type];
+      for (int q = 0; q < M; ++q) s += J[(long)(q * C + ca) * n + f] * J[(long)(q * C + cb) * n + f];
     }
-    VUS_SYNC();
-    const int D = A.D;
-    for (int w = tid; w < 297 * VUS_IMU_TILE; w += nthr) {
-      const int e = w / VUS_IMU_TILE, fl = w - e * VUS_IMU_TILE;
-      if (fl >= nf) continue;
-      const long f = f0 + fl;
-      const long p = A.idx[f], q = A.idx[2 * n + f];
-      int a, b, kind;                             // kind 0 pp, 1 qq, 2 pq, 3 Fp, 4 Fq, 5 gradient
-      if (e < 90) {
-        int t = e < 45 ? e : e - 45;
-        a = 0;
-        while (t >= 9 - a) { t -= 9 - a; ++a; }
-        b = a + t;
-        kind = e < 45 ? 0 : 1;
-        if (kind == 1) { a += 9; b += 9; }
-      } else if (e < 171) { const int t = e - 90; a = t / 9; b = 9 + t % 9; kind = 2; }
-      else if (e < 225) { const int t = e - 171; a = t / 6; b = 18 + t % 6; kind = 3; }
-      else if (e < 279) { const int t = e - 225; a = 9 + t / 6; b = 18 + t % 6; kind = 4; }
-      else { a = e - 279; b = 0; kind = 5; }
-      double h = 0.0;
-      if (kind == 5) {
-#pragma unroll
-        for (int r = 0; r < 9; ++r) h += sJ[(r * 24 + a) * VUS_IMU_TILE + fl] * sR[r * VUS_IMU_TILE + fl];
-        atomic_add(&A.g[(a < 9 ? p : q) * D + (a < 9 ? a : a - 9)], -h);
-        continue;
-      }
-#pragma unroll
-      for (int r = 0; r < 9; ++r) h += sJ[(r * 24 + a) * VUS_IMU_TILE + fl] * sJ[(r * 24 + b) * VUS_IMU_TILE + fl];
-      if (kind <= 1) {
-        const long node = kind == 0 ? p : q;
-        const int la = kind == 0 ? a : a - 9, lb = kind == 0 ? b : b - 9;
-        atomic_add(&A.Hval[diag_off(node, la, lb, D, A.k, A.ld, A.bs)], h);
-        if (la != lb) atomic_add(&A.Hval[diag_off(node, lb, la, D, A.k, A.ld, A.bs)], h);
-      } else if (kind == 2) {
-        const int la = a, lb = b - 9;
-        const PairDst d = A.pair[f];
-        if (d.transposed) atomic_add(&A.Hval[d.off + (long)lb * d.ld + la], h);
-        else atomic_add(&A.Hval[d.off + (long)la * d.ld + lb], h);
-        if (d.moff >= 0) atomic_add(&A.Hval[d.moff + (long)lb * d.mld + la], h);
-      } else {
-        const long node = kind == 3 ? p : q;
-        const int la = kind == 3 ? a : a - 9;
-        atomic_add(&A.F[(node * D + la) * 6 + (b - 18)], h);
-      }
-    }
+    const PairDst d = A.dst[grp];
+    if (d.transposed) A.Hval[d.off + (long)b * d.ld + a] = s;
+    else A.Hval[d.off + (long)a * d.ld + b] = s;
+    if (d.moff >= 0) A.Hval[d.moff + (long)b * d.mld + a] = s;
   }
 };
 

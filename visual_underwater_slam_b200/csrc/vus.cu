@@ -126,7 +126,6 @@ struct FactorTable {
   std::vector<int> perm;         // stereo only: table row f holds the caller's row perm[f] (rows are kept landmark-major)
   DBuf<int> idx;
   DBuf<double> meas, sinfo, r, J;
-  DBuf<PairDst> pair;
   DBuf<int> d_order;             // stereo only: pending row re-ordering whose orig / perm bookkeeping has not been derived yet
   long e_off = 0;                // offset into the concatenated per-factor error buffer
 };
@@ -229,6 +228,9 @@ struct vus_handle {
   long Ns_band = 0;              // supernodes the band preconditioner / operator rows cover: all, or the owned prefix of a partition
   long nrem = 0, sd_off = 0, su_off = 0, rem_off = 0, hlen = 0;
   DBuf<double> H0, H;            // SD | SU | REM   (undamped base / damped + Schur)
+  DBuf<int> na_ptr, na_code, na_fac;      // node -> incident chain factors (NodeAsmBody)
+  DBuf<int> pg_ptr, pg_code, pg_fac;      // node pair -> its two-node factors (PairAsmBody)
+  DBuf<PairDst> pg_dst; long npairs = 0;
   DBuf<int> rem_ptr, rem_col;
   DBuf<double> g0, gs, F, Hbb0, Hbb, gb;     // gs = [reduced camera gradient ; gb] (length L)
   // stereo
@@ -771,27 +773,80 @@ int analyze(vus_handle* h, rt::stream_t st) {
   h->rem_off = h->su_off + (h->Ns > 1 ? (h->Ns - 1) * BB : 0);
   h->hlen = h->rem_off + h->nrem * D * D;
   tick("band width + remainder");
-  // ---- per-factor pair destinations
-  auto build_pairs = [&](FactorTable& T, int slot_p, int slot_q) {
-    std::vector<PairDst> v(T.n);
-    for (long f = 0; f < T.n; ++f) {
-      const long p = T.h_idx[slot_p * T.n + f], q = T.h_idx[slot_q * T.n + f];
-      if (p == q) { h->err = "a two-pose factor connects a pose with itself"; return false; }
-      v[f] = band_dst(h, p, q, rem_index);
+  // ---- gather lists of the chain-factor assembly (NodeAsmBody / PairAsmBody): node -> incident factors, node pair -> factors
+  {
+    FactorTable* tabs[VUS_F_NTYPES] = {&h->ft[VUS_F_PRIOR_POSE], &h->ft[VUS_F_PRIOR_VEL], &FB, &h->ft[VUS_F_DVL], nullptr, &FI};
+    const int slot_p[VUS_F_NTYPES] = {0, 0, 0, 1, 0, 0}, slot_q[VUS_F_NTYPES] = {-1, -1, 1, -1, -1, 2};
+    std::vector<int> nptr(NX + 1, 0);
+    for (int t = 0; t < VUS_F_NTYPES; ++t) {
+      if (!tabs[t]) continue;
+      const FactorTable& T = *tabs[t];
+      for (long f = 0; f < T.n; ++f) {
+        const long p = T.h_idx[slot_p[t] * T.n + f];
+        nptr[p + 1]++;
+        if (slot_q[t] >= 0) {
+          const long q = T.h_idx[slot_q[t] * T.n + f];
+          if (p == q) return fail(h, VUS_ERR_INVALID, "a two-pose factor connects a pose with itself");
+          nptr[q + 1]++;
+        }
+      }
     }
-    T.pair.upload(v, st);
-    return true;
-  };
-  if (FB.n && !build_pairs(FB, 0, 1)) return VUS_ERR_INVALID;
-  if (FI.n && !build_pairs(FI, 0, 2)) return VUS_ERR_INVALID;
-  tick("pair destinations");
+    for (long i = 0; i < NX; ++i) nptr[i + 1] += nptr[i];
+    std::vector<int> ncode(nptr[NX]), nfac(nptr[NX]);
+    // pair groups in order of first appearance (factor order: neighbouring groups read neighbouring table rows); an in-band
+    // pair is found through a direct table over (lo, hi - lo), an off-band one through its remainder block
+    std::vector<int> inband_grp((size_t)NX * 2 * k, -1), rem_grp(h->nrem, -1), gcount, fgroup[VUS_F_NTYPES];
+    std::vector<PairDst> gdst;
+    {
+      std::vector<int> fill(nptr.begin(), nptr.end() - 1);
+      for (int t = 0; t < VUS_F_NTYPES; ++t) {          // types in enum order, rows in insertion order, p before q: the summation order
+        if (!tabs[t]) continue;
+        const FactorTable& T = *tabs[t];
+        if (slot_q[t] >= 0) fgroup[t].resize(T.n);
+        for (long f = 0; f < T.n; ++f) {
+          const long p = T.h_idx[slot_p[t] * T.n + f];
+          ncode[fill[p]] = 2 * t; nfac[fill[p]++] = (int)f;
+          if (slot_q[t] < 0) continue;
+          const long q = T.h_idx[slot_q[t] * T.n + f];
+          ncode[fill[q]] = 2 * t + 1; nfac[fill[q]++] = (int)f;
+          const long lo = std::min(p, q), hi = std::max(p, q);
+          int* slot = inband(lo, hi) ? &inband_grp[(size_t)lo * 2 * k + (hi - lo)] : &rem_grp[rem_index.at({lo, hi})];
+          if (*slot < 0) { *slot = (int)gdst.size(); gdst.push_back(band_dst(h, lo, hi, rem_index)); gcount.push_back(0); }
+          fgroup[t][f] = *slot;
+          gcount[*slot]++;
+        }
+      }
+    }
+    h->npairs = (long)gdst.size();
+    std::vector<int> gptr(h->npairs + 1, 0);
+    for (long gi = 0; gi < h->npairs; ++gi) gptr[gi + 1] = gptr[gi] + gcount[gi];
+    std::vector<int> gcode(gptr[h->npairs]), gfac(gptr[h->npairs]);
+    {
+      std::vector<int> fill(gptr.begin(), gptr.end() - 1);
+      for (int t = 0; t < VUS_F_NTYPES; ++t) {
+        if (!tabs[t] || slot_q[t] < 0) continue;
+        const FactorTable& T = *tabs[t];
+        for (long f = 0; f < T.n; ++f) {
+          const int gi = fgroup[t][f];
+          const bool flip = T.h_idx[slot_p[t] * T.n + f] > T.h_idx[slot_q[t] * T.n + f];
+          gcode[fill[gi]] = 2 * t + (flip ? 1 : 0); gfac[fill[gi]++] = (int)f;
+        }
+      }
+    }
+    h->na_ptr.upload(nptr, st); h->na_code.upload(ncode, st); h->na_fac.upload(nfac, st);
+    h->pg_ptr.upload(gptr, st); h->pg_code.upload(gcode, st); h->pg_fac.upload(gfac, st); h->pg_dst.upload(gdst, st);
+  }
+  tick("chain-factor gather lists");
   // ---- uploads / allocations
   h->rem_ptr.upload(rem_ptr, st); h->rem_col.upload(rem_col, st);
   h->pose_ptr.upload(pose_ptr, st); if (!pose_obs_on_device) h->pose_obs.upload(pose_obs, st); h->pose_ids.upload(pose_ids, st);
   h->lm_ptr.upload(lm_ptr, st);
   h->H0.alloc(h->hlen); h->H.alloc(h->hlen);
   h->g0.alloc(h->Lc); h->gs.alloc(h->L);
-  h->F.alloc(h->Lc * 6); h->Hbb0.alloc(36 * std::max<long>(NB, 1)); h->Hbb.alloc(36 * std::max<long>(NB, 1)); h->gb.alloc(6 * std::max<long>(NB, 1));
+  h->F.alloc(h->Lc * 6);
+  // zero-filled once: the assembly kernels store every entry a factor can touch, nothing else ever writes the rest
+  h->H0.zero(st); h->g0.zero(st); h->F.zero(st);
+  h->Hbb0.alloc(36 * std::max<long>(NB, 1)); h->Hbb.alloc(36 * std::max<long>(NB, 1)); h->gb.alloc(6 * std::max<long>(NB, 1));
   h->C.alloc(9 * NL); h->gl.alloc(3 * NL); h->Cinv.alloc(9 * NL); h->E.alloc(18 * FS.n); h->Pp.alloc(28 * FS.n); h->Pl.alloc(12 * FS.n);
   {   // the reduction's own blocks are padded [KP][LD] tiles; the padding must be (and stays) zero
     // Stereo-scale supernodes on one long chain: block Cholesky inside P chunks (one per SM), cyclic reduction across the
@@ -864,32 +919,27 @@ int analyze(vus_handle* h, rt::stream_t st) {
 }
 
 // ------------------------------------------------------------------ kernel 2 driver: base (undamped) system
-template <int T>
-void launch_asm(vus_handle* h, rt::stream_t st) {
-  FactorTable& F = h->ft[T];
-  if (!F.n) return;
-  AsmArgs a;
-  a.type = T; a.n = F.n; a.idx = F.idx.p; a.J = F.J.p; a.r = F.r.p;
-  a.D = h->D; a.k = h->k; a.B = h->B; a.ld = bcr_ld(h->B); a.bs = bcr_bbp(h->B);
-  a.Hval = h->H0.p; a.g = h->g0.p; a.F = h->F.p; a.Hbb = h->Hbb0.p; a.gb = h->gb.p; a.pair = F.pair.p;
-  const long items = (long)(kFactorCols[T] * kFactorCols[T] + kFactorCols[T]) * F.n;
-  L_elem<AsmBody<T>>(items, st, a);
+ChainTables chain_tables(vus_handle* h) {
+  ChainTables T;
+  for (int t = 0; t < VUS_F_NTYPES; ++t) { T.n[t] = h->ft[t].n; T.J[t] = h->ft[t].J.p; T.r[t] = h->ft[t].r.p; }
+  return T;
 }
-
 void assemble_base(vus_handle* h, rt::stream_t st) {
   ClassGuard kc_guard(KC_ASSEMBLE);
-  h->H0.zero(st); h->g0.zero(st); h->F.zero(st); h->Hbb0.zero(st); h->gb.zero(st);
-  launch_asm<VUS_F_PRIOR_POSE>(h, st);
-  launch_asm<VUS_F_PRIOR_VEL>(h, st);
-  launch_asm<VUS_F_BETWEEN>(h, st);
-  launch_asm<VUS_F_DVL>(h, st);
-  if (h->ft[VUS_F_IMU].n) {
-    FactorTable& I = h->ft[VUS_F_IMU];
-    AsmArgs a;
-    a.type = VUS_F_IMU; a.n = I.n; a.idx = I.idx.p; a.J = I.J.p; a.r = I.r.p;
-    a.D = h->D; a.k = h->k; a.B = h->B; a.ld = bcr_ld(h->B); a.bs = bcr_bbp(h->B);
-    a.Hval = h->H0.p; a.g = h->g0.p; a.F = h->F.p; a.Hbb = h->Hbb0.p; a.gb = h->gb.p; a.pair = I.pair.p;
-    L_coop<ImuAsmBody>((int)((I.n + VUS_IMU_TILE - 1) / VUS_IMU_TILE), 256, (size_t)225 * VUS_IMU_TILE * sizeof(double), st, a);
+  h->Hbb0.zero(st); h->gb.zero(st);
+  {
+    NodeAsmArgs a;
+    a.T = chain_tables(h); a.nnodes = h->N; a.D = h->D; a.k = h->k; a.ld = bcr_ld(h->B); a.bs = bcr_bbp(h->B);
+    a.has_bias = h->has_bias ? 1 : 0; a.ne = h->D * (h->D + 1) / 2 + h->D + (h->has_bias ? 6 * h->D : 0);
+    a.ptr = h->na_ptr.p; a.code = h->na_code.p; a.fac = h->na_fac.p;
+    a.SD = h->H0.p + h->sd_off; a.g = h->g0.p; a.F = h->F.p;
+    L_elem<NodeAsmBody>((h->N + 31) / 32 * 32 * a.ne, st, a);
+  }
+  if (h->npairs) {
+    PairAsmArgs a;
+    a.T = chain_tables(h); a.ngroups = h->npairs; a.D = h->D;
+    a.ptr = h->pg_ptr.p; a.code = h->pg_code.p; a.fac = h->pg_fac.p; a.dst = h->pg_dst.p; a.Hval = h->H0.p;
+    L_elem<PairAsmBody>((h->npairs + 31) / 32 * 32 * (long)(h->D * h->D), st, a);
   }
   if (h->ft[VUS_F_IMU].n) {
     FactorTable& I = h->ft[VUS_F_IMU];
@@ -1238,6 +1288,8 @@ void xpby(vus_handle* h, double* y, const double* x, int slot, rt::stream_t st) 
 }
 
 const int kPcgBlock = 8;     // most PCG iterations replayed per look of the host at the residual norm
+// a PCG run that stopped short of pcg_rel_tol still counts as a solve when its TRUE relative residual is below this
+const double kPcgAcceptRelRes = 1e-6;
 struct SetScalarArgs { double* dst; double v; };
 struct SetScalarBody {
   static VUS_DEV void run(const SetScalarArgs& A, long) { *A.dst = A.v; }
@@ -1278,7 +1330,7 @@ void set_scalar(vus_handle* h, int slot, double v, rt::stream_t st) {
 // The recursion is device resident: the host replays kPcgBlock iterations at a time and reads the residual norm once per
 // block; a recursion that met its tolerance inside a block freezes itself (alpha = beta = 0), so the extra iterations of the
 // block leave the iterate untouched.
-int pcg(vus_handle* h, rt::stream_t st, bool* converged, bool* bad_out = nullptr) {
+int pcg(vus_handle* h, rt::stream_t st, bool* converged, bool* bad_out = nullptr, double accept_rel = kPcgAcceptRelRes) {
   const long L = h->L;
   VecArgs v; v.z = nullptr; v.scal = h->scal.p; v.slot = 0; v.n = L; v.Z = nullptr; v.xb = nullptr; v.zstride = 0;
   h->x.zero(st);
@@ -1310,8 +1362,9 @@ int pcg(vus_handle* h, rt::stream_t st, bool* converged, bool* bad_out = nullptr
     set_scalar(h, S_TOL2, tol2, st);
     int since_best = 0;
     double best = rr_outer;
-    bool bad = false;
+    bool bad = false, stalled = true;                   // stalled: the recursion ended on a stall, not on its tolerance
     int looks = 0;
+    const int live_before = live_its;
     while (it < h->prm.pcg_max_iterations) {
       // an exactly factored band converges in one to three iterations: look after every one of the first three, then let the
       // block grow (closure-dominated graphs run a hundred iterations per solve)
@@ -1332,7 +1385,7 @@ int pcg(vus_handle* h, rt::stream_t st, bool* converged, bool* bad_out = nullptr
       live_its = (int)sc[S_ITS];
       if (h->prm.verbose > 1) std::fprintf(stderr, "    pcg %d.%d rel_res %.3e\n", outer, it, std::sqrt(rr / rr0));
       if (!(rr == rr) || two[1] > 0.0) { bad = true; break; }
-      if (rr <= tol2) break;
+      if (rr <= tol2) { stalled = false; break; }
       if (rr < best) { best = rr; since_best = 0; }
       else if ((since_best += nb) >= 40) break;          // CG residuals are not monotone: only a long stall ends the recursion
     }
@@ -1352,6 +1405,11 @@ int pcg(vus_handle* h, rt::stream_t st, bool* converged, bool* bad_out = nullptr
     h->last_rel_res = std::sqrt(rr_true / rr0);
     if (rr_true <= tol2) { *converged = true; break; }
     if (!(rr_true < 0.25 * rr_outer) || it >= h->prm.pcg_max_iterations) break;   // no further progress possible
+    // A recursion that met its tolerance within three iterations (exactly factored band: configs 2 and 3) has not drifted:
+    // its true residual already sits at the attainable floor eps |A| |x| / |b| (1e-9 .. 1e-8 on these systems, IMU
+    // information 1e10 next to lambda 1e-5), and another pass would spend a band solve and two operator products to
+    // find the same floor again (measured: the third iteration never lowered the true residual at config 3).
+    if (!stalled && live_its - live_before <= 3 && rr_true <= accept_rel * accept_rel * rr0) break;
     rr_outer = rr_true;
   }
   return live_its;
@@ -1388,8 +1446,6 @@ int read_fail(vus_handle* h, rt::stream_t st) {
   return f;
 }
 
-// a PCG run that stopped short of pcg_rel_tol still counts as a solve when its TRUE relative residual is below this
-const double kPcgAcceptRelRes = 1e-6;
 // solve the damped system at the current linearization; delta in h->x (camera+bias) and h->xl
 bool solve_damped(vus_handle* h, double lambda, rt::stream_t st, int* iters, bool timing) {
   double t0 = timing ? now_ms() : 0;
@@ -1697,6 +1753,8 @@ int pcg_b(vus_handle* h, rt::stream_t st, bool* converged, bool* bad_out = nullp
     bdot(h, h->r.p, h->z.p, S_RZ, BOP_RZ0, st);
     int since_best = 0;
     double best = worst_outer;
+    const int it_before = it;
+    bool stalled = true;                                 // the recursion ended on a stall, not on its tolerance
     while (it < h->prm.pcg_max_iterations) {
       apply_A_b(h, h->Ap.p, h->p.p, st);
       bdot(h, h->p.p, h->Ap.p, S_PAP, BOP_PAP, st);
@@ -1706,7 +1764,7 @@ int pcg_b(vus_handle* h, rt::stream_t st, bool* converged, bool* bad_out = nullp
       bdot(h, h->r.p, h->r.p, S_RR, BOP_STORE, st);
       worst = worst_ratio(h, sb, st, &bad);
       if (h->prm.verbose > 1) std::fprintf(stderr, "    pcg_b %d.%d worst rr/tol2 %.3e\n", outer, it, worst);
-      if (bad || worst <= 1.0) break;
+      if (bad || worst <= 1.0) { stalled = false; break; }
       if (worst < best) { best = worst; since_best = 0; }
       else if (++since_best >= 40) break;
       precond_full_b(h, h->z.p, h->r.p, st);
@@ -1725,6 +1783,10 @@ int pcg_b(vus_handle* h, rt::stream_t st, bool* converged, bool* bad_out = nullp
     if (bad) { if (bad_out) *bad_out = true; break; }
     if (worst_true <= 1.0) { *converged = true; break; }
     if (!(worst_true < 0.25 * worst_outer) || it >= h->prm.pcg_max_iterations) break;
+    {                                                    // as in pcg(): a recursion of at most three iterations sits at its floor
+      const double a = kPcgAcceptRelRes / h->prm.pcg_rel_tol;
+      if (!stalled && it - it_before <= 3 && worst_true <= a * a) break;
+    }
     worst_outer = worst_true;
   }
   return it;
@@ -1920,7 +1982,7 @@ int marginal_covariance(vus_handle* h, rt::stream_t st, long nq, const int32_t* 
       else if (kd == VUS_VAR_BIAS) u.pos = h->Lc + j;
       L_elem<UnitRhsBody>(1, st, u);
       bool conv = false;
-      pcg(h, st, &conv);
+      pcg(h, st, &conv, nullptr, 1e-7);
       // The undamped system can be far harder than the damped ones of the LM loop (no lambda, unit right-hand sides that excite
       // the weakest directions; graphs whose tracks exceed the band leave most of the stereo information to PCG): refuse to
       // hand back a covariance column whose solve did not reach a small true residual.
