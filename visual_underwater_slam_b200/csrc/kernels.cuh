@@ -253,17 +253,20 @@ struct NodeAsmArgs {
   const int* code; const int* fac;     // [nent]
   double* SD; double* g; double* F;
 };
-// work item = (tile of 32 consecutive nodes, output e, lane = node): a warp walks the same output of 32 neighbouring nodes,
-// whose incident chain factors are neighbouring rows of the component-major J tables (coalesced).
+// One CTA per tile of 32 consecutive nodes, lane = node, the warps stride over the node's outputs e: a warp walks the same
+// output of 32 neighbouring nodes, whose incident chain factors are neighbouring rows of the component-major J tables
+// (coalesced), and every output of a tile re-reads the same ~65 KB of Jacobians from the SM's own L1.  (An item-per-thread
+// grid spread the outputs of one tile over a dozen SMs and was bound by L2 -> L1 traffic: 590 us per launch at config 3.)
 //   e < nd = D (D + 1) / 2 : diagonal block entry (a <= b), stored with its mirror image
 //   nd <= e < nd + D       : gradient  g_a = -sum J[:, a] . r
 //   nd + D <= e            : bias border F[a][b] = sum J[:, a] . J[:, 18 + b]   (IMU factors only)
+#define VUS_ASM_THREADS 256
 struct NodeAsmBody {
-  static VUS_DEV void run(const NodeAsmArgs& A, long w) {
-    const long tile = w / (32 * A.ne);
-    const int rem = (int)(w - tile * 32 * A.ne);
-    const int e = rem >> 5;
-    const long node = tile * 32 + (rem & 31);
+  static VUS_DEV void run(const NodeAsmArgs& A, int tile, int tid, int nthr, double*) {
+    for (int w = tid; w < 32 * A.ne; w += nthr) item(A, tile, w >> 5, w & 31);
+  }
+  static VUS_DEV void item(const NodeAsmArgs& A, long tile, int e, int lane) {
+    const long node = tile * 32 + lane;
     if (node >= A.nnodes) return;
     const int D = A.D, nd = D * (D + 1) / 2;
     int kind, a = 0, b = 0;
@@ -313,12 +316,12 @@ struct PairAsmArgs {
   double* Hval;                // base of SD | SU | REM
 };
 struct PairAsmBody {
-  static VUS_DEV void run(const PairAsmArgs& A, long w) {
-    const int D = A.D, ne = D * D;
-    const long tile = w / (32 * ne);
-    const int rem = (int)(w - tile * 32 * ne);
-    const int e = rem >> 5;
-    const long grp = tile * 32 + (rem & 31);
+  static VUS_DEV void run(const PairAsmArgs& A, int tile, int tid, int nthr, double*) {
+    for (int w = tid; w < 32 * A.D * A.D; w += nthr) item(A, tile, w >> 5, w & 31);
+  }
+  static VUS_DEV void item(const PairAsmArgs& A, long tile, int e, int lane) {
+    const int D = A.D;
+    const long grp = tile * 32 + lane;
     if (grp >= A.ngroups) return;
     const int a = e / D, b = e - a * D;
     double s = 0.0;
@@ -478,72 +481,58 @@ struct SchurPartnerBody {
     A.partner[w] = q;
   }
 };
-// per lambda, work item (pose slot pi, dj, half): rows 3 half .. 3 half + 2 of the 6 x 6 block  S(i, i + dj) -= sum_o W_o E_q^T
-// (W_o = E_o Cinv_l, q the partner of o at pose i + dj) accumulated in registers: 18 outputs per 12 loaded values per
-// observation pair, no shared memory, exactly one thread writes an entry, and the two halves of a block sit in neighbouring
-// lanes so their E_q loads hit the same sectors.  The kernel it replaces (one thread per block ENTRY, partial blocks in
-// shared memory) was bound by L1 sector throughput: 516 M sectors per launch at C3 (profiles/r1_ncu_schur_c3.txt).
+// per lambda, work item (pose slot pi, dj, row r): row r of the 6 x 6 block  S(i, i + dj) -= sum_o W_o E_q^T  (W_o = E_o Cinv_l,
+// q the partner of o at pose i + dj) accumulated in registers, no shared memory, exactly one thread writes an entry (fixed
+// summation order).  The six rows of a block sit in neighbouring lanes: their Cinv / E_q / partner loads are the same
+// addresses (one transaction per warp instruction), so splitting a block over six threads costs no extra memory traffic but
+// gives three times the loads in flight of the half-block version, which was bound by the latency of its dependent
+// partner -> E_q loads (20 observations per pose, one after another: 1.39 ms per launch at config 3, 0.31 of the HBM
+// roofline).  History: a thread per block ENTRY with partial blocks in shared memory was bound by L1 sector throughput
+// (516 M sectors per launch, profiles/r1_ncu_schur_c3.txt); a thread per half block (round 1) by latency.
 // The dj = 0 items also reduce the gradient  gs_i -= sum_o W_o gl_l.
 struct SchurBlockBody {
   static VUS_DEV void run(const SchurArgs& A, long w) {
-    const int r0 = 3 * (int)(w & 1);
-    const int dj = (int)((w >> 1) % A.ndj);
-    const long pi = (w >> 1) / A.ndj;
+    const int r = (int)(w % 6);
+    const int dj = (int)((w / 6) % A.ndj);
+    const long pi = (w / 6) / A.ndj;
     const long i = A.pose_ids[pi];
-    double acc[18], gacc[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-    for (int e = 0; e < 18; ++e) acc[e] = 0.0;
+    double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, gacc = 0.0;
     bool any = false;
-    for (int t = A.pose_ptr[pi]; t < A.pose_ptr[pi + 1]; ++t) {
-      const int q = A.partner[(long)t * A.ndj + dj];
+    const int t0 = A.pose_ptr[pi], t1 = A.pose_ptr[pi + 1];
+    int qn = t0 < t1 ? A.partner[(long)t0 * A.ndj + dj] : -1;          // the partner of the next observation is fetched one
+    for (int t = t0; t < t1; ++t) {                                    // iteration ahead of the record it points to
+      const int q = qn;
+      if (t + 1 < t1) qn = A.partner[(long)(t + 1) * A.ndj + dj];
       if (q < 0 && dj != 0) continue;
       const long o = A.pose_obs[t];
       const long l = A.idx[A.n + o];
-      double W[9];
-      {
-        double ci[9];
-#pragma unroll
-        for (int e = 0; e < 9; ++e) ci[e] = A.Cinv[e * A.nl + l];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const double* er = A.E + o * 18 + (r0 + r) * 3;
-          const double e0 = er[0], e1 = er[1], e2 = er[2];
-          W[r * 3] = e0 * ci[0] + e1 * ci[3] + e2 * ci[6];
-          W[r * 3 + 1] = e0 * ci[1] + e1 * ci[4] + e2 * ci[7];
-          W[r * 3 + 2] = e0 * ci[2] + e1 * ci[5] + e2 * ci[8];
-        }
-      }
+      const double* er = A.E + o * 18 + r * 3;
+      const double e0 = er[0], e1 = er[1], e2 = er[2];
+      const double* ci = A.Cinv + l;
+      const long nl = A.nl;
+      const double w0 = e0 * ci[0] + e1 * ci[3 * nl] + e2 * ci[6 * nl];
+      const double w1 = e0 * ci[nl] + e1 * ci[4 * nl] + e2 * ci[7 * nl];
+      const double w2 = e0 * ci[2 * nl] + e1 * ci[5 * nl] + e2 * ci[8 * nl];
       if (dj == 0) {
-        const double g0 = A.gl[l], g1 = A.gl[A.nl + l], g2 = A.gl[2 * A.nl + l];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) gacc[r] += W[r * 3] * g0 + W[r * 3 + 1] * g1 + W[r * 3 + 2] * g2;
+        gacc += w0 * A.gl[l] + w1 * A.gl[nl + l] + w2 * A.gl[2 * nl + l];
         if (q < 0) continue;                           // long track: only the gradient is reduced here (LongSchur*Body)
       }
       any = true;
       const double* eq = A.E + (long)q * 18;
 #pragma unroll
-      for (int sc = 0; sc < 6; ++sc) {
-        const double v0 = eq[sc * 3], v1 = eq[sc * 3 + 1], v2 = eq[sc * 3 + 2];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) acc[r * 6 + sc] += W[r * 3] * v0 + W[r * 3 + 1] * v1 + W[r * 3 + 2] * v2;
-      }
+      for (int sc = 0; sc < 6; ++sc) acc[sc] += w0 * eq[sc * 3] + w1 * eq[sc * 3 + 1] + w2 * eq[sc * 3 + 2];
     }
     const int D = A.D, k = A.k, B = A.ld;
-    if (dj == 0) {
-#pragma unroll
-      for (int r = 0; r < 3; ++r) A.gs[i * D + r0 + r] -= gacc[r];
-    }
+    if (dj == 0) A.gs[i * D + r] -= gacc;
     if (!any) return;
     const long I = i / k, j = i + dj, J = j / k;
     const int ri = (int)(i - I * k), rj = (int)(j - J * k);
     double* blk = (J == I ? A.SD : A.SU) + I * A.bs;
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int sc = 0; sc < 6; ++sc) {
-        blk[(long)(ri * D + r0 + r) * B + rj * D + sc] -= acc[r * 6 + sc];
-        if (J == I && dj) blk[(long)(rj * D + sc) * B + ri * D + r0 + r] -= acc[r * 6 + sc];
-      }
+    for (int sc = 0; sc < 6; ++sc) {
+      blk[(long)(ri * D + r) * B + rj * D + sc] -= acc[sc];
+      if (J == I && dj) blk[(long)(rj * D + sc) * B + ri * D + r] -= acc[sc];
+    }
   }
 };
 struct LmInvertBody {    // per landmark

@@ -933,13 +933,13 @@ void assemble_base(vus_handle* h, rt::stream_t st) {
     a.has_bias = h->has_bias ? 1 : 0; a.ne = h->D * (h->D + 1) / 2 + h->D + (h->has_bias ? 6 * h->D : 0);
     a.ptr = h->na_ptr.p; a.code = h->na_code.p; a.fac = h->na_fac.p;
     a.SD = h->H0.p + h->sd_off; a.g = h->g0.p; a.F = h->F.p;
-    L_elem<NodeAsmBody>((h->N + 31) / 32 * 32 * a.ne, st, a);
+    L_coop<NodeAsmBody>((int)((h->N + 31) / 32), VUS_ASM_THREADS, 0, st, a);
   }
   if (h->npairs) {
     PairAsmArgs a;
     a.T = chain_tables(h); a.ngroups = h->npairs; a.D = h->D;
     a.ptr = h->pg_ptr.p; a.code = h->pg_code.p; a.fac = h->pg_fac.p; a.dst = h->pg_dst.p; a.Hval = h->H0.p;
-    L_elem<PairAsmBody>((h->npairs + 31) / 32 * 32 * (long)(h->D * h->D), st, a);
+    L_coop<PairAsmBody>((int)((h->npairs + 31) / 32), VUS_ASM_THREADS, 0, st, a);
   }
   if (h->ft[VUS_F_IMU].n) {
     FactorTable& I = h->ft[VUS_F_IMU];
@@ -995,7 +995,7 @@ void form_system(vus_handle* h, double lambda, rt::stream_t st) {
   if (h->nobs) {
     SchurArgs a = schur_args(h, lambda);
     L_elem<LmInvertBody>(a.nl, st, a);
-    L_elem<SchurBlockBody>(2 * h->nposes_obs * h->schur_ndj, st, a);
+    L_elem<SchurBlockBody>(6 * h->nposes_obs * h->schur_ndj, st, a);
   }
 }
 
