@@ -17,8 +17,12 @@ timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --
   python tools/ncu_target.py 100000 > $O/${TAG}_ncu_list.log 2>&1; echo "ncu list rc $?"
 fi
 if [ "$2" != "noncu" ]; then
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
+timeout 600 ncu --set full --clock-control none --kernel-name-base demangled \
   -k "regex:(SchurBlockBody|StereoPoseBody|StereoLmBody|NodeAsmBody|PairAsmBody|LinStereoTileBody|LinBody|ChunkFwdBody|ChunkBwdBody|BandMatvecBody|ChunkFactorBody|LmInvertBody|DampBody|LmBacksubBody)" \
-  -c 36 -o $O/${TAG}_hot -f python tools/ncu_target.py 100000 > $O/${TAG}_ncu_hot.log 2>&1; echo "ncu full rc $?"
+  -c 36 -o /tmp/${TAG}_hot -f python tools/ncu_target.py 100000 > $O/${TAG}_ncu_hot.log 2>&1; echo "ncu full rc $?"
+ncu -i /tmp/${TAG}_hot.ncu-rep --page details > $O/${TAG}_hot_details.txt 2>&1
+ncu -i /tmp/${TAG}_hot.ncu-rep --page raw --csv > $O/${TAG}_hot_raw.csv 2>&1
+SZ=$(stat -c %s /tmp/${TAG}_hot.ncu-rep 2>/dev/null || echo 0); echo "ncu-rep bytes $SZ"
+if [ "$SZ" -gt 0 ] && [ "$SZ" -lt 40000000 ]; then cp /tmp/${TAG}_hot.ncu-rep $O/; fi
 fi
 ls -la $O | tail -12

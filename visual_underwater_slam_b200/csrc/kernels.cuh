@@ -248,66 +248,90 @@ struct NodeAsmArgs {
   ChainTables T;
   long nnodes;                 // real nodes
   int D, k, ld; long bs;       // node dof, nodes per supernode, row / block stride of the padded supernode tiles
-  int has_bias, ne;            // ne = D (D + 1) / 2 + D + (has_bias ? 6 D : 0) outputs per node
+  int has_bias;
   const int* ptr;              // [nnodes + 1]
   const int* code; const int* fac;     // [nent]
   double* SD; double* g; double* F;
 };
-// One CTA per tile of 32 consecutive nodes, lane = node, the warps stride over the node's outputs e: a warp walks the same
-// output of 32 neighbouring nodes, whose incident chain factors are neighbouring rows of the component-major J tables
-// (coalesced), and every output of a tile re-reads the same ~65 KB of Jacobians from the SM's own L1.  (An item-per-thread
-// grid spread the outputs of one tile over a dozen SMs and was bound by L2 -> L1 traffic: 590 us per launch at config 3.)
-//   e < nd = D (D + 1) / 2 : diagonal block entry (a <= b), stored with its mirror image
-//   nd <= e < nd + D       : gradient  g_a = -sum J[:, a] . r
-//   nd + D <= e            : bias border F[a][b] = sum J[:, a] . J[:, 18 + b]   (IMU factors only)
-#define VUS_ASM_THREADS 256
+// One CTA per tile of 32 consecutive nodes: lane = node, warp = local dof a.  A thread owns ROW a of its node's outputs --
+// the diagonal block entries (a, b >= a) with their mirror images, the gradient entry a and the six bias-border entries of row
+// a -- and walks the node's incident factors once: column a of the factor's Jacobian goes into registers (<= 9 values) and
+// is multiplied with every partner column.  A warp reads the same column of 32 neighbouring factors (component-major J:
+// coalesced) and the D warps of a tile re-read the same ~65 KB of Jacobians from the SM's own L1.
+// (History: an item-per-thread grid, one output each, spread the outputs of a tile over a dozen SMs and was bound by
+// L2 -> L1 traffic, 590 us per launch at config 3; a CTA per tile with one output per thread, 323 us, was bound by
+// instruction issue -- two loads and the index arithmetic for every multiply-add.)
+#define VUS_ASM_MAXD 9
+VUS_DEV void chain_load_col(double (&v)[VUS_ASM_MAXD], const double* J, int M, int C, int c, long n, long f) {
+  const double* p = J + (long)c * n + f;
+  const long stride = (long)C * n;
+#pragma unroll
+  for (int q = 0; q < VUS_ASM_MAXD; ++q) { v[q] = q < M ? *p : 0.0; p += stride; }
+}
+VUS_DEV double chain_dot_col(const double (&v)[VUS_ASM_MAXD], const double* J, int M, int C, int c, long n, long f) {
+  const double* p = J + (long)c * n + f;
+  const long stride = (long)C * n;
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < VUS_ASM_MAXD; ++q) { if (q < M) s += v[q] * *p; p += stride; }
+  return s;
+}
 struct NodeAsmBody {
   static VUS_DEV void run(const NodeAsmArgs& A, int tile, int tid, int nthr, double*) {
-    for (int w = tid; w < 32 * A.ne; w += nthr) item(A, tile, w >> 5, w & 31);
+    for (int w = tid; w < 32 * A.D; w += nthr) item(A, tile, w >> 5, w & 31);
   }
-  static VUS_DEV void item(const NodeAsmArgs& A, long tile, int e, int lane) {
+  static VUS_DEV void item(const NodeAsmArgs& A, long tile, int a, int lane) {
     const long node = tile * 32 + lane;
     if (node >= A.nnodes) return;
-    const int D = A.D, nd = D * (D + 1) / 2;
-    int kind, a = 0, b = 0;
-    if (e < nd) {
-      int t = e;
-      while (t >= D - a) { t -= D - a; ++a; }
-      b = a + t; kind = 0;
-    } else if (e < nd + D) { a = e - nd; kind = 1; }
-    else { const int t = e - nd - D; a = t / 6; b = t - 6 * a; kind = 2; }
-    double s = 0.0;
+    const int D = A.D;
+    double acc[VUS_ASM_MAXD], accF[6], accg = 0.0, va[VUS_ASM_MAXD];
+#pragma unroll
+    for (int j = 0; j < VUS_ASM_MAXD; ++j) acc[j] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) accF[j] = 0.0;
     for (int t = A.ptr[node]; t < A.ptr[node + 1]; ++t) {
       const int code = A.code[t], type = code >> 1, side = code & 1;
-      if (kind == 2 && type != VUS_F_IMU) continue;
       const int ca = chain_col(type, side, a);
       if (ca < 0) continue;
-      const int cb = kind == 0 ? chain_col(type, side, b) : (kind == 2 ? 18 + b : 0);
-      if (cb < 0) continue;
       const long n = A.T.n[type], f = A.fac[t];
       const int M = chain_rows(type), C = chain_cols(type);
       const double* J = A.T.J[type];
-      if (kind == 1) {
-        const double* r = A.T.r[type];
-        for (int q = 0; q < M; ++q) s += J[(long)(q * C + ca) * n + f] * r[(long)q * n + f];
-      } else {
-        for (int q = 0; q < M; ++q) s += J[(long)(q * C + ca) * n + f] * J[(long)(q * C + cb) * n + f];
+      chain_load_col(va, J, M, C, ca, n, f);
+#pragma unroll
+      for (int j = 0; j < VUS_ASM_MAXD; ++j) {
+        if (a + j >= D) continue;
+        const int cb = j == 0 ? ca : chain_col(type, side, a + j);
+        if (cb >= 0) acc[j] += chain_dot_col(va, J, M, C, cb, n, f);
+      }
+      {
+        const double* r = A.T.r[type] + f;
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < VUS_ASM_MAXD; ++q) if (q < M) s += va[q] * r[(long)q * n];
+        accg += s;
+      }
+      if (type == VUS_F_IMU && A.has_bias) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) accF[j] += chain_dot_col(va, J, M, C, 18 + j, n, f);
       }
     }
-    if (kind == 0) {
-      A.SD[diag_off(node, a, b, D, A.k, A.ld, A.bs)] = s;
-      if (a != b) A.SD[diag_off(node, b, a, D, A.k, A.ld, A.bs)] = s;
-    } else if (kind == 1) {
-      A.g[node * D + a] = -s;
-    } else {
-      A.F[(node * D + a) * 6 + b] = s;
+#pragma unroll
+    for (int j = 0; j < VUS_ASM_MAXD; ++j) {
+      if (a + j >= D) continue;
+      A.SD[diag_off(node, a, a + j, D, A.k, A.ld, A.bs)] = acc[j];
+      if (j) A.SD[diag_off(node, a + j, a, D, A.k, A.ld, A.bs)] = acc[j];
+    }
+    A.g[node * D + a] = -accg;
+    if (A.has_bias) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) A.F[(node * D + a) * 6 + j] = accF[j];
     }
   }
 };
 
 // coupling blocks: one group per unordered node pair {lo < hi} with at least one two-node factor; entry (a, b) of block
 // (lo, hi) = sum over the group's factors of J[:, col(lo, a)] . J[:, col(hi, b)].   code = type * 2 + flip  (flip: the
-// factor's first node is hi)
+// factor's first node is hi).  One CTA per tile of 32 groups, lane = group, warp = row a of the block.
 struct PairAsmArgs {
   ChainTables T;
   long ngroups; int D;
@@ -317,29 +341,47 @@ struct PairAsmArgs {
 };
 struct PairAsmBody {
   static VUS_DEV void run(const PairAsmArgs& A, int tile, int tid, int nthr, double*) {
-    for (int w = tid; w < 32 * A.D * A.D; w += nthr) item(A, tile, w >> 5, w & 31);
+    for (int w = tid; w < 32 * A.D; w += nthr) item(A, tile, w >> 5, w & 31);
   }
-  static VUS_DEV void item(const PairAsmArgs& A, long tile, int e, int lane) {
+  static VUS_DEV void item(const PairAsmArgs& A, long tile, int a, int lane) {
     const int D = A.D;
     const long grp = tile * 32 + lane;
     if (grp >= A.ngroups) return;
-    const int a = e / D, b = e - a * D;
-    double s = 0.0;
+    double acc[VUS_ASM_MAXD], va[VUS_ASM_MAXD];
+#pragma unroll
+    for (int j = 0; j < VUS_ASM_MAXD; ++j) acc[j] = 0.0;
     for (int t = A.ptr[grp]; t < A.ptr[grp + 1]; ++t) {
       const int code = A.code[t], type = code >> 1, flip = code & 1;
-      const int ca = chain_col(type, flip, a), cb = chain_col(type, 1 - flip, b);
-      if (ca < 0 || cb < 0) continue;
+      const int ca = chain_col(type, flip, a);
+      if (ca < 0) continue;
       const long n = A.T.n[type], f = A.fac[t];
       const int M = chain_rows(type), C = chain_cols(type);
       const double* J = A.T.J[type];
-      for (int q = 0; q < M; ++q) s += J[(long)(q * C + ca) * n + f] * J[(long)(q * C + cb) * n + f];
+      chain_load_col(va, J, M, C, ca, n, f);
+#pragma unroll
+      for (int b = 0; b < VUS_ASM_MAXD; ++b) {
+        if (b >= D) continue;
+        const int cb = chain_col(type, 1 - flip, b);
+        if (cb >= 0) acc[b] += chain_dot_col(va, J, M, C, cb, n, f);
+      }
     }
     const PairDst d = A.dst[grp];
-    if (d.transposed) A.Hval[d.off + (long)b * d.ld + a] = s;
-    else A.Hval[d.off + (long)a * d.ld + b] = s;
-    if (d.moff >= 0) A.Hval[d.moff + (long)b * d.mld + a] = s;
+#pragma unroll
+    for (int b = 0; b < VUS_ASM_MAXD; ++b) {
+      if (b >= D) continue;
+      if (d.transposed) A.Hval[d.off + (long)b * d.ld + a] = acc[b];
+      else A.Hval[d.off + (long)a * d.ld + b] = acc[b];
+      if (d.moff >= 0) A.Hval[d.moff + (long)b * d.mld + a] = acc[b];
+    }
   }
 };
+
+#ifndef VUS_EMU
+namespace rt {     // 32 * D <= 288 threads per CTA: room for the register-resident column and accumulators
+template <> struct CoopBounds<NodeAsmBody> { static constexpr int kMaxThreads = 32 * VUS_ASM_MAXD, kMinBlocks = 2; };
+template <> struct CoopBounds<PairAsmBody> { static constexpr int kMaxThreads = 32 * VUS_ASM_MAXD, kMinBlocks = 2; };
+}  // namespace rt
+#endif
 
 // shared-bias block: Hbb = sum_f Jb^T Jb (36) and gb = -sum_f Jb^T r (6) over ALL imu factors -- every factor hits the
 // same 42 addresses, so this is a two-stage block reduction instead of atomics.  partials [grid][42]
@@ -443,6 +485,7 @@ struct SchurArgs {
   const double* C; const double* gl; // undamped landmark blocks [9][nl], [3][nl]
   double* Cinv;                      // [9][nl]  (C + lambda I)^-1
   const double* E;                   // [n][18]  E_o = Jp^T Jl (6x3 row-major)
+  double* W;                         // [n][18]  W_o = E_o Cinv_l (per lambda, SchurWBody)
   double lambda;
   int D, k, B;
   int ld; long bs;                   // row / block stride of the padded supernode tiles
@@ -490,6 +533,7 @@ struct SchurPartnerBody {
 // roofline).  History: a thread per block ENTRY with partial blocks in shared memory was bound by L1 sector throughput
 // (516 M sectors per launch, profiles/r1_ncu_schur_c3.txt); a thread per half block (round 1) by latency.
 // The dj = 0 items also reduce the gradient  gs_i -= sum_o W_o gl_l.
+struct alignas(16) Pair2 { double x, y; };       // 16-byte load of two neighbouring doubles (LDG.128)
 struct SchurBlockBody {
   static VUS_DEV void run(const SchurArgs& A, long w) {
     const int r = (int)(w % 6);
@@ -505,22 +549,22 @@ struct SchurBlockBody {
       if (t + 1 < t1) qn = A.partner[(long)(t + 1) * A.ndj + dj];
       if (q < 0 && dj != 0) continue;
       const long o = A.pose_obs[t];
-      const long l = A.idx[A.n + o];
-      const double* er = A.E + o * 18 + r * 3;
-      const double e0 = er[0], e1 = er[1], e2 = er[2];
-      const double* ci = A.Cinv + l;
-      const long nl = A.nl;
-      const double w0 = e0 * ci[0] + e1 * ci[3 * nl] + e2 * ci[6 * nl];
-      const double w1 = e0 * ci[nl] + e1 * ci[4 * nl] + e2 * ci[7 * nl];
-      const double w2 = e0 * ci[2 * nl] + e1 * ci[5 * nl] + e2 * ci[8 * nl];
+      const double* wr = A.W + o * 18 + r * 3;                         // row r of W_o = E_o Cinv_l (SchurWBody)
+      const double w0 = wr[0], w1 = wr[1], w2 = wr[2];
       if (dj == 0) {
+        const long l = A.idx[A.n + o], nl = A.nl;
         gacc += w0 * A.gl[l] + w1 * A.gl[nl + l] + w2 * A.gl[2 * nl + l];
         if (q < 0) continue;                           // long track: only the gradient is reduced here (LongSchur*Body)
       }
       any = true;
-      const double* eq = A.E + (long)q * 18;
-#pragma unroll
-      for (int sc = 0; sc < 6; ++sc) acc[sc] += w0 * eq[sc * 3] + w1 * eq[sc * 3 + 1] + w2 * eq[sc * 3 + 2];
+      const Pair2* eq = reinterpret_cast<const Pair2*>(A.E + (long)q * 18);   // 144-byte records: 16-byte aligned
+      const Pair2 v0 = eq[0], v1 = eq[1], v2 = eq[2], v3 = eq[3], v4 = eq[4], v5 = eq[5], v6 = eq[6], v7 = eq[7], v8 = eq[8];
+      acc[0] += w0 * v0.x + w1 * v0.y + w2 * v1.x;
+      acc[1] += w0 * v1.y + w1 * v2.x + w2 * v2.y;
+      acc[2] += w0 * v3.x + w1 * v3.y + w2 * v4.x;
+      acc[3] += w0 * v4.y + w1 * v5.x + w2 * v5.y;
+      acc[4] += w0 * v6.x + w1 * v6.y + w2 * v7.x;
+      acc[5] += w0 * v7.y + w1 * v8.x + w2 * v8.y;
     }
     const int D = A.D, k = A.k, B = A.ld;
     if (dj == 0) A.gs[i * D + r] -= gacc;
@@ -533,6 +577,22 @@ struct SchurBlockBody {
       blk[(long)(ri * D + r) * B + rj * D + sc] -= acc[sc];
       if (J == I && dj) blk[(long)(rj * D + sc) * B + ri * D + r] -= acc[sc];
     }
+  }
+};
+// per lambda, work item (observation o, row r): row r of W_o = E_o (C_l + lambda I)^-1, stored like E ([n][18], 6 x 3 row-major).
+// SchurBlockBody reads a row of W for every (pose offset, row) instead of rebuilding it from E_o and the nine Cinv entries.
+struct SchurWBody {
+  static VUS_DEV void run(const SchurArgs& A, long w) {
+    const long o = w / 6;
+    const int r = (int)(w - o * 6);
+    const long l = A.idx[A.n + o], nl = A.nl;
+    const double* er = A.E + o * 18 + r * 3;
+    const double e0 = er[0], e1 = er[1], e2 = er[2];
+    const double* ci = A.Cinv + l;
+    double* wr = A.W + o * 18 + r * 3;
+    wr[0] = e0 * ci[0] + e1 * ci[3 * nl] + e2 * ci[6 * nl];
+    wr[1] = e0 * ci[nl] + e1 * ci[4 * nl] + e2 * ci[7 * nl];
+    wr[2] = e0 * ci[2 * nl] + e1 * ci[5 * nl] + e2 * ci[8 * nl];
   }
 };
 struct LmInvertBody {    // per landmark
