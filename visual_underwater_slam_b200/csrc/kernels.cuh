@@ -485,7 +485,6 @@ struct SchurArgs {
   const double* C; const double* gl; // undamped landmark blocks [9][nl], [3][nl]
   double* Cinv;                      // [9][nl]  (C + lambda I)^-1
   const double* E;                   // [n][18]  E_o = Jp^T Jl (6x3 row-major)
-  double* W;                         // [n][18]  W_o = E_o Cinv_l (per lambda, SchurWBody)
   double lambda;
   int D, k, B;
   int ld; long bs;                   // row / block stride of the padded supernode tiles
@@ -533,7 +532,6 @@ struct SchurPartnerBody {
 // roofline).  History: a thread per block ENTRY with partial blocks in shared memory was bound by L1 sector throughput
 // (516 M sectors per launch, profiles/r1_ncu_schur_c3.txt); a thread per half block (round 1) by latency.
 // The dj = 0 items also reduce the gradient  gs_i -= sum_o W_o gl_l.
-struct alignas(16) Pair2 { double x, y; };       // 16-byte load of two neighbouring doubles (LDG.128)
 struct SchurBlockBody {
   static VUS_DEV void run(const SchurArgs& A, long w) {
     const int r = (int)(w % 6);
@@ -549,22 +547,22 @@ struct SchurBlockBody {
       if (t + 1 < t1) qn = A.partner[(long)(t + 1) * A.ndj + dj];
       if (q < 0 && dj != 0) continue;
       const long o = A.pose_obs[t];
-      const double* wr = A.W + o * 18 + r * 3;                         // row r of W_o = E_o Cinv_l (SchurWBody)
-      const double w0 = wr[0], w1 = wr[1], w2 = wr[2];
+      const long l = A.idx[A.n + o];
+      const double* er = A.E + o * 18 + r * 3;
+      const double e0 = er[0], e1 = er[1], e2 = er[2];
+      const double* ci = A.Cinv + l;
+      const long nl = A.nl;
+      const double w0 = e0 * ci[0] + e1 * ci[3 * nl] + e2 * ci[6 * nl];
+      const double w1 = e0 * ci[nl] + e1 * ci[4 * nl] + e2 * ci[7 * nl];
+      const double w2 = e0 * ci[2 * nl] + e1 * ci[5 * nl] + e2 * ci[8 * nl];
       if (dj == 0) {
-        const long l = A.idx[A.n + o], nl = A.nl;
         gacc += w0 * A.gl[l] + w1 * A.gl[nl + l] + w2 * A.gl[2 * nl + l];
         if (q < 0) continue;                           // long track: only the gradient is reduced here (LongSchur*Body)
       }
       any = true;
-      const Pair2* eq = reinterpret_cast<const Pair2*>(A.E + (long)q * 18);   // 144-byte records: 16-byte aligned
-      const Pair2 v0 = eq[0], v1 = eq[1], v2 = eq[2], v3 = eq[3], v4 = eq[4], v5 = eq[5], v6 = eq[6], v7 = eq[7], v8 = eq[8];
-      acc[0] += w0 * v0.x + w1 * v0.y + w2 * v1.x;
-      acc[1] += w0 * v1.y + w1 * v2.x + w2 * v2.y;
-      acc[2] += w0 * v3.x + w1 * v3.y + w2 * v4.x;
-      acc[3] += w0 * v4.y + w1 * v5.x + w2 * v5.y;
-      acc[4] += w0 * v6.x + w1 * v6.y + w2 * v7.x;
-      acc[5] += w0 * v7.y + w1 * v8.x + w2 * v8.y;
+      const double* eq = A.E + (long)q * 18;
+#pragma unroll
+      for (int sc = 0; sc < 6; ++sc) acc[sc] += w0 * eq[sc * 3] + w1 * eq[sc * 3 + 1] + w2 * eq[sc * 3 + 2];
     }
     const int D = A.D, k = A.k, B = A.ld;
     if (dj == 0) A.gs[i * D + r] -= gacc;
@@ -577,22 +575,6 @@ struct SchurBlockBody {
       blk[(long)(ri * D + r) * B + rj * D + sc] -= acc[sc];
       if (J == I && dj) blk[(long)(rj * D + sc) * B + ri * D + r] -= acc[sc];
     }
-  }
-};
-// per lambda, work item (observation o, row r): row r of W_o = E_o (C_l + lambda I)^-1, stored like E ([n][18], 6 x 3 row-major).
-// SchurBlockBody reads a row of W for every (pose offset, row) instead of rebuilding it from E_o and the nine Cinv entries.
-struct SchurWBody {
-  static VUS_DEV void run(const SchurArgs& A, long w) {
-    const long o = w / 6;
-    const int r = (int)(w - o * 6);
-    const long l = A.idx[A.n + o], nl = A.nl;
-    const double* er = A.E + o * 18 + r * 3;
-    const double e0 = er[0], e1 = er[1], e2 = er[2];
-    const double* ci = A.Cinv + l;
-    double* wr = A.W + o * 18 + r * 3;
-    wr[0] = e0 * ci[0] + e1 * ci[3 * nl] + e2 * ci[6 * nl];
-    wr[1] = e0 * ci[nl] + e1 * ci[4 * nl] + e2 * ci[7 * nl];
-    wr[2] = e0 * ci[2 * nl] + e1 * ci[5 * nl] + e2 * ci[8 * nl];
   }
 };
 struct LmInvertBody {    // per landmark

@@ -243,7 +243,7 @@ struct vus_handle {
   DBuf<int> partner;
   double last_rel_res = 0.0;     // true relative residual ||rhs - A x|| / ||rhs|| at the end of the last pcg()
   bool z0_valid = false;         // column 6 of Z holds M^-1 gs (band part of the first preconditioner application)
-  DBuf<double> C, gl, Cinv, E, Wo, Pp, Pl;
+  DBuf<double> C, gl, Cinv, E, Pp, Pl;
   // BCR
   DBuf<double> Dw, U1, U2, Dinv, Gl, Gr, Z, Zr, SbInv;
   // chunked band factorization (chunk.cuh): P chunks + the separator system, which is the one the cyclic reduction then factors.
@@ -847,7 +847,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
   // zero-filled once: the assembly kernels store every entry a factor can touch, nothing else ever writes the rest
   h->H0.zero(st); h->g0.zero(st); h->F.zero(st);
   h->Hbb0.alloc(36 * std::max<long>(NB, 1)); h->Hbb.alloc(36 * std::max<long>(NB, 1)); h->gb.alloc(6 * std::max<long>(NB, 1));
-  h->C.alloc(9 * NL); h->gl.alloc(3 * NL); h->Cinv.alloc(9 * NL); h->E.alloc(18 * FS.n); h->Wo.alloc(18 * FS.n); h->Pp.alloc(28 * FS.n); h->Pl.alloc(12 * FS.n);
+  h->C.alloc(9 * NL); h->gl.alloc(3 * NL); h->Cinv.alloc(9 * NL); h->E.alloc(18 * FS.n); h->Pp.alloc(28 * FS.n); h->Pl.alloc(12 * FS.n);
   {   // the reduction's own blocks are padded [KP][LD] tiles; the padding must be (and stays) zero
     // Stereo-scale supernodes on one long chain: block Cholesky inside P chunks (one per SM), cyclic reduction across the
     // P - 1 separators only (chunk.cuh).  Tiny supernodes (chain graphs), batched and partitioned graphs keep the plain reduction.
@@ -971,7 +971,7 @@ void assemble_base(vus_handle* h, rt::stream_t st) {
 SchurArgs schur_args(vus_handle* h, double lambda) {
   FactorTable& S = h->ft[VUS_F_STEREO];
   SchurArgs a;
-  a.n = S.n; a.nl = h->nvar[3]; a.idx = S.idx.p; a.C = h->C.p; a.gl = h->gl.p; a.Cinv = h->Cinv.p; a.E = h->E.p; a.W = h->Wo.p;
+  a.n = S.n; a.nl = h->nvar[3]; a.idx = S.idx.p; a.C = h->C.p; a.gl = h->gl.p; a.Cinv = h->Cinv.p; a.E = h->E.p;
   a.lambda = lambda; a.D = h->D; a.k = h->k; a.B = h->B; a.ld = bcr_ld(h->B); a.bs = bcr_bbp(h->B);
   a.SD = h->H.p + h->sd_off; a.SU = h->H.p + h->su_off; a.gs = h->gs.p;
   a.pose_ptr = h->pose_ptr.p; a.pose_obs = h->pose_obs.p; a.pose_ids = h->pose_ids.p; a.nposes_obs = h->nposes_obs;
@@ -995,7 +995,6 @@ void form_system(vus_handle* h, double lambda, rt::stream_t st) {
   if (h->nobs) {
     SchurArgs a = schur_args(h, lambda);
     L_elem<LmInvertBody>(a.nl, st, a);
-    L_elem<SchurWBody>(6 * a.n, st, a);
     L_elem<SchurBlockBody>(6 * h->nposes_obs * h->schur_ndj, st, a);
   }
 }
