@@ -146,6 +146,15 @@ enum vus_comm_op { VUS_COMM_ALLREDUCE_SUM = 0, VUS_COMM_HALO = 1 };
 typedef int (*vus_comm_fn)(void* ctx, int op, void* buf, int64_t count);
 int vus_set_partition(vus_handle* h, int64_t n_owned_nodes, const int64_t n_owned_factors[6]);
 int vus_set_comm(vus_handle* h, vus_comm_fn fn, void* ctx);
+/* Where this rank sits in the chain of pose ranges (rank r owns the poses right after rank r - 1's): prev_local[j] / next_local[j],
+ * j < nside, are the LOCAL indices of the halo poses that are the (j + 1)-th pose before its first / after its last owned pose
+ * globally (-1: not in the halo or beyond the ends of the chain); nside >= the supernode width the analysis will find (16 always
+ * is).  With it the per-rank band factorizations are tied together exactly (a partitioned solve over the rank interfaces: one
+ * extra all-reduce of 12 k nranks doubles per preconditioner application, csrc/spike.cuh), so the partitioned PCG takes the
+ * iterations of the one-rank solve; without it -- or when a rank's owned range is not a whole number of supernodes -- the band
+ * preconditioner is block-Jacobi across ranks.  Call before vus_analyze, on every rank.  Replaces nothing in the reference:
+ * gtsam runs batch.py:337 in one process. */
+int vus_set_partition_chain(vus_handle* h, int32_t nside, const int64_t* prev_local, const int64_t* next_local, int32_t rank, int32_t nranks);
 /* stream_ordered = 1: the callback enqueues its collective ON THE STREAM passed to vus_optimize (NCCL through torch.distributed
  * with that stream current) and returns without waiting; the library then neither synchronises before the call nor expects
  * the result on the host -- the stream orders everything.  0 (default): host-synchronous callbacks (gloo, the CPU tests). */

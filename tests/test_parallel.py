@@ -171,3 +171,34 @@ def test_partitioned_two_rank_gloo_matches_one_rank(tmp_path):
     p1, p2 = np.load(one), np.load(two)
     assert p1.shape == p2.shape == (240, 12)
     assert np.abs(p1[:, 9:] - p2[:, 9:]).max() < 1e-6 and np.abs(p1[:, :9] - p2[:, :9]).max() < 1e-6
+
+
+def test_partitioned_ranks_share_one_exact_band(tmp_path):
+    """A long chain with few loop closures over 4 ranks: the per-rank band factorizations are tied together exactly
+    (vus_set_partition_chain, csrc/spike.cuh), so the partitioned solve takes the one-rank LM path with (nearly) the one-rank
+    PCG iteration count and ends on the same poses.  With block-Jacobi across ranks the same graph needs 4 x the PCG
+    iterations, fails a damped solve and ends 1.6e-5 away (measured before the scheme existed)."""
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "visual_underwater_slam_b200", "csrc"), "emu"], check=True)
+    import json
+    one, four = tmp_path / "q1.npy", tmp_path / "q4.npy"
+    _run_part(1, 1200, 3, one, tmp_path)
+    _run_part(4, 1200, 3, four, tmp_path)
+    m1, m4 = json.load(open(str(one) + ".json")), json.load(open(str(four) + ".json"))
+    assert m1["iterations"] == m4["iterations"] and m1["tries"] == m4["tries"]
+    assert m4["pcg"] <= 1.1 * m1["pcg"] + 8, (m1["pcg"], m4["pcg"])
+    assert abs(m1["final_error"] - m4["final_error"]) <= 1e-9 * m1["final_error"]
+    p1, p4 = np.load(one), np.load(four)
+    assert np.abs(p1 - p4).max() < 1e-8
+
+
+def test_pose_range_is_aligned_and_covers_everything():
+    for n in (10, 100, 1200, 4001):
+        for world in (1, 2, 3, 8):
+            spans = [parallel.pose_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[r][1] == spans[r + 1][0] for r in range(world - 1))
+            if -(-n // parallel.CHAIN_SIDE) >= 2 * world:
+                assert all(b % parallel.CHAIN_SIDE == 0 for _, b in spans[:-1])
+            for t in range(0, n, 7):
+                r = parallel.pose_owner(t, n, world)
+                assert spans[r][0] <= t < spans[r][1]

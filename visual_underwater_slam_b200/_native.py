@@ -68,6 +68,7 @@ EXPORTS = {
     "vus_set_lm_params": (C.c_int, [C.c_void_p, C.POINTER(LmParams)]),
     "vus_set_gtsam_build": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "vus_set_partition": (C.c_int, [C.c_void_p, C.c_int64, c_i64_p]),
+    "vus_set_partition_chain": (C.c_int, [C.c_void_p, C.c_int32, c_i64_p, c_i64_p, C.c_int32, C.c_int32]),
     "vus_set_comm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vus_set_comm_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "vus_nccl_unique_id": (C.c_int, [C.c_void_p]),

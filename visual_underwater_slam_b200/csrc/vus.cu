@@ -7,6 +7,7 @@
 #include "rt.h"
 #include "kernels.cuh"
 #include "chunk.cuh"
+#include "spike.cuh"
 #include "frontend.cuh"
 #include <algorithm>
 #include <chrono>
@@ -272,6 +273,12 @@ struct vus_handle {
   DBuf<double> halo_sendbuf;
   long halo_nsend = 0;
   bool comm_stream_ordered = false;   // the callback enqueues its collective on the stream the library runs on: no host sync around it
+  // exact band across ranks (spike.cuh): chain position of this rank and the halo nodes that continue the chain
+  int sp_rank = 0, sp_nranks = 1;
+  std::vector<long> sp_prev, sp_next; // local index of the j-th pose before the first / after the last owned pose (-1: none)
+  int spike_state = 0;                // 0 undecided, 1 on (every rank can), -1 off (block-Jacobi across ranks)
+  DBuf<PairDst> spPairs;              // [2][k][k] coupling blocks to the next / previous rank
+  DBuf<double> spZ, spG, spR, spRinv, spY, spCoef;
   // batched mode: independent components (trajectories) in one block-diagonal system (batch.cuh)
   int ncomp = 1;
   long bcr_stop = 1L << 62;      // cyclic reduction needs no stride beyond the longest component (in supernodes)
@@ -717,7 +724,12 @@ int analyze(vus_handle* h, rt::stream_t st) {
   // spans up to kcap widen the band; longer links (loop closures, very long tracks) stay in the off-band remainder.
   // NOTE: the band is only guaranteed positive definite when every landmark track fits in it (the Schur complement
   // subtracts from the blocks it touches); tracks longer than kcap poses degrade the preconditioner.
-  auto consider = [&](long p, long q) { long s = p > q ? p - q : q - p; if (s <= kcap && s > span) span = s; };
+  // (a rank of a partitioned graph: owned poses only -- the local index distance to a halo pose means nothing, and the couplings
+  // to the neighbouring ranks' poses are tied in by spike.cuh)
+  auto consider = [&](long p, long q) {
+    if (h->n_owned >= 0 && (p >= h->n_owned || q >= h->n_owned)) return;
+    long s = p > q ? p - q : q - p; if (s <= kcap && s > span) span = s;
+  };
   for (long f = 0; f < FB.n; ++f) consider(FB.h_idx[f], FB.h_idx[FB.n + f]);
   for (long f = 0; f < FI.n; ++f) consider(FI.h_idx[f], FI.h_idx[2 * FI.n + f]);
   for (long l = 0; l < NL; ++l) {
@@ -837,6 +849,23 @@ int analyze(vus_handle* h, rt::stream_t st) {
     h->pg_ptr.upload(gptr, st); h->pg_code.upload(gcode, st); h->pg_fac.upload(gfac, st); h->pg_dst.upload(gdst, st);
   }
   tick("chain-factor gather lists");
+  // ---- pose-range partition: the blocks that couple the owned chain to the neighbouring ranks (spike.cuh)
+  h->spike_state = 0;
+  if (h->n_owned >= 2 * k && h->sp_nranks > 1 && (long)h->sp_prev.size() >= k && (long)h->sp_next.size() >= k) {
+    std::vector<PairDst> pairs((size_t)2 * k * k);
+    for (auto& d : pairs) { d.off = -1; d.moff = -1; d.ld = d.mld = d.transposed = d.pad = 0; }
+    auto coupled = [&](long p, long q) { return q >= 0 && q < NX && (inband(p, q) || rem_index.count({p, q}) > 0); };
+    for (int p = 0; p < k; ++p)
+      for (int j = 0; j < k; ++j) {
+        const long last_p = h->n_owned - k + p, nxt = h->sp_next[j];           // next pose j: global b + j
+        if (coupled(last_p, nxt)) pairs[(size_t)p * k + j] = band_dst(h, last_p, nxt, rem_index);
+        const long prv = h->sp_prev[k - 1 - j];                                 // previous pose j: global a - k + j
+        if (coupled(p, prv)) pairs[(size_t)(k + p) * k + j] = band_dst(h, p, prv, rem_index);
+      }
+    h->spPairs.upload(pairs, st);
+  } else if (h->sp_nranks > 1) {
+    h->spike_state = -2;                                  // cannot here: says so in the first set-up's all-reduce
+  }
   // ---- uploads / allocations
   h->rem_ptr.upload(rem_ptr, st); h->rem_col.upload(rem_col, st);
   h->pose_ptr.upload(pose_ptr, st); if (!pose_obs_on_device) h->pose_obs.upload(pose_obs, st); h->pose_ids.upload(pose_ids, st);
@@ -1194,12 +1223,16 @@ void apply_band(vus_handle* h, double* Y, long ystride, const double* X, long xs
   L_coop<BandMatvecBody>((int)h->Ns_band, 256, smem, st, a);
 }
 
+bool spike_enabled(vus_handle* h, rt::stream_t st);
+void spike_setup(vus_handle* h, rt::stream_t st);
+void spike_apply(vus_handle* h, double* z, rt::stream_t st);
 // preconditioner set-up for the current damped system: BCR of the band, Z = M^-1 F, Sb^-1
 // with_rhs: the band solve of the right-hand side gs rides along as a seventh vector (the DMMA panel is 8 wide, so it
 // costs nothing): the first preconditioner application of the PCG that follows takes it from there.
 void precond_setup(vus_handle* h, rt::stream_t st, bool with_rhs = false) {
   bcr_factor(h, st);
   h->z0_valid = false;
+  if (spike_enabled(h, st)) spike_setup(h, st);
   if (h->has_bias) {
     BorderColsArgs c; c.F = h->F.p; c.Z = h->Z.p; c.len = h->Lc; c.zstride = h->Lc; c.R = h->Zr.p;
     L_elem<BorderColsBody>(h->Lc * 6, st, c);
@@ -1228,6 +1261,65 @@ void precond_setup(vus_handle* h, rt::stream_t st, bool with_rhs = false) {
   }
 }
 
+// ---- exact band across the ranks of a pose-range partition (spike.cuh)
+SpikeArgs spike_args(vus_handle* h) {
+  SpikeArgs a;
+  a.P = h->sp_nranks; a.rank = h->sp_rank; a.k = h->k; a.K = 6 * h->k; a.Ls = h->Ns_band * h->B; a.n_owned = h->n_owned;
+  a.pairs = h->spPairs.p; a.Hval = h->H.p;
+  a.Z = h->spZ.p; a.G = h->spG.p; a.R = h->spR.p; a.Rinv = h->spRinv.p; a.Y = h->spY.p; a.coef = h->spCoef.p;
+  a.z = nullptr; a.fail = h->fail.p;
+  return a;
+}
+// Every rank must take part in the collectives or none, with the same supernode width: the first set-up all-reduces
+// (cannot, k, k^2) and the scheme is on only if nobody said "cannot" and every rank has the same k.
+bool spike_enabled(vus_handle* h, rt::stream_t st) {
+  if (h->n_owned < 0 || h->sp_nranks <= 1 || !has_comm(h)) return false;
+  if (h->spike_state == 0 || h->spike_state == -2) {
+    const int P = h->sp_nranks, K = 6 * h->k;
+    // a rank whose owned range is not a whole number of supernodes shares its last supernode with a halo pose
+    const bool can = h->spike_state == 0 && h->D == 6 && !h->has_bias && h->B <= VUS_SMALLB_MAX && h->ncomp <= 1 && 2 * K * P <= 384 &&
+                     (h->n_owned % h->k == 0 || h->sp_rank == P - 1);
+    double v[3] = {can ? 0.0 : 1.0, (double)h->k, (double)h->k * h->k};
+    h->spCoef.alloc(std::max(3, 2 * K));
+    rt::h2d(h->spCoef.p, v, sizeof v, st);
+    comm_call(h, VUS_COMM_ALLREDUCE_SUM, h->spCoef.p, 3, st);
+    rt::d2h(v, h->spCoef.p, sizeof v, st);
+    rt::sync(st);
+    const bool same_k = std::fabs(P * v[2] - v[1] * v[1]) < 0.5;
+    h->spike_state = (v[0] > 0.0 || !same_k) ? -1 : 1;
+    if (h->spike_state == 1) {
+      const size_t n = (size_t)2 * K * P;
+      h->spZ.alloc((size_t)2 * K * h->Ns_band * h->B); h->spG.alloc((size_t)P * 4 * K * K); h->spR.alloc(n * n); h->spRinv.alloc(n * n);
+      h->spY.alloc(n);
+    }
+    if (h->prm.verbose) std::fprintf(stderr, "pose-range partition: band tied across %d ranks exactly: %s\n", P, h->spike_state == 1 ? "yes" : "no (block-Jacobi)");
+  }
+  return h->spike_state == 1;
+}
+void spike_setup(vus_handle* h, rt::stream_t st) {
+  ClassGuard kc_guard(KC_BORDER);
+  SpikeArgs a = spike_args(h);
+  const int K = a.K;
+  h->spZ.zero(st);
+  L_elem<SpikeRhsBody>((long)2 * K * K, st, a);
+  for (int c = 0; c < 2 * K; c += VUS_SMALLB_MAXV)
+    bcr_solve(h, h->spZ.p + (long)c * a.Ls, a.Ls, std::min(VUS_SMALLB_MAXV, 2 * K - c), st);
+  h->spG.zero(st);
+  L_elem<SpikeGatherBody>((long)4 * K * K, st, a);
+  comm_call(h, VUS_COMM_ALLREDUCE_SUM, h->spG.p, (long)a.P * 4 * K * K, st);
+  L_coop<SpikeInvertBody>(1, 256, (size_t)(2 * K * a.P + 2) * sizeof(double), st, a);
+}
+void spike_apply(vus_handle* h, double* z, rt::stream_t st) {
+  ClassGuard kc_guard(KC_BORDER);
+  SpikeArgs a = spike_args(h);
+  a.z = z;
+  h->spY.zero(st);
+  L_elem<SpikeYBody>(2 * a.K, st, a);
+  comm_call(h, VUS_COMM_ALLREDUCE_SUM, h->spY.p, (long)2 * a.K * a.P, st);
+  L_elem<SpikeCoefBody>(2 * a.K, st, a);
+  L_elem<SpikeCorrBody>(h->n_owned * 6, st, a);
+}
+
 // z = P^-1 r  (z and r are full vectors of length L)
 void precond_apply(vus_handle* h, double* z, const double* r, rt::stream_t st) {
   if (h->z0_valid) {                                   // r is gs: its band solve was done with the border columns
@@ -1237,6 +1329,7 @@ void precond_apply(vus_handle* h, double* z, const double* r, rt::stream_t st) {
   } else {
     rt::d2d(z, r, h->L * sizeof(double), st);
     bcr_solve(h, z, h->Lc, 1, st);
+    if (h->spike_state == 1) spike_apply(h, z, st);
   }
   if (h->has_bias) {
     border_dot(h, z, h->Lc, 1, st);
@@ -2197,6 +2290,15 @@ int vus_set_partition(vus_handle* h, int64_t n_owned_nodes, const int64_t n_owne
   if (!h || n_owned_nodes < 0 || !n_owned_factors) return fail(h, VUS_ERR_INVALID, "vus_set_partition: bad arguments");
   h->n_owned = n_owned_nodes;
   for (int t = 0; t < VUS_F_NTYPES; ++t) h->nf_owned[t] = n_owned_factors[t];
+  h->analyzed = false;
+  return VUS_OK;
+}
+
+int vus_set_partition_chain(vus_handle* h, int32_t nside, const int64_t* prev_local, const int64_t* next_local, int32_t rank, int32_t nranks) {
+  if (!h || nside < 0 || (nside > 0 && (!prev_local || !next_local)) || rank < 0 || nranks < 1 || rank >= nranks)
+    return fail(h, VUS_ERR_INVALID, "vus_set_partition_chain: bad arguments");
+  h->sp_prev.assign(prev_local, prev_local + nside); h->sp_next.assign(next_local, next_local + nside);
+  h->sp_rank = rank; h->sp_nranks = nranks;
   h->analyzed = false;
   return VUS_OK;
 }

@@ -125,6 +125,11 @@ class Session:
             if partition is not None:                   # (n_owned_nodes, [owned factors per type]) -- parallel.py
                 nf = (C.c_int64 * 6)(*[int(x) for x in partition[1]])
                 self._check(self.lib.vus_set_partition(self._h, int(partition[0]), nf))
+                if len(partition) > 2 and partition[2] is not None:   # (prev_local[16], next_local[16], rank, nranks): chain position
+                    pl, nl_, rk, nr = partition[2]
+                    pl = np.ascontiguousarray(pl, dtype=np.int64); nl_ = np.ascontiguousarray(nl_, dtype=np.int64)
+                    self._check(self.lib.vus_set_partition_chain(self._h, len(pl), pl.ctypes.data_as(_native.c_i64_p),
+                                                                 nl_.ctypes.data_as(_native.c_i64_p), int(rk), int(nr)))
             if comm is not None:                        # a _native.COMM_FN instance (kept alive by the caller and here)
                 self._comm = comm
                 self._check(self.lib.vus_set_comm(self._h, C.cast(comm, C.c_void_p), None))

@@ -32,6 +32,28 @@ def shard_range(n_items, rank, world):
     return first, first + base + (1 if rank < extra else 0)
 
 
+CHAIN_SIDE = 16      # poses either side of a rank's range handed to vus_set_partition_chain (>= the widest supernode of a pose graph)
+
+
+def pose_range(n_poses, rank, world):
+    """Pose range of `rank` in a pose-range partition: shard_range in units of CHAIN_SIDE poses, so that every rank but the
+    last owns a whole number of supernodes whatever width (1, 2, 4, 8 or 16 poses) the analysis finds -- the condition for
+    tying the per-rank band factorizations together exactly (csrc/spike.cuh).  Short graphs fall back to shard_range."""
+    nb = -(-int(n_poses) // CHAIN_SIDE)
+    if nb < 2 * world:
+        return shard_range(n_poses, rank, world)
+    a, b = shard_range(nb, rank, world)
+    return min(a * CHAIN_SIDE, n_poses), min(b * CHAIN_SIDE, n_poses)
+
+
+def pose_owner(pose, n_poses, world):
+    """Inverse of pose_range."""
+    nb = -(-int(n_poses) // CHAIN_SIDE)
+    if nb < 2 * world:
+        return owner_of(pose, n_poses, world)
+    return owner_of(pose // CHAIN_SIDE, nb, world)
+
+
 def owner_of(item, n_items, world):
     """Inverse of shard_range."""
     base, extra = divmod(int(n_items), int(world))
@@ -198,7 +220,7 @@ def solve_sharded(make_problem, n_trajectories, params=None, lib=None, device=0,
 def partition_pose_graph(prob, world):
     """Split a packed pose-graph problem (poses, prior_pose, between only) into `world` local problems.
 
-    Rank r owns poses shard_range(n, r, world).  Its local graph holds every factor touching an owned pose; a factor is
+    Rank r owns poses pose_range(n, r, world).  Its local graph holds every factor touching an owned pose; a factor is
     OWNED by the rank of its lowest pose (its error is counted there), the other copy is a duplicate.  Local pose order
     is [owned (ascending) | halo (ascending global index)]; owned factors come first in every table.
     -> list over ranks of dict(prob, n_owned, nf_owned, owned (first, last), halo_global [nh], send {peer: local idx},
@@ -212,7 +234,7 @@ def partition_pose_graph(prob, world):
     lo = np.minimum(x1, x2)
     parts = []
     for r in range(world):
-        a, b = shard_range(n, r, world)
+        a, b = pose_range(n, r, world)
         in1, in2 = (x1 >= a) & (x1 < b), (x2 >= a) & (x2 < b)
         sel = np.nonzero(in1 | in2)[0]
         mine = (lo[sel] >= a) & (lo[sel] < b)
@@ -238,11 +260,15 @@ def partition_pose_graph(prob, world):
         lp["prior_pose"] = dict(meas=np.ascontiguousarray(pp["meas"][selp]), sqrt_info=np.ascontiguousarray(pp["sqrt_info"][selp]),
                                 orig=np.arange(len(selp), dtype=np.int64), x=loc[xp[selp]].astype(np.int32))
         lp["n_factors"] = len(selp) + len(sel)
+        # the halo poses that continue the chain on either side (vus_set_partition_chain): local index or -1
+        prev_local = [int(loc[a - 1 - j]) if a - 1 - j >= 0 else -1 for j in range(CHAIN_SIDE)]
+        next_local = [int(loc[b + j]) if b + j < n else -1 for j in range(CHAIN_SIDE)]
         parts.append(dict(prob=lp, n_owned=b - a, nf_owned=[len(selp), 0, n_own_b, 0, 0, 0], owned=(a, b), halo_global=halo,
-                          global_factor_index=dict(prior_pose=selp, between=sel), n_own_between=n_own_b))
+                          global_factor_index=dict(prior_pose=selp, between=sel), n_own_between=n_own_b,
+                          chain=(prev_local, next_local, r, world)))
     for r, P in enumerate(parts):                                       # halo lists: who sends what to whom
         P["recv"], P["send"] = {}, {}
-        owners = np.array([owner_of(int(g), n, world) for g in P["halo_global"]], np.int64) if len(P["halo_global"]) else np.zeros(0, np.int64)
+        owners = np.array([pose_owner(int(g), n, world) for g in P["halo_global"]], np.int64) if len(P["halo_global"]) else np.zeros(0, np.int64)
         for s_ in range(world):
             idx = np.nonzero(owners == s_)[0]
             if len(idx):
@@ -260,7 +286,7 @@ class PartitionedSolver:
     """One rank of a pose graph split by pose range.  `part` is this rank's entry of partition_pose_graph(); the process
     group must already exist (nccl on GPUs, gloo for the CPU tests)."""
 
-    def __init__(self, part, params=None, lib=None, device=0, group=None, stream_ordered=True, nccl_in_library=None):
+    def __init__(self, part, params=None, lib=None, device=0, group=None, stream_ordered=True, nccl_in_library=None, exact_band=True):
         import torch
         import torch.distributed as dist
         from . import _native
@@ -287,7 +313,8 @@ class PartitionedSolver:
             nccl_in_library = self.cuda and self.world > 1 and dist.get_backend(group) == "nccl"
         self.nccl_in_library = bool(nccl_in_library) and self.world > 1
         self.stream = torch.cuda.Stream(self.device) if (self.cuda and self.world > 1 and stream_ordered and not self.nccl_in_library) else None
-        self.session = Session(part["prob"], params, lib=lib, device=device, partition=(self.n_owned, part["nf_owned"]),
+        self.session = Session(part["prob"], params, lib=lib, device=device,
+                               partition=(self.n_owned, part["nf_owned"], part.get("chain") if (self.world > 1 and exact_band) else None),
                                comm=self._cb if (self.world > 1 and not self.nccl_in_library) else None)
         if self.nccl_in_library:
             uid = torch.zeros(128, dtype=torch.uint8)
@@ -370,7 +397,7 @@ class PartitionedSolver:
         mine = self.torch.from_numpy(np.ascontiguousarray(self.owned_poses()))
         if self.world == 1:
             return mine.numpy()
-        sizes = [shard_range(self._n_global(), r, self.world) for r in range(self.world)]
+        sizes = [pose_range(self._n_global(), r, self.world) for r in range(self.world)]
         width = max(b - a for a, b in sizes)
         send = self.torch.zeros((width, 12), dtype=self.torch.float64, device=self.device)
         send[:self.n_owned] = mine.to(self.device)
