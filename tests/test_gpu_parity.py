@@ -370,3 +370,25 @@ def test_lm_parity_manifold_build_with_exact_between(lib):
         gtsam.set_gtsam_build(**prev)
     pc.check_factor_parity(lib, prob)
     pc.check_lm_parity(lib, prob)
+
+
+def test_incremental_resolve_on_the_gpu(lib):
+    """gtsam.ISAM2.update / calculateEstimate (isam.py:341-342) through the CUDA library: after every update the estimate is
+    the LM optimum of the accumulated graph from the previous estimate, checked against the oracle from the same warm start."""
+    import visual_underwater_slam_b200 as gtsam
+    from oracle import lm
+    d, _ = pc.make(60, n_lm=40, n_loops=2, loop_min_gap=20)
+    isam = gtsam.ISAM2(lib=lib)
+    acc_graph = gtsam.NonlinearFactorGraph()
+    for G, V in pc.split_for_incremental(d, [25, 45, 60]):
+        warm = gtsam.Values(isam.calculateEstimate())
+        warm.insert(V)
+        acc_graph.push_back(G)
+        res = isam.update(G, V)
+        vals, info = lm.lm_optimize(acc_graph.to_problem(warm))
+        est = isam.calculateEstimate()
+        assert abs(res.getErrorAfter() - info["error"]) <= 1e-6 * info["error"]
+        assert np.abs(est.table("pose")[1] - vals["poses"]).max() < 1e-6
+        assert np.abs(est.table("vel")[1] - vals["vels"]).max() < 1e-6
+    c = isam.marginalCovariance(gtsam.symbol_shorthand.X(59))
+    assert c.shape == (6, 6) and np.all(np.linalg.eigvalsh(c) > 0)

@@ -2283,6 +2283,7 @@ int vus_set_gtsam_build(vus_handle* h, int tangent_preintegration, int slow_but_
 int vus_set_lm_params(vus_handle* h, const vus_lm_params* p) {
   if (!h || !p) return VUS_ERR_INVALID;
   h->prm = *p;
+  if (const char* v = std::getenv("VUS_VERBOSE")) h->prm.verbose = std::max(h->prm.verbose, std::atoi(v));   // diagnostics without touching the caller
   return VUS_OK;
 }
 
