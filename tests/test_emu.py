@@ -306,3 +306,21 @@ def test_lm_parity_manifold_build_with_exact_between(emu):
 def test_golden_configs_on_the_emulation(emu):
     """The reduced config-2 fixture through the host emulation (the full-size ones run on the GPU)."""
     pc.check_golden_config(emu, os.path.join(ROOT, "tests", "golden", "lm_c2s.npz"))
+
+
+def test_damped_system_refresh_leaves_nothing_stale(emu):
+    """form_system copies the whole base system once per graph and afterwards refreshes only the node / pair blocks and lets
+    the Schur kernel assign its blocks: solving at lambda A, then B, then A again must reproduce the first answer bit for bit,
+    and a fresh handle must give the same bits (stereo + loop closures + IMU chain: every kind of block)."""
+    from visual_underwater_slam_b200.optimizer import Session
+    _, prob = pc.make(90, n_lm=150, n_loops=3, loop_min_gap=30)
+    s = Session(prob, lib=emu)
+    a1 = s.solve_step(1e-3)
+    s.solve_step(10.0)
+    a2 = s.solve_step(1e-3)
+    s.close()
+    s = Session(prob, lib=emu)
+    a3 = s.solve_step(1e-3)
+    s.close()
+    for k in ("pose", "vel", "lm", "bias"):
+        assert np.array_equal(a1[k], a2[k]) and np.array_equal(a1[k], a3[k]), k

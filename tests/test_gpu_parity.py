@@ -392,3 +392,20 @@ def test_incremental_resolve_on_the_gpu(lib):
         assert np.abs(est.table("vel")[1] - vals["vels"]).max() < 1e-6
     c = isam.marginalCovariance(gtsam.symbol_shorthand.X(59))
     assert c.shape == (6, 6) and np.all(np.linalg.eigvalsh(c) > 0)
+
+
+def test_damped_system_refresh_leaves_nothing_stale(lib):
+    """As tests/test_emu.py: lambda A, then B, then A again reproduces the first solve bit for bit (form_system refreshes only
+    the blocks that change instead of copying the 2.3 GB base system per try), and so does a fresh handle."""
+    from visual_underwater_slam_b200.optimizer import Session
+    _, prob = pc.make(300, n_lm=600, n_loops=3, loop_min_gap=100)
+    s = Session(prob, lib=lib)
+    a1 = s.solve_step(1e-3)
+    s.solve_step(10.0)
+    a2 = s.solve_step(1e-3)
+    s.close()
+    s = Session(prob, lib=lib)
+    a3 = s.solve_step(1e-3)
+    s.close()
+    for k in ("pose", "vel", "lm", "bias"):
+        assert np.array_equal(a1[k], a2[k]) and np.array_equal(a1[k], a3[k]), k

@@ -489,6 +489,7 @@ struct SchurArgs {
   int D, k, B;
   int ld; long bs;                   // row / block stride of the padded supernode tiles
   double* SD; double* SU;            // damped system being formed (Schur complement subtracted in place)
+  const double* SD0; const double* SU0;   // the base (undamped, unreduced) system
   double* gs;                        // reduced gradient (in/out)
   const int* pose_ptr; const int* pose_obs; const int* pose_ids; long nposes_obs;
   const int* lm_ptr;
@@ -570,11 +571,36 @@ struct SchurBlockBody {
     const long I = i / k, j = i + dj, J = j / k;
     const int ri = (int)(i - I * k), rj = (int)(j - J * k);
     double* blk = (J == I ? A.SD : A.SU) + I * A.bs;
+    // dj = 0: the node's diagonal block was refreshed (base system + lambda) just before; dj >= 1: the block is ASSIGNED from the
+    // base system, so the damped system needs no full copy per lambda try (form_system: only node and pair blocks are copied)
+    const double* blk0 = (J == I ? A.SD0 : A.SU0) + I * A.bs;
 #pragma unroll
     for (int sc = 0; sc < 6; ++sc) {
-      blk[(long)(ri * D + r) * B + rj * D + sc] -= acc[sc];
-      if (J == I && dj) blk[(long)(rj * D + sc) * B + ri * D + r] -= acc[sc];
+      const long o1 = (long)(ri * D + r) * B + rj * D + sc;
+      if (dj == 0) { blk[o1] -= acc[sc]; continue; }
+      blk[o1] = blk0[o1] - acc[sc];
+      if (J == I) { const long o2 = (long)(rj * D + sc) * B + ri * D + r; blk[o2] = blk0[o2] - acc[sc]; }
     }
+  }
+};
+// damped system <- base system on the blocks that change between linearizations: the diagonal block of every node and the
+// coupling block (with its mirror image) of every node pair that shares a chain factor.  Everything else in SD | SU | REM is
+// either structurally zero for the life of the graph or assigned by SchurBlockBody.
+struct CopyBlocksArgs { const double* H0; double* H; long nnodes, ngroups; int D, k, ld; long bs, sd_off; const PairDst* dst; };
+struct CopyBlocksBody {
+  static VUS_DEV void run(const CopyBlocksArgs& A, long w) {
+    const int DD = A.D * A.D;
+    const long blkid = w / DD;
+    const int e = (int)(w - blkid * DD), a = e / A.D, b = e - a * A.D;
+    if (blkid < A.nnodes) {
+      const long o = A.sd_off + diag_off(blkid, a, b, A.D, A.k, A.ld, A.bs);
+      A.H[o] = A.H0[o];
+      return;
+    }
+    const PairDst d = A.dst[blkid - A.nnodes];
+    const long o = d.off + (long)a * d.ld + b;
+    A.H[o] = A.H0[o];
+    if (d.moff >= 0) { const long m = d.moff + (long)a * d.mld + b; A.H[m] = A.H0[m]; }
   }
 };
 struct LmInvertBody {    // per landmark
@@ -656,13 +682,13 @@ struct LmBacksubBody {   // per landmark: xl = Cinv (gl - sum_o E_o^T xc[pose_o]
 };
 
 // add lambda (and identity on padding dofs) to the diagonal of SD and Hbb
-struct DampArgs { double* SD; double* Hbb; long ndof; long nreal; int B; double lambda; int ld; long bs; };
+struct DampArgs { double* SD; double* Hbb; long ndof; long nreal; int B; double lambda; int ld; long bs; double pad_add; };   // pad_add: 1 when SD was just copied from the base system (padding diagonal 0 -> 1), 0 when the padding rows were left alone
 struct DampBody {
   static VUS_DEV void run(const DampArgs& A, long i) {
     if (i < A.ndof) {
       const long I = i / A.B;
       const int r = (int)(i % A.B);
-      A.SD[I * A.bs + (long)r * A.ld + r] += (i < A.nreal) ? A.lambda : 1.0;
+      A.SD[I * A.bs + (long)r * A.ld + r] += (i < A.nreal) ? A.lambda : A.pad_add;
     } else {
       const int c = (int)(i - A.ndof);
       A.Hbb[c * 6 + c] += A.lambda;

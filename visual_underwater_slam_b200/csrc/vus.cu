@@ -229,6 +229,7 @@ struct vus_handle {
   long Ns_band = 0;              // supernodes the band preconditioner / operator rows cover: all, or the owned prefix of a partition
   long nrem = 0, sd_off = 0, su_off = 0, rem_off = 0, hlen = 0;
   DBuf<double> H0, H;            // SD | SU | REM   (undamped base / damped + Schur)
+  bool H_synced = false;         // H holds a full copy of H0's structure (form_system then refreshes only the blocks that change)
   DBuf<int> na_ptr, na_code, na_fac;      // node -> incident chain factors (NodeAsmBody)
   DBuf<int> pg_ptr, pg_code, pg_fac;      // node pair -> its two-node factors (PairAsmBody)
   DBuf<PairDst> pg_dst; long npairs = 0;
@@ -870,7 +871,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
   h->rem_ptr.upload(rem_ptr, st); h->rem_col.upload(rem_col, st);
   h->pose_ptr.upload(pose_ptr, st); if (!pose_obs_on_device) h->pose_obs.upload(pose_obs, st); h->pose_ids.upload(pose_ids, st);
   h->lm_ptr.upload(lm_ptr, st);
-  h->H0.alloc(h->hlen); h->H.alloc(h->hlen);
+  h->H0.alloc(h->hlen); h->H.alloc(h->hlen); h->H_synced = false;
   h->g0.alloc(h->Lc); h->gs.alloc(h->L);
   h->F.alloc(h->Lc * 6);
   // zero-filled once: the assembly kernels store every entry a factor can touch, nothing else ever writes the rest
@@ -1003,6 +1004,7 @@ SchurArgs schur_args(vus_handle* h, double lambda) {
   a.n = S.n; a.nl = h->nvar[3]; a.idx = S.idx.p; a.C = h->C.p; a.gl = h->gl.p; a.Cinv = h->Cinv.p; a.E = h->E.p;
   a.lambda = lambda; a.D = h->D; a.k = h->k; a.B = h->B; a.ld = bcr_ld(h->B); a.bs = bcr_bbp(h->B);
   a.SD = h->H.p + h->sd_off; a.SU = h->H.p + h->su_off; a.gs = h->gs.p;
+  a.SD0 = h->H0.p + h->sd_off; a.SU0 = h->H0.p + h->su_off;
   a.pose_ptr = h->pose_ptr.p; a.pose_obs = h->pose_obs.p; a.pose_ids = h->pose_ids.p; a.nposes_obs = h->nposes_obs;
   a.lm_ptr = h->lm_ptr.p; a.lm_long = h->lm_long.p;
   a.fail = h->fail.p; a.xc = h->x.p; a.xl = h->xl.p;
@@ -1015,11 +1017,22 @@ SchurArgs schur_args(vus_handle* h, double lambda) {
 void form_system(vus_handle* h, double lambda, rt::stream_t st) {
   ClassGuard kc_guard(KC_SCHUR);
   h->cur_lambda = lambda;
-  rt::d2d(h->H.p, h->H0.p, h->hlen * sizeof(double), st);
+  // The first system of a graph is a full copy of the base system (2.3 GB at config 3); after that only the blocks that can
+  // change are refreshed (CopyBlocksBody: ~0.2 GB) -- the rest of SD | SU | REM is structurally zero or assigned by the Schur kernel.
+  const bool full = !h->H_synced;
+  if (full) {
+    rt::d2d(h->H.p, h->H0.p, h->hlen * sizeof(double), st);
+    h->H_synced = true;
+  } else {
+    CopyBlocksArgs c; c.H0 = h->H0.p; c.H = h->H.p; c.nnodes = h->N; c.ngroups = h->npairs; c.D = h->D; c.k = h->k; c.ld = bcr_ld(h->B);
+    c.bs = bcr_bbp(h->B); c.sd_off = h->sd_off; c.dst = h->pg_dst.p;
+    L_elem<CopyBlocksBody>((h->N + h->npairs) * (long)(h->D * h->D), st, c);
+  }
   rt::d2d(h->Hbb.p, h->Hbb0.p, 36 * sizeof(double), st);
   rt::d2d(h->gs.p, h->g0.p, h->Lc * sizeof(double), st);
   if (h->has_bias) rt::d2d(h->gs.p + h->Lc, h->gb.p, 6 * sizeof(double), st);
   DampArgs d; d.SD = h->H.p + h->sd_off; d.Hbb = h->Hbb.p; d.ndof = h->Lc; d.nreal = h->N * h->D; d.B = h->B; d.lambda = lambda; d.ld = bcr_ld(h->B); d.bs = bcr_bbp(h->B);
+  d.pad_add = full ? 1.0 : 0.0;
   L_elem<DampBody>(h->Lc + (h->has_bias ? 6 : 0), st, d);
   if (h->nobs) {
     SchurArgs a = schur_args(h, lambda);
