@@ -324,3 +324,40 @@ def test_damped_system_refresh_leaves_nothing_stale(emu):
     s.close()
     for k in ("pose", "vel", "lm", "bias"):
         assert np.array_equal(a1[k], a2[k]) and np.array_equal(a1[k], a3[k]), k
+
+
+def _with_extra_between(prob, rows, swap):
+    """Copy of a packed problem with between-factor rows `rows` appended again (swap[i]: with x1 / x2 exchanged)."""
+    out = dict(prob)
+    bt = prob["between"]
+    rows = np.asarray(rows)
+    x1, x2 = np.asarray(bt["x1"])[rows].copy(), np.asarray(bt["x2"])[rows].copy()
+    sw = np.asarray(swap, bool)
+    x1[sw], x2[sw] = np.asarray(bt["x2"])[rows][sw], np.asarray(bt["x1"])[rows][sw]
+    n0 = int(prob["n_factors"])
+    out["between"] = dict(meas=np.concatenate([bt["meas"], bt["meas"][rows]]), sqrt_info=np.concatenate([bt["sqrt_info"], bt["sqrt_info"][rows]]),
+                          orig=np.concatenate([bt["orig"], n0 + np.arange(len(rows), dtype=np.int64)]),
+                          x1=np.concatenate([bt["x1"], x1]).astype(np.int32), x2=np.concatenate([bt["x2"], x2]).astype(np.int32))
+    out["n_factors"] = n0 + len(rows)
+    return out
+
+
+def test_several_factors_on_one_pose_pair_and_both_orientations(emu):
+    """The pair gather (PairAsmBody) sums EVERY factor of a pose pair, whichever pose the factor names first: an odometry
+    factor doubled, a skip factor doubled the other way round, an off-band loop closure tripled (one copy reversed)."""
+    from visual_underwater_slam_b200 import synthetic
+    d = synthetic.make_pose_graph(130, seed=8, n_loops=6)
+    prob = d["graph"].to_problem(d["initial"])
+    nb = len(prob["between"]["orig"])
+    closure = nb - 1                                      # the generator appends the loop closures last
+    prob2 = _with_extra_between(prob, [3, 129 + 7, closure, closure], [False, True, False, True])
+    pc.check_factor_parity(emu, prob2)
+    pc.check_solve_parity(emu, prob2, 1e-2, 1e-6)
+    pc.check_lm_parity(emu, prob2)
+
+
+def test_pose_without_chain_factor_of_its_own_keeps_a_defined_block(emu):
+    """NodeAsmBody writes every entry of every node's block on every linearization (there is no zero-fill any more): a stereo
+    graph re-linearized many times, with rejected tries in between, must keep matching the oracle."""
+    _, prob = pc.make(50, n_lm=120, n_loops=2, loop_min_gap=20)
+    pc.check_lm_parity(emu, prob)

@@ -107,6 +107,12 @@ world = int(os.environ["WORLD_SIZE"]); rank = int(os.environ["RANK"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
 d = synthetic.make_pose_graph(int(sys.argv[2]), seed=5, n_loops=int(sys.argv[3]))
 prob = d["graph"].to_problem(d["initial"])
+if len(sys.argv) > 5 and sys.argv[5] == "noskip":       # odometry + loop closures only: one pose per supernode (k = 1)
+    n = int(sys.argv[2]); bt = prob["between"]
+    keep = np.concatenate([np.arange(n - 1), np.arange(2 * n - 3, len(bt["orig"]))])
+    prob["between"] = {k: np.ascontiguousarray(np.asarray(v)[keep]) for k, v in bt.items()}
+    prob["between"]["orig"] = np.arange(1, 1 + len(keep), dtype=np.int64)
+    prob["n_factors"] = 1 + len(keep)
 part = parallel.partition_pose_graph(prob, world)[rank]
 ps = parallel.PartitionedSolver(part, lib=lib)
 res = ps.optimize()
@@ -120,14 +126,14 @@ dist.barrier(); dist.destroy_process_group()
 '''
 
 
-def _run_part(world, n, loops, out, tmp_path):
+def _run_part(world, n, loops, out, tmp_path, extra=()):
     script = tmp_path / "part_worker.py"
     script.write_text(PART_WORKER)
     port = 29500 + ((os.getpid() + 7 * world) % 500)
     procs = []
     for rank in range(world):
         env = dict(os.environ, WORLD_SIZE=str(world), RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
-        procs.append(subprocess.Popen([sys.executable, str(script), ROOT, str(n), str(loops), str(out)], env=env,
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT, str(n), str(loops), str(out), *extra], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     for p in procs:
         o, _ = p.communicate(timeout=900)
@@ -202,3 +208,17 @@ def test_pose_range_is_aligned_and_covers_everything():
             for t in range(0, n, 7):
                 r = parallel.pose_owner(t, n, world)
                 assert spans[r][0] <= t < spans[r][1]
+
+
+def test_partitioned_exact_band_with_one_pose_per_supernode(tmp_path):
+    """The same tie across ranks when the graph has no skip factors (k = 1: 6 x 6 interface blocks), on 3 ranks."""
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "visual_underwater_slam_b200", "csrc"), "emu"], check=True)
+    import json
+    one, three = tmp_path / "k1.npy", tmp_path / "k3.npy"
+    _run_part(1, 960, 3, one, tmp_path, extra=("noskip",))
+    _run_part(3, 960, 3, three, tmp_path, extra=("noskip",))
+    m1, m3 = json.load(open(str(one) + ".json")), json.load(open(str(three) + ".json"))
+    assert m1["iterations"] == m3["iterations"] and m1["tries"] == m3["tries"]
+    assert m3["pcg"] <= 1.1 * m1["pcg"] + 8, (m1["pcg"], m3["pcg"])
+    p1, p3 = np.load(one), np.load(three)
+    assert np.abs(p1 - p3).max() < 1e-8
