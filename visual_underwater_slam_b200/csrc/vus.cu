@@ -456,9 +456,27 @@ void export_table(double* dst, const double* src, long n, int dim, int mem, rt::
 }
 
 // ------------------------------------------------------------------ symbolic analysis
-struct PairKey { long p, q; };
+// Off-band node pairs (both orientations) -> index of their remainder block, blocks in (p, q) lexicographic order.  A sorted
+// key vector with binary search: a std::map of the 12 M pairs of config 5 cost ~1.2 us per insert and per look-up.
+struct RemIndex {
+  std::vector<uint64_t> keys;                            // (p << 32) | q, sorted and unique after finalize()
+  static uint64_t key(long p, long q) { return ((uint64_t)p << 32) | (uint64_t)(uint32_t)q; }
+  void add(long p, long q) { keys.push_back(key(p, q)); }
+  void finalize() { std::sort(keys.begin(), keys.end()); keys.erase(std::unique(keys.begin(), keys.end()), keys.end()); }
+  long find(long p, long q) const {
+    const uint64_t k = key(p, q);
+    auto it = std::lower_bound(keys.begin(), keys.end(), k);
+    return (it != keys.end() && *it == k) ? (long)(it - keys.begin()) : -1;
+  }
+  long at(long p, long q) const { const long i = find(p, q); if (i < 0) throw std::out_of_range("no remainder block for this node pair"); return i; }
+  bool has(long p, long q) const { return find(p, q) >= 0; }
+  bool empty() const { return keys.empty(); }
+  long size() const { return (long)keys.size(); }
+  long p_of(long i) const { return (long)(keys[i] >> 32); }
+  long q_of(long i) const { return (long)(keys[i] & 0xffffffffu); }
+};
 
-PairDst band_dst(const vus_handle* h, long p, long q, const std::map<std::pair<long, long>, long>& rem_index) {
+PairDst band_dst(const vus_handle* h, long p, long q, const RemIndex& rem_index) {
   // destination of block (p,q), p != q allowed to be in any order
   PairDst d; d.pad = 0;
   const int D = h->D, k = h->k, B = bcr_ld(h->B);          // B: row stride of the padded supernode tiles
@@ -473,7 +491,7 @@ PairDst band_dst(const vus_handle* h, long p, long q, const std::map<std::pair<l
   } else if (J == I - 1) {
     d.off = h->su_off + J * BB + (long)(rq * D) * B + rp * D; d.ld = B; d.transposed = 1; d.moff = -1; d.mld = 0;
   } else {
-    const long b1 = rem_index.at({p, q}), b2 = rem_index.at({q, p});
+    const long b1 = rem_index.at(p, q), b2 = rem_index.at(q, p);
     d.off = h->rem_off + b1 * D * D; d.ld = D; d.transposed = 0;
     d.moff = h->rem_off + b2 * D * D; d.mld = D;
   }
@@ -483,7 +501,7 @@ PairDst band_dst(const vus_handle* h, long p, long q, const std::map<std::pair<l
 SchurArgs schur_args(vus_handle* h, double lambda);
 
 // batched mode: component of every node, dof segments, per-component factor lists (errors) and IMU lists (bias blocks)
-int analyze_components(vus_handle* h, rt::stream_t st, const std::map<std::pair<long, long>, long>& rem_index) {
+int analyze_components(vus_handle* h, rt::stream_t st, const RemIndex& rem_index) {
   const int nc = h->ncomp;
   const long NX = h->nvar[0];
   std::vector<int> node_comp(h->Npad, nc - 1);
@@ -529,19 +547,19 @@ int analyze_components(vus_handle* h, rt::stream_t st, const std::map<std::pair<
   h->wb_R = 0; h->wb_lmax = 0;
   if (!rem_index.empty()) {
     std::vector<int> cnt(nc, 0);
-    for (const auto& kv : rem_index)
-      if (kv.first.first < kv.first.second) cnt[node_comp[kv.first.first]]++;
+    for (long b = 0; b < rem_index.size(); ++b)
+      if (rem_index.p_of(b) < rem_index.q_of(b)) cnt[node_comp[rem_index.p_of(b)]]++;
     const int lmax = *std::max_element(cnt.begin(), cnt.end());
     if (lmax >= 1 && lmax <= 8) {
       std::vector<int> wnode((size_t)nc * lmax * 2, -1);
       std::vector<long> wblk((size_t)nc * lmax, 0);
       std::fill(cnt.begin(), cnt.end(), 0);
-      for (const auto& kv : rem_index) {
-        const long p = kv.first.first, q = kv.first.second;
+      for (long b = 0; b < rem_index.size(); ++b) {
+        const long p = rem_index.p_of(b), q = rem_index.q_of(b);
         if (p >= q) continue;
         const int c = node_comp[p], l = cnt[c]++;
         wnode[((size_t)c * lmax + l) * 2] = (int)p; wnode[((size_t)c * lmax + l) * 2 + 1] = (int)q;
-        wblk[(size_t)c * lmax + l] = h->rem_off + kv.second * h->D * h->D;
+        wblk[(size_t)c * lmax + l] = h->rem_off + b * h->D * h->D;
       }
       h->wb_lmax = lmax; h->wb_R = 12 * lmax;
       h->wb_node.upload(wnode, st); h->wb_blk.upload(wblk, st);
@@ -751,14 +769,15 @@ int analyze(vus_handle* h, rt::stream_t st) {
   const long BB = bcr_bbp(h->B);                     // SD / SU are padded [KP][LD] tiles (bulk-copy layout, bcr.cuh)
   auto inband = [&](long p, long q) { long I = p / k, J = q / k; return (I - J <= 1) && (J - I <= 1); };
   // ---- off-band remainder blocks
-  std::map<std::pair<long, long>, long> rem_index;
+  RemIndex rem_index;
   // (Measured and dropped: keeping sparse loop closures out of the band entirely -- diagonal blocks too -- makes the
   // operator a rank-6 instead of rank-12 update per closure and saves ~30 % of the PCG iterations, but the preconditioned
   // operator then has very large eigenvalues, the attainable true residual degrades from 1e-12 to ~1e-9 at small lambda
   // and the LM path leaves the oracle's.  The diagonal blocks of every factor stay in the band.)
-  auto add_rem = [&](long p, long q) { if (p != q && !inband(p, q)) { rem_index[{p, q}] = 0; rem_index[{q, p}] = 0; } };
+  auto add_rem = [&](long p, long q) { if (p != q && !inband(p, q)) { rem_index.add(p, q); rem_index.add(q, p); } };
   for (long f = 0; f < FB.n; ++f) add_rem(FB.h_idx[f], FB.h_idx[FB.n + f]);
   for (long f = 0; f < FI.n; ++f) add_rem(FI.h_idx[f], FI.h_idx[2 * FI.n + f]);
+  rem_index.finalize();
   // landmarks whose track does not fit inside the band keep their Schur term implicit (LongSchur*Body)
   std::vector<int> lm_long(NL, 0), long_ids;
   long track_span = 0;                                  // longest pose span of a track that is folded into the band
@@ -776,10 +795,10 @@ int analyze(vus_handle* h, rt::stream_t st) {
   if (h->nlong) { h->long_ids.upload(long_ids, st); h->ulong.alloc((size_t)3 * h->nlong); }
   std::vector<int> rem_ptr(NX + 1, 0), rem_col;
   {
-    long id = 0;
-    for (auto& kv : rem_index) { kv.second = id++; rem_ptr[kv.first.first + 1]++; rem_col.push_back((int)kv.first.second); }
+    rem_col.resize(rem_index.size());
+    for (long b = 0; b < rem_index.size(); ++b) { rem_ptr[rem_index.p_of(b) + 1]++; rem_col[b] = (int)rem_index.q_of(b); }
     for (long i = 0; i < NX; ++i) rem_ptr[i + 1] += rem_ptr[i];
-    h->nrem = id;
+    h->nrem = rem_index.size();
   }
   h->sd_off = 0;
   h->su_off = h->Ns * BB;
@@ -823,7 +842,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
           const long q = T.h_idx[slot_q[t] * T.n + f];
           ncode[fill[q]] = 2 * t + 1; nfac[fill[q]++] = (int)f;
           const long lo = std::min(p, q), hi = std::max(p, q);
-          int* slot = inband(lo, hi) ? &inband_grp[(size_t)lo * 2 * k + (hi - lo)] : &rem_grp[rem_index.at({lo, hi})];
+          int* slot = inband(lo, hi) ? &inband_grp[(size_t)lo * 2 * k + (hi - lo)] : &rem_grp[rem_index.at(lo, hi)];
           if (*slot < 0) { *slot = (int)gdst.size(); gdst.push_back(band_dst(h, lo, hi, rem_index)); gcount.push_back(0); }
           fgroup[t][f] = *slot;
           gcount[*slot]++;
@@ -855,7 +874,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
   if (h->n_owned >= 2 * k && h->sp_nranks > 1 && (long)h->sp_prev.size() >= k && (long)h->sp_next.size() >= k) {
     std::vector<PairDst> pairs((size_t)2 * k * k);
     for (auto& d : pairs) { d.off = -1; d.moff = -1; d.ld = d.mld = d.transposed = d.pad = 0; }
-    auto coupled = [&](long p, long q) { return q >= 0 && q < NX && (inband(p, q) || rem_index.count({p, q}) > 0); };
+    auto coupled = [&](long p, long q) { return q >= 0 && q < NX && (inband(p, q) || rem_index.has(p, q)); };
     for (int p = 0; p < k; ++p)
       for (int j = 0; j < k; ++j) {
         const long last_p = h->n_owned - k + p, nxt = h->sp_next[j];           // next pose j: global b + j
