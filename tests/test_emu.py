@@ -361,3 +361,21 @@ def test_pose_without_chain_factor_of_its_own_keeps_a_defined_block(emu):
     graph re-linearized many times, with rejected tries in between, must keep matching the oracle."""
     _, prob = pc.make(50, n_lm=120, n_loops=2, loop_min_gap=20)
     pc.check_lm_parity(emu, prob)
+
+
+def test_long_tracks_keep_the_oracle_path_with_a_strong_preconditioner(emu):
+    """13 observations per landmark: longer than any band.  The operator keeps the exact implicit Schur term; the band
+    preconditioner carries the track cut into segments that fit (every segment a landmark of its own), so a damped solve takes
+    ~10 PCG iterations instead of 130-200, the LM path is the oracle's, and marginal queries are answered, not refused."""
+    from visual_underwater_slam_b200 import synthetic
+    from visual_underwater_slam_b200.optimizer import Session
+    d = synthetic.make_trajectory_graph(74, seed=1, n_landmarks=60, obs_per_landmark=13, pixel_noise=1.0)
+    prob = d["graph"].to_problem(d["initial"])
+    s = Session(prob, lib=emu)
+    assert s.layout()["k"] == 9
+    st = s.solve_step(1e-5)
+    s.close()
+    assert st["pcg_iterations"] <= 20, st["pcg_iterations"]
+    res, info = pc.check_lm_parity(emu, prob)
+    assert res["pcg_iterations"] <= 20 * res["inner_iterations"]
+    pc.check_marginals(emu, prob, [("pose", 40), ("lm", 7), ("vel", 12), ("bias", 0)], rtol=1e-5)

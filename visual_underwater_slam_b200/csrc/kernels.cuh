@@ -503,6 +503,10 @@ struct SchurArgs {
   // SchurBlockBody: partner[t * ndj + dj] = row of the observation of the same landmark from pose i + dj (-1: none), t over
   // the pose-major observation list; ndj = longest short-track span + 1
   int* partner; int ndj;
+  // long-track landmarks in the PRECONDITIONER (the operator keeps their exact implicit term): the track is cut into segments
+  // that fit in the band, every segment acts as a landmark of its own (obs_seg[o] = segment of observation o, -1: short track;
+  // seg_ptr[2 s], seg_ptr[2 s + 1]: observation rows of segment s; CinvSeg [9][nseg]); long_pass = 1: SchurBlockBody subtracts only these terms
+  const int* obs_seg; const int* seg_ptr; double* CinvSeg; long nseg; const double* Pl; int long_pass; int has_long;
 };
 // analysis time, work item (t, dj): the partner of observation pose_obs[t] at pose offset dj.  Tracks are pose-sorted and
 // hold every pose at most once (a landmark seen twice from one pose is handled by the implicit path, like a long track).
@@ -513,13 +517,13 @@ struct SchurPartnerBody {
     const int o = A.pose_obs[t];
     const int l = A.idx[A.n + o];
     int q = -1;
-    if (!A.lm_long[l]) {
-      const int target = A.idx[o] + dj;
-      for (int c = o; c < A.lm_ptr[l + 1]; ++c) {
-        const int pc = A.idx[c];
-        if (pc == target) { q = c; break; }
-        if (pc > target) break;
-      }
+    // a long track pairs observations only inside one of its segments (the relaxed term of the preconditioner)
+    const int end = !A.lm_long[l] ? A.lm_ptr[l + 1] : ((A.obs_seg && A.obs_seg[o] >= 0) ? A.seg_ptr[2 * A.obs_seg[o] + 1] : o);
+    const int target = A.idx[o] + dj;
+    for (int c = o; c < end; ++c) {
+      const int pc = A.idx[c];
+      if (pc == target) { q = c; break; }
+      if (pc > target) break;
     }
     A.partner[w] = q;
   }
@@ -546,19 +550,22 @@ struct SchurBlockBody {
     for (int t = t0; t < t1; ++t) {                                    // iteration ahead of the record it points to
       const int q = qn;
       if (t + 1 < t1) qn = A.partner[(long)(t + 1) * A.ndj + dj];
-      if (q < 0 && dj != 0) continue;
+      if (q < 0 && (dj != 0 || A.long_pass)) continue;
       const long o = A.pose_obs[t];
       const long l = A.idx[A.n + o];
+      const bool lng = A.has_long && A.lm_long[l] != 0;    // has_long = 0: no extra load on graphs whose tracks all fit in the band
+      if (lng != (A.long_pass != 0) && !(lng && dj == 0 && !A.long_pass)) continue;   // pass 0: short tracks (+ the gradient of long ones); pass 1: long tracks
       const double* er = A.E + o * 18 + r * 3;
       const double e0 = er[0], e1 = er[1], e2 = er[2];
-      const double* ci = A.Cinv + l;
-      const long nl = A.nl;
+      // pass 1 uses the inverse of the SEGMENT's landmark block: the segment is a landmark of its own in the preconditioner
+      const double* ci = A.long_pass ? A.CinvSeg + A.obs_seg[o] : A.Cinv + l;
+      const long nl = A.long_pass ? A.nseg : A.nl;
       const double w0 = e0 * ci[0] + e1 * ci[3 * nl] + e2 * ci[6 * nl];
       const double w1 = e0 * ci[nl] + e1 * ci[4 * nl] + e2 * ci[7 * nl];
       const double w2 = e0 * ci[2 * nl] + e1 * ci[5 * nl] + e2 * ci[8 * nl];
-      if (dj == 0) {
-        gacc += w0 * A.gl[l] + w1 * A.gl[nl + l] + w2 * A.gl[2 * nl + l];
-        if (q < 0) continue;                           // long track: only the gradient is reduced here (LongSchur*Body)
+      if (dj == 0 && !A.long_pass) {
+        gacc += w0 * A.gl[l] + w1 * A.gl[A.nl + l] + w2 * A.gl[2 * A.nl + l];
+        if (q < 0 || lng) continue;                    // long track: only the (exact) gradient is reduced here (LongSchur*Body)
       }
       any = true;
       const double* eq = A.E + (long)q * 18;
@@ -566,21 +573,48 @@ struct SchurBlockBody {
       for (int sc = 0; sc < 6; ++sc) acc[sc] += w0 * eq[sc * 3] + w1 * eq[sc * 3 + 1] + w2 * eq[sc * 3 + 2];
     }
     const int D = A.D, k = A.k, B = A.ld;
-    if (dj == 0) A.gs[i * D + r] -= gacc;
+    if (dj == 0 && !A.long_pass) A.gs[i * D + r] -= gacc;
     if (!any) return;
     const long I = i / k, j = i + dj, J = j / k;
     const int ri = (int)(i - I * k), rj = (int)(j - J * k);
     double* blk = (J == I ? A.SD : A.SU) + I * A.bs;
-    // dj = 0: the node's diagonal block was refreshed (base system + lambda) just before; dj >= 1: the block is ASSIGNED from the
-    // base system, so the damped system needs no full copy per lambda try (form_system: only node and pair blocks are copied)
+    // pass 0, dj = 0: the node's diagonal block was refreshed (base system + lambda) just before; dj >= 1: the block is ASSIGNED
+    // from the base system, so the damped system needs no full copy per lambda try (form_system: only node and pair blocks are
+    // copied).  pass 1 works on a fresh copy of the finished damped system: plain subtraction.
     const double* blk0 = (J == I ? A.SD0 : A.SU0) + I * A.bs;
 #pragma unroll
     for (int sc = 0; sc < 6; ++sc) {
       const long o1 = (long)(ri * D + r) * B + rj * D + sc;
-      if (dj == 0) { blk[o1] -= acc[sc]; continue; }
+      const long o2 = (long)(rj * D + sc) * B + ri * D + r;
+      if (dj == 0 || A.long_pass) {
+        blk[o1] -= acc[sc];
+        if (dj && J == I) blk[o2] -= acc[sc];
+        continue;
+      }
       blk[o1] = blk0[o1] - acc[sc];
-      if (J == I) { const long o2 = (long)(rj * D + sc) * B + ri * D + r; blk[o2] = blk0[o2] - acc[sc]; }
+      if (J == I) blk[o2] = blk0[o2] - acc[sc];
     }
+  }
+};
+// per lambda and segment of a long track: CinvSeg = (sum of the segment's J_l^T J_l + lambda I)^-1  (products Pl of the stereo
+// linearize kernel, as StereoLmBody / LmInvertBody do for whole landmarks)
+struct SegInvertBody {
+  static VUS_DEV void run(const SchurArgs& A, long sg) {
+    double u[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int t = A.seg_ptr[2 * sg]; t < A.seg_ptr[2 * sg + 1]; ++t)
+#pragma unroll
+      for (int e = 0; e < 6; ++e) u[e] += A.Pl[(long)t * 12 + e];
+    // unique entries in the order (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)
+    const double c0 = u[0] + A.lambda, c1 = u[1], c2 = u[2], c4 = u[3] + A.lambda, c5 = u[4], c8 = u[5] + A.lambda;
+    const double c00 = c4 * c8 - c5 * c5, c01 = c5 * c2 - c1 * c8, c02 = c1 * c5 - c4 * c2;
+    const double det = c0 * c00 + c1 * c01 + c2 * c02;
+    if (!(det > 0.0)) { *A.fail = 1; }
+    const double id = 1.0 / det;
+    const long ns = A.nseg;
+    double* o = A.CinvSeg + sg;
+    o[0] = c00 * id;          o[ns] = c01 * id;                      o[2 * ns] = c02 * id;
+    o[3 * ns] = c01 * id;     o[4 * ns] = (c0 * c8 - c2 * c2) * id;  o[5 * ns] = (c2 * c1 - c0 * c5) * id;
+    o[6 * ns] = c02 * id;     o[7 * ns] = (c2 * c1 - c0 * c5) * id;  o[8 * ns] = (c0 * c4 - c1 * c1) * id;
   }
 };
 // damped system <- base system on the blocks that change between linearizations: the diagonal block of every node and the

@@ -239,6 +239,9 @@ struct vus_handle {
   long nobs = 0, nposes_obs = 0;
   DBuf<int> pose_ptr, pose_obs, pose_ids, lm_ptr, lm_long, long_ids;
   long nlong = 0;
+  // long tracks in the preconditioner: segments that fit in the band (SchurArgs), and the preconditioner's own band matrix
+  DBuf<int> obs_seg, seg_ptr; long nseg = 0;
+  DBuf<double> CinvSeg, Hp;
   DBuf<double> ulong;
   double cur_lambda = 0.0;
   int schur_ndj = 1;
@@ -753,7 +756,11 @@ int analyze(vus_handle* h, rt::stream_t st) {
   for (long f = 0; f < FI.n; ++f) consider(FI.h_idx[f], FI.h_idx[2 * FI.n + f]);
   for (long l = 0; l < NL; ++l) {
     const int a = lm_ptr[l], b = lm_ptr[l + 1] - 1;
-    consider(FS.h_idx[a], FS.h_idx[b]);
+    // a track longer than the cap still wants a wide band: most such tracks then fit in two neighbouring supernodes after
+    // all, and the segments of the others (below) are long.  Nine poses per supernode, not the cap of ten: 81 x 81 is the
+    // block size every BASELINE stereo configuration runs (and the GPU test-suite covers).
+    const long pa = FS.h_idx[a], pb = FS.h_idx[b], kwide = std::min<long>(kcap, 9);
+    consider(pa, pb - pa > kcap ? pa + kwide : pb);
   }
   h->k = (int)std::min<long>(span, kcap);
   if (h->k < 1) h->k = 1;
@@ -788,6 +795,28 @@ int analyze(vus_handle* h, rt::stream_t st) {
     if (pl / k - pf / k <= 1 && !twice) { track_span = std::max(track_span, pl - pf); continue; }   // whole track inside the band
     long_ids.push_back((int)l);
     lm_long[l] = (int)long_ids.size();                  // 1 + position in long_ids
+  }
+  // The exact Schur term of a long track stays implicit in the OPERATOR.  For the PRECONDITIONER the track is cut into segments
+  // that each fit in the band (two neighbouring supernodes, every pose at most once) and every segment acts as a landmark of
+  // its own: the exact Schur complement of the problem in which the copies of the landmark are not tied together -- symmetric
+  // positive definite, below the true reduced matrix in the SPD order, and far closer to it than a band without the track.
+  h->nseg = 0;
+  if (!long_ids.empty()) {
+    std::vector<int> obs_seg(FS.n, -1), seg_ptr;          // seg_ptr: [begin, end) observation rows of every segment
+    for (int l : long_ids) {
+      int a = lm_ptr[l];
+      while (a < lm_ptr[l + 1]) {
+        int c = a + 1;
+        while (c < lm_ptr[l + 1] && FS.h_idx[c] != FS.h_idx[c - 1] && FS.h_idx[c] / k - FS.h_idx[a] / k <= 1) ++c;
+        for (int o = a; o < c; ++o) obs_seg[o] = (int)(seg_ptr.size() / 2);
+        track_span = std::max<long>(track_span, FS.h_idx[c - 1] - FS.h_idx[a]);
+        seg_ptr.push_back(a); seg_ptr.push_back(c);
+        a = c;
+      }
+    }
+    h->nseg = (long)(seg_ptr.size() / 2);
+    h->obs_seg.upload(obs_seg, st); h->seg_ptr.upload(seg_ptr, st);
+    h->CinvSeg.alloc((size_t)9 * h->nseg);
   }
   h->schur_ndj = (int)track_span + 1;
   h->nlong = (long)long_ids.size();
@@ -891,6 +920,7 @@ int analyze(vus_handle* h, rt::stream_t st) {
   h->pose_ptr.upload(pose_ptr, st); if (!pose_obs_on_device) h->pose_obs.upload(pose_obs, st); h->pose_ids.upload(pose_ids, st);
   h->lm_ptr.upload(lm_ptr, st);
   h->H0.alloc(h->hlen); h->H.alloc(h->hlen); h->H_synced = false;
+  if (h->nseg) h->Hp.alloc(h->hlen);
   h->g0.alloc(h->Lc); h->gs.alloc(h->L);
   h->F.alloc(h->Lc * 6);
   // zero-filled once: the assembly kernels store every entry a factor can touch, nothing else ever writes the rest
@@ -1029,6 +1059,7 @@ SchurArgs schur_args(vus_handle* h, double lambda) {
   a.fail = h->fail.p; a.xc = h->x.p; a.xl = h->xl.p;
   a.nlong = h->nlong; a.long_ids = h->long_ids.p; a.ulong = h->ulong.p; a.xin = nullptr; a.yout = nullptr;
   a.partner = h->partner.p; a.ndj = h->schur_ndj;
+  a.obs_seg = h->nseg ? h->obs_seg.p : nullptr; a.seg_ptr = h->seg_ptr.p; a.CinvSeg = h->CinvSeg.p; a.nseg = h->nseg; a.Pl = h->Pl.p; a.long_pass = 0; a.has_long = h->nlong > 0;
   return a;
 }
 
@@ -1057,8 +1088,18 @@ void form_system(vus_handle* h, double lambda, rt::stream_t st) {
     SchurArgs a = schur_args(h, lambda);
     L_elem<LmInvertBody>(a.nl, st, a);
     L_elem<SchurBlockBody>(6 * h->nposes_obs * h->schur_ndj, st, a);
+    if (h->nseg) {                                       // the preconditioner's band: the finished system minus the segment terms
+      L_elem<SegInvertBody>(h->nseg, st, a);
+      rt::d2d(h->Hp.p, h->H.p, h->hlen * sizeof(double), st);
+      SchurArgs b = a;
+      b.long_pass = 1; b.SD = h->Hp.p + h->sd_off; b.SU = h->Hp.p + h->su_off;
+      L_elem<SchurBlockBody>(6 * h->nposes_obs * h->schur_ndj, st, b);
+    }
   }
 }
+// the band matrix the preconditioner factors (and that the border elimination refers to): the damped system itself, or -- with
+// long tracks -- the copy that also carries their segment terms
+double* band_matrix(vus_handle* h) { return h->nseg ? h->Hp.p : h->H.p; }
 
 // ------------------------------------------------------------------ kernel 3 drivers
 // The reduction stops at the first stride that no coupling can span: the whole chain for one graph; the longest component
@@ -1077,7 +1118,7 @@ BandSys band_sys(vus_handle* h) {
     y.Ns = h->chunk_P - 1; y.D = h->Dsep.p; y.U = h->Usep.p;
     y.Dw = h->sDw.p; y.U1 = h->sU1.p; y.U2 = h->sU2.p; y.Dinv = h->sDinv.p; y.Gl = h->sGl.p; y.Gr = h->sGr.p;
   } else {
-    y.Ns = h->Ns_band; y.D = h->H.p + h->sd_off; y.U = h->H.p + h->su_off;
+    y.Ns = h->Ns_band; y.D = band_matrix(h) + h->sd_off; y.U = band_matrix(h) + h->su_off;
     y.Dw = h->Dw.p; y.U1 = h->U1.p; y.U2 = h->U2.p; y.Dinv = h->Dinv.p; y.Gl = h->Gl.p; y.Gr = h->Gr.p;
   }
   return y;
@@ -1102,7 +1143,7 @@ BcrArgs bcr_args(vus_handle* h, const BandSys& y) {
 ChunkArgs chunk_args(vus_handle* h) {
   ChunkArgs c;
   c.G = h->cgeom; c.B = h->B; c.D = h->D;
-  c.SD = h->H.p + h->sd_off; c.SU = h->H.p + h->su_off;
+  c.SD = band_matrix(h) + h->sd_off; c.SU = band_matrix(h) + h->su_off;
   c.Linv = h->Dinv.p; c.X = h->Gl.p; c.W = h->Gr.p;
   c.SepL = h->SepL.p; c.SepR = h->SepR.p; c.SepU = h->SepU.p; c.Dsep = h->Dsep.p; c.Usep = h->Usep.p;
   c.fail = h->fail.p;
@@ -1246,7 +1287,7 @@ void small_matvec(vus_handle* h, long items, const MatvecArgs& a, rt::stream_t s
 void apply_band(vus_handle* h, double* Y, long ystride, const double* X, long xstride, int nv, rt::stream_t st) {
   ClassGuard kc_guard(KC_MATVEC);
   MatvecArgs a;
-  a.SD = h->H.p + h->sd_off; a.SU = h->H.p + h->su_off; a.Ns = h->Ns; a.B = h->B; a.x = X; a.y = Y;
+  a.SD = band_matrix(h) + h->sd_off; a.SU = band_matrix(h) + h->su_off; a.Ns = h->Ns; a.B = h->B; a.x = X; a.y = Y;
   a.nv = nv; a.xstride = xstride; a.ystride = ystride; a.Nrows = h->Ns_band;
   a.rem_ptr = nullptr; a.rem_col = nullptr; a.rem_val = nullptr; a.nnodes = h->N; a.D = h->D;
   a.F = nullptr; a.Hbb = nullptr; a.xb = nullptr; a.yb = nullptr; a.has_bias = 0;
@@ -2579,8 +2620,8 @@ int vus_debug_band_solve(vus_handle* h, void* stream, double lambda, double* SD_
       for (int i = 0; i < h->B; ++i)
         for (int j = 0; j < h->B; ++j) out[b * BB + (long)i * h->B + j] = tmp[b * BBP + (long)i * LD + j];
   };
-  if (SD_out) unpad(SD_out, h->H.p + h->sd_off, h->Ns);
-  if (SU_out && h->Ns > 1) unpad(SU_out, h->H.p + h->su_off, h->Ns - 1);
+  if (SD_out) unpad(SD_out, band_matrix(h) + h->sd_off, h->Ns);
+  if (SU_out && h->Ns > 1) unpad(SU_out, band_matrix(h) + h->su_off, h->Ns - 1);
   bcr_factor(h, st);
   if (x_inout && nrhs > 0) {
     DBuf<double> X;
