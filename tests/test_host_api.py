@@ -294,3 +294,18 @@ def test_batch_py_import_list_resolves():
         plot.plot_trajectory(1, None)
     with pytest.raises(NotImplementedError):
         gtsam.NavState()
+
+
+def test_partition_chain_arguments_are_checked(emu):
+    """vus_set_partition_chain rejects an impossible chain position instead of storing it."""
+    import ctypes as C
+    h = C.c_void_p()
+    assert emu.vus_create(0, C.byref(h)) == 0
+    try:
+        side = (C.c_int64 * 16)(*([-1] * 16))
+        assert emu.vus_set_partition_chain(h, 16, side, side, 0, 2) == 0
+        assert emu.vus_set_partition_chain(h, 16, side, side, 2, 2) != 0            # rank >= nranks
+        assert emu.vus_set_partition_chain(h, 16, None, side, 0, 2) != 0            # missing list
+        assert b"vus_set_partition_chain" in emu.vus_last_error(h)
+    finally:
+        emu.vus_destroy(h)
