@@ -29,6 +29,10 @@ for line in sass.splitlines():
     if not m:
         continue
     op = m.group(1).split(".")[0]
+    if op.startswith("ATOM"):          # ATOM / ATOMG / ATOMS
+        op = "ATOM"
+    elif op in ("REDG", "REDS", "REDUX"):
+        op = "RED" if op != "REDUX" else op
     tab[cur]["total"] += 1
     if op in tab[cur]:
         tab[cur][op] += 1
