@@ -111,7 +111,11 @@ def cpu_oracle_run(a, d, prob, max_steps, budget_s):
     accepted, error evaluations), continuing the same solve; the run stops at convergence, after `max_steps` iterations, or
     when `budget_s` seconds are used up (a 100 000-pose iteration costs ~45 s of one core; the whole solve ~13 min).
     -> (cpu_baseline dict, seconds per step, steps timed)"""
+    import oracle
     from oracle import lm
+    # run-time probe for a real gtsam (none in this image): the arm still times the port, but says whether a gtsam was importable
+    gtsam_probe = ("a real gtsam IS importable on this host (version %s) -- run tests/test_real_gtsam_pin.py" % getattr(oracle.real_gtsam(), "__version__", "?")
+                   if oracle.real_gtsam() is not None else "no gtsam importable on this host (probe: oracle.real_gtsam())")
     vals = lm.values_of(prob)
     lam = lm.LM_DEFAULTS["lambdaInitial"]
     nf = d["meta"]["n_factors"]
@@ -131,7 +135,7 @@ def cpu_oracle_run(a, d, prob, max_steps, budget_s):
     sample = (f"the first {len(times)} LM iteration(s) ({tries} lambda tries) of the SAME {nf}-factor graph the GPU arm solves, from the same "
               f"initial estimate: {t:.1f} s, error {err:.6e}{' (converged)' if converged else ''}.  CPU restatement of gtsam's LM in numpy / scipy "
               f"(oracle/lm.py: vectorised linearization, exact solve by LAPACK banded Cholesky or SuperLU), NOT gtsam; one graph is one "
-              f"thread, as in gtsam's own LM without TBB, so of the {os.cpu_count()} host cores it uses 1")
+              f"thread, as in gtsam's own LM without TBB, so of the {os.cpu_count()} host cores it uses 1; {gtsam_probe}")
     return dict(value=nf * lin / t, unit=UNIT, cores=1, kind="port", sample=sample, seconds=t, iterations=lin,
                 final_error=err), t / len(times), len(times)
 
